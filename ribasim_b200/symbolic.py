@@ -1,0 +1,261 @@
+"""Host symbolic factorisation for the batched sparse LU of `W_inner`.
+
+The reference factorises `W_inner` with KLU (PureKLU 1.4.1 via LinearSolve,
+core/src/config.jl:420-422, core/src/differentiation.jl:278-359) once per Jacobian refresh.
+Here the pattern is fixed for all ensemble members, so everything that depends only on the
+pattern is computed once on the host:
+
+* a fill-reducing ordering by *rake-and-compress rounds*: every round eliminates an
+  independent set of minimum-degree vertices (degree <= 2 whenever possible).  Leaves are
+  raked, chain vertices are compressed, so trees and chains finish in O(log n) rounds with
+  O(n) fill (a tridiagonal chain becomes cyclic reduction);
+* the static fill pattern of L+U on the symmetrised pattern (no pivoting — `-W_inner` is
+  column diagonally dominant for monotone flows);
+* for every L/U entry the ordered list of `L[i,k]*U[k,j]` products it subtracts and a
+  dependency level, so the numeric phase is a sequence of data-parallel levels in which each
+  entry is written by exactly one thread: no atomics, bit-reproducible;
+* level schedules for the forward and backward substitutions.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .interp import as_i32
+
+
+@dataclass
+class Symbolic:
+    n: int
+    perm: np.ndarray          # new index -> old index
+    iperm: np.ndarray         # old index -> new index
+    lu_row: np.ndarray        # permuted row of each LU entry (entries sorted by level)
+    lu_col: np.ndarray
+    lu_wsrc: np.ndarray       # index of the W entry feeding this LU entry, -1 for fill
+    lu_pivot: np.ndarray      # for L entries: index of U[k,k]; -1 for U entries
+    lu_prod_ptr: np.ndarray
+    lu_prod_l: np.ndarray
+    lu_prod_u: np.ndarray
+    lu_level_ptr: np.ndarray
+    lu_diag: np.ndarray       # index of U[i,i] per permuted row
+    fwd_level_ptr: np.ndarray
+    fwd_row: np.ndarray       # permuted rows sorted by level
+    fwd_ptr: np.ndarray       # per position in fwd_row
+    fwd_l: np.ndarray         # L entry index
+    fwd_k: np.ndarray         # permuted column (index into y)
+    bwd_level_ptr: np.ndarray
+    bwd_row: np.ndarray
+    bwd_ptr: np.ndarray
+    bwd_u: np.ndarray
+    bwd_k: np.ndarray
+    n_rounds: int
+
+    @property
+    def n_lu(self) -> int:
+        return len(self.lu_row)
+
+
+def rake_compress_order(n: int, adj: list[set[int]]) -> tuple[list[int], list[list[int]], int]:
+    """Return (elimination order, higher-ordered neighbour set of each pivot, #rounds).
+
+    `adj` is consumed (it becomes the quotient graph)."""
+    alive = np.ones(n, dtype=bool)
+    order: list[int] = []
+    struct: list[list[int]] = [[] for _ in range(n)]
+    deg = np.array([len(a) for a in adj], dtype=np.int64)
+    rounds = 0
+    remaining = n
+    while remaining:
+        rounds += 1
+        live = np.flatnonzero(alive)
+        d = deg[live]
+        thr = max(int(d.min()), 2)
+        cand = live[d <= thr]
+        cand = cand[np.argsort(deg[cand], kind="stable")]
+        blocked: set[int] = set()
+        picked: list[int] = []
+        for v in cand.tolist():
+            if v in blocked:
+                continue
+            picked.append(v)
+            blocked.update(adj[v])
+        for v in picked:
+            nb = adj[v]
+            struct[v] = sorted(nb)
+            for a in nb:
+                s = adj[a]
+                s.discard(v)
+                s.update(nb)
+                s.discard(a)
+                deg[a] = len(s)
+            adj[v] = set()
+            alive[v] = False
+            order.append(v)
+        remaining -= len(picked)
+    return order, struct, rounds
+
+
+def analyse(n: int, wrow_ptr: np.ndarray, wcol: np.ndarray) -> Symbolic:
+    """Symbolic LU of an n x n CSR pattern (diagonal assumed present)."""
+    adj: list[set[int]] = [set() for _ in range(n)]
+    wpos: dict[tuple[int, int], int] = {}
+    for i in range(n):
+        for k in range(int(wrow_ptr[i]), int(wrow_ptr[i + 1])):
+            j = int(wcol[k])
+            wpos[(i, j)] = k
+            if i != j:
+                adj[i].add(j)
+                adj[j].add(i)
+    order, struct_old, rounds = rake_compress_order(n, adj)
+    perm = np.array(order, dtype=np.int64)
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n)
+
+    # entries: U row k = {k} + S_k, L column k = S_k (all in permuted indices)
+    ent_row: list[int] = []
+    ent_col: list[int] = []
+    ent_idx: dict[tuple[int, int], int] = {}
+    S: list[list[int]] = []
+    for k in range(n):
+        sk = sorted(int(iperm[v]) for v in struct_old[order[k]])
+        S.append(sk)
+        for j in [k] + sk:
+            ent_idx[(k, j)] = len(ent_row)
+            ent_row.append(k)
+            ent_col.append(j)
+        for i in sk:
+            ent_idx[(i, k)] = len(ent_row)
+            ent_row.append(i)
+            ent_col.append(k)
+    n_lu = len(ent_row)
+    prods: list[list[tuple[int, int]]] = [[] for _ in range(n_lu)]
+    level = np.zeros(n_lu, dtype=np.int64)
+    acc = np.full(n_lu, -1, dtype=np.int64)
+    pivot = np.full(n_lu, -1, dtype=np.int64)
+    diag = np.empty(n, dtype=np.int64)
+    for k in range(n):
+        sk = S[k]
+        dk = ent_idx[(k, k)]
+        diag[k] = dk
+        level[dk] = acc[dk] + 1
+        for j in sk:
+            e = ent_idx[(k, j)]
+            level[e] = acc[e] + 1
+        for i in sk:
+            e = ent_idx[(i, k)]
+            pivot[e] = dk
+            level[e] = max(acc[e], level[dk]) + 1
+        for i in sk:
+            el = ent_idx[(i, k)]
+            ll = level[el]
+            for j in sk:
+                eu = ent_idx[(k, j)]
+                t = ent_idx[(i, j)]
+                prods[t].append((el, eu))
+                lv = max(ll, level[eu])
+                if lv > acc[t]:
+                    acc[t] = lv
+
+    # sort entries by level (stable) and renumber
+    order_e = np.argsort(level, kind="stable")
+    new_of = np.empty(n_lu, dtype=np.int64)
+    new_of[order_e] = np.arange(n_lu)
+    n_levels = int(level.max()) + 1 if n_lu else 0
+    level_ptr = np.searchsorted(level[order_e], np.arange(n_levels + 1), side="left")
+    lu_row = np.array(ent_row, dtype=np.int64)[order_e]
+    lu_col = np.array(ent_col, dtype=np.int64)[order_e]
+    lu_pivot = np.where(pivot[order_e] >= 0, new_of[np.maximum(pivot[order_e], 0)], -1)
+    lu_wsrc = np.full(n_lu, -1, dtype=np.int64)
+    for e_new, e_old in enumerate(order_e.tolist()):
+        i_old, j_old = order[ent_row[e_old]], order[ent_col[e_old]]
+        lu_wsrc[e_new] = wpos.get((i_old, j_old), -1)
+    prod_ptr = [0]
+    prod_l: list[int] = []
+    prod_u: list[int] = []
+    for e_old in order_e.tolist():
+        for (el, eu) in prods[e_old]:
+            prod_l.append(int(new_of[el]))
+            prod_u.append(int(new_of[eu]))
+        prod_ptr.append(len(prod_l))
+    lu_diag = new_of[diag]
+
+    # substitution schedules
+    Lrow: list[list[tuple[int, int]]] = [[] for _ in range(n)]  # (col k, entry)
+    Urow: list[list[tuple[int, int]]] = [[] for _ in range(n)]
+    for k in range(n):
+        for i in S[k]:
+            Lrow[i].append((k, int(new_of[ent_idx[(i, k)]])))
+        for j in S[k]:
+            Urow[k].append((j, int(new_of[ent_idx[(k, j)]])))
+    lvl_y = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        if Lrow[i]:
+            lvl_y[i] = 1 + max(lvl_y[k] for k, _ in Lrow[i])
+    lvl_x = np.zeros(n, dtype=np.int64)
+    for i in range(n - 1, -1, -1):
+        if Urow[i]:
+            lvl_x[i] = 1 + max(lvl_x[j] for j, _ in Urow[i])
+
+    def schedule(lvl, rows):
+        idx = np.argsort(lvl, kind="stable")
+        nl = int(lvl.max()) + 1 if n else 0
+        lptr = np.searchsorted(lvl[idx], np.arange(nl + 1), side="left")
+        ptr = [0]
+        ent: list[int] = []
+        col: list[int] = []
+        for i in idx.tolist():
+            for k, e in sorted(rows[i]):
+                ent.append(e)
+                col.append(k)
+            ptr.append(len(ent))
+        return as_i32(lptr), as_i32(idx), as_i32(ptr), as_i32(ent), as_i32(col)
+
+    f_lptr, f_row, f_ptr, f_l, f_k = schedule(lvl_y, Lrow)
+    b_lptr, b_row, b_ptr, b_u, b_k = schedule(lvl_x, Urow)
+    return Symbolic(
+        n=n, perm=as_i32(perm), iperm=as_i32(iperm),
+        lu_row=as_i32(lu_row), lu_col=as_i32(lu_col), lu_wsrc=as_i32(lu_wsrc),
+        lu_pivot=as_i32(lu_pivot), lu_prod_ptr=as_i32(prod_ptr), lu_prod_l=as_i32(prod_l),
+        lu_prod_u=as_i32(prod_u), lu_level_ptr=as_i32(level_ptr), lu_diag=as_i32(lu_diag),
+        fwd_level_ptr=f_lptr, fwd_row=f_row, fwd_ptr=f_ptr, fwd_l=f_l, fwd_k=f_k,
+        bwd_level_ptr=b_lptr, bwd_row=b_row, bwd_ptr=b_ptr, bwd_u=b_u, bwd_k=b_k,
+        n_rounds=rounds,
+    )
+
+
+# ------------------------------------------------------------------ reference numeric phase
+def numeric_factor(sym: Symbolic, wvals: np.ndarray) -> np.ndarray:
+    """NumPy restatement of the device numeric phase (used by the CPU tests of the schedule)."""
+    lu = np.zeros(sym.n_lu)
+    for lv in range(len(sym.lu_level_ptr) - 1):
+        for e in range(sym.lu_level_ptr[lv], sym.lu_level_ptr[lv + 1]):
+            v = wvals[sym.lu_wsrc[e]] if sym.lu_wsrc[e] >= 0 else 0.0
+            for q in range(sym.lu_prod_ptr[e], sym.lu_prod_ptr[e + 1]):
+                v -= lu[sym.lu_prod_l[q]] * lu[sym.lu_prod_u[q]]
+            if sym.lu_pivot[e] >= 0:
+                v /= lu[sym.lu_pivot[e]]
+            lu[e] = v
+    return lu
+
+
+def numeric_solve(sym: Symbolic, lu: np.ndarray, b: np.ndarray) -> np.ndarray:
+    x = b[sym.perm].astype(np.float64).copy()
+    for lv in range(len(sym.fwd_level_ptr) - 1):
+        for pos in range(sym.fwd_level_ptr[lv], sym.fwd_level_ptr[lv + 1]):
+            i = sym.fwd_row[pos]
+            v = x[i]
+            for q in range(sym.fwd_ptr[pos], sym.fwd_ptr[pos + 1]):
+                v -= lu[sym.fwd_l[q]] * x[sym.fwd_k[q]]
+            x[i] = v
+    for lv in range(len(sym.bwd_level_ptr) - 1):
+        for pos in range(sym.bwd_level_ptr[lv], sym.bwd_level_ptr[lv + 1]):
+            i = sym.bwd_row[pos]
+            v = x[i]
+            for q in range(sym.bwd_ptr[pos], sym.bwd_ptr[pos + 1]):
+                v -= lu[sym.bwd_u[q]] * x[sym.bwd_k[q]]
+            x[i] = v / lu[sym.lu_diag[i]]
+    out = np.empty_like(x)
+    out[sym.perm] = x
+    return out
