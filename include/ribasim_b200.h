@@ -1,0 +1,124 @@
+/* ribasim_b200.h — C ABI of librbs.so, the B200 (sm_100a) implicit-integration inner loop
+ * for Ribasim networks, batched over ensemble members.
+ *
+ * This is the drop-in boundary for the hot path only (level B3).  A Julia
+ * host keeps the model, TOML/GeoPackage input, BMI and callbacks, and `ccall`s these entry
+ * points from inside the SciML plug-in seams of the reference (INTEGRATION.md shows the
+ * binding).  Each entry point cites the reference interface it replaces, relative to
+ * /root/reference.
+ *
+ * Conventions
+ *  - plain C linkage, plain pointers and sizes; no torch / C++ types cross the boundary;
+ *  - every function returning `int` returns 0 on success, non-zero on failure; the message
+ *    is fetched with rbs_last_error (mirrors libribasim's get_last_bmi_error,
+ *    build/libribasim.jl:40-52, 192-201);
+ *  - host buffers are borrowed for the duration of the call; the library owns all device
+ *    memory; one handle per device; calls on one handle are serialised by the caller and are
+ *    stream-ordered inside the library;
+ *  - per-member arrays are structure-of-arrays `[entity][member]`, member fastest
+ *    (`value[e * n_members + m]`), Float64; indices are 0-based Int32;
+ *  - state order is the reference's `state_components` (core/src/parameter.jl:11-22);
+ *    the reduced state is `[basins sorted by node_id ; PID integrals]`
+ *    (core/src/read.jl:1758-1766).
+ *  - there is no CPU fallback: rbs_create fails loudly when no CUDA device is usable.
+ */
+#ifndef RIBASIM_B200_H
+#define RIBASIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbs_builder rbs_builder; /* network description under construction */
+typedef struct rbs_handle rbs_handle;   /* one ensemble shard resident on one device */
+
+/* ---- network description ------------------------------------------------------------
+ * Replaces the in-memory `ParametersIndependent` the Julia core builds in
+ * `Parameters(db, config)` (core/src/read.jl:1692-1802).  The host fills named Int32 /
+ * Float64 arrays (names listed in DESIGN.md §"descriptor keys"; produced by
+ * ribasim_b200/flatten.py and ribasim_b200/symbolic.py) and hands the builder to rbs_create. */
+rbs_builder* rbs_builder_create(void);
+int rbs_builder_set_i32(rbs_builder* b, const char* key, const int32_t* data, int64_t n);
+int rbs_builder_set_f64(rbs_builder* b, const char* key, const double* data, int64_t n);
+void rbs_builder_destroy(rbs_builder* b);
+
+/* Allocate device state for `n_members` ensemble members on CUDA device `device`.
+ * Returns NULL on failure (see rbs_last_error).  Replaces `Model(config)`'s allocation of
+ * u, du, caches and the linear-solve cache (core/src/model.jl:174-237,
+ * core/src/differentiation.jl:278-300). */
+rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device);
+void rbs_destroy(rbs_handle* h);
+
+/* Copy the last error message (NUL terminated) into buf; returns its length. */
+int rbs_last_error(char* buf, int32_t len);
+/* Library version string. */
+const char* rbs_version(void);
+/* Number of kernels launched on this handle since creation (for benchmarks). */
+int64_t rbs_kernel_launches(const rbs_handle* h);
+
+/* ---- parameters and forcing ---------------------------------------------------------
+ * Shared (member-independent) parameter arrays, e.g. "lb_level", "pump_flow_rate",
+ * "trc_table_idx": what `eval_time_interpolation` caches per RHS time in the reference
+ * (core/src/util.jl:1216-1231, core/src/parameter.jl:812-842), and the values swapped by
+ * DiscreteControl / allocation (core/src/callback.jl:765-786). */
+int rbs_set_param_f64(rbs_handle* h, const char* key, const double* host, int64_t n);
+int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64_t n);
+/* Per-member arrays `[n_entity][n_members]`: Basin vertical fluxes ("precipitation",
+ * "surface_runoff", "potential_evaporation", "drainage", "infiltration" — the BMI-writable
+ * forcing arrays, core/src/bmi.jl:64-88), "fb_rate", state "u", exact cumulatives.
+ * `broadcast != 0`: host holds one value per entity that is replicated to every member. */
+int rbs_set_member_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity,
+                       int32_t broadcast);
+int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_entity);
+/* Previous accepted time `tprev` (core/src/parameter.jl:1126-1130). */
+int rbs_set_tprev(rbs_handle* h, double tprev);
+
+/* ---- SciML plug-in seams (host buffers in, host buffers out) ------------------------ */
+/* u_reduced = A*u : `reduce_state!` (core/src/util.jl:745-791).  u: [n_state][B]. */
+int rbs_reduce(rbs_handle* h, const double* u, double* u_reduced);
+/* du = g(u_reduced, t): `water_balance!` (core/src/solve.jl:35-84).  Optional outputs
+ * (may be NULL): the basin caches current_storage/level/area/low_storage_factor
+ * [n_basin][B] (core/src/parameter.jl:793-803). */
+int rbs_rhs(rbs_handle* h, const double* u_reduced, double t, double* du, double* storage,
+            double* level, double* area, double* factor);
+/* Analytic J_intermediate = dg/du_reduced in the fixed CSR pattern (values [nnz_j][B]) and
+ * W_inner = A*J_intermediate - I/gamma (values [nnz_w][B]); replaces `get_jacobian!`
+ * (core/src/differentiation.jl:361-390) and `calc_W_inner!` (:153-271).  Either output may
+ * be NULL.  The factorisation of W_inner is refreshed as a side effect. */
+int rbs_jac(rbs_handle* h, const double* u_reduced, double t, double gamma, double* j_vals,
+            double* w_vals);
+/* Solve W_inner x = b with the current factors; b, x: [n_reduced][B].  Replaces the KLU
+ * solve inside `dolinsolve` (core/src/differentiation.jl:307-359). */
+int rbs_solve(rbs_handle* h, const double* b, double* x);
+/* `limit_flow!` (core/src/solve.jl:840-984): clamp u given uprev, dt at time t. */
+int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, double t);
+
+/* ---- device-resident time stepping ---------------------------------------------------
+ * One fixed-dt implicit-Euler step with NLNewton for every member, on the state resident in
+ * the handle ("u"): what OrdinaryDiffEq's perform_step!/nlsolve! do through the seams above
+ * (core/src/model.jl:219-237), followed by limit_flow!, the negative-storage
+ * check (core/src/util.jl:918-924) and the exact-forcing bookkeeping of
+ * `update_cumulative_flows!` (core/src/callback.jl:125-182).
+ * status_per_member (may be NULL): 0 converged, 1 Newton failure, |2 negative storage. */
+int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member);
+/* Solver options: abstol, reltol (core/src/config.jl:187-188), max Newton iterations. */
+int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter);
+/* Counters since creation: [0] steps, [1] Newton iterations (sum over steps of the maximum
+ * over members), [2] Jacobian/W refreshes, [3] member-steps that failed to converge. */
+int rbs_get_stats(rbs_handle* h, int64_t* out4);
+/* Refresh the basin caches (storage, level, area, factor) and du at the resident state. */
+int rbs_refresh(rbs_handle* h, double t);
+
+/* Raw device pointer of a per-member array (for zero-copy interop, e.g. NCCL gathers or
+ * torch tensors wrapping library memory); NULL if unknown. */
+void* rbs_device_ptr(rbs_handle* h, const char* key);
+/* The CUDA stream all work of this handle is ordered on (cudaStream_t as void*). */
+void* rbs_stream(rbs_handle* h);
+int rbs_synchronize(rbs_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIBASIM_B200_H */

@@ -1,0 +1,668 @@
+// rbs.cu — host side of librbs.so: the C ABI declared in include/ribasim_b200.h.
+//
+// Everything here is plumbing around the kernels in rbs_kernels.cuh: named device arrays,
+// the `Net` kernel argument, launch sequencing of one RHS / Jacobian / linear solve / Newton
+// step.  There is no CPU compute path: without a usable CUDA device rbs_create fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ribasim_b200.h"
+#include "rbs_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                   \
+    } while (0)
+
+struct DevArr {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool is_int = false;
+};
+
+}  // namespace
+
+struct rbs_builder {
+    std::map<std::string, std::vector<int32_t>> i;
+    std::map<std::string, std::vector<double>> d;
+};
+
+struct rbs_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int B = 0;
+    Net net{};
+    std::map<std::string, std::vector<int32_t>> hi;  // host copies of the integer descriptor
+    std::map<std::string, DevArr> shared;            // descriptor + shared parameters
+    std::map<std::string, DevArr> member;            // [n_entity][B] arrays
+    std::map<std::string, int64_t> member_entities;
+    double* staging = nullptr;  // device scratch for host<->device seam calls
+    size_t staging_bytes = 0;
+    int* h_active = nullptr;  // pinned
+    double tprev = 0.0;
+    double abstol = 1e-5, reltol = 1e-5;
+    int max_iter = 10;
+    int64_t launches = 0;
+    int64_t stats[4] = {0, 0, 0, 0};
+    // schedules (host)
+    std::vector<int> lu_level_ptr, fwd_level_ptr, bwd_level_ptr;
+    int *d_lu_level_ptr = nullptr, *d_fwd_level_ptr = nullptr, *d_bwd_level_ptr = nullptr;
+    bool tile_mode = true;
+    int tile = 8;
+    std::vector<int> list_phase[3];
+    int* d_list_phase[3] = {nullptr, nullptr, nullptr};
+    int n_part = 1, rows_per_block = 64;
+    bool factor_valid = false;
+};
+
+namespace {
+
+inline int grid_for(long long total, int block = 256) { return (int)((total + block - 1) / block); }
+
+template <class T> int upload(rbs_handle* h, const std::string& key, const std::vector<T>& v, bool is_int) {
+    DevArr& a = h->shared[key];
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    if (a.bytes != bytes) {
+        if (a.p) cudaFree(a.p);
+        CUDA_TRY(cudaMalloc(&a.p, bytes));
+        a.bytes = bytes;
+        a.is_int = is_int;
+    }
+    if (!v.empty())
+        CUDA_TRY(cudaMemcpyAsync(a.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int alloc_member(rbs_handle* h, const std::string& key, int64_t n_entity, bool is_int = false) {
+    DevArr a;
+    size_t elem = is_int ? sizeof(int) : sizeof(double);
+    a.bytes = std::max<size_t>((size_t)n_entity * h->B, 1) * elem;
+    a.is_int = is_int;
+    CUDA_TRY(cudaMalloc(&a.p, a.bytes));
+    CUDA_TRY(cudaMemsetAsync(a.p, 0, a.bytes, h->stream));
+    h->member[key] = a;
+    h->member_entities[key] = n_entity;
+    return 0;
+}
+
+template <class T> T* sp(rbs_handle* h, const char* key) {
+    auto it = h->shared.find(key);
+    return it == h->shared.end() ? nullptr : (T*)it->second.p;
+}
+double* mp(rbs_handle* h, const char* key) {
+    auto it = h->member.find(key);
+    return it == h->member.end() ? nullptr : (double*)it->second.p;
+}
+
+int geti(const rbs_builder* b, const char* key, int dflt = 0) {
+    auto it = b->i.find(key);
+    return it == b->i.end() || it->second.empty() ? dflt : it->second[0];
+}
+
+void bind_net(rbs_handle* h) {
+    Net& n = h->net;
+#define S_D(name) n.name = sp<double>(h, #name)
+#define S_I(name) n.name = sp<int>(h, #name)
+#define M_D(name) n.name = mp(h, #name)
+    S_D(storage0); S_D(low_storage_threshold); S_D(fixed_area);
+    S_I(prof_ptr); S_D(prof_level); S_D(prof_dSdh); S_D(prof_dSdh_slope); S_D(prof_cumS);
+    S_D(prof_area); S_D(prof_area_slope);
+    S_I(inc_ptr); S_I(inc_state); S_D(inc_sign); S_I(bfb_ptr); S_I(bfb_idx);
+    S_I(conn_type); S_I(conn_idx); S_I(src_kind); S_I(src_idx); S_I(dst_kind); S_I(dst_idx);
+    S_D(lr_resistance); S_D(lr_max_flow_rate);
+    S_D(mn_length); S_D(mn_manning_n); S_D(mn_profile_width); S_D(mn_profile_slope);
+    S_D(mn_upstream_bottom); S_D(mn_downstream_bottom);
+    S_I(tab_ptr); S_D(tab_t); S_D(tab_u); S_D(tab_du); S_D(tab_c1); S_D(tab_c2);
+    S_D(tab_slope_left); S_D(tab_slope_right);
+    S_I(pump_control_type); S_I(outlet_control_type);
+    S_I(ud_link_ptr); S_I(ud_of_link); S_D(ud_min_level); S_D(ud_link_alloc);
+    S_D(lb_level); S_I(trc_table_idx); S_D(trc_max_downstream_level);
+    S_D(pump_flow_rate); S_D(pump_min_flow_rate); S_D(pump_max_flow_rate);
+    S_D(pump_min_upstream_level); S_D(pump_max_downstream_level); S_D(pump_flow_demand);
+    S_D(outlet_flow_rate); S_D(outlet_min_flow_rate); S_D(outlet_max_flow_rate);
+    S_D(outlet_min_upstream_level); S_D(outlet_max_downstream_level); S_D(outlet_flow_demand);
+    S_D(ud_total_demand); S_D(ud_return_factor);
+    S_D(pid_target); S_D(pid_proportional); S_D(pid_integral); S_D(pid_derivative);
+    S_D(cc_sv_const);
+    S_I(pid_listen_basin); S_I(pid_target_is_outlet); S_I(pid_target_idx); S_I(pid_target_state);
+    S_I(pid_jpos_listen); S_I(pid_jpos_integral); S_I(pid_int_jpos);
+    S_I(pid_term_ptr); S_I(pid_term_state); S_D(pid_term_sign);
+    S_I(pid_jterm_ptr); S_I(pid_jterm_src); S_I(pid_jterm_dst); S_D(pid_jterm_sign);
+    S_I(cc_target_is_outlet); S_I(cc_target_idx); S_I(cc_target_state); S_I(cc_sv_ptr);
+    S_I(cc_sv_kind); S_I(cc_sv_idx); S_D(cc_sv_weight);
+    S_I(cc_term_ptr); S_I(cc_term_kind); S_I(cc_term_sv); S_I(cc_term_src); S_I(cc_term_dst);
+    S_I(jrow_ptr); S_I(jcol); S_I(jpos_src); S_I(jpos_dst); S_I(ud_out_jpos);
+    S_I(wsrc_ptr); S_I(wsrc_pos); S_I(wdiag_flag); S_D(wsrc_sign);
+    S_I(lu_wsrc); S_I(lu_pivot); S_I(lu_prod_ptr); S_I(lu_prod_l); S_I(lu_prod_u); S_I(lu_diag);
+    S_I(perm); S_I(fwd_row); S_I(fwd_ptr); S_I(fwd_l); S_I(fwd_k); S_I(bwd_row); S_I(bwd_ptr);
+    S_I(bwd_u); S_I(bwd_k);
+    M_D(u); M_D(uprev); M_D(z); M_D(du); M_D(ur); M_D(br); M_D(xs);
+    M_D(storage); M_D(level); M_D(factor); M_D(area); M_D(dlevel); M_D(dfactor); M_D(darea);
+    M_D(precipitation); M_D(surface_runoff); M_D(potential_evaporation); M_D(drainage);
+    M_D(infiltration); M_D(cum_precipitation); M_D(cum_surface_runoff); M_D(cum_drainage);
+    M_D(exact); M_D(fb_rate); M_D(fb_cum); M_D(frp); M_D(fro); M_D(jv); M_D(wv); M_D(lu);
+    M_D(norm_part); M_D(ndz); M_D(ndz_prev); M_D(eta); M_D(storage_prev); M_D(level_prev);
+    n.nstat = (int*)h->member["nstat"].p;
+    n.status = (int*)h->member["status"].p;
+    n.active_count = (int*)h->member["active_count"].p;
+#undef S_D
+#undef S_I
+#undef M_D
+}
+
+#define LAUNCH(h, kernel, total, ...)                                                          \
+    do {                                                                                       \
+        long long tot_ = (total);                                                              \
+        if (tot_ > 0) {                                                                        \
+            kernel<<<grid_for(tot_), 256, 0, (h)->stream>>>(__VA_ARGS__);                      \
+            (h)->launches++;                                                                   \
+        }                                                                                      \
+    } while (0)
+
+// RHS phases on the caches prepared by k_exact: ur -> du (and J values when JAC)
+template <bool JAC> void launch_rhs(rbs_handle* h, const double* ur) {
+    Net& n = h->net;
+    long long B = n.B;
+    // controllers read du of flows that may not be formulated yet: those must read 0
+    // (water_balance! zeroes du first, core/src/solve.jl:54)
+    if (n.n_pid > 0 || n.n_cc > 0)
+        cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream);
+    LAUNCH(h, k_basin<JAC>, (long long)n.n_basin * B, n, ur, true);
+    LAUNCH(h, k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0);
+    if (n.n_cc > 0) {
+        LAUNCH(h, k_continuous_control<JAC>, (long long)n.n_cc * B, n);
+        LAUNCH(h, k_links<JAC>, (long long)h->list_phase[1].size() * B, n, 1, h->d_list_phase[1],
+               (int)h->list_phase[1].size());
+    }
+    if (n.n_pid > 0) {
+        LAUNCH(h, k_pid<JAC>, (long long)n.n_pid * B, n, ur);
+        LAUNCH(h, k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
+               (int)h->list_phase[2].size());
+    }
+}
+
+void launch_factor(rbs_handle* h, double inv_gamma) {
+    Net& n = h->net;
+    long long B = n.B;
+    LAUNCH(h, k_assemble_w, (long long)n.nnz_w * B, n, inv_gamma);
+    int n_levels = (int)h->lu_level_ptr.size() - 1;
+    if (h->tile_mode) {
+        int blocks = (n.B + h->tile - 1) / h->tile;
+        k_lu_tile<<<blocks, 256, 0, h->stream>>>(n, h->d_lu_level_ptr, n_levels, h->tile);
+        h->launches++;
+    } else {
+        for (int lv = 0; lv < n_levels; lv++) {
+            int e0 = h->lu_level_ptr[lv], e1 = h->lu_level_ptr[lv + 1];
+            LAUNCH(h, k_lu_level, (long long)(e1 - e0) * B, n, e0, e1);
+        }
+    }
+    h->factor_valid = true;
+    h->stats[2]++;
+}
+
+void launch_solve(rbs_handle* h, const double* b, double* x) {
+    Net& n = h->net;
+    long long B = n.B;
+    int n_fwd = (int)h->fwd_level_ptr.size() - 1, n_bwd = (int)h->bwd_level_ptr.size() - 1;
+    if (h->tile_mode) {
+        int blocks = (n.B + h->tile - 1) / h->tile;
+        k_solve_tile<<<blocks, 256, 0, h->stream>>>(n, b, x, h->d_fwd_level_ptr, n_fwd,
+                                                    h->d_bwd_level_ptr, n_bwd, h->tile);
+        h->launches++;
+    } else {
+        LAUNCH(h, k_solve_load, (long long)n.n_reduced * B, n, b);
+        for (int lv = 1; lv < n_fwd; lv++) {
+            int p0 = h->fwd_level_ptr[lv], p1 = h->fwd_level_ptr[lv + 1];
+            LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 0);
+        }
+        for (int lv = 0; lv < n_bwd; lv++) {
+            int p0 = h->bwd_level_ptr[lv], p1 = h->bwd_level_ptr[lv + 1];
+            LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 1);
+        }
+        LAUNCH(h, k_solve_store, (long long)n.n_reduced * B, n, x);
+    }
+}
+
+int ensure_staging(rbs_handle* h, size_t bytes) {
+    if (h->staging_bytes >= bytes) return 0;
+    if (h->staging) cudaFree(h->staging);
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    return 0;
+}
+
+int check_async(rbs_handle* h, const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string(where) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rbs_version(void) { return "ribasim_b200 0.1.0 (sm_100a)"; }
+
+int rbs_last_error(char* buf, int32_t len) {
+    if (buf && len > 0) {
+        strncpy(buf, g_err.c_str(), (size_t)len - 1);
+        buf[len - 1] = 0;
+    }
+    return (int)g_err.size();
+}
+
+rbs_builder* rbs_builder_create(void) { return new rbs_builder(); }
+void rbs_builder_destroy(rbs_builder* b) { delete b; }
+int rbs_builder_set_i32(rbs_builder* b, const char* key, const int32_t* data, int64_t n) {
+    if (!b || !key || (n > 0 && !data)) return fail("rbs_builder_set_i32: null argument");
+    b->i[key].assign(data, data + n);
+    return 0;
+}
+int rbs_builder_set_f64(rbs_builder* b, const char* key, const double* data, int64_t n) {
+    if (!b || !key || (n > 0 && !data)) return fail("rbs_builder_set_f64: null argument");
+    b->d[key].assign(data, data + n);
+    return 0;
+}
+
+rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) {
+    if (!b) { fail("rbs_create: null builder"); return nullptr; }
+    if (n_members < 1) { fail("rbs_create: n_members must be >= 1"); return nullptr; }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        fail(std::string("rbs_create: no usable CUDA device (") + cudaGetErrorString(e) +
+             "); librbs has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= n_dev) { fail("rbs_create: invalid device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("rbs_create: cudaSetDevice failed"); return nullptr; }
+    rbs_handle* h = new rbs_handle();
+    h->device = device;
+    h->B = n_members;
+    auto bail = [&](const char* why) -> rbs_handle* {
+        if (g_err.empty()) fail(why);
+        rbs_destroy(h);
+        return nullptr;
+    };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail("rbs_create: stream creation failed");
+    if (cudaMallocHost(&h->h_active, sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
+    for (auto& kv : b->i) { h->hi[kv.first] = kv.second; if (upload(h, kv.first, kv.second, true)) return bail("upload"); }
+    for (auto& kv : b->d) if (upload(h, kv.first, kv.second, false)) return bail("upload");
+    Net& n = h->net;
+    n.B = n_members;
+    const char* required[] = {"n_basin", "n_state", "n_conn", "n_reduced", "nnz_j", "nnz_w", "n_lu"};
+    for (const char* k : required)
+        if (b->i.find(k) == b->i.end()) { fail(std::string("rbs_create: missing descriptor key ") + k); return bail(""); }
+#define GI(name) n.name = geti(b, #name)
+    GI(n_basin); GI(n_pid); GI(n_state); GI(n_conn); GI(n_reduced); GI(n_trc); GI(n_pump);
+    GI(n_outlet); GI(n_ud); GI(n_ud_link); GI(n_lr); GI(n_manning); GI(n_lb); GI(n_fb); GI(n_cc);
+    GI(n_tab); GI(off_trc); GI(off_pump); GI(off_outlet); GI(off_ud_in); GI(off_ud_out); GI(off_lr);
+    GI(off_manning); GI(off_evap); GI(off_infil); GI(off_integral); GI(nnz_j); GI(nnz_w); GI(n_lu);
+    GI(cc_tab_offset);
+#undef GI
+    {
+        auto it = b->d.find("level_difference_threshold");
+        n.ldt = it == b->d.end() || it->second.empty() ? 0.02 : it->second[0];
+    }
+    // shared time-dependent parameters: allocate with neutral defaults
+    struct PD { const char* key; int count; double dflt; };
+    const double inf = INFINITY, nan = NAN;
+    PD pds[] = {
+        {"lb_level", n.n_lb, 0}, {"trc_max_downstream_level", n.n_trc, inf},
+        {"pump_flow_rate", n.n_pump, 0}, {"pump_min_flow_rate", n.n_pump, 0},
+        {"pump_max_flow_rate", n.n_pump, inf}, {"pump_min_upstream_level", n.n_pump, -inf},
+        {"pump_max_downstream_level", n.n_pump, inf}, {"pump_flow_demand", n.n_pump, nan},
+        {"outlet_flow_rate", n.n_outlet, 0}, {"outlet_min_flow_rate", n.n_outlet, 0},
+        {"outlet_max_flow_rate", n.n_outlet, inf}, {"outlet_min_upstream_level", n.n_outlet, -inf},
+        {"outlet_max_downstream_level", n.n_outlet, inf}, {"outlet_flow_demand", n.n_outlet, nan},
+        {"ud_total_demand", n.n_ud, 0}, {"ud_return_factor", n.n_ud, 0},
+        {"ud_alloc_total", n.n_ud, 0},
+        {"pid_target", n.n_pid, 0}, {"pid_proportional", n.n_pid, 0}, {"pid_integral", n.n_pid, 0},
+        {"pid_derivative", n.n_pid, 0},
+    };
+    for (auto& pd : pds)
+        if (h->shared.find(pd.key) == h->shared.end())
+            if (upload(h, pd.key, std::vector<double>((size_t)pd.count, pd.dflt), false)) return bail("param alloc");
+    if (h->shared.find("trc_table_idx") == h->shared.end())
+        if (upload(h, "trc_table_idx", std::vector<int32_t>((size_t)n.n_trc, 0), true)) return bail("param alloc");
+    if (h->shared.find("ud_demand_from_timeseries") == h->shared.end())
+        if (upload(h, "ud_demand_from_timeseries", std::vector<int32_t>((size_t)n.n_ud, 0), true)) return bail("param alloc");
+    if (h->shared.find("cc_sv_const") == h->shared.end()) {
+        size_t nsv = h->hi.count("cc_sv_kind") ? h->hi["cc_sv_kind"].size() : 0;
+        if (upload(h, "cc_sv_const", std::vector<double>(nsv, 0.0), false)) return bail("param alloc");
+    }
+    // per-member arrays
+    h->rows_per_block = 64;
+    h->n_part = (n.n_state + h->rows_per_block - 1) / h->rows_per_block;
+    struct MD { const char* key; int64_t n; };
+    MD mds[] = {
+        {"u", n.n_state}, {"uprev", n.n_state}, {"z", n.n_state}, {"du", n.n_state},
+        {"ur", n.n_reduced}, {"br", n.n_reduced}, {"xs", n.n_reduced}, {"cvec", n.n_reduced},
+        {"storage", n.n_basin}, {"level", n.n_basin}, {"factor", n.n_basin}, {"area", n.n_basin},
+        {"dlevel", n.n_basin}, {"dfactor", n.n_basin}, {"darea", n.n_basin},
+        {"precipitation", n.n_basin}, {"surface_runoff", n.n_basin},
+        {"potential_evaporation", n.n_basin}, {"drainage", n.n_basin}, {"infiltration", n.n_basin},
+        {"cum_precipitation", n.n_basin}, {"cum_surface_runoff", n.n_basin},
+        {"cum_drainage", n.n_basin}, {"exact", n.n_basin}, {"storage_prev", n.n_basin},
+        {"level_prev", n.n_basin}, {"fb_rate", n.n_fb}, {"fb_cum", n.n_fb}, {"frp", n.n_pump},
+        {"fro", n.n_outlet}, {"jv", n.nnz_j}, {"wv", n.nnz_w}, {"lu", n.n_lu},
+        {"norm_part", h->n_part}, {"ndz", 1}, {"ndz_prev", 1}, {"eta", 1},
+    };
+    for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
+    if (alloc_member(h, "nstat", 1, true) || alloc_member(h, "status", 1, true)) return bail("member alloc");
+    {
+        DevArr a; a.bytes = sizeof(int); a.is_int = true;
+        if (cudaMalloc(&a.p, a.bytes) != cudaSuccess) return bail("active_count alloc");
+        cudaMemsetAsync(a.p, 0, a.bytes, h->stream);
+        h->member["active_count"] = a; h->member_entities["active_count"] = 0;
+    }
+    // eta_old starts at 1 (nlsolver.ηold)
+    k_fill<<<grid_for(n.B), 256, 0, h->stream>>>(mp(h, "eta"), n.B, 1.0);
+    // storage_prev = storage0 (core/src/read.jl:944-946)
+    k_broadcast<<<grid_for((long long)n.n_basin * n.B), 256, 0, h->stream>>>(
+        mp(h, "storage_prev"), sp<double>(h, "storage0"), n.n_basin, n.B);
+    // schedules
+    auto getv = [&](const char* k) { auto it = b->i.find(k); return it == b->i.end() ? std::vector<int32_t>{0} : it->second; };
+    h->lu_level_ptr = getv("lu_level_ptr");
+    h->fwd_level_ptr = getv("fwd_level_ptr");
+    h->bwd_level_ptr = getv("bwd_level_ptr");
+    h->d_lu_level_ptr = sp<int>(h, "lu_level_ptr");
+    h->d_fwd_level_ptr = sp<int>(h, "fwd_level_ptr");
+    h->d_bwd_level_ptr = sp<int>(h, "bwd_level_ptr");
+    // controlled pump/outlet states per phase
+    auto& pct = h->hi["pump_control_type"];
+    auto& oct = h->hi["outlet_control_type"];
+    for (int k = 0; k < n.n_pump; k++) if (pct[k] != CONTROL_NONE) h->list_phase[pct[k]].push_back(n.off_pump + k);
+    for (int k = 0; k < n.n_outlet; k++) if (oct[k] != CONTROL_NONE) h->list_phase[oct[k]].push_back(n.off_outlet + k);
+    for (int ph = 1; ph <= 2; ph++) {
+        std::string key = std::string("list_phase") + char('0' + ph);
+        if (upload(h, key, std::vector<int32_t>(h->list_phase[ph].begin(), h->list_phase[ph].end()), true)) return bail("list upload");
+        h->d_list_phase[ph] = sp<int>(h, key.c_str());
+    }
+    // execution mode of the sparse LU: member tiles per block when there are enough members to
+    // fill the machine, one launch per level otherwise
+    int tile = geti(b, "lu_tile", 0);
+    if (tile <= 0) tile = 8;
+    h->tile = tile;
+    int mode = geti(b, "lu_mode", -1);  // 0 wide, 1 tile, -1 auto
+    if (mode < 0) h->tile_mode = (n.B / tile) >= 64 || n.n_lu < 4096;
+    else h->tile_mode = mode == 1;
+    bind_net(h);
+    n.cc_tab_offset = geti(b, "cc_tab_offset");
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return bail("rbs_create: device initialisation failed");
+    return h;
+}
+
+void rbs_destroy(rbs_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& kv : h->shared) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto& kv : h->member) if (kv.second.p) cudaFree(kv.second.p);
+    if (h->staging) cudaFree(h->staging);
+    if (h->h_active) cudaFreeHost(h->h_active);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int64_t rbs_kernel_launches(const rbs_handle* h) { return h ? h->launches : 0; }
+
+int rbs_set_param_f64(rbs_handle* h, const char* key, const double* host, int64_t n) {
+    if (!h || !key) return fail("rbs_set_param_f64: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->shared.find(key);
+    if (it == h->shared.end() || it->second.is_int) return fail(std::string("unknown f64 parameter ") + key);
+    if ((size_t)n * sizeof(double) > it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // host buffer is borrowed only for the call
+    return 0;
+}
+int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64_t n) {
+    if (!h || !key) return fail("rbs_set_param_i32: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->shared.find(key);
+    if (it == h->shared.end() || !it->second.is_int) return fail(std::string("unknown i32 parameter ") + key);
+    if ((size_t)n * sizeof(int32_t) > it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rbs_set_member_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity, int32_t broadcast) {
+    if (!h || !key) return fail("rbs_set_member_f64: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || it->second.is_int) return fail(std::string("unknown member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    if (broadcast) {
+        if (ensure_staging(h, (size_t)n_entity * sizeof(double))) return 1;
+        CUDA_TRY(cudaMemcpyAsync(h->staging, host, (size_t)n_entity * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        k_broadcast<<<grid_for(n_entity * (long long)h->B), 256, 0, h->stream>>>((double*)it->second.p, h->staging, (int)n_entity, h->B);
+        h->launches++;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n_entity * h->B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_set_member_f64");
+}
+int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_entity) {
+    if (!h || !key || !host) return fail("rbs_get_member_f64: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || it->second.is_int) return fail(std::string("unknown member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(host, it->second.p, (size_t)n_entity * h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int rbs_set_tprev(rbs_handle* h, double tprev) {
+    if (!h) return fail("rbs_set_tprev: null handle");
+    h->tprev = tprev;
+    return 0;
+}
+int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter) {
+    if (!h) return fail("rbs_set_solver: null handle");
+    if (!(abstol >= 0) || !(reltol >= 0) || max_iter < 1) return fail("rbs_set_solver: invalid option");
+    h->abstol = abstol; h->reltol = reltol; h->max_iter = max_iter;
+    return 0;
+}
+int rbs_get_stats(rbs_handle* h, int64_t* out4) {
+    if (!h || !out4) return fail("rbs_get_stats: null argument");
+    for (int k = 0; k < 4; k++) out4[k] = h->stats[k];
+    return 0;
+}
+
+void* rbs_device_ptr(rbs_handle* h, const char* key) {
+    if (!h || !key) return nullptr;
+    auto it = h->member.find(key);
+    return it == h->member.end() ? nullptr : it->second.p;
+}
+void* rbs_stream(rbs_handle* h) { return h ? (void*)h->stream : nullptr; }
+int rbs_synchronize(rbs_handle* h) {
+    if (!h) return fail("rbs_synchronize: null handle");
+    cudaSetDevice(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_synchronize");
+}
+
+// ------------------------------------------------------------------------------------------ seams
+int rbs_reduce(rbs_handle* h, const double* u, double* u_reduced) {
+    if (!h || !u || !u_reduced) return fail("rbs_reduce: null argument");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    size_t nb = (size_t)n.n_state * n.B * sizeof(double);
+    if (ensure_staging(h, nb)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(h->staging, u, nb, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * n.B, n, h->staging, nullptr, n.ur, 0.0, 0.0);
+    CUDA_TRY(cudaMemcpyAsync(u_reduced, n.ur, (size_t)n.n_reduced * n.B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_reduce");
+}
+
+static int copy_out(rbs_handle* h, double* host, const double* dev, int64_t n_entity) {
+    if (!host || n_entity == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(host, dev, (size_t)n_entity * h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+int rbs_rhs(rbs_handle* h, const double* u_reduced, double t, double* du, double* storage,
+            double* level, double* area, double* factor) {
+    if (!h || !u_reduced) return fail("rbs_rhs: null argument");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    CUDA_TRY(cudaMemcpyAsync(n.ur, u_reduced, (size_t)n.n_reduced * n.B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
+    LAUNCH(h, k_exact, (long long)n.n_basin * n.B, n, t, h->tprev);
+    launch_rhs<false>(h, n.ur);
+    if (copy_out(h, du, n.du, n.n_state) || copy_out(h, storage, n.storage, n.n_basin) ||
+        copy_out(h, level, n.level, n.n_basin) || copy_out(h, area, n.area, n.n_basin) ||
+        copy_out(h, factor, n.factor, n.n_basin)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_rhs");
+}
+
+int rbs_jac(rbs_handle* h, const double* u_reduced, double t, double gamma, double* j_vals, double* w_vals) {
+    if (!h || !u_reduced) return fail("rbs_jac: null argument");
+    if (!(gamma > 0)) return fail("rbs_jac: gamma must be positive");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    CUDA_TRY(cudaMemcpyAsync(n.ur, u_reduced, (size_t)n.n_reduced * n.B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
+    CUDA_TRY(cudaMemsetAsync(n.jv, 0, (size_t)std::max(n.nnz_j, 1) * n.B * sizeof(double), h->stream));
+    LAUNCH(h, k_exact, (long long)n.n_basin * n.B, n, t, h->tprev);
+    launch_rhs<true>(h, n.ur);
+    launch_factor(h, 1.0 / gamma);
+    if (copy_out(h, j_vals, n.jv, n.nnz_j) || copy_out(h, w_vals, n.wv, n.nnz_w)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_jac");
+}
+
+int rbs_solve(rbs_handle* h, const double* b, double* x) {
+    if (!h || !b || !x) return fail("rbs_solve: null argument");
+    if (!h->factor_valid) return fail("rbs_solve: no factorisation; call rbs_jac first");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    size_t nb = (size_t)n.n_reduced * n.B * sizeof(double);
+    CUDA_TRY(cudaMemcpyAsync(n.br, b, nb, cudaMemcpyHostToDevice, h->stream));
+    double* c = mp(h, "cvec");
+    launch_solve(h, n.br, c);
+    CUDA_TRY(cudaMemcpyAsync(x, c, nb, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_solve");
+}
+
+static void launch_limit(rbs_handle* h, double* u, const double* uprev, double dt, double t) {
+    Net& n = h->net;
+    long long B = n.B;
+    LAUNCH(h, k_exact, (long long)n.n_basin * B, n, t, h->tprev);
+    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * B, n, u, nullptr, n.ur, 0.0, 0.0);
+    LAUNCH(h, k_basin<false>, (long long)n.n_basin * B, n, n.ur, false);
+    LAUNCH(h, k_limit_flow, (long long)n.off_integral * B, n, u, uprev, dt);
+    LAUNCH(h, k_limit_user_demand, (long long)n.n_ud_link * B, n, u, uprev, dt,
+           sp<int>(h, "ud_demand_from_timeseries"), sp<double>(h, "ud_alloc_total"));
+}
+
+int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, double t) {
+    if (!h || !u || !uprev) return fail("rbs_limit_flow: null argument");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    size_t nb = (size_t)n.n_state * n.B * sizeof(double);
+    CUDA_TRY(cudaMemcpyAsync(n.u, u, nb, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(n.uprev, uprev, nb, cudaMemcpyHostToDevice, h->stream));
+    launch_limit(h, n.u, n.uprev, dt, t);
+    CUDA_TRY(cudaMemcpyAsync(u, n.u, nb, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_limit_flow");
+}
+
+int rbs_refresh(rbs_handle* h, double t) {
+    if (!h) return fail("rbs_refresh: null handle");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    long long B = n.B;
+    CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
+    LAUNCH(h, k_exact, (long long)n.n_basin * B, n, t, h->tprev);
+    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * B, n, n.u, nullptr, n.ur, 0.0, 0.0);
+    launch_rhs<false>(h, n.ur);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_refresh");
+}
+
+int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member) {
+    if (!h) return fail("rbs_step_implicit_euler: null handle");
+    if (!(dt > 0)) return fail("rbs_step_implicit_euler: dt must be positive");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    long long B = n.B;
+    double tn = t + dt;
+    double inv_dt = 1.0 / dt;
+    double* c = mp(h, "cvec");
+    CUDA_TRY(cudaMemsetAsync(n.status, 0, (size_t)n.B * sizeof(int), h->stream));
+    LAUNCH(h, k_exact, (long long)n.n_basin * B, n, tn, h->tprev);
+    LAUNCH(h, k_step_begin, std::max((long long)n.n_state * B, B), n);
+    int iters = 0;
+    for (int iter = 1; iter <= h->max_iter; iter++) {
+        iters = iter;
+        LAUNCH(h, k_reduce<1>, (long long)n.n_reduced * B, n, n.uprev, n.z, n.ur, 0.0, 0.0);
+        if (iter == 1) {
+            // Jacobian and W = J - I/dt at (uprev, t + dt): refreshed once per step
+            launch_rhs<true>(h, n.ur);
+            launch_factor(h, inv_dt);
+        } else {
+            launch_rhs<false>(h, n.ur);
+        }
+        LAUNCH(h, k_reduce<2>, (long long)n.n_reduced * B, n, n.du, n.z, n.br, dt, inv_dt);
+        launch_solve(h, n.br, c);
+        CUDA_TRY(cudaMemsetAsync(n.active_count, 0, sizeof(int), h->stream));
+        {
+            dim3 block(32, RBS_DZ_ROWS), grid((n.B + 31) / 32, h->n_part);
+            k_newton_update<<<grid, block, 0, h->stream>>>(n, c, dt, inv_dt, h->abstol, h->reltol,
+                                                           h->rows_per_block);
+            h->launches++;
+        }
+        LAUNCH(h, k_newton_converge, B, n, iter, h->n_part, h->max_iter, 0.01);
+        CUDA_TRY(cudaMemcpyAsync(h->h_active, n.active_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (*h->h_active == 0) break;
+    }
+    LAUNCH(h, k_apply_z, (long long)n.n_state * B, n);
+    launch_limit(h, n.u, n.uprev, dt, tn);
+    // caches at the accepted state (check_negative_storage's water_balance! call)
+    CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
+    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * B, n, n.u, nullptr, n.ur, 0.0, 0.0);
+    launch_rhs<false>(h, n.ur);
+    LAUNCH(h, k_step_end, std::max((long long)(n.n_basin + n.n_fb) * B, B), n, tn - h->tprev);
+    h->tprev = tn;
+    h->stats[0]++;
+    h->stats[1] += iters;
+    if (status_per_member) {
+        CUDA_TRY(cudaMemcpyAsync(status_per_member, n.status, (size_t)n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int m = 0; m < n.B; m++) if (status_per_member[m] & 1) h->stats[3]++;
+    }
+    return check_async(h, "rbs_step_implicit_euler");
+}
+
+}  // extern "C"

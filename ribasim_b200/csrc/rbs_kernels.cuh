@@ -1,0 +1,711 @@
+// rbs_kernels.cuh — sm_100a kernels of the batched implicit-integration inner loop.
+//
+// Layout: every per-member quantity is structure-of-arrays `[entity][member]`, member
+// fastest, so a warp reads 32 consecutive members of one entity: fully coalesced 256 B
+// requests, network topology / link parameters / profile tables are warp-uniform broadcast
+// loads served from L1.  With a single member the same index arithmetic degenerates to
+// `[entity]`, still coalesced over entities.
+//
+// Determinism: every output element is written by exactly one thread and every sum runs in a
+// fixed order taken from the host-built index lists.  No floating-point atomics anywhere.
+#pragma once
+#include <stdint.h>
+
+#include "rbs_math.cuh"
+
+enum { KIND_BASIN = 0, KIND_LEVEL_BOUNDARY = 1, KIND_TERMINAL = 2, KIND_NONE = 3 };
+enum { CT_TRC = 0, CT_PUMP = 1, CT_OUTLET = 2, CT_UD_IN = 3, CT_UD_OUT = 4, CT_LR = 5, CT_MANNING = 6 };
+enum { CONTROL_NONE = 0, CONTROL_CONTINUOUS = 1, CONTROL_PID = 2 };
+enum { NEWTON_ACTIVE = 0, NEWTON_CONVERGED = 1, NEWTON_FAILED = 2 };
+
+struct Net {
+    // sizes
+    int B;  // members on this device
+    int n_basin, n_pid, n_state, n_conn, n_reduced;
+    int n_trc, n_pump, n_outlet, n_ud, n_ud_link, n_lr, n_manning, n_lb, n_fb, n_cc, n_tab;
+    int off_trc, off_pump, off_outlet, off_ud_in, off_ud_out, off_lr, off_manning, off_evap,
+        off_infil, off_integral;
+    int nnz_j, nnz_w, n_lu;
+    double ldt;  // level_difference_threshold
+    // basins (shared)
+    const double *storage0, *low_storage_threshold, *fixed_area;
+    const int* prof_ptr;
+    const double *prof_level, *prof_dSdh, *prof_dSdh_slope, *prof_cumS, *prof_area, *prof_area_slope;
+    const int *inc_ptr, *inc_state;
+    const double* inc_sign;
+    const int *bfb_ptr, *bfb_idx;
+    // connectors (shared)
+    const int *conn_type, *conn_idx, *src_kind, *src_idx, *dst_kind, *dst_idx;
+    const double *lr_resistance, *lr_max_flow_rate;
+    const double *mn_length, *mn_manning_n, *mn_profile_width, *mn_profile_slope,
+        *mn_upstream_bottom, *mn_downstream_bottom;
+    const int* tab_ptr;
+    const double *tab_t, *tab_u, *tab_du, *tab_c1, *tab_c2, *tab_slope_left, *tab_slope_right;
+    const int *pump_control_type, *outlet_control_type;
+    const int *ud_link_ptr, *ud_of_link;
+    const double *ud_min_level, *ud_link_alloc;
+    // time-dependent shared parameters (host refreshed)
+    const double* lb_level;
+    const int* trc_table_idx;
+    const double* trc_max_downstream_level;
+    const double *pump_flow_rate, *pump_min_flow_rate, *pump_max_flow_rate,
+        *pump_min_upstream_level, *pump_max_downstream_level, *pump_flow_demand;
+    const double *outlet_flow_rate, *outlet_min_flow_rate, *outlet_max_flow_rate,
+        *outlet_min_upstream_level, *outlet_max_downstream_level, *outlet_flow_demand;
+    const double *ud_total_demand, *ud_return_factor;
+    const double *pid_target, *pid_proportional, *pid_integral, *pid_derivative;
+    const double* cc_sv_const;
+    // control structure (shared)
+    const int *pid_listen_basin, *pid_target_is_outlet, *pid_target_idx, *pid_target_state;
+    const int *pid_jpos_listen, *pid_jpos_integral, *pid_int_jpos;
+    const int *pid_term_ptr, *pid_term_state;
+    const double* pid_term_sign;
+    const int *pid_jterm_ptr, *pid_jterm_src, *pid_jterm_dst;
+    const double* pid_jterm_sign;
+    const int *cc_target_is_outlet, *cc_target_idx, *cc_target_state, *cc_sv_ptr, *cc_sv_kind,
+        *cc_sv_idx;
+    const double* cc_sv_weight;
+    const int *cc_term_ptr, *cc_term_kind, *cc_term_sv, *cc_term_src, *cc_term_dst;
+    int cc_tab_offset;
+    // Jacobian / W patterns (shared)
+    const int *jrow_ptr, *jcol, *jpos_src, *jpos_dst, *ud_out_jpos;
+    const int *wsrc_ptr, *wsrc_pos, *wdiag_flag;
+    const double* wsrc_sign;
+    // LU schedule (shared)
+    const int *lu_wsrc, *lu_pivot, *lu_prod_ptr, *lu_prod_l, *lu_prod_u, *lu_diag, *perm;
+    const int *fwd_row, *fwd_ptr, *fwd_l, *fwd_k, *bwd_row, *bwd_ptr, *bwd_u, *bwd_k;
+    // per-member state
+    double *u, *uprev, *z, *du, *ur, *br, *xs;
+    double *storage, *level, *factor, *area, *dlevel, *dfactor, *darea;
+    double *precipitation, *surface_runoff, *potential_evaporation, *drainage, *infiltration;
+    double *cum_precipitation, *cum_surface_runoff, *cum_drainage, *exact;
+    double *fb_rate, *fb_cum;
+    double *frp, *fro;  // current_flow_rate_pump / outlet (control caches)
+    double *jv, *wv, *lu;
+    double *norm_part, *ndz, *ndz_prev, *eta;
+    int *nstat, *status, *active_count;
+    double* storage_prev;  // limiter memory (basin.storage_prev, frozen: SURVEY row 22)
+    double* level_prev;
+};
+
+#define RBS_TID (blockIdx.x * (long long)blockDim.x + threadIdx.x)
+
+struct RbsEnd { double h, f, dh, df; };
+
+template <bool JAC>
+__device__ __forceinline__ RbsEnd rbs_fetch_end(const Net& n, int kind, int idx, int m) {
+    RbsEnd e;
+    if (kind == KIND_BASIN) {
+        long long o = (long long)idx * n.B + m;
+        e.h = n.level[o];
+        e.f = n.factor[o];
+        e.dh = JAC ? n.dlevel[o] : 0.0;
+        e.df = JAC ? n.dfactor[o] : 0.0;
+    } else if (kind == KIND_LEVEL_BOUNDARY) {
+        e.h = n.lb_level[idx]; e.f = 1.0; e.dh = 0.0; e.df = 0.0;
+    } else {  // Terminal: bottomless pit (core/src/util.jl:184-187)
+        e.h = -RBS_INF; e.f = 1.0; e.dh = 0.0; e.df = 0.0;
+    }
+    return e;
+}
+
+// ---- exact cumulative forcing up to the RHS time (solve.jl:137-150, 86-99) -------------------
+__global__ void k_exact(Net n, double t, double tprev) {
+    long long tid = RBS_TID;
+    int b = (int)(tid / n.B);
+    if (b >= n.n_basin) return;
+    int m = (int)(tid - (long long)b * n.B);
+    long long o = (long long)b * n.B + m;
+    double dt = t - tprev;
+    double ccp = n.cum_precipitation[o] + n.fixed_area[b] * n.precipitation[o] * dt;
+    double ccr = n.cum_surface_runoff[o] + dt * n.surface_runoff[o];
+    double ccd = n.cum_drainage[o] + dt * n.drainage[o];
+    double ex = (ccp + ccr) + ccd;
+    for (int k = n.bfb_ptr[b]; k < n.bfb_ptr[b + 1]; k++) {
+        long long f = (long long)n.bfb_idx[k] * n.B + m;
+        ex += n.fb_cum[f] + n.fb_rate[f] * dt;
+    }
+    n.exact[o] = ex;
+}
+
+// ---- u_reduced = A * x (reduce_state!, util.jl:745-791) ---------------------------------------
+// MODE 0: x = a;  MODE 1: x = a + b (uprev + z);  MODE 2: x = (dt*a - b) * inv_dt (Newton rhs)
+template <int MODE>
+__device__ __forceinline__ double rbs_red_in(const double* a, const double* b, long long o,
+                                             double dt, double inv_dt) {
+    if (MODE == 0) return a[o];
+    if (MODE == 1) return a[o] + b[o];
+    return (dt * a[o] - b[o]) * inv_dt;
+}
+
+template <int MODE>
+__global__ void k_reduce(Net n, const double* __restrict__ a, const double* __restrict__ b,
+                         double* __restrict__ out, double dt, double inv_dt) {
+    long long tid = RBS_TID;
+    int r = (int)(tid / n.B);
+    if (r >= n.n_reduced) return;
+    int m = (int)(tid - (long long)r * n.B);
+    if (r < n.n_basin) {
+        double acc = 0.0;
+        for (int k = n.inc_ptr[r]; k < n.inc_ptr[r + 1]; k++) {
+            double v = rbs_red_in<MODE>(a, b, (long long)n.inc_state[k] * n.B + m, dt, inv_dt);
+            acc = n.inc_sign[k] > 0.0 ? acc + v : acc - v;
+        }
+        acc -= rbs_red_in<MODE>(a, b, (long long)(n.off_evap + r) * n.B + m, dt, inv_dt);
+        acc -= rbs_red_in<MODE>(a, b, (long long)(n.off_infil + r) * n.B + m, dt, inv_dt);
+        out[(long long)r * n.B + m] = acc;
+    } else {
+        int p = r - n.n_basin;
+        out[(long long)r * n.B + m] =
+            rbs_red_in<MODE>(a, b, (long long)(n.off_integral + p) * n.B + m, dt, inv_dt);
+    }
+}
+
+// ---- basin properties + vertical fluxes (solve.jl:120-227) -------------------------------------
+template <bool JAC>
+__global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du) {
+    long long tid = RBS_TID;
+    int b = (int)(tid / n.B);
+    if (b >= n.n_basin) return;
+    int m = (int)(tid - (long long)b * n.B);
+    long long o = (long long)b * n.B + m;
+    double S = (n.storage0[b] + ur[o]) + n.exact[o];
+    double dphi;
+    double phi = rbs_reduction_factor(S, n.low_storage_threshold[b], dphi);
+    int p0 = n.prof_ptr[b], np = n.prof_ptr[b + 1] - p0;
+    RbsBasinEval e = rbs_basin_eval(S, np, n.prof_level + p0, n.prof_dSdh + p0,
+                                    n.prof_dSdh_slope + p0, n.prof_cumS + p0, n.prof_area + p0,
+                                    n.prof_area_slope + p0);
+    n.storage[o] = S;
+    n.factor[o] = phi;
+    n.level[o] = e.level;
+    n.area[o] = e.area;
+    if (JAC) {
+        n.dlevel[o] = e.dlevel;
+        n.dfactor[o] = dphi;
+        n.darea[o] = e.darea;
+    }
+    if (write_du) {
+        double E = n.potential_evaporation[o], I = n.infiltration[o];
+        n.du[(long long)(n.off_evap + b) * n.B + m] = e.area * phi * E;
+        n.du[(long long)(n.off_infil + b) * n.B + m] = phi * I;
+        if (JAC) {
+            n.jv[(long long)n.jrow_ptr[n.off_evap + b] * n.B + m] = (e.darea * phi + e.area * dphi) * E;
+            n.jv[(long long)n.jrow_ptr[n.off_infil + b] * n.B + m] = dphi * I;
+        }
+    }
+}
+
+// ---- one user-demand inflow link (solve.jl:385-397) ---------------------------------------------
+template <bool JAC>
+__device__ __forceinline__ double rbs_ud_link(const Net& n, int k, int m, double& dq) {
+    int i = n.ud_of_link[k];
+    int s = n.off_ud_in + k;
+    RbsEnd a = rbs_fetch_end<JAC>(n, n.src_kind[s], n.src_idx[s], m);
+    int n_links = n.ud_link_ptr[i + 1] - n.ud_link_ptr[i];
+    double equal_split = n_links == 0 ? 0.0 : n.ud_total_demand[i] / n_links;
+    double alloc = n.ud_link_alloc[k];
+    double qt = isinf(alloc) ? equal_split : alloc;
+    double rp;
+    double r = rbs_reduction_factor(a.h - n.ud_min_level[i], n.ldt, rp);
+    if (JAC) dq = qt * a.df * r + qt * a.f * (rp * a.dh);
+    return qt * a.f * r;
+}
+
+// ---- connector flows (formulate_flows!, solve.jl:811-834) ---------------------------------------
+// PHASE 0: every connector state whose flow does not depend on a controller;
+// PHASE 1/2: the pumps/outlets listed in `list` (controlled by ContinuousControl / PidControl).
+template <bool JAC>
+__global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_list) {
+    long long tid = RBS_TID;
+    int li = (int)(tid / n.B);
+    int count = phase == 0 ? n.n_conn : n_list;
+    if (li >= count) return;
+    int m = (int)(tid - (long long)li * n.B);
+    int s = phase == 0 ? li : list[li];
+    int ct = n.conn_type[s], k = n.conn_idx[s];
+    long long so = (long long)s * n.B + m;
+    double q = 0.0, dq_a = 0.0, dq_b = 0.0;
+    if (ct == CT_UD_OUT) {
+        // outflow = (sum of the node's link flows) * return_factor (solve.jl:384-401)
+        double total = 0.0;
+        for (int l = n.ud_link_ptr[k]; l < n.ud_link_ptr[k + 1]; l++) {
+            double dq;
+            double qk = rbs_ud_link<JAC>(n, l, m, dq);
+            total += qk;
+            if (JAC && n.ud_out_jpos[l] >= 0)
+                n.jv[(long long)n.ud_out_jpos[l] * n.B + m] = dq * n.ud_return_factor[k];
+        }
+        n.du[so] = total * n.ud_return_factor[k];
+        return;
+    }
+    if (ct == CT_UD_IN) {
+        q = rbs_ud_link<JAC>(n, k, m, dq_a);
+        n.du[so] = q;
+        if (JAC && n.jpos_src[s] >= 0) n.jv[(long long)n.jpos_src[s] * n.B + m] = dq_a;
+        return;
+    }
+    bool controlled = false;
+    double g_fr = 0.0;
+    if (ct == CT_PUMP || ct == CT_OUTLET) {
+        bool outlet = ct == CT_OUTLET;
+        int control = outlet ? n.outlet_control_type[k] : n.pump_control_type[k];
+        if (control != phase) return;
+        controlled = control != CONTROL_NONE;
+        RbsEnd a = rbs_fetch_end<JAC>(n, n.src_kind[s], n.src_idx[s], m);
+        RbsEnd b = rbs_fetch_end<JAC>(n, n.dst_kind[s], n.dst_idx[s], m);
+        double fr = controlled ? (outlet ? n.fro : n.frp)[(long long)k * n.B + m]
+                               : (outlet ? n.outlet_flow_rate : n.pump_flow_rate)[k];
+        q = rbs_pump_outlet_flow(
+            fr, a.h, b.h, a.f, a.dh, b.dh, a.df,
+            (outlet ? n.outlet_min_flow_rate : n.pump_min_flow_rate)[k],
+            (outlet ? n.outlet_max_flow_rate : n.pump_max_flow_rate)[k],
+            (outlet ? n.outlet_flow_demand : n.pump_flow_demand)[k],
+            (outlet ? n.outlet_min_upstream_level : n.pump_min_upstream_level)[k],
+            (outlet ? n.outlet_max_downstream_level : n.pump_max_downstream_level)[k], n.ldt,
+            outlet, g_fr, dq_a, dq_b);
+    } else {
+        RbsEnd a = rbs_fetch_end<JAC>(n, n.src_kind[s], n.src_idx[s], m);
+        RbsEnd b = rbs_fetch_end<JAC>(n, n.dst_kind[s], n.dst_idx[s], m);
+        if (ct == CT_LR) {
+            q = rbs_lr_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df, n.lr_resistance[k],
+                            n.lr_max_flow_rate[k], dq_a, dq_b);
+        } else if (ct == CT_MANNING) {
+            q = rbs_manning_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df, n.mn_length[k],
+                                 n.mn_manning_n[k], n.mn_profile_width[k], n.mn_profile_slope[k],
+                                 n.mn_upstream_bottom[k], n.mn_downstream_bottom[k], dq_a, dq_b, JAC);
+        } else {  // CT_TRC
+            int tb = n.trc_table_idx[k];
+            int t0 = n.tab_ptr[tb], tn = n.tab_ptr[tb + 1] - t0;
+            double dQ;
+            double Q = rbs_pchip_eval(a.h, tn, n.tab_t + t0, n.tab_u + t0, n.tab_du + t0,
+                                      n.tab_c1 + t0, n.tab_c2 + t0, n.tab_slope_left[tb],
+                                      n.tab_slope_right[tb], dQ);
+            q = rbs_trc_flow(a.h, b.h, a.f, a.dh, b.dh, a.df, Q, dQ,
+                             n.trc_max_downstream_level[k], n.ldt, dq_a, dq_b);
+        }
+    }
+    n.du[so] = q;
+    if (JAC) {
+        if (controlled) {
+            // the controller left d(flow_rate)/dS in this row's slots: chain through dq/dflow_rate
+            for (int e = n.jrow_ptr[s]; e < n.jrow_ptr[s + 1]; e++) n.jv[(long long)e * n.B + m] *= g_fr;
+            if (n.jpos_src[s] >= 0) n.jv[(long long)n.jpos_src[s] * n.B + m] += dq_a;
+            if (n.jpos_dst[s] >= 0) n.jv[(long long)n.jpos_dst[s] * n.B + m] += dq_b;
+        } else {
+            if (n.jpos_src[s] >= 0) n.jv[(long long)n.jpos_src[s] * n.B + m] = dq_a;
+            if (n.jpos_dst[s] >= 0) n.jv[(long long)n.jpos_dst[s] * n.B + m] = dq_b;
+        }
+    }
+}
+
+// ---- ContinuousControl (solve.jl:101-113, callback.jl:757-763) ----------------------------------
+template <bool JAC>
+__global__ void k_continuous_control(Net n) {
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.B);
+    if (i >= n.n_cc) return;
+    int m = (int)(tid - (long long)i * n.B);
+    double value = 0.0;
+    for (int j = n.cc_sv_ptr[i]; j < n.cc_sv_ptr[i + 1]; j++) {
+        int kind = n.cc_sv_kind[j], idx = n.cc_sv_idx[j];
+        double x;
+        if (kind == 0) x = n.level[(long long)idx * n.B + m];
+        else if (kind == 1) x = n.storage[(long long)idx * n.B + m];
+        else if (kind == 2) x = n.du[(long long)idx * n.B + m];
+        else x = n.cc_sv_const[j];
+        value += n.cc_sv_weight[j] * x;
+    }
+    int tb = n.cc_tab_offset + i;
+    int t0 = n.tab_ptr[tb], tn = n.tab_ptr[tb + 1] - t0;
+    double df;
+    double out = rbs_pchip_eval(value, tn, n.tab_t + t0, n.tab_u + t0, n.tab_du + t0, n.tab_c1 + t0,
+                                n.tab_c2 + t0, n.tab_slope_left[tb], n.tab_slope_right[tb], df);
+    (n.cc_target_is_outlet[i] ? n.fro : n.frp)[(long long)n.cc_target_idx[i] * n.B + m] = out;
+    if (JAC) {
+        int row = n.cc_target_state[i];
+        for (int e = n.jrow_ptr[row]; e < n.jrow_ptr[row + 1]; e++) n.jv[(long long)e * n.B + m] = 0.0;
+        for (int q = n.cc_term_ptr[i]; q < n.cc_term_ptr[i + 1]; q++) {
+            double w = n.cc_sv_weight[n.cc_term_sv[q]];
+            int kind = n.cc_term_kind[q], src = n.cc_term_src[q];
+            double dx = kind == 0 ? n.dlevel[(long long)src * n.B + m]
+                                  : (kind == 1 ? 1.0 : n.jv[(long long)src * n.B + m]);
+            n.jv[(long long)n.cc_term_dst[q] * n.B + m] += df * (w * dx);
+        }
+    }
+}
+
+// ---- PidControl (solve.jl:229-346) ---------------------------------------------------------------
+template <bool JAC>
+__global__ void k_pid(Net n, const double* __restrict__ ur) {
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.B);
+    if (i >= n.n_pid) return;
+    int m = (int)(tid - (long long)i * n.B);
+    int L = n.pid_listen_basin[i];
+    long long lo = (long long)L * n.B + m;
+    double err = n.pid_target[i] - n.level[lo];
+    n.du[(long long)(n.off_integral + i) * n.B + m] = err;
+    double K_p = n.pid_proportional[i], K_i = n.pid_integral[i], K_d = n.pid_derivative[i];
+    double integral = ur[(long long)(n.n_basin + i) * n.B + m];
+    double area = 1.0, D = 1.0;
+    if (K_d != 0.0) {
+        area = n.area[lo];
+        D = 1.0 - K_d / area;
+    }
+    double flow_rate = 0.0;
+    if (K_p != 0.0) flow_rate += K_p * err / D;
+    if (K_i != 0.0) flow_rate += K_i * integral / D;
+    double dS = 0.0, N = 0.0;
+    if (K_d != 0.0) {
+        // formulate_dstorage_wrt_time (solve.jl:321-346) on the flows formulated so far
+        for (int k = n.pid_term_ptr[i]; k < n.pid_term_ptr[i + 1]; k++) {
+            double v = n.du[(long long)n.pid_term_state[k] * n.B + m];
+            dS = n.pid_term_sign[k] > 0.0 ? dS + v : dS - v;
+        }
+        // FlowBoundary inflows enter with their instantaneous rate (graph.jl:346-366)
+        // inflow order: neighbour list order is (connector states..., boundaries) — the
+        // boundary rates are added after the connector flows (rounding-level difference only)
+        for (int k = n.bfb_ptr[L]; k < n.bfb_ptr[L + 1]; k++)
+            dS += n.fb_rate[(long long)n.bfb_idx[k] * n.B + m];
+        dS += n.fixed_area[L] * n.precipitation[lo];
+        dS += n.surface_runoff[lo];
+        dS += n.drainage[lo];
+        dS -= n.du[(long long)(n.off_evap + L) * n.B + m];
+        dS -= n.du[(long long)(n.off_infil + L) * n.B + m];
+        N = 0.0 - dS / area;  // dtarget = 0 for a ConstantInterpolation target (solve.jl:298-300)
+        flow_rate += K_d * N / D;
+    }
+    (n.pid_target_is_outlet[i] ? n.fro : n.frp)[(long long)n.pid_target_idx[i] * n.B + m] = flow_rate;
+    if (JAC) {
+        double dh = n.dlevel[lo];
+        // integral row: d(err)/dS_L
+        n.jv[(long long)n.pid_int_jpos[i] * n.B + m] = -dh;
+        int row = n.pid_target_state[i];
+        for (int e = n.jrow_ptr[row]; e < n.jrow_ptr[row + 1]; e++) n.jv[(long long)e * n.B + m] = 0.0;
+        double dA = K_d != 0.0 ? n.darea[lo] : 0.0;
+        double dD = K_d != 0.0 ? K_d * dA / (area * area) : 0.0;  // dD/dS_L
+        double d_listen = 0.0;
+        if (K_p != 0.0) d_listen += K_p * ((-dh) * D - err * dD) / (D * D);
+        if (K_i != 0.0) {
+            d_listen += -K_i * integral * dD / (D * D);
+            n.jv[(long long)n.pid_jpos_integral[i] * n.B + m] = K_i / D;
+        }
+        if (K_d != 0.0) {
+            // d(N)/dS_c = -(d(dS)/dS_c * area - dS * dA[c == L]) / area^2
+            double coef = K_d / D;
+            for (int k = n.pid_jterm_ptr[i]; k < n.pid_jterm_ptr[i + 1]; k++) {
+                double v = n.pid_jterm_sign[k] * n.jv[(long long)n.pid_jterm_src[k] * n.B + m];
+                n.jv[(long long)n.pid_jterm_dst[k] * n.B + m] += coef * (-(v) / area);
+            }
+            double dvert = n.jv[(long long)n.jrow_ptr[n.off_evap + L] * n.B + m] +
+                           n.jv[(long long)n.jrow_ptr[n.off_infil + L] * n.B + m];
+            d_listen += coef * (dvert / area);       // -(-dvert)/area
+            d_listen += coef * (dS * dA / (area * area));
+            d_listen += -K_d * N * dD / (D * D);
+        }
+        n.jv[(long long)n.pid_jpos_listen[i] * n.B + m] += d_listen;
+    }
+}
+
+// ---- W_inner = A*J_i - I/gamma (calc_J_inner! + jacobian2W!, differentiation.jl:153-271) --------
+__global__ void k_assemble_w(Net n, double inv_gamma) {
+    long long tid = RBS_TID;
+    int e = (int)(tid / n.B);
+    if (e >= n.nnz_w) return;
+    int m = (int)(tid - (long long)e * n.B);
+    double acc = 0.0;
+    for (int k = n.wsrc_ptr[e]; k < n.wsrc_ptr[e + 1]; k++) {
+        double v = n.jv[(long long)n.wsrc_pos[k] * n.B + m];
+        acc = n.wsrc_sign[k] > 0.0 ? acc + v : acc - v;
+    }
+    if (n.wdiag_flag[e]) acc = acc - inv_gamma;
+    n.wv[(long long)e * n.B + m] = acc;
+}
+
+// ---- static-pattern LU: one entry of L or U (see ribasim_b200/symbolic.py) ----------------------
+__device__ __forceinline__ void rbs_lu_entry(const Net& n, int e, int m) {
+    int src = n.lu_wsrc[e];
+    double v = src >= 0 ? n.wv[(long long)src * n.B + m] : 0.0;
+    for (int q = n.lu_prod_ptr[e]; q < n.lu_prod_ptr[e + 1]; q++)
+        v -= n.lu[(long long)n.lu_prod_l[q] * n.B + m] * n.lu[(long long)n.lu_prod_u[q] * n.B + m];
+    int pv = n.lu_pivot[e];
+    if (pv >= 0) v /= n.lu[(long long)pv * n.B + m];
+    n.lu[(long long)e * n.B + m] = v;
+}
+
+// wide mode: one launch per dependency level, grid over (entries of the level) x members
+__global__ void k_lu_level(Net n, int e0, int e1) {
+    long long tid = RBS_TID;
+    int e = e0 + (int)(tid / n.B);
+    if (e >= e1) return;
+    int m = (int)(tid - (long long)(e - e0) * n.B);
+    rbs_lu_entry(n, e, m);
+}
+
+// tile mode: a block owns a tile of members for the whole factorisation; levels are separated
+// by __syncthreads() only (no grid-wide dependency because members are independent).
+__global__ void k_lu_tile(Net n, const int* __restrict__ level_ptr, int n_levels, int tile) {
+    int m0 = blockIdx.x * tile;
+    int tm = min(tile, n.B - m0);
+    if (tm <= 0) return;
+    for (int lv = 0; lv < n_levels; lv++) {
+        int e0 = level_ptr[lv], e1 = level_ptr[lv + 1];
+        int work = (e1 - e0) * tm;
+        for (int w = threadIdx.x; w < work; w += blockDim.x) {
+            int e = e0 + w / tm;
+            int m = m0 + w % tm;
+            rbs_lu_entry(n, e, m);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- triangular solves ----------------------------------------------------------------------------
+__global__ void k_solve_load(Net n, const double* __restrict__ b) {  // xs = P b
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.B);
+    if (i >= n.n_reduced) return;
+    int m = (int)(tid - (long long)i * n.B);
+    n.xs[(long long)i * n.B + m] = b[(long long)n.perm[i] * n.B + m];
+}
+__device__ __forceinline__ void rbs_fwd_row(const Net& n, int pos, int m) {
+    int i = n.fwd_row[pos];
+    double v = n.xs[(long long)i * n.B + m];
+    for (int q = n.fwd_ptr[pos]; q < n.fwd_ptr[pos + 1]; q++)
+        v -= n.lu[(long long)n.fwd_l[q] * n.B + m] * n.xs[(long long)n.fwd_k[q] * n.B + m];
+    n.xs[(long long)i * n.B + m] = v;
+}
+__device__ __forceinline__ void rbs_bwd_row(const Net& n, int pos, int m) {
+    int i = n.bwd_row[pos];
+    double v = n.xs[(long long)i * n.B + m];
+    for (int q = n.bwd_ptr[pos]; q < n.bwd_ptr[pos + 1]; q++)
+        v -= n.lu[(long long)n.bwd_u[q] * n.B + m] * n.xs[(long long)n.bwd_k[q] * n.B + m];
+    n.xs[(long long)i * n.B + m] = v / n.lu[(long long)n.lu_diag[i] * n.B + m];
+}
+__global__ void k_solve_level(Net n, int p0, int p1, int backward) {
+    long long tid = RBS_TID;
+    int pos = p0 + (int)(tid / n.B);
+    if (pos >= p1) return;
+    int m = (int)(tid - (long long)(pos - p0) * n.B);
+    if (backward) rbs_bwd_row(n, pos, m); else rbs_fwd_row(n, pos, m);
+}
+__global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __restrict__ x,
+                             const int* __restrict__ fwd_level_ptr, int n_fwd,
+                             const int* __restrict__ bwd_level_ptr, int n_bwd, int tile) {
+    int m0 = blockIdx.x * tile;
+    int tm = min(tile, n.B - m0);
+    if (tm <= 0) return;
+    for (int w = threadIdx.x; w < n.n_reduced * tm; w += blockDim.x) {
+        int i = w / tm, m = m0 + w % tm;
+        n.xs[(long long)i * n.B + m] = b[(long long)n.perm[i] * n.B + m];
+    }
+    __syncthreads();
+    for (int lv = 1; lv < n_fwd; lv++) {  // level 0 rows have no dependencies
+        int p0 = fwd_level_ptr[lv], p1 = fwd_level_ptr[lv + 1];
+        for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x)
+            rbs_fwd_row(n, p0 + w / tm, m0 + w % tm);
+        __syncthreads();
+    }
+    for (int lv = 0; lv < n_bwd; lv++) {
+        int p0 = bwd_level_ptr[lv], p1 = bwd_level_ptr[lv + 1];
+        for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x)
+            rbs_bwd_row(n, p0 + w / tm, m0 + w % tm);
+        __syncthreads();
+    }
+    for (int w = threadIdx.x; w < n.n_reduced * tm; w += blockDim.x) {
+        int i = w / tm, m = m0 + w % tm;
+        x[(long long)n.perm[i] * n.B + m] = n.xs[(long long)i * n.B + m];
+    }
+}
+__global__ void k_solve_store(Net n, double* __restrict__ x) {  // x = P^T xs
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.B);
+    if (i >= n.n_reduced) return;
+    int m = (int)(tid - (long long)i * n.B);
+    x[(long long)n.perm[i] * n.B + m] = n.xs[(long long)i * n.B + m];
+}
+
+// ---- Newton update (dolinsolve tail + compute_step!/apply_step!) --------------------
+// dz = gamma*dt * (J_i c - b),  b = (dt k - z)/(gamma dt);  z <- z - dz;
+// atmp = dz / (abstol + max(|uprev|, |uprev + z_old|) * reltol); partial sums of atmp^2.
+#define RBS_DZ_ROWS 8
+__global__ void k_newton_update(Net n, const double* __restrict__ c, double dt, double inv_dt,
+                                double abstol, double reltol, int rows_per_block) {
+    int m = blockIdx.x * 32 + threadIdx.x;
+    int r0 = blockIdx.y * rows_per_block;
+    double acc = 0.0;
+    bool live = m < n.B && n.nstat[m] == NEWTON_ACTIVE;
+    if (live) {
+        int r1 = min(r0 + rows_per_block, n.n_state);
+        for (int r = r0 + threadIdx.y; r < r1; r += RBS_DZ_ROWS) {
+            long long o = (long long)r * n.B + m;
+            double jc = 0.0;
+            for (int e = n.jrow_ptr[r]; e < n.jrow_ptr[r + 1]; e++)
+                jc += n.jv[(long long)e * n.B + m] * c[(long long)n.jcol[e] * n.B + m];
+            double zo = n.z[o];
+            double b = (dt * n.du[o] - zo) * inv_dt;
+            double dz = (jc - b) * dt;
+            double up = n.uprev[o];
+            double ustep = up + zo;
+            double sc = abstol + fmax(fabs(up), fabs(ustep)) * reltol;
+            double a = dz / sc;
+            acc += a * a;
+            n.z[o] = zo - dz;
+        }
+    }
+    __shared__ double sh[RBS_DZ_ROWS][33];
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && m < n.B) {
+        double s = 0.0;
+        for (int y = 0; y < RBS_DZ_ROWS; y++) s += sh[y][threadIdx.x];
+        n.norm_part[(long long)blockIdx.y * n.B + m] = s;
+    }
+}
+
+// per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve)
+__global__ void k_newton_converge(Net n, int iter, int n_part, int max_iter, double kappa) {
+    int m = (int)RBS_TID;
+    if (m >= n.B) return;
+    if (n.nstat[m] != NEWTON_ACTIVE) return;
+    double s = 0.0;
+    for (int p = 0; p < n_part; p++) s += n.norm_part[(long long)p * n.B + m];
+    double ndz = sqrt(s / n.n_state);
+    double eta = n.eta[m];
+    int st = NEWTON_ACTIVE;
+    if (!isfinite(ndz)) st = NEWTON_FAILED;
+    else {
+        double theta = 0.0;
+        if (iter > 1) {
+            theta = ndz / n.ndz_prev[m];
+            if (theta > 2.0) st = NEWTON_FAILED;
+            else eta = theta / (1.0 - theta);
+        }
+        if (st == NEWTON_ACTIVE &&
+            ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0.0 && eta * ndz < kappa)))
+            st = NEWTON_CONVERGED;
+    }
+    if (st == NEWTON_ACTIVE && iter >= max_iter) st = NEWTON_FAILED;
+    n.ndz_prev[m] = ndz;
+    n.ndz[m] = ndz;
+    n.eta[m] = eta;
+    n.nstat[m] = st;
+    if (st == NEWTON_ACTIVE) atomicAdd(n.active_count, 1);  // integer counter only
+}
+
+__global__ void k_step_begin(Net n) {
+    // uprev <- u, z <- 0, Newton state reset; eta0 = max(eta_old, eps)^0.8 (initial_eta)
+    long long tid = RBS_TID;
+    long long total = (long long)n.n_state * n.B;
+    if (tid < total) {
+        n.uprev[tid] = n.u[tid];
+        n.z[tid] = 0.0;
+    }
+    if (tid < n.B) {
+        n.nstat[tid] = NEWTON_ACTIVE;
+        n.eta[tid] = pow(fmax(n.eta[tid], 2.220446049250313e-16), 0.8);
+        n.ndz_prev[tid] = 0.0;
+    }
+}
+
+__global__ void k_apply_z(Net n) {  // u = uprev + z
+    long long tid = RBS_TID;
+    if (tid < (long long)n.n_state * n.B) n.u[tid] = n.uprev[tid] + n.z[tid];
+}
+
+// ---- limit_flow! (solve.jl:840-984); needs storage/level at the proposed u ------------------------
+__device__ __forceinline__ double rbs_min_low_storage_factor(const Net& n, int kind, int idx, int m) {
+    if (kind != KIND_BASIN) return 1.0;
+    long long o = (long long)idx * n.B + m;
+    double thr = n.low_storage_threshold[idx];
+    return rbs_reduction_factor(fmin(n.storage[o], n.storage_prev[o]) - 2 * thr, thr);
+}
+__global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __restrict__ uprev,
+                             double dt) {
+    long long tid = RBS_TID;
+    int s = (int)(tid / n.B);
+    if (s >= n.off_integral) return;
+    int m = (int)(tid - (long long)s * n.B);
+    long long o = (long long)s * n.B + m;
+    double lo, hi;
+    if (s < n.n_conn) {
+        int ct = n.conn_type[s], k = n.conn_idx[s];
+        if (ct == CT_TRC) { lo = 0.0; hi = RBS_INF; }
+        else if (ct == CT_PUMP) { lo = n.pump_min_flow_rate[k]; hi = n.pump_max_flow_rate[k]; }
+        else if (ct == CT_OUTLET) { lo = n.outlet_min_flow_rate[k]; hi = n.outlet_max_flow_rate[k]; }
+        else if (ct == CT_LR) { hi = n.lr_max_flow_rate[k]; lo = -hi; }
+        else return;  // UserDemand: handled by k_limit_user_demand; Manning: unbounded
+    } else if (s < n.off_infil) {
+        lo = 0.0; hi = RBS_INF;
+    } else {
+        int b = s - n.off_infil;
+        double fmin_ = rbs_min_low_storage_factor(n, KIND_BASIN, b, m);
+        double infil = n.infiltration[(long long)b * n.B + m];
+        lo = fmin_ * infil; hi = infil;
+    }
+    double up = uprev[o];
+    double a = up + lo * dt, b = up + hi * dt;
+    double v = u[o];
+    u[o] = v > b ? b : (v < a ? a : v);
+}
+__global__ void k_limit_user_demand(Net n, double* __restrict__ u, const double* __restrict__ uprev,
+                                    double dt, const int* __restrict__ from_ts,
+                                    const double* __restrict__ alloc_total) {
+    long long tid = RBS_TID;
+    int k = (int)(tid / n.B);
+    if (k >= n.n_ud_link) return;
+    int m = (int)(tid - (long long)k * n.B);
+    int i = n.ud_of_link[k];
+    int s = n.off_ud_in + k;
+    long long o = (long long)s * n.B + m;
+    double lo, hi;
+    if (from_ts[i]) { lo = 0.0; hi = RBS_INF; }
+    else {
+        int n_links = n.ud_link_ptr[i + 1] - n.ud_link_ptr[i];
+        double equal_split = n_links == 0 ? 0.0 : alloc_total[i] / n_links;
+        double alloc = n.ud_link_alloc[k];
+        double q_k_max = isinf(alloc) ? equal_split : alloc;
+        double fb = rbs_min_low_storage_factor(n, n.src_kind[s], n.src_idx[s], m);
+        double fl = 1.0;
+        if (n.src_kind[s] == KIND_BASIN) {
+            long long bo = (long long)n.src_idx[s] * n.B + m;
+            fl = rbs_reduction_factor(fmin(n.level[bo], n.level_prev[bo]) - n.ud_min_level[i] -
+                                          2 * n.ldt, n.ldt);
+        }
+        lo = fb * fl * q_k_max; hi = q_k_max;
+    }
+    double up = uprev[o];
+    double a = up + lo * dt, b = up + hi * dt;
+    double v = u[o];
+    u[o] = v > b ? b : (v < a ? a : v);
+}
+
+// ---- end-of-step bookkeeping (callback.jl:125-182) + negative storage flag ------------------------
+__global__ void k_step_end(Net n, double dt_exact) {
+    long long tid = RBS_TID;
+    int b = (int)(tid / n.B);
+    int m = (int)(tid - (long long)b * n.B);
+    if (b < n.n_basin) {
+        long long o = (long long)b * n.B + m;
+        n.cum_precipitation[o] += n.fixed_area[b] * n.precipitation[o] * dt_exact;
+        n.cum_surface_runoff[o] += dt_exact * n.surface_runoff[o];
+        n.cum_drainage[o] += dt_exact * n.drainage[o];
+        if (n.storage[o] < 0.0) atomicOr(&n.status[m], 2);
+    } else if (b < n.n_basin + n.n_fb) {
+        long long o = (long long)(b - n.n_basin) * n.B + m;
+        n.fb_cum[o] += n.fb_rate[o] * dt_exact;
+    }
+    if (tid < n.B) {
+        if (n.nstat[tid] != NEWTON_CONVERGED) atomicOr(&n.status[tid], 1);
+    }
+}
+
+__global__ void k_fill(double* p, long long nelem, double v) {
+    long long tid = RBS_TID;
+    if (tid < nelem) p[tid] = v;
+}
+__global__ void k_broadcast(double* __restrict__ dst, const double* __restrict__ src, int n_entity, int B) {
+    long long tid = RBS_TID;
+    if (tid < (long long)n_entity * B) dst[tid] = src[tid / B];
+}

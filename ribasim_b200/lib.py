@@ -1,0 +1,311 @@
+"""ctypes binding of librbs.so (include/ribasim_b200.h) and its build recipe.
+
+The product path has no CPU fallback: `load()` raises if the CUDA library is missing and
+`Handle.create` raises if no device is usable.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from .flatten import Flat
+from .symbolic import Symbolic, analyse
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "librbs.so"
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",  # keep the reference's operation order (no FMA contraction)
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class RbsError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile librbs.so for sm_100a in-tree (so that it travels with the repo snapshot)."""
+    srcs = [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_math.cuh",
+            PKG_DIR.parent / "include" / "ribasim_b200.h"]
+    if not force and LIB_PATH.exists() and all(
+            LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(CSRC / "rbs.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RbsError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if os.environ.get("RBS_NO_BUILD"):
+            raise RbsError(f"{LIB_PATH} is missing (run __graft_entry__.build())")
+        build()
+    L = ctypes.CDLL(str(LIB_PATH))
+    vp, cp = ctypes.c_void_p, ctypes.c_char_p
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+    sig = {
+        "rbs_builder_create": (vp, []),
+        "rbs_builder_set_i32": (ctypes.c_int, [vp, cp, ip, i64]),
+        "rbs_builder_set_f64": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_builder_destroy": (None, [vp]),
+        "rbs_create": (vp, [vp, i32, i32]),
+        "rbs_destroy": (None, [vp]),
+        "rbs_last_error": (ctypes.c_int, [cp, i32]),
+        "rbs_version": (cp, []),
+        "rbs_kernel_launches": (i64, [vp]),
+        "rbs_set_param_f64": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_set_param_i32": (ctypes.c_int, [vp, cp, ip, i64]),
+        "rbs_set_member_f64": (ctypes.c_int, [vp, cp, dp, i64, i32]),
+        "rbs_get_member_f64": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_set_tprev": (ctypes.c_int, [vp, f64]),
+        "rbs_reduce": (ctypes.c_int, [vp, dp, dp]),
+        "rbs_rhs": (ctypes.c_int, [vp, dp, f64, dp, dp, dp, dp, dp]),
+        "rbs_jac": (ctypes.c_int, [vp, dp, f64, f64, dp, dp]),
+        "rbs_solve": (ctypes.c_int, [vp, dp, dp]),
+        "rbs_limit_flow": (ctypes.c_int, [vp, dp, dp, f64, f64]),
+        "rbs_step_implicit_euler": (ctypes.c_int, [vp, f64, f64, ip]),
+        "rbs_set_solver": (ctypes.c_int, [vp, f64, f64, i32]),
+        "rbs_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(i64)]),
+        "rbs_refresh": (ctypes.c_int, [vp, f64]),
+        "rbs_device_ptr": (vp, [vp, cp]),
+        "rbs_stream": (vp, [vp]),
+        "rbs_synchronize": (ctypes.c_int, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # raises AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
+    "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
+    "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64",
+    "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
+    "rbs_step_implicit_euler", "rbs_set_solver", "rbs_get_stats", "rbs_refresh",
+    "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
+]
+
+
+def _dp(a: np.ndarray | None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a: np.ndarray | None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def last_error() -> str:
+    L = load()
+    buf = ctypes.create_string_buffer(1025)
+    L.rbs_last_error(buf, 1025)
+    return buf.value.decode(errors="replace")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RbsError(last_error())
+
+
+# parameters refreshed by the host whenever the RHS time crosses a tstop
+PARAM_F64 = [
+    "lb_level", "trc_max_downstream_level",
+    "pump_flow_rate", "pump_min_flow_rate", "pump_max_flow_rate", "pump_min_upstream_level",
+    "pump_max_downstream_level", "pump_flow_demand",
+    "outlet_flow_rate", "outlet_min_flow_rate", "outlet_max_flow_rate",
+    "outlet_min_upstream_level", "outlet_max_downstream_level", "outlet_flow_demand",
+    "ud_total_demand", "ud_return_factor", "pid_target", "pid_proportional", "pid_integral",
+    "pid_derivative", "cc_sv_const",
+]
+PARAM_I32 = ["trc_table_idx"]
+
+
+class Handle:
+    """One ensemble shard on one GPU (`rbs_handle`)."""
+
+    def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
+                 device: int = 0, lu_mode: int = -1, lu_tile: int = 0):
+        self.L = load()
+        self.flat = flat
+        if sym is None:
+            sym = analyse(flat.ints["n_reduced"], flat.arrays["wrow_ptr"], flat.arrays["wcol"])
+        self.sym = sym
+        self.B = int(n_members)
+        self.n_state = flat.ints["n_state"]
+        self.n_reduced = flat.ints["n_reduced"]
+        self.n_basin = flat.ints["n_basin"]
+        b = self.L.rbs_builder_create()
+        try:
+            def set_i(key, arr):
+                a = np.ascontiguousarray(np.asarray(arr, dtype=np.int32)).reshape(-1)
+                _check(self.L.rbs_builder_set_i32(b, key.encode(), _ip(a), a.size))
+
+            def set_d(key, arr):
+                a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64)).reshape(-1)
+                _check(self.L.rbs_builder_set_f64(b, key.encode(), _dp(a), a.size))
+
+            for k, v in flat.ints.items():
+                set_i(k, [v])
+            for k, v in flat.floats.items():
+                set_d(k, [v])
+            for k, v in flat.arrays.items():
+                if v.dtype == np.int32:
+                    set_i(k, v)
+                else:
+                    set_d(k, v)
+            wdiag_flag = np.zeros(flat.ints["nnz_w"], dtype=np.int32)
+            wdiag_flag[flat.arrays["wdiag"]] = 1
+            set_i("wdiag_flag", wdiag_flag)
+            set_i("n_lu", [sym.n_lu])
+            for name in ("perm", "lu_wsrc", "lu_pivot", "lu_prod_ptr", "lu_prod_l", "lu_prod_u",
+                         "lu_level_ptr", "lu_diag", "fwd_level_ptr", "fwd_row", "fwd_ptr", "fwd_l",
+                         "fwd_k", "bwd_level_ptr", "bwd_row", "bwd_ptr", "bwd_u", "bwd_k"):
+                set_i(name, getattr(sym, name))
+            set_i("lu_mode", [lu_mode])
+            set_i("lu_tile", [lu_tile])
+            self.h = self.L.rbs_create(b, self.B, int(device))
+        finally:
+            self.L.rbs_builder_destroy(b)
+        if not self.h:
+            raise RbsError(last_error())
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.rbs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def set_param(self, key: str, arr) -> None:
+        if key in PARAM_I32 or (isinstance(arr, np.ndarray) and arr.dtype == np.int32):
+            a = np.ascontiguousarray(np.asarray(arr, dtype=np.int32)).reshape(-1)
+            _check(self.L.rbs_set_param_i32(self.h, key.encode(), _ip(a), a.size))
+        else:
+            a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64)).reshape(-1)
+            _check(self.L.rbs_set_param_f64(self.h, key.encode(), _dp(a), a.size))
+
+    def set_time_params(self, tp: dict[str, np.ndarray]) -> None:
+        for k in PARAM_F64:
+            if k in tp:
+                self.set_param(k, tp[k])
+        for k in PARAM_I32:
+            if k in tp:
+                self.set_param(k, np.asarray(tp[k], dtype=np.int32))
+
+    def set_member(self, key: str, arr, broadcast: bool = False) -> None:
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64))
+        n_entity = a.size if broadcast else a.size // self.B
+        if not broadcast and a.size != n_entity * self.B:
+            raise ValueError(f"{key}: size {a.size} is not a multiple of n_members={self.B}")
+        _check(self.L.rbs_set_member_f64(self.h, key.encode(), _dp(a.reshape(-1)), n_entity,
+                                         int(broadcast)))
+
+    def get_member(self, key: str, n_entity: int) -> np.ndarray:
+        out = np.empty((n_entity, self.B), dtype=np.float64)
+        _check(self.L.rbs_get_member_f64(self.h, key.encode(), _dp(out.reshape(-1)), n_entity))
+        return out
+
+    def set_tprev(self, t: float) -> None:
+        _check(self.L.rbs_set_tprev(self.h, float(t)))
+
+    def set_solver(self, abstol: float, reltol: float, max_iter: int = 10) -> None:
+        _check(self.L.rbs_set_solver(self.h, abstol, reltol, max_iter))
+
+    # ------------------------------------------------------------------ seams
+    def _mat(self, x, n_entity: int) -> np.ndarray:
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        if a.size != n_entity * self.B:
+            raise ValueError(f"expected {n_entity} x {self.B} values, got {a.size}")
+        return a.reshape(n_entity, self.B)
+
+    def reduce(self, u) -> np.ndarray:
+        u = self._mat(u, self.n_state)
+        out = np.empty((self.n_reduced, self.B))
+        _check(self.L.rbs_reduce(self.h, _dp(u), _dp(out)))
+        return out
+
+    def rhs(self, u_reduced, t: float, with_cache: bool = False):
+        ur = self._mat(u_reduced, self.n_reduced)
+        du = np.empty((self.n_state, self.B))
+        if with_cache:
+            c = {k: np.empty((self.n_basin, self.B)) for k in ("storage", "level", "area", "factor")}
+            _check(self.L.rbs_rhs(self.h, _dp(ur), t, _dp(du), _dp(c["storage"]), _dp(c["level"]),
+                                  _dp(c["area"]), _dp(c["factor"])))
+            return du, c
+        _check(self.L.rbs_rhs(self.h, _dp(ur), t, _dp(du), None, None, None, None))
+        return du
+
+    def jac(self, u_reduced, t: float, gamma: float):
+        ur = self._mat(u_reduced, self.n_reduced)
+        jv = np.empty((self.flat.ints["nnz_j"], self.B))
+        wv = np.empty((self.flat.ints["nnz_w"], self.B))
+        _check(self.L.rbs_jac(self.h, _dp(ur), t, gamma, _dp(jv), _dp(wv)))
+        return jv, wv
+
+    def solve(self, b) -> np.ndarray:
+        b = self._mat(b, self.n_reduced)
+        x = np.empty_like(b)
+        _check(self.L.rbs_solve(self.h, _dp(b), _dp(x)))
+        return x
+
+    def limit_flow(self, u, uprev, dt: float, t: float) -> np.ndarray:
+        u = self._mat(u, self.n_state).copy()
+        up = self._mat(uprev, self.n_state)
+        _check(self.L.rbs_limit_flow(self.h, _dp(u), _dp(up), dt, t))
+        return u
+
+    def step(self, t: float, dt: float, want_status: bool = True):
+        st = np.zeros(self.B, dtype=np.int32) if want_status else None
+        _check(self.L.rbs_step_implicit_euler(self.h, t, dt, _ip(st)))
+        return st
+
+    def refresh(self, t: float) -> None:
+        _check(self.L.rbs_refresh(self.h, t))
+
+    def stats(self) -> dict[str, int]:
+        out = (ctypes.c_int64 * 4)()
+        _check(self.L.rbs_get_stats(self.h, out))
+        return dict(steps=out[0], newton_iters=out[1], jac_refreshes=out[2], failed=out[3])
+
+    def kernel_launches(self) -> int:
+        return int(self.L.rbs_kernel_launches(self.h))
+
+    def device_ptr(self, key: str) -> int:
+        return int(self.L.rbs_device_ptr(self.h, key.encode()) or 0)
+
+    def synchronize(self) -> None:
+        _check(self.L.rbs_synchronize(self.h))

@@ -1,0 +1,164 @@
+"""Host-side model driver: the role `Ribasim.Model` + the SciML integrator loop play in the
+reference (core/src/model.jl:108-297, core/src/bmi.jl:6-99), for an ensemble of members that
+share one network.
+
+The time loop is fixed-step implicit Euler.  Per accepted step it reproduces the reference's
+callback bookkeeping (core/src/callback.jl:18-72):
+RHS caches at the new state -> exact cumulative forcings + tprev -> new vertical fluxes at
+forcing tstops.  All floating-point work of the step runs on the GPU through librbs.
+"""
+
+from __future__ import annotations
+
+import math
+from pathlib import Path
+
+import numpy as np
+
+from . import lib
+from .flatten import Flat, flatten
+from .network import Params, build_params
+from .symbolic import Symbolic, analyse
+from .tables import ModelTables
+from .timecache import (
+    eval_time_params,
+    flow_boundary_increment,
+    forcing_tstops,
+    update_vertical_flux,
+)
+
+FORCING_NAMES = ("precipitation", "surface_runoff", "potential_evaporation", "drainage",
+                 "infiltration")
+
+
+class Model:
+    """An ensemble of `n_members` instances of one Ribasim network on one GPU."""
+
+    def __init__(self, model: str | Path | ModelTables | Params, n_members: int = 1,
+                 device: int = 0, dt: float | None = None, flat: Flat | None = None,
+                 sym: Symbolic | None = None, lu_mode: int = -1, lu_tile: int = 0):
+        if isinstance(model, Params):
+            self.p = model
+        else:
+            tables = model if isinstance(model, ModelTables) else ModelTables.read(model)
+            self.p = build_params(tables)
+        self.tables = self.p.tables
+        self.flat = flat if flat is not None else flatten(self.p)
+        self.sym = sym if sym is not None else analyse(
+            self.flat.ints["n_reduced"], self.flat.arrays["wrow_ptr"], self.flat.arrays["wcol"])
+        self.B = int(n_members)
+        cfg_dt = self.tables.solver_option("dt")
+        self.dt = float(dt if dt is not None else (cfg_dt if cfg_dt else 3600.0))
+        self.t = 0.0
+        self.t_end = self.tables.t_end
+        self.tstops = [x for x in self.p.tstops if x <= self.t_end]
+        self._ftstops = set(forcing_tstops(self.p, self.t_end))
+        self._k_stop = 0
+        self.h = lib.Handle(self.flat, self.sym, n_members=self.B, device=device, lu_mode=lu_mode,
+                            lu_tile=lu_tile)
+        self.h.set_solver(self.tables.solver_option("abstol"), self.tables.solver_option("reltol"))
+        n = self.p.nodes
+        ud = n["user_demand"]
+        self.h.set_param("ud_demand_from_timeseries",
+                         np.asarray(ud["demand_from_timeseries"], dtype=np.int32))
+        alloc_total = np.minimum(ud["demand"], ud["allocated"]).sum(axis=1) \
+            if len(ud["node_id"]) else np.zeros(0)
+        self.h.set_param("ud_alloc_total", alloc_total)
+        # forcing at t0 is the same for all members until the caller perturbs it
+        for name in FORCING_NAMES:
+            self.h.set_member(name, self.p.basin.vertical_flux[name], broadcast=True)
+        self._fb_rate_members: np.ndarray | None = None
+        self._push_time_params(0.0)
+        self._push_fb_rate(0.0, min(self.dt, self.t_end))
+        self.h.set_tprev(0.0)
+        # level_prev = level at t0 (core/src/model.jl:187-191)
+        self.h.refresh(0.0)
+        nb = self.flat.ints["n_basin"]
+        self.h.set_member("level_prev", self.h.get_member("level", nb))
+        self.status_counts = dict(newton_failed=0, negative_storage=0)
+
+    # ------------------------------------------------------------------ forcing / parameters
+    def _push_time_params(self, t: float) -> None:
+        self._tp = eval_time_params(self.p, t)
+        self.h.set_time_params(self._tp)
+
+    def _push_fb_rate(self, t0: float, t1: float) -> None:
+        nfb = self.flat.ints["n_fb"]
+        if nfb == 0:
+            return
+        if self._fb_rate_members is not None:
+            self.h.set_member("fb_rate", self._fb_rate_members)
+            return
+        incr = flow_boundary_increment(self.p, t0, t1)
+        kind = self.p.nodes["flow_boundary"]["flow_rate"][0].kind if nfb else "constant"
+        if kind == "constant":
+            rate = np.array([s(t0) for s in self.p.nodes["flow_boundary"]["flow_rate"]])
+        else:  # linear interpolation: mean rate over the step
+            rate = incr / (t1 - t0) if t1 > t0 else incr * 0.0
+        self.h.set_member("fb_rate", rate, broadcast=True)
+
+    def set_forcing(self, name: str, values: np.ndarray) -> None:
+        """Overwrite a Basin vertical flux for all members: values `[n_basin][n_members]`
+        (the BMI-writable arrays `basin.infiltration` etc., core/src/bmi.jl:64-88)."""
+        if name not in FORCING_NAMES:
+            raise KeyError(name)
+        self.h.set_member(name, values)
+        self._member_forcing = True
+
+    def set_flow_boundary_rate(self, values: np.ndarray | None) -> None:
+        """Per-member FlowBoundary rates `[n_fb][n_members]` for the coming steps."""
+        self._fb_rate_members = None if values is None else np.ascontiguousarray(values)
+        if values is not None:
+            self.h.set_member("fb_rate", self._fb_rate_members)
+
+    # ------------------------------------------------------------------ time stepping
+    def _next_time(self, limit: float) -> float:
+        while self._k_stop < len(self.tstops) and self.tstops[self._k_stop] <= self.t:
+            self._k_stop += 1
+        nxt = self.tstops[self._k_stop] if self._k_stop < len(self.tstops) else self.t_end
+        return min(self.t + self.dt, nxt, limit)
+
+    def update(self, want_status: bool = True):
+        """One solver step (BMI.update, core/src/bmi.jl:36-39)."""
+        return self._step_to(self._next_time(self.t_end), want_status)
+
+    def _step_to(self, t_next: float, want_status: bool = True):
+        t0 = self.t
+        self._push_time_params(t_next)
+        self._push_fb_rate(t0, t_next)
+        st = self.h.step(t0, t_next - t0, want_status)
+        self.t = t_next
+        if st is not None:
+            self.status_counts["newton_failed"] += int(np.count_nonzero(st & 1))
+            self.status_counts["negative_storage"] += int(np.count_nonzero(st & 2))
+        if self.t in self._ftstops and not getattr(self, "_member_forcing", False):
+            if update_vertical_flux(self.p, self.t):
+                for name in FORCING_NAMES:
+                    self.h.set_member(name, self.p.basin.vertical_flux[name], broadcast=True)
+        return st
+
+    def update_until(self, time: float, want_status: bool = True) -> None:
+        """BMI.update_until (core/src/bmi.jl:41-52)."""
+        if time < self.t:
+            raise ValueError("The model has already passed the given timestamp.")
+        while self.t < time:
+            self._step_to(self._next_time(time), want_status)
+
+    def run(self) -> None:
+        self.update_until(self.t_end)
+
+    # ------------------------------------------------------------------ results
+    def storage(self) -> np.ndarray:
+        return self.h.get_member("storage", self.flat.ints["n_basin"])
+
+    def level(self) -> np.ndarray:
+        return self.h.get_member("level", self.flat.ints["n_basin"])
+
+    def u(self) -> np.ndarray:
+        return self.h.get_member("u", self.flat.ints["n_state"])
+
+    def flow(self) -> np.ndarray:
+        return self.h.get_member("du", self.flat.ints["n_state"])
+
+    def finalize(self) -> None:
+        self.h.close()
