@@ -70,6 +70,7 @@ def lib() -> ctypes.CDLL:
         L.orc_limit_flow.argtypes = [vp, dp, dp, ctypes.c_double, ctypes.c_double]
         L.orc_step.argtypes = [vp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                ctypes.c_double, ctypes.c_int, dp, ip, ip, ip]
+        L.orc_advance.argtypes = [vp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, ip]
         L.orc_reduction_factor.argtypes = [ctypes.c_double, ctypes.c_double]
         L.orc_reduction_factor.restype = ctypes.c_double
         L.orc_relaxed_root.argtypes = [ctypes.c_double, ctypes.c_double]
@@ -320,9 +321,29 @@ class OracleModel:
                              ctypes.byref(eta), ctypes.byref(it), ctypes.byref(cv), ctypes.byref(ng))
         return rc, it.value, cv.value, ng.value, eta.value
 
+    def advance(self, u: np.ndarray, t0: float, dt: float, opts: np.ndarray, h_try: float,
+                eta_old: float = 1.0):
+        """One outer step with sub-stepping, in place on `u`.
+        Returns (rc, dict(iters, substeps, rejects, negative, converged), h_try, eta)."""
+        assert u.dtype == np.float64 and u.flags.c_contiguous
+        h = ctypes.c_double(h_try)
+        eta = ctypes.c_double(eta_old)
+        out = np.zeros(5, dtype=np.int32)
+        rc = self.L.orc_advance(self.h, _dp(u), t0, dt, _dp(opts), ctypes.byref(h),
+                                ctypes.byref(eta), _ip(out))
+        return rc, dict(iters=int(out[0]), substeps=int(out[1]), rejects=int(out[2]),
+                        negative=int(out[3]), converged=int(out[4])), h.value, eta.value
+
+
+def advance_opts(abstol=1e-5, reltol=1e-5, max_iter=10, full_newton=0, grow_iters=4,
+                 max_halvings=0, predictor=0) -> np.ndarray:
+    return np.array([abstol, reltol, max_iter, full_newton, grow_iters, max_halvings, predictor],
+                    dtype=np.float64)
+
 
 def run_oracle(p, dt: float, t_end: float | None = None, flat=None, abstol: float | None = None,
-               reltol: float | None = None, merged_exact: bool = False, max_steps: int | None = None):
+               reltol: float | None = None, merged_exact: bool = False, max_steps: int | None = None,
+               full_newton: int = 0, max_halvings: int = 0, grow_iters: int = 4, predictor: int = 0):
     """Fixed-step implicit-Euler run of one instance with the reference's step bookkeeping
     (SURVEY Appendix A.6).  Returns (u, storage, level, stats)."""
     from ribasim_b200.flatten import flatten
@@ -348,18 +369,22 @@ def run_oracle(p, dt: float, t_end: float | None = None, flat=None, abstol: floa
     t = 0.0
     k_stop = 0
     eta = 1.0
-    stats = dict(steps=0, iters=0, failed=0, negative=0)
+    stats = dict(steps=0, iters=0, failed=0, negative=0, substeps=0, rejects=0)
+    opts = advance_opts(abstol, reltol, 10, full_newton, grow_iters, max_halvings, predictor)
+    h_try = dt
     while t < t_end:
         while k_stop < len(tstops) and tstops[k_stop] <= t:
             k_stop += 1
         t_next = min(t + dt, tstops[k_stop] if k_stop < len(tstops) else t_end, t_end)
         om.set_time_params(eval_time_params(p, t_next))
         om.set_f64("fb_incr", flow_boundary_increment(p, t, t_next))
-        rc, it, cv, ng, eta = om.step(u, t, t_next - t, abstol, reltol, eta)
+        rc, st, h_try, eta = om.advance(u, t, t_next - t, opts, min(h_try, t_next - t), eta)
         stats["steps"] += 1
-        stats["iters"] += it
+        stats["iters"] += st["iters"]
         stats["failed"] += int(rc != 0)
-        stats["negative"] += ng
+        stats["negative"] += st["negative"]
+        stats["substeps"] += st["substeps"]
+        stats["rejects"] += st["rejects"]
         t = t_next
         if t in ftstops and update_vertical_flux(p, t):
             for name, v in p.basin.vertical_flux.items():

@@ -272,6 +272,8 @@ struct Model {
         off_infil, off_integral, n_state, n_reduced;
     double level_difference_threshold = 0.02;
     double tprev = 0.0;
+    double h_override = -1.0;  // >= 0: exact forcing integrates over this sub-step length
+    std::vector<double> zlast; double hlast = 0.0;  // last accepted increment (predictor)
     int merged_exact = 0;  // 1: sum the exact forcing terms first (device association)
     std::vector<Pchip> tabs;
     // colouring of J_intermediate columns
@@ -281,7 +283,7 @@ struct Model {
     std::vector<double> storage_prev, level_prev;
 
     // bound views of the named arrays (rebound by bind() after every set/clone)
-#define RBS_D_FIELDS(X) X(cc_sv_const) X(cc_sv_weight) X(cumulative_drainage) X(cumulative_precipitation) X(cumulative_surface_runoff) X(drainage) X(fb_cumulative_flow) X(fb_incr) X(fb_rate_now) X(fixed_area) X(infiltration) X(lb_level) X(low_storage_threshold) X(lr_max_flow_rate) X(lr_resistance) X(mn_downstream_bottom) X(mn_length) X(mn_manning_n) X(mn_profile_slope) X(mn_profile_width) X(mn_upstream_bottom) X(pid_derivative) X(pid_integral) X(pid_proportional) X(pid_target) X(potential_evaporation) X(precipitation) X(prof_area) X(prof_cumS) X(prof_dSdh) X(prof_level) X(storage0) X(surface_runoff) X(tab_t) X(tab_u) X(trc_max_downstream_level) X(ud_allocated) X(ud_demand) X(ud_demand_static) X(ud_link_alloc) X(ud_min_level) X(ud_return_factor) X(pump_flow_rate) X(pump_min_flow_rate) X(pump_max_flow_rate) X(pump_min_upstream_level) X(pump_max_downstream_level) X(pump_flow_demand) X(outlet_flow_rate) X(outlet_min_flow_rate) X(outlet_max_flow_rate) X(outlet_min_upstream_level) X(outlet_max_downstream_level) X(outlet_flow_demand)
+#define RBS_D_FIELDS(X) X(cc_sv_const) X(cc_sv_weight) X(cumulative_drainage) X(cumulative_precipitation) X(cumulative_surface_runoff) X(drainage) X(fb_cumulative_flow) X(fb_incr) X(fb_rate_now) X(fb_rate_step) X(fixed_area) X(infiltration) X(lb_level) X(low_storage_threshold) X(lr_max_flow_rate) X(lr_resistance) X(mn_downstream_bottom) X(mn_length) X(mn_manning_n) X(mn_profile_slope) X(mn_profile_width) X(mn_upstream_bottom) X(pid_derivative) X(pid_integral) X(pid_proportional) X(pid_target) X(potential_evaporation) X(precipitation) X(prof_area) X(prof_cumS) X(prof_dSdh) X(prof_level) X(storage0) X(surface_runoff) X(tab_t) X(tab_u) X(trc_max_downstream_level) X(ud_allocated) X(ud_demand) X(ud_demand_static) X(ud_link_alloc) X(ud_min_level) X(ud_return_factor) X(pump_flow_rate) X(pump_min_flow_rate) X(pump_max_flow_rate) X(pump_min_upstream_level) X(pump_max_downstream_level) X(pump_flow_demand) X(outlet_flow_rate) X(outlet_min_flow_rate) X(outlet_max_flow_rate) X(outlet_min_upstream_level) X(outlet_max_downstream_level) X(outlet_flow_demand)
 #define RBS_I_FIELDS(X) X(bin_idx) X(bin_ptr) X(bin_type) X(bout_idx) X(bout_ptr) X(bout_type) X(cc_sv_idx) X(cc_sv_kind) X(cc_sv_ptr) X(cc_table_idx) X(cc_target_idx) X(cc_target_is_outlet) X(fb_dst_idx) X(fb_dst_type) X(lr_dst_idx) X(lr_dst_type) X(lr_src_idx) X(lr_src_type) X(mn_dst_idx) X(mn_dst_type) X(mn_src_idx) X(mn_src_type) X(pid_listen_basin) X(pid_target_idx) X(pid_target_is_outlet) X(prof_ptr) X(tab_left_linear) X(tab_ptr) X(tab_right_linear) X(trc_dst_idx) X(trc_dst_type) X(trc_src_idx) X(trc_src_type) X(trc_table_idx) X(ud_demand_from_timeseries) X(ud_dst_idx) X(ud_dst_type) X(ud_has_priority) X(ud_link_ptr) X(ud_link_src_idx) X(ud_link_src_type) X(pump_control_type) X(pump_src_type) X(pump_src_idx) X(pump_dst_type) X(pump_dst_idx) X(outlet_control_type) X(outlet_src_type) X(outlet_src_idx) X(outlet_dst_type) X(outlet_dst_idx)
 #define X(name) double* name = nullptr;
     RBS_D_FIELDS(X)
@@ -307,7 +309,7 @@ struct Model {
         off_trc = o.off_trc; off_pump = o.off_pump; off_outlet = o.off_outlet; off_ud_in = o.off_ud_in;
         off_ud_out = o.off_ud_out; off_lr = o.off_lr; off_manning = o.off_manning; off_evap = o.off_evap;
         off_infil = o.off_infil; off_integral = o.off_integral; n_state = o.n_state; n_reduced = o.n_reduced;
-        level_difference_threshold = o.level_difference_threshold; tprev = o.tprev;
+        level_difference_threshold = o.level_difference_threshold; tprev = o.tprev; h_override = o.h_override; zlast = o.zlast; hlast = o.hlast;
         merged_exact = o.merged_exact; tabs = o.tabs; color_of_col = o.color_of_col; n_colors = o.n_colors;
         pat_rows = o.pat_rows; pat_cols = o.pat_cols; storage_prev = o.storage_prev; level_prev = o.level_prev;
         lu = o.lu; lu_ready = o.lu_ready;
@@ -442,8 +444,10 @@ template <class T> T storage_to_level(const Model& m, int b, T S) {
     T dS = S - T(cs[idx]);
     double x = a[idx];
     double slope = (a[idx + 1] - a[idx]) / (h[idx + 1] - h[idx]);
-    if (slope == 0.0) return T(h[idx]) + dS / T(x);
-    return T(h[idx]) + (T(-x) + xsqrt(T(x * x) + T(2.0 * slope) * dS)) / T(slope);
+    // cancellation-free form of the quadratic root (exact for slope == 0); the reference builds
+    // dS_dh by finite differences of the integrated profile (read.jl:2171-2185), which leaves
+    // slopes like -5.7e-15 on constant-area segments
+    return T(h[idx]) + T(2.0) * dS / (T(x) + xsqrt(T(x * x) + T(slope) * (T(2.0) * dS)));
 }
 
 // level_to_area: LinearInterpolation with Constant extrapolation (read.jl:2303-2315)
@@ -474,7 +478,7 @@ template <class T> T low_storage_factor(const Cache<T>& c, int type, int idx) {
 
 // set_current_basin_properties! + formulate_storages! — core/src/solve.jl:120-204
 template <class T> void basin_properties(const Model& m, Cache<T>& c, const T* ur, double t) {
-    double dt = t - m.tprev;
+    double dt = m.h_override >= 0.0 ? m.h_override : t - m.tprev;
     auto& s0 = m.storage0;
     auto& fa = m.fixed_area;
     std::vector<double> fb_cum(m.n_fb);
@@ -498,7 +502,7 @@ template <class T> void basin_properties(const Model& m, Cache<T>& c, const T* u
     } else {
         std::vector<double> exact(m.n_basin);
         for (int i = 0; i < m.n_basin; i++) {
-            double dtl = t - m.tprev;
+            double dtl = dt;
             double ccp = m.cumulative_precipitation[i] + fa[i] * m.precipitation[i] * dtl;
             double ccr = m.cumulative_surface_runoff[i] + dtl * m.surface_runoff[i];
             double ccd = m.cumulative_drainage[i] + dtl * m.drainage[i];
@@ -923,26 +927,35 @@ void limit_flow(const Model& m, double* u, const double* uprev, double dt, doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// fixed-step implicit Euler with NLNewton (OrdinaryDiffEq, third-party; semantics as recalled
-// in SURVEY §8(c)): z0 = 0, gamma = 1, W = J - I/dt evaluated at the start of the step,
-// solve W dz = (dt f(uprev+z) - z)/dt, z <- z - dz, kappa = 1/100, max_iter = 10.
+// Implicit Euler with NLNewton (OrdinaryDiffEq, third-party; semantics as recalled in SURVEY
+// §8(c)): z0 = 0, gamma = 1, W = J - I/h, solve W dz = (h f(uprev+z) - z)/h, z <- z - dz,
+// kappa = 1/100, max_iter = 10.  `full_newton = 0` evaluates J and W once per (sub-)step at
+// (uprev, t + h) like the reference's nlsolve!; `full_newton = 1` refreshes them every
+// iteration.
+//
+// One outer step [t0, t0 + dt] is covered by sub-steps: a sub-step whose Newton iteration
+// fails, or that ends with negative storage (isoutofdomain, core/src/util.jl:918-924), is
+// rejected and retried with half the length (what the reference's adaptive controller does on
+// a failed nonlinear solve); after an accepted sub-step that converged within `grow_iters`
+// iterations the nominal length doubles again, capped at dt.  With max_halvings = 0 this is
+// plain fixed-step implicit Euler.
 // ------------------------------------------------------------------------------------------
-struct StepStats { int iters; int converged; int negative_storage; double ndz; };
+struct AdvanceOpts {
+    double abstol = 1e-5, reltol = 1e-5;
+    int max_iter = 10, full_newton = 0, grow_iters = 4, max_halvings = 0, predictor = 0;
+};
+struct StepStats { int iters = 0, converged = 0, negative_storage = 0, substeps = 0, rejects = 0; double ndz = 0; };
 
-int newton_step(Model& m, double* u, double t, double dt, double abstol, double reltol,
-                int max_iter, double* eta_old, StepStats* stats, bool use_dense) {
-    int n = m.n_state, nr = m.n_reduced;
-    double tn = t + dt;
-    std::vector<double> uprev(u, u + n), z(n, 0.0), ustep(n), k(n), b(n), dz(n), ur(nr), br(nr);
-    std::vector<double> jv(m.pat_rows.size());
-    Cache<double> c; c.resize(m);
-    // Jacobian and W at (uprev, tn)
-    m.reduce_state(uprev.data(), ur.data());
-    jac_colored(m, ur.data(), tn, jv.data());
-    // factorise W once per step (the reference refactors when W is refreshed)
-    bool sparse = nr > 48;
-    std::vector<double> W;
+struct NewtonWork {
+    std::vector<double> z, ustep, k, b, dz, ur, br, jv, W;
     std::vector<int> piv;
+    Cache<double> c;
+};
+
+// factorise W = A J - I/h with J at `ur`; returns false if singular
+static bool refresh_W(Model& m, NewtonWork& w, const double* ur, double tn, double h, bool sparse) {
+    int nr = m.n_reduced;
+    jac_colored(m, ur, tn, w.jv.data());
     if (sparse) {
         if (!m.lu_ready) {
             std::vector<std::vector<int>> pattern(nr);
@@ -954,35 +967,51 @@ int newton_step(Model& m, double* u, double t, double dt, double abstol, double 
             m.lu_ready = true;
         }
         m.lu.clear();
-        assemble_W(m, jv.data(), dt, [&](int i, int j) -> double& {
+        assemble_W(m, w.jv.data(), h, [&](int i, int j) -> double& {
             return m.lu.at(m.lu.pos_of[i], m.lu.pos_of[j]); });
-        if (!m.lu.factor()) { if (stats) { stats->iters = 0; stats->converged = 0; } return 1; }
+        return m.lu.factor();
+    }
+    w.W.assign((size_t)nr * nr, 0.0);
+    calc_W_inner(m, w.jv.data(), h, w.W.data());
+    return dense_factor(nr, w.W, w.piv);
+}
+
+// one nlsolve! attempt from uprev over a sub-step of length h ending at tn; z is the result
+static int newton_attempt(Model& m, NewtonWork& w, const double* uprev, double tn, double h,
+                          const AdvanceOpts& o, double* eta_io, int* iters_out, double* ndz_out) {
+    int n = m.n_state, nr = m.n_reduced;
+    bool sparse = nr > 48;
+    // initial guess: z = 0 (OrdinaryDiffEq `extrapolant = :constant`) or the last accepted
+    // increment rescaled to this sub-step (constant-flow predictor)
+    if (o.predictor && m.hlast > 0.0 && (int)m.zlast.size() == n) {
+        double r = h / m.hlast;
+        for (int i = 0; i < n; i++) w.z[i] = m.zlast[i] * r;
     } else {
-        W.resize((size_t)nr * nr);
-        calc_W_inner(m, jv.data(), dt, W.data());
-        if (!dense_factor(nr, W, piv)) { if (stats) { stats->iters = 0; stats->converged = 0; } return 1; }
+        std::fill(w.z.begin(), w.z.end(), 0.0);
     }
     const double kappa = 0.01;
-    double eta = std::pow(std::max(*eta_old, 2.220446049250313e-16), 0.8);
+    double eta = std::pow(std::max(*eta_io, 2.220446049250313e-16), 0.8);
     double ndz = 0, ndz_prev = 0;
     int status = 0, iter = 0;
-    (void)use_dense;
-    for (iter = 1; iter <= max_iter; iter++) {
-        for (int i = 0; i < n; i++) ustep[i] = uprev[i] + z[i];
-        m.reduce_state(ustep.data(), ur.data());
-        water_balance(m, c, ur.data(), tn, k.data());
-        for (int i = 0; i < n; i++) b[i] = (dt * k[i] - z[i]) * (1.0 / dt);
-        m.reduce_state(b.data(), br.data());
-        if (sparse) m.lu.solve(br.data());
-        else dense_apply(nr, W, piv, br.data());
+    for (iter = 1; iter <= o.max_iter; iter++) {
+        for (int i = 0; i < n; i++) w.ustep[i] = uprev[i] + w.z[i];
+        m.reduce_state(w.ustep.data(), w.ur.data());
+        if (iter == 1 || o.full_newton)
+            if (!refresh_W(m, w, w.ur.data(), tn, h, sparse)) { status = -1; break; }
+        water_balance(m, w.c, w.ur.data(), tn, w.k.data());
+        for (int i = 0; i < n; i++) w.b[i] = (h * w.k[i] - w.z[i]) * (1.0 / h);
+        m.reduce_state(w.b.data(), w.br.data());
+        if (sparse) m.lu.solve(w.br.data());
+        else dense_apply(nr, w.W, w.piv, w.br.data());
         // linu = gamma * (J_i c - b)
-        std::fill(dz.begin(), dz.end(), 0.0);
-        for (size_t e = 0; e < m.pat_rows.size(); e++) dz[m.pat_rows[e]] += jv[e] * br[m.pat_cols[e]];
-        for (int i = 0; i < n; i++) dz[i] = (dz[i] - b[i]) * dt;
+        std::fill(w.dz.begin(), w.dz.end(), 0.0);
+        for (size_t e = 0; e < m.pat_rows.size(); e++)
+            w.dz[m.pat_rows[e]] += w.jv[e] * w.br[m.pat_cols[e]];
+        for (int i = 0; i < n; i++) w.dz[i] = (w.dz[i] - w.b[i]) * h;
         double acc = 0;
         for (int i = 0; i < n; i++) {
-            double sc = abstol + std::max(std::fabs(uprev[i]), std::fabs(ustep[i])) * reltol;
-            double r = dz[i] / sc;
+            double sc = o.abstol + std::max(std::fabs(uprev[i]), std::fabs(w.ustep[i])) * o.reltol;
+            double r = w.dz[i] / sc;
             acc += r * r;
         }
         ndz_prev = ndz;
@@ -993,31 +1022,90 @@ int newton_step(Model& m, double* u, double t, double dt, double abstol, double 
             theta = ndz / ndz_prev;
             if (theta > 2) { status = -1; break; }
         }
-        for (int i = 0; i < n; i++) z[i] -= dz[i];
+        for (int i = 0; i < n; i++) w.z[i] -= w.dz[i];
         if (iter > 1) eta = theta / (1 - theta);
         if ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0 && eta * ndz < kappa)) { status = 1; break; }
     }
-    if (iter > max_iter) iter = max_iter;
-    *eta_old = eta;
-    for (int i = 0; i < n; i++) u[i] = uprev[i] + z[i];
-    limit_flow(m, u, uprev.data(), dt, tn);
-    // isoutofdomain / check_negative_storage: RHS at the accepted state refreshes the caches
-    m.reduce_state(u, ur.data());
-    water_balance(m, c, ur.data(), tn, k.data());
-    int neg = 0;
-    for (int i = 0; i < m.n_basin; i++) if (c.storage[i] < 0) neg++;
-    // update_cumulative_flows! — core/src/callback.jl:125-182
-    double dtl = tn - m.tprev;
-    auto& fa = m.fixed_area;
-    for (int i = 0; i < m.n_basin; i++) {
-        m.cumulative_precipitation[i] += fa[i] * m.precipitation[i] * dtl;
-        m.cumulative_surface_runoff[i] += dtl * m.surface_runoff[i];
-        m.cumulative_drainage[i] += dtl * m.drainage[i];
+    if (iter > o.max_iter) iter = o.max_iter;
+    *eta_io = eta;
+    *iters_out = iter;
+    *ndz_out = ndz;
+    return status == 1;
+}
+
+int advance(Model& m, double* u, double t0, double dt, const AdvanceOpts& o, double* h_try,
+            double* eta_old, StepStats* stats) {
+    int n = m.n_state, nr = m.n_reduced;
+    NewtonWork w;
+    w.z.assign(n, 0.0); w.ustep.resize(n); w.k.resize(n); w.b.resize(n); w.dz.resize(n);
+    w.ur.resize(nr); w.br.resize(nr); w.jv.resize(m.pat_rows.size()); w.c.resize(m);
+    std::vector<double> uprev(n), uprop(n);
+    std::vector<double> fb_full(m.fb_incr, m.fb_incr + m.n_fb);
+    bool have_rate = m.fb_rate_step != nullptr && m.n_fb > 0;
+    double h_min = std::ldexp(dt, -o.max_halvings);
+    double h_nom = std::min(*h_try > 0 ? *h_try : dt, dt);
+    double elapsed = 0.0;
+    StepStats st;
+    int failed_members_steps = 0;
+    while (elapsed < dt) {
+        double rem = dt - elapsed;
+        bool last = h_nom >= rem;
+        double h = last ? rem : h_nom;
+        double tn = last ? t0 + dt : t0 + (elapsed + h);
+        for (int kf = 0; kf < m.n_fb; kf++)
+            m.fb_incr[kf] = have_rate ? m.fb_rate_step[kf] * h : fb_full[kf] * (h / dt);
+        m.h_override = h;
+        std::copy(u, u + n, uprev.begin());
+        int iters = 0; double ndz = 0;
+        int conv = newton_attempt(m, w, uprev.data(), tn, h, o, eta_old, &iters, &ndz);
+        st.iters += iters; st.ndz = ndz;
+        for (int i = 0; i < n; i++) uprop[i] = uprev[i] + w.z[i];
+        limit_flow(m, uprop.data(), uprev.data(), h, tn);
+        // isoutofdomain / check_negative_storage at the proposed state
+        m.reduce_state(uprop.data(), w.ur.data());
+        basin_properties(m, w.c, w.ur.data(), tn);
+        int neg = 0;
+        for (int i = 0; i < m.n_basin; i++) if (w.c.storage[i] < 0) neg++;
+        bool can_halve = o.max_halvings > 0 && 0.5 * h >= h_min * (1.0 - 1e-12);
+        if ((conv && neg == 0) || !can_halve) {
+            std::copy(uprop.begin(), uprop.end(), u);
+            m.zlast.resize(n);
+            for (int i = 0; i < n; i++) m.zlast[i] = uprop[i] - uprev[i];
+            m.hlast = h;
+            // update_cumulative_flows! — core/src/callback.jl:125-182
+            auto& fa = m.fixed_area;
+            for (int i = 0; i < m.n_basin; i++) {
+                m.cumulative_precipitation[i] += fa[i] * m.precipitation[i] * h;
+                m.cumulative_surface_runoff[i] += h * m.surface_runoff[i];
+                m.cumulative_drainage[i] += h * m.drainage[i];
+            }
+            for (int kf = 0; kf < m.n_fb; kf++) m.fb_cumulative_flow[kf] += m.fb_incr[kf];
+            m.tprev = tn;
+            elapsed = last ? dt : elapsed + h;
+            st.substeps++;
+            st.negative_storage += neg;
+            if (!conv) failed_members_steps++;
+            if (conv && iters <= o.grow_iters) h_nom = std::min(2.0 * h_nom, dt);
+        } else {
+            h_nom = 0.5 * h;
+            *eta_old = 1.0;
+            st.rejects++;
+        }
     }
-    for (int kf = 0; kf < m.n_fb; kf++) m.fb_cumulative_flow[kf] += m.fb_incr[kf];
-    m.tprev = tn;
-    if (stats) { stats->iters = iter; stats->converged = status == 1; stats->negative_storage = neg; stats->ndz = ndz; }
-    return status == 1 ? 0 : 1;
+    m.h_override = -1.0;
+    for (int kf = 0; kf < m.n_fb; kf++) m.fb_incr[kf] = fb_full[kf];
+    *h_try = h_nom;
+    st.converged = failed_members_steps == 0;
+    if (stats) *stats = st;
+    return failed_members_steps == 0 ? 0 : 1;
+}
+
+// plain fixed-step implicit Euler (no sub-stepping): one nlsolve!, limiter, bookkeeping
+int newton_step(Model& m, double* u, double t, double dt, double abstol, double reltol,
+                int max_iter, double* eta_old, StepStats* stats, bool) {
+    AdvanceOpts o; o.abstol = abstol; o.reltol = reltol; o.max_iter = max_iter;
+    double h_try = dt;
+    return advance(m, u, t, dt, o, &h_try, eta_old, stats);
 }
 
 }  // namespace
@@ -1098,6 +1186,20 @@ int orc_step(void* h, double* u, double t, double dt, double abstol, double relt
     if (iters) *iters = st.iters;
     if (converged) *converged = st.converged;
     if (negative_storage) *negative_storage = st.negative_storage;
+    return rc;
+}
+
+// sub-stepping implicit Euler: opts = {abstol, reltol, max_iter, full_newton, grow_iters,
+// max_halvings}; out = {iters, substeps, rejects, negative_storage, converged}
+int orc_advance(void* h, double* u, double t0, double dt, const double* opts, double* h_try,
+                double* eta_old, int* out5) {
+    AdvanceOpts o;
+    o.abstol = opts[0]; o.reltol = opts[1]; o.max_iter = (int)opts[2]; o.full_newton = (int)opts[3];
+    o.grow_iters = (int)opts[4]; o.max_halvings = (int)opts[5]; o.predictor = (int)opts[6];
+    StepStats st;
+    int rc = advance(*(Model*)h, u, t0, dt, o, h_try, eta_old, &st);
+    if (out5) { out5[0] = st.iters; out5[1] = st.substeps; out5[2] = st.rejects;
+                out5[3] = st.negative_storage; out5[4] = st.converged; }
     return rc;
 }
 

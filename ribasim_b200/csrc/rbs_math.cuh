@@ -78,14 +78,10 @@ __device__ __forceinline__ RbsBasinEval rbs_basin_eval(double S, int n, const do
         double dS = S - cs[i];
         double x = a[i];
         double m = a_slope[i];
-        if (m == 0.0) {
-            r.level = h[i] + dS / x;
-            r.dlevel = 1.0 / x;
-        } else {
-            double root = sqrt(x * x + 2.0 * m * dS);
-            r.level = h[i] + (-x + root) / m;
-            r.dlevel = 1.0 / root;
-        }
+        // cancellation-free quadratic root; dh/dS = 1/root
+        double root = sqrt(x * x + m * (2.0 * dS));
+        r.level = h[i] + 2.0 * dS / (x + root);
+        r.dlevel = 1.0 / root;
     }
     double lv = r.level;
     if (lv < h[0]) {

@@ -267,9 +267,9 @@ def storage_to_level(S: float, level, dSdh, slope, cumS) -> float:
     dS = S - cumS[idx]
     x = dSdh[idx]
     m = slope[idx]
-    if m == 0.0:
-        return level[idx] + dS / x
-    return level[idx] + (-x + math.sqrt(x * x + 2 * m * dS)) / m
+    # cancellation-free quadratic root (finite-difference slopes of constant-area segments are
+    # ~1e-15, not 0: core/src/read.jl:2171-2185)
+    return level[idx] + 2 * dS / (x + math.sqrt(x * x + m * (2 * dS)))
 
 
 # ------------------------------------------------------------------------- PCHIP

@@ -53,6 +53,7 @@ def oracle_for_member(case, m: int, merged_exact: bool = True, tprev: float = 0.
     for k in FORCING:
         om.set_f64(k, case["forcing"][k][:, m])
     om.set_f64("fb_incr", case["fb_rate"][:, m] * (case["t"] - tprev))
+    om.set_f64("fb_rate_now", case["fb_rate"][:, m])  # instantaneous rate seen by the PID D-term
     om.L.orc_set_tprev(om.h, tprev)
     return om
 

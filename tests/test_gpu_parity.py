@@ -1,0 +1,265 @@
+"""Parity of the CUDA path (through the C ABI of librbs.so) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): topology/indexing bit-exact (tested on the host in
+test_host_goldens.py); RHS and Jacobian entries 1e-12 relative in fp64; end-of-run storages and
+cumulative flows within the solver's reltol at matched fixed-step implicit Euler.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests.helpers import (FORCING, csc_vals_from_dense, csr_to_dense, gpu_handle_for, make_case,
+                           oracle_for_member, rel_err, w_to_dense)
+
+pytestmark = pytest.mark.gpu
+
+RTOL_ENTRY = 1e-12
+MODELS_RHS = ["basic", "basic_transient", "backwater", "trivial", "bucket", "linear_resistance",
+              "rating_curve", "rating_curve_between_basins", "manning_resistance", "misc_nodes",
+              "user_demand", "pid_control", "pid_control_equation", "outlet_continuous_control",
+              "pump_discrete_control"]
+
+
+def _scaled_err(a: np.ndarray, b: np.ndarray, axis_scale: np.ndarray) -> float:
+    d = np.abs(a - b)
+    d[(a == b) | (np.isnan(a) & np.isnan(b))] = 0.0
+    return float(np.max(d / axis_scale)) if d.size else 0.0
+
+
+@pytest.mark.parametrize("name", MODELS_RHS)
+def test_rhs_jacobian_w_solve_parity(name):
+    B = 9
+    case = make_case(name, B, seed=1)
+    flat, t = case["flat"], case["t"]
+    h = gpu_handle_for(case)
+    try:
+        du_g, cache_g = h.rhs(case["ur"], t, with_cache=True)
+        gamma = 3600.0
+        jv, wv = h.jac(case["ur"], t, gamma=gamma)
+        rng = np.random.default_rng(5)
+        b = rng.normal(size=(flat["n_reduced"], B))
+        x = h.solve(b)
+        for m in range(B):
+            om = oracle_for_member(case, m)
+            du_o, cache_o = om.rhs(case["ur"][:, m], t, with_cache=True)
+            # basin caches: storage is a pure sum (bit-exact), level/area/factor to rounding
+            assert np.array_equal(cache_g["storage"][:, m], cache_o["storage"])
+            for k in ("level", "area", "factor"):
+                assert rel_err(cache_g[k][:, m], cache_o[k]) <= 4e-16, (name, k)
+            # RHS entries: 1e-12 relative (to the entry, with a floor at 1e-12 of the vector scale)
+            scale = np.maximum(np.abs(du_o), 1e-12 * max(np.abs(du_o).max(), 1e-300))
+            assert _scaled_err(du_g[:, m], du_o, scale) <= RTOL_ENTRY, name
+            # Jacobian entries vs the oracle's forward-mode duals: 1e-12 of the row scale
+            Jo = om.jac_dense(case["ur"][:, m], t)
+            Jg = csr_to_dense(flat, jv[:, m])
+            assert np.array_equal(Jg != 0, (Jg != 0) & (Jo != 0) | (Jg != 0)), name
+            assert not np.any((Jo != 0) & (Jg == 0) & (np.abs(Jo) > 0)), \
+                f"{name}: analytic pattern misses a non-zero of the dual-number Jacobian"
+            rs = np.maximum(np.abs(Jo).max(axis=1, keepdims=True), 1e-300)
+            assert float(np.max(np.abs(Jg - Jo) / rs)) <= RTOL_ENTRY, name
+            # W_inner = A J - I/gamma
+            Wo = om.W_inner(csc_vals_from_dense(flat, Jo), gamma)
+            Wg = w_to_dense(flat, wv[:, m])
+            assert float(np.max(np.abs(Wg - Wo)) / np.abs(Wo).max()) <= RTOL_ENTRY, name
+            # linear solve: backward-stable residual, forward error bounded by cond(W)
+            res = np.abs(Wg @ x[:, m] - b[:, m]).max()
+            assert res <= 1e-13 * (np.abs(Wg).max() * np.abs(x[:, m]).max() + np.abs(b[:, m]).max()) * \
+                flat["n_reduced"], name
+            xo = np.linalg.solve(Wg, b[:, m])
+            cond = np.linalg.cond(Wg)
+            assert np.abs(x[:, m] - xo).max() <= 1e-14 * cond * np.abs(xo).max() + 1e-300, name
+    finally:
+        h.close()
+
+
+@pytest.mark.parametrize("name", ["basic", "backwater", "user_demand", "pid_control"])
+@pytest.mark.parametrize("lu_mode", [0, 1])
+def test_lu_modes_agree_bitwise(name, lu_mode):
+    """Level-per-launch and member-tile LU run the same schedule: identical bits."""
+    B = 37
+    case = make_case(name, B, seed=2)
+    flat = case["flat"]
+    rng = np.random.default_rng(9)
+    b = rng.normal(size=(flat["n_reduced"], B))
+    ref = None
+    for mode in (lu_mode, 1 - lu_mode):
+        h = gpu_handle_for(case, lu_mode=mode)
+        try:
+            h.jac(case["ur"], case["t"], gamma=600.0)
+            x = h.solve(b)
+        finally:
+            h.close()
+        if ref is None:
+            ref = x
+        else:
+            assert np.array_equal(ref, x)
+
+
+@pytest.mark.parametrize("name", ["basic", "user_demand", "misc_nodes", "outlet_continuous_control"])
+def test_reduce_and_limit_flow_parity(name):
+    B = 5
+    case = make_case(name, B, seed=3)
+    flat = case["flat"]
+    n = flat["n_state"]
+    rng = np.random.default_rng(4)
+    uprev = np.abs(rng.normal(0, 50.0, size=(n, B)))
+    u = uprev + rng.normal(0, 5.0, size=(n, B))
+    h = gpu_handle_for(case)
+    try:
+        ur_g = h.reduce(u)
+        dt = 3600.0
+        lim_g = h.limit_flow(u, uprev, dt, case["t"])
+        for m in range(B):
+            om = oracle_for_member(case, m)
+            assert np.array_equal(ur_g[:, m], om.reduce(u[:, m])), "reduce_state! is a fixed-order sum"
+            # level_prev of the oracle defaults to the level at t0, like the handle's zero state
+            lim_o = om.limit_flow(u[:, m], uprev[:, m], dt, case["t"])
+            assert rel_err(lim_g[:, m], lim_o) <= 1e-15, name
+    finally:
+        h.close()
+
+
+@pytest.mark.parametrize("name,dt,n_steps", [("basic", 3600.0, 24), ("trivial", 21600.0, 12),
+                                             ("user_demand", 3600.0, 12),
+                                             ("outlet_continuous_control", 3600.0, 12),
+                                             ("pid_control", 3600.0, 12),
+                                             ("backwater", 1.0, 40)])
+def test_implicit_euler_steps_parity(name, dt, n_steps):
+    """Device-resident Newton steps against the oracle's NLNewton restatement: same iteration
+    counts, states equal within Newton round-off."""
+    from oracle.oracle import _dp
+
+    B = 4
+    case = make_case(name, B, seed=7, t=0.0)
+    flat = case["flat"]
+    n = flat["n_state"]
+    h = gpu_handle_for(case)
+    try:
+        h.set_solver(1e-5, 1e-5, 10)
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
+        oms = []
+        for m in range(B):
+            om = oracle_for_member(case, m)
+            _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
+            lv = np.ascontiguousarray(c0["level"])
+            om.L.orc_set_level_prev(om.h, _dp(lv))
+            oms.append(om)
+        us = [np.zeros(n) for _ in range(B)]
+        etas = [1.0] * B
+        t = 0.0
+        for s in range(n_steps):
+            st = h.step(t, dt)
+            for m, om in enumerate(oms):
+                om.set_f64("fb_incr", case["fb_rate"][:, m] * dt)
+                rc, it, cv, ng, etas[m] = om.step(us[m], t, dt, 1e-5, 1e-5, etas[m])
+                assert (st[m] & 1) == (0 if cv else 1), (name, s, m)
+            t += dt
+        ug = h.get_member("u", n)
+        Sg = h.get_member("storage", flat["n_basin"])
+        for m, om in enumerate(oms):
+            scale = 1e-5 + np.abs(us[m]) * 1e-5  # the solver's own abstol/reltol
+            assert np.max(np.abs(ug[:, m] - us[m]) / scale) <= 1e-3, name
+            _, co = om.rhs(om.reduce(us[m]), t, with_cache=True)
+            assert np.max(np.abs(Sg[:, m] - co["storage"]) /
+                          (1e-5 + np.abs(co["storage"]) * 1e-5)) <= 1e-2, name
+        stats = h.stats()
+        assert stats["steps"] == n_steps
+    finally:
+        h.close()
+
+
+def test_model_driver_matches_oracle_run():
+    """Host driver + device stepping for 10 days of `basic` against run_oracle (same dt)."""
+    from oracle.oracle import run_oracle
+    from ribasim_b200.model import Model
+    from ribasim_b200.network import build_params
+    from ribasim_b200.testmodels import MODELS
+
+    t_end = 10 * 86400.0
+    p = build_params(MODELS["basic"]())
+    u_o, S_o, lv_o, st_o = run_oracle(p, 3600.0, t_end=t_end)
+    model = Model(build_params(MODELS["basic"]()), n_members=3, dt=3600.0)
+    try:
+        model.update_until(t_end)
+        S_g, u_g = model.storage(), model.u()
+        for m in range(3):
+            assert np.allclose(S_g[:, m], S_o, rtol=1e-5, atol=1e-5)
+            assert np.allclose(u_g[:, m], u_o, rtol=1e-5, atol=1e-5)
+        assert model.status_counts["negative_storage"] == 0
+    finally:
+        model.finalize()
+
+
+def test_member_independence_and_determinism():
+    """A member's result must not depend on the batch around it (that is what makes sharding
+    over GPUs exact), and two runs give identical bits (no float atomics)."""
+    name = "hws_like"
+    from ribasim_b200.testmodels import hws_like_model
+    tables = hws_like_model(n_basins=60, n_days=2)
+    big = make_case(tables, 64, seed=5, t=0.0)
+    flat = big["flat"]
+    n = flat["n_state"]
+
+    def run(case, members):
+        sub = dict(case)
+        sub["B"] = len(members)
+        sub["forcing"] = {k: np.ascontiguousarray(v[:, members]) for k, v in case["forcing"].items()}
+        sub["fb_rate"] = np.ascontiguousarray(case["fb_rate"][:, members])
+        h = gpu_handle_for(sub)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
+            t = 0.0
+            for _ in range(6):
+                h.step(t, 1800.0)
+                t += 1800.0
+            return h.get_member("u", n), h.get_member("storage", flat["n_basin"])
+        finally:
+            h.close()
+
+    members = list(range(64))
+    u_all, S_all = run(big, members)
+    u_again, S_again = run(big, members)
+    assert np.array_equal(u_all, u_again) and np.array_equal(S_all, S_again), name
+    pick = [63, 5, 17]
+    u_sub, S_sub = run(big, pick)
+    assert np.array_equal(u_sub, u_all[:, pick])
+    assert np.array_equal(S_sub, S_all[:, pick])
+
+
+def test_water_balance_closes_at_full_size():
+    """Size-independent property on a large ensemble: after k steps every basin satisfies
+    S = S0 + A u + exact inflows (the identity reduce_state! + formulate_storages! encode)."""
+    from ribasim_b200.testmodels import hws_like_model
+    tables = hws_like_model(n_basins=200, n_days=2)
+    B = 512
+    case = make_case(tables, B, seed=8, t=0.0)
+    flat = case["flat"]
+    nb, n = flat["n_basin"], flat["n_state"]
+    h = gpu_handle_for(case)
+    try:
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        t, dt = 0.0, 3600.0
+        for _ in range(4):
+            h.step(t, dt)
+            t += dt
+        u = h.get_member("u", n)
+        S = h.get_member("storage", nb)
+        ur = h.reduce(u)[:nb]
+        p = case["p"]
+        exact = case["forcing"]["precipitation"] * np.array([a[-1] for a in p.basin.areas])[:, None] * t \
+            + case["forcing"]["surface_runoff"] * t + case["forcing"]["drainage"] * t
+        for k in range(flat["n_fb"]):
+            for b in range(nb):
+                lo, hi = flat["bfb_ptr"][b], flat["bfb_ptr"][b + 1]
+                if k in flat["bfb_idx"][lo:hi]:
+                    exact[b] += case["fb_rate"][k] * t
+        S_expect = p.basin.storage0[:, None] + ur + exact
+        scale = np.maximum(np.abs(S_expect), 1.0)
+        assert np.max(np.abs(S - S_expect) / scale) < 1e-11
+    finally:
+        h.close()

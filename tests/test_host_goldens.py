@@ -1,0 +1,220 @@
+"""Host network compiler against the reference's own golden values (no GPU).
+
+Everything here is integer layout: state order, incidence matrix A, Jacobian sparsity,
+W_inner assembly lists, symbolic LU.  Citations are relative to /root/reference.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from ribasim_b200.flatten import flatten
+from ribasim_b200.network import build_params
+from ribasim_b200.symbolic import analyse, numeric_factor, numeric_solve
+from ribasim_b200.tables import ModelTables
+from ribasim_b200.testmodels import MODELS
+
+
+@pytest.fixture(scope="module")
+def basic():
+    p = build_params(MODELS["basic"]())
+    return p, flatten(p)
+
+
+@pytest.fixture(scope="module")
+def pid():
+    p = build_params(MODELS["pid_control"]())
+    return p, flatten(p)
+
+
+def dense_A(flat) -> np.ndarray:
+    nb, n, nr = flat["n_basin"], flat["n_state"], flat["n_reduced"]
+    A = np.zeros((nr, n))
+    for b in range(nb):
+        for k in range(flat["inc_ptr"][b], flat["inc_ptr"][b + 1]):
+            A[b, flat["inc_state"][k]] += flat["inc_sign"][k]
+        A[b, flat["off_evap"] + b] -= 1.0
+        A[b, flat["off_infil"] + b] -= 1.0
+    for i in range(flat["n_pid"]):
+        A[nb + i, flat["off_integral"] + i] = 1.0
+    return A
+
+
+def test_basic_state_node_ids(basic):
+    # core/test/run_models_test.jl:217
+    p, flat = basic
+    assert [s.value for s in p.state_node_id] == [4, 5, 8, 7, 10, 12, 2, 1, 3, 6, 9, 1, 3, 6, 9]
+    assert flat["n_basin"] == 4 and flat["n_conn"] == 7 and flat["n_state"] == 15
+
+
+def test_trivial_state_axes():
+    # core/test/run_models_test.jl:17-20: one TRC state + evaporation + infiltration
+    p = build_params(MODELS["trivial"]())
+    sr = p.state_ranges
+    assert sr["tabulated_rating_curve"] == (0, 1)
+    assert sr["evaporation"] == (1, 2) and sr["infiltration"] == (2, 3)
+    assert p.n_states == 3
+
+
+def test_basic_jacobian_sparsity(basic):
+    # core/test/utils_test.jl:266-271
+    _, flat = basic
+    rows = [7, 8, 12, 1, 2, 3, 6, 7, 9, 13, 2, 4, 10, 14, 3, 4, 5, 11, 15]
+    cols = [1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4]
+    assert list(flat.jac_rows_csc) == rows
+    assert list(flat.jac_cols_csc) == cols
+    assert flat["nnz_j"] == 19
+
+
+def test_pid_jacobian_sparsity(pid):
+    # core/test/utils_test.jl:287-292
+    _, flat = pid
+    assert list(flat.jac_rows_csc) == [1, 2, 3, 4, 1]
+    assert list(flat.jac_cols_csc) == [1, 1, 1, 1, 2]
+
+
+def test_basic_incidence_matrix(basic):
+    # core/test/utils_test.jl:423-428
+    _, flat = basic
+    rows = [2, 2, 3, 2, 4, 3, 4, 4, 2, 1, 2, 1, 2, 3, 4, 1, 2, 3, 4]
+    cols = [1, 2, 2, 3, 3, 4, 4, 5, 6, 7, 7, 8, 9, 10, 11, 12, 13, 14, 15]
+    vals = [-1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0, -1.0, -1.0, -1.0, -1.0,
+            -1.0, -1.0, -1.0, -1.0]
+    A_expected = np.zeros((4, 15))
+    for r, c, v in zip(rows, cols, vals):
+        A_expected[r - 1, c - 1] = v
+    assert np.array_equal(dense_A(flat), A_expected)
+
+
+def test_pid_incidence_matrix(pid):
+    # core/test/utils_test.jl:445-450
+    _, flat = pid
+    A_expected = np.zeros((2, 4))
+    for r, c, v in zip([1, 1, 1, 2], [1, 2, 3, 4], [-1.0, -1.0, -1.0, 1.0]):
+        A_expected[r - 1, c - 1] = v
+    assert np.array_equal(dense_A(flat), A_expected)
+
+
+def _w_from_lists(flat, jvals_csr: np.ndarray, inv_gamma: float) -> np.ndarray:
+    """What k_assemble_w computes, on the host."""
+    nr = flat["n_reduced"]
+    W = np.zeros((nr, nr))
+    rp, col = flat["wrow_ptr"], flat["wcol"]
+    diag = set(int(x) for x in flat["wdiag"])
+    e = 0
+    for i in range(nr):
+        for e in range(rp[i], rp[i + 1]):
+            acc = 0.0
+            for k in range(flat["wsrc_ptr"][e], flat["wsrc_ptr"][e + 1]):
+                acc += flat["wsrc_sign"][k] * jvals_csr[flat["wsrc_pos"][k]]
+            if e in diag:
+                acc -= inv_gamma
+            W[i, col[e]] = acc
+    return W
+
+
+def _csr_from_csc_vals(flat, vals_csc) -> tuple[np.ndarray, np.ndarray]:
+    n, nr = flat["n_state"], flat["n_reduced"]
+    J = np.zeros((n, nr))
+    for r, c, v in zip(flat.jac_rows_csc, flat.jac_cols_csc, vals_csc):
+        J[r - 1, c - 1] = v
+    rp, col = flat["jrow_ptr"], flat["jcol"]
+    csr = np.array([J[r, col[e]] for r in range(n) for e in range(rp[r], rp[r + 1])])
+    return J, csr
+
+
+def test_basic_J_inner_is_A_times_J(basic):
+    # core/test/utils_test.jl:430-435 with the reference's arbitrary nzval
+    _, flat = basic
+    nz = [0.020047016741082002, 0.8755256160248737, 0.36909649531559285, 0.7632298275012108,
+          0.9240314657308235, 0.49544793385910524, 0.10528087709131306, 0.020608175445295474,
+          0.9691738934605421, 0.4218954216679456, 0.5058554068921941, 0.2896077753195684,
+          0.8694315735708924, 0.8458965765906646, 0.7966585871607135, 0.2581915440964345,
+          0.6505806124461845, 0.8411882038236067, 0.8067685192045705]
+    J, csr = _csr_from_csc_vals(flat, nz)
+    W = _w_from_lists(flat, csr, 0.0)
+    assert np.allclose(W, dense_A(flat) @ J, rtol=1e-14, atol=0)
+    gamma = 3600.0
+    W = _w_from_lists(flat, csr, 1.0 / gamma)
+    assert np.allclose(W, dense_A(flat) @ J - np.eye(4) / gamma, rtol=1e-14, atol=0)
+
+
+def test_pid_J_inner_is_A_times_J(pid):
+    # core/test/utils_test.jl:452-459
+    _, flat = pid
+    nz = [0.449381314574683, 0.4542317082538514, 0.599934409205972, 0.30717602583409154,
+          0.9795352040440034]
+    J, csr = _csr_from_csc_vals(flat, nz)
+    assert np.allclose(_w_from_lists(flat, csr, 0.0), dense_A(flat) @ J, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_patterns_are_consistent(name):
+    """W pattern = pattern(A * J_pattern) + diagonal, for every re-expressed test model."""
+    p = build_params(MODELS[name]())
+    flat = flatten(p)
+    n, nr = flat["n_state"], flat["n_reduced"]
+    Jp = np.zeros((n, nr))
+    rp, col = flat["jrow_ptr"], flat["jcol"]
+    for r in range(n):
+        cs = col[rp[r]:rp[r + 1]]
+        assert list(cs) == sorted(set(int(c) for c in cs)), "CSR columns sorted and unique"
+        Jp[r, cs] = 1.0
+    Wp = (np.abs(dense_A(flat)) @ Jp > 0) | np.eye(nr, dtype=bool)
+    got = np.zeros((nr, nr), dtype=bool)
+    wrp, wcol = flat["wrow_ptr"], flat["wcol"]
+    for i in range(nr):
+        got[i, wcol[wrp[i]:wrp[i + 1]]] = True
+    assert np.array_equal(got, Wp)
+
+
+@pytest.mark.parametrize("name,kw", [("basic", {}), ("backwater", {}), ("pid_control", {}),
+                                     ("outlet_continuous_control", {}), ("user_demand", {})])
+def test_symbolic_lu_solves(name, kw):
+    p = build_params(MODELS[name](**kw))
+    flat = flatten(p)
+    nr = flat["n_reduced"]
+    sym = analyse(nr, flat["wrow_ptr"], flat["wcol"])
+    rng = np.random.default_rng(3)
+    nnz = flat["nnz_w"]
+    wv = rng.normal(size=nnz)
+    wv[flat["wdiag"]] -= 8.0  # diagonally dominant like W = J - I/gamma
+    W = np.zeros((nr, nr))
+    wrp, wcol = flat["wrow_ptr"], flat["wcol"]
+    for i in range(nr):
+        for e in range(wrp[i], wrp[i + 1]):
+            W[i, wcol[e]] = wv[e]
+    b = rng.normal(size=nr)
+    lu = numeric_factor(sym, wv)
+    x = numeric_solve(sym, lu, b)
+    assert np.allclose(W @ x, b, rtol=1e-10, atol=1e-10)
+
+
+def test_symbolic_lu_chain_is_logarithmic():
+    """Rake-and-compress ordering: a 51-basin chain (tridiagonal W) factorises in O(log n)
+    rounds with O(n) fill (cyclic reduction) instead of 51 sequential pivots."""
+    p = build_params(MODELS["backwater"]())
+    flat = flatten(p)
+    sym = analyse(flat["n_reduced"], flat["wrow_ptr"], flat["wcol"])
+    assert sym.n_rounds <= 8
+    assert flat["nnz_w"] <= sym.n_lu <= 2 * flat["nnz_w"]
+    assert len(sym.lu_level_ptr) - 1 <= 4 * sym.n_rounds
+
+
+def test_tables_roundtrip(tmp_path):
+    """TOML + GeoPackage(SQLite) writer/reader: same tables, same compiled network."""
+    m = MODELS["basic"]()
+    toml = m.write(tmp_path / "basic")
+    m2 = ModelTables.read(toml)
+    f1 = flatten(build_params(m))
+    f2 = flatten(build_params(m2))
+    assert f1.ints == f2.ints
+    for k, v in f1.arrays.items():
+        assert np.array_equal(v, f2.arrays[k], equal_nan=True), k
+
+
+def test_pump_discrete_control_compiles():
+    p = build_params(MODELS["pump_discrete_control"]())
+    flat = flatten(p)
+    assert flat["n_pump"] >= 1

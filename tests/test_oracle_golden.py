@@ -1,0 +1,258 @@
+"""Pins the CPU oracle (oracle/rbs_oracle.cpp) to the reference's own known-answer tests.
+
+No GPU.  Citations are relative to /root/reference.  The oracle is test infrastructure; these
+tests are what allows it to stand in for the Julia core (which cannot run in this image).
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleModel, lib, run_oracle
+from ribasim_b200.flatten import flatten
+from ribasim_b200.interp import PchipTable, storage_to_level
+from ribasim_b200.network import build_params
+from ribasim_b200.tables import ModelTables
+from ribasim_b200.testmodels import MODELS
+from ribasim_b200.timecache import eval_time_params
+
+
+def test_reduction_factor_goldens():
+    # core/test/utils_test.jl:331-342
+    f = lib().orc_reduction_factor
+    assert f(-2.0, 2.0) == 0.0
+    assert f(0.0, 2.0) == 0.0
+    assert f(1.0, 2.0) == 0.5
+    assert f(3.0, 2.0) == 1.0
+    assert f(math.inf, 2.0) == 1.0
+    assert f(-math.inf, 2.0) == 0.0
+
+
+def test_relaxed_root_goldens():
+    # core/test/utils_test.jl:483-514
+    r = lib().orc_relaxed_root
+    assert r(0.0, 1.0e-3) == 0.0
+    assert r(2.0, 1.0) == pytest.approx(math.sqrt(2.0), rel=1e-15)
+    assert r(-2.0, 1.0) == pytest.approx(-math.sqrt(2.0), rel=1e-15)
+    eps = 1.0e-3
+    assert abs(r(eps, eps) - math.sqrt(eps)) < 1e-12
+    assert abs(r(-eps, eps) + math.sqrt(eps)) < 1e-12
+    assert abs(r(eps / 2, eps) - math.sqrt(eps / 2)) < 0.2
+    assert r(1.0e-8, 1.0e-8) == pytest.approx(math.sqrt(1.0e-8), rel=1e-12)
+    assert r(-1.0e-8, 1.0e-8) == pytest.approx(-math.sqrt(1.0e-8), rel=1e-12)
+
+
+def _one_basin(area, level) -> ModelTables:
+    m = MODELS["bucket"]()
+    m.tables["Basin / profile"] = [dict(node_id=1, area=a, level=h) for a, h in zip(area, level)]
+    m.tables["Basin / state"] = [dict(node_id=1, level=level[0] + 1e-3)]
+    return m
+
+
+def test_profile_lookup_goldens():
+    # core/test/utils_test.jl:38-122: storage -> (area, level) on A=[1e-9,100,100], h=[0,10,15]
+    p = build_params(_one_basin([1.0e-9, 100.0, 100.0], [0.0, 10.0, 15.0]))
+    om = OracleModel(p)
+    L = om.L
+    lookup = lambda S: (L.orc_level_to_area(om.h, 0, L.orc_storage_to_level(om.h, 0, max(S, 0.0))),  # noqa: E731
+                        L.orc_storage_to_level(om.h, 0, max(S, 0.0)))
+    cumS = p.basin.cumS[0]
+    assert cumS[0] == 0.0 and cumS[1] == pytest.approx(500.0, rel=1e-9)
+    for S, A, h in zip(cumS, [1.0e-9, 100.0, 100.0], [0.0, 10.0, 15.0]):
+        a, lv = lookup(S)
+        assert lv == pytest.approx(h, abs=1e-12) and a == pytest.approx(A, rel=1e-9, abs=1e-12)
+    assert lookup(-1.0) == (1.0e-9, 0.0)
+    a, lv = lookup(100.0)
+    assert lv == pytest.approx(math.sqrt(100.0 / 5), rel=1e-8)
+    assert a == pytest.approx(10 * lv, rel=1e-8)
+    a, lv = lookup(600.0)
+    assert lv == pytest.approx(11.0, rel=1e-9) and a == 100.0
+    # extrapolation above the table: constant area (core/src/read.jl:2303-2315)
+    a, lv = lookup(1100.0)
+    assert lv == pytest.approx(16.0, rel=1e-9) and a == 100.0
+
+
+def test_profile_roundtrip():
+    # core/test/utils_test.jl:124-189: level(storage) inverts storage(level)
+    level = [0.0, 0.42601923740838954, 1.1726055542568279, 1.9918063978301288, 2.945965660308591,
+             3.7918607426596513, 4.378609443214641, 4.500422081139986, 4.638188322915925,
+             5.462975756944211]
+    area = [0.5284895347829252, 0.7036603783547138, 0.6831597656207129, 0.7582032614294112,
+            0.5718206017422349, 0.5390282084391234, 0.9650081130058792, 0.07071025361013983,
+            0.10659325339342585, 1.1]
+    p = build_params(_one_basin(area, level))
+    om = OracleModel(p)
+    b = p.basin
+    cumS, lv_t, dS = np.array(b.cumS[0]), np.array(b.levels[0]), np.array(b.dSdh[0])
+    for S in np.linspace(0.0, 2 * cumS[-1], 50):
+        h = om.L.orc_storage_to_level(om.h, 0, float(S))
+        assert h == storage_to_level(float(S), b.levels[0], b.dSdh[0], b.dSdh_slope[0], b.cumS[0])
+        # storage from level: integral of the piecewise-linear area up to h
+        if h >= lv_t[-1]:
+            S_back = cumS[-1] + (h - lv_t[-1]) * dS[-1]
+        else:
+            i = max(int(np.searchsorted(lv_t, h, side="right")) - 1, 0)
+            slope = (dS[i + 1] - dS[i]) / (lv_t[i + 1] - lv_t[i])
+            S_back = cumS[i] + dS[i] * (h - lv_t[i]) + 0.5 * slope * (h - lv_t[i]) ** 2
+        assert S_back == pytest.approx(S, rel=1e-10, abs=1e-10)
+
+
+def test_initial_level_golden():
+    # python/ribasim_api/tests/test_bmi.py:102-110 and basic.py:45:
+    # storage 1.0 on A=[0.01,1000], h=[0,1] <-> level 0.04471158417652035
+    p = build_params(MODELS["basic"]())
+    om = OracleModel(p)
+    assert p.basin.storage0[0] == pytest.approx(1.0, rel=1e-12)
+    h = om.L.orc_storage_to_level(om.h, 0, 1.0)
+    assert h == pytest.approx(0.04471158417652035, rel=2e-15)
+    # regression_test.jl:37-38: S = 62.2290641115 -> level 0.352778
+    assert om.L.orc_storage_to_level(om.h, 0, 62.2290641115) == pytest.approx(0.352778, abs=1e-6)
+
+
+def test_pchip_is_monotone_and_interpolates():
+    """PCHIP (Fritsch-Carlson) properties DataInterpolations guarantees: hits the knots and
+    preserves monotonicity; rating curves get the point (h0 - 1, 0) prepended
+    (core/src/util.jl:130-140)."""
+    t = [0.0, 1.0, 2.5, 3.0, 7.0]
+    u = [0.0, 0.1, 2.0, 2.1, 30.0]
+    tab = PchipTable(u, t, left="constant", right="linear")
+    xs = np.linspace(0.0, 7.0, 2001)
+    ys = np.array([tab(float(x)) for x in xs])
+    assert np.all(np.diff(ys) >= -1e-14)
+    for ti, ui in zip(t, u):
+        assert tab(ti) == pytest.approx(ui, abs=1e-14)
+    p = build_params(MODELS["rating_curve"]())
+    trc = p.nodes["tabulated_rating_curve"]["interpolations"][0]
+    assert trc.u[0] == 0.0 and trc.t[0] == pytest.approx(trc.t[1] - 1.0)
+    om = OracleModel(p)
+    for x in np.linspace(trc.t[0] - 0.5, trc.t[-1] + 1.0, 57):
+        assert om.L.orc_pchip_eval(om.h, 0, float(x)) == pytest.approx(trc(float(x)), rel=1e-14,
+                                                                       abs=1e-300)
+
+
+def test_bucket_and_leaky_bucket_rhs():
+    # core/test/run_models_test.jl:127-176
+    p = build_params(MODELS["bucket"]())
+    om = OracleModel(p)
+    om.set_time_params(eval_time_params(p, 0.0))
+    du, cache = om.rhs(np.zeros(om.n_reduced), 0.0, with_cache=True)
+    assert cache["storage"][0] == pytest.approx(1000.0, rel=1e-12)
+    assert du[flatten(p)["off_evap"]] == 0.0 and du[flatten(p)["off_infil"]] == 0.0
+
+
+def test_trivial_end_state_implicit_euler():
+    # core/regression_test/regression_test.jl:8,35-41 (ImplicitEuler is in the solver list)
+    p = build_params(MODELS["trivial"]())
+    u, S, lv, st = run_oracle(p, 86400.0 / 4, abstol=1e-7, reltol=1e-7)
+    assert st["failed"] == 0
+    assert S[0] == pytest.approx(62.2290641115, abs=0.02)
+    assert lv[0] == pytest.approx(0.352778, abs=1e-4)
+
+
+def test_basic_end_state():
+    # core/test/run_models_test.jl:221-222
+    p = build_params(MODELS["basic"]())
+    u, S, lv, st = run_oracle(p, 3600.0)
+    assert np.allclose(S, [775.23576, 775.23365, 572.60102, 1130.005], atol=1.5, rtol=0)
+    assert st["negative"] == 0
+
+
+def test_basic_transient_end_state():
+    # core/test/run_models_test.jl:288-289
+    p = build_params(MODELS["basic_transient"]())
+    u, S, lv, st = run_oracle(p, 3600.0)
+    assert np.allclose(S, [693.1112, 693.10895, 463.9762, 1136.9476], atol=2.0 + 1.5, rtol=0)
+
+
+def test_linear_resistance_analytic():
+    # core/test/equations_test.jl:18-44: linear drain at Q_max, then exponential decay
+    p = build_params(MODELS["linear_resistance"]())
+    lr = p.nodes["linear_resistance"]
+    R, Q_max = float(lr["resistance"][0]), float(lr["max_flow_rate"][0])
+    A = p.basin.areas[0][-1]
+    L = p.nodes["level_boundary"]["level"][0](0.0)
+    u0 = A * 10.0
+    t_shift = (u0 - A * (L + R * Q_max)) / Q_max
+    for t_end in (30 * 86400.0, 366 * 86400.0):
+        u, S, lv, st = run_oracle(p, 3600.0, t_end=t_end)
+        if t_end < t_shift:
+            expect = u0 - Q_max * t_end
+        else:
+            expect = A * L + A * R * Q_max * math.exp(-(t_end - t_shift) / (A * R))
+        assert S[0] == pytest.approx(expect, rel=1e-4)
+
+
+@pytest.mark.parametrize("name", ["basic", "backwater", "pid_control", "outlet_continuous_control",
+                                  "user_demand", "misc_nodes"])
+def test_dual_jacobian_matches_finite_differences(name):
+    """The oracle's forward-mode Jacobian (its ForwardDiff stand-in) against central
+    differences of the oracle RHS, and coloured compression == dense columns
+    (core/test/differentiation_test.jl:29-55)."""
+    p = build_params(MODELS[name]())
+    flat = flatten(p)
+    om = OracleModel(p)
+    om.set_pattern(flat.jac_rows_csc, flat.jac_cols_csc)
+    om.set_time_params(eval_time_params(p, 0.0))
+    rng = np.random.default_rng(11)
+    nb = flat["n_basin"]
+    ur = np.zeros(om.n_reduced)
+    ur[:nb] = p.basin.storage0 * rng.uniform(0.2, 2.0, size=nb)
+    J = om.jac_dense(ur, 0.0)
+    vals = om.jac_colored(ur, 0.0)
+    Jc = np.zeros_like(J)
+    for r, c, v in zip(flat.jac_rows_csc, flat.jac_cols_csc, vals):
+        Jc[r - 1, c - 1] = v
+    assert np.array_equal(J != 0, (J != 0) & (Jc != 0)), "pattern covers every non-zero"
+    assert np.allclose(J, Jc, rtol=1e-14, atol=0)
+    for j in range(om.n_reduced):
+        h = 1e-6 * max(1.0, abs(ur[j]))
+        xp, xm = ur.copy(), ur.copy()
+        xp[j] += h
+        xm[j] -= h
+        fp, fm = om.rhs(xp, 0.0), om.rhs(xm, 0.0)
+        fd = (fp - fm) / (2 * h)
+        scale = np.maximum(np.abs(J[:, j]).max(), 1e-12)
+        noise = 1e-15 * np.abs(fp).max() / h  # rounding of the difference quotient
+        assert np.max(np.abs(fd - J[:, j])) < 1e-5 * scale + 10 * noise, (name, j)
+
+
+def _standard_step_method(x, Q, w, n, h_right, h_close):
+    """Backwater curve of a rectangular channel (core/test/run_models_test.jl:431-487)."""
+    def friction_slope(Q, w, d, n):
+        A = d * w
+        R_h = A / (w + 2 * d)
+        return Q ** 2 * n ** 2 / (A ** 2 * R_h ** (4 / 3))
+
+    h = np.full(len(x), h_right)
+    h1 = h_right
+    for i in range(len(x) - 2, -1, -1):
+        h2 = h1
+        dh = h_close + 1.0
+        L = x[i + 1] - x[i]
+        while dh > h_close:
+            h2new = h1 + 0.5 * (friction_slope(Q, w, h1, n) + friction_slope(Q, w, h2, n)) * L
+            dh = abs(h2new - h2)
+            h2 = h2new
+        h[i] = h2
+        h1 = h2
+    return h
+
+
+def test_backwater_against_standard_step_method():
+    # core/test/run_models_test.jl:489-523: levels within 0.02 m, flow in = flow out = 5 +- 1e-3
+    p = build_params(MODELS["backwater"]())
+    flat = flatten(p)
+    u, S, lv, st = run_oracle(p, 3600.0, full_newton=1, max_halvings=20, predictor=1)
+    assert st["failed"] == 0 and st["negative"] == 0
+    h_actual = lv[:50]
+    x = np.arange(10.0, 991.0, 20.0)
+    h_expected = _standard_step_method(x, 5.0, 1.0, 0.04, h_actual[-1], 1.0e-6)
+    assert np.all(np.abs(h_expected - h_actual) < 0.02)
+    om = OracleModel(p)
+    om.set_time_params(eval_time_params(p, p.tables.t_end))
+    du = om.rhs(om.reduce(u) * 0 + (S - p.basin.storage0), p.tables.t_end)
+    assert du[flat["off_manning"] + 49] == pytest.approx(5.0, abs=1e-3)
+    assert du[flat["off_manning"]] == pytest.approx(5.0, abs=1e-3)
