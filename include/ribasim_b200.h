@@ -72,6 +72,9 @@ int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64
 int rbs_set_member_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity,
                        int32_t broadcast);
 int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_entity);
+/* Device-to-device copy of a per-member array into caller-owned device memory (e.g. the send
+ * buffer of the final NCCL gather of an ensemble sharded over GPUs). */
+int rbs_copy_member_to_device(rbs_handle* h, const char* key, void* dst_device, int64_t n_entity);
 /* Previous accepted time `tprev` (core/src/parameter.jl:1126-1130). */
 int rbs_set_tprev(rbs_handle* h, double tprev);
 
@@ -96,20 +99,41 @@ int rbs_solve(rbs_handle* h, const double* b, double* x);
 int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, double t);
 
 /* ---- device-resident time stepping ---------------------------------------------------
- * One fixed-dt implicit-Euler step with NLNewton for every member, on the state resident in
- * the handle ("u"): what OrdinaryDiffEq's perform_step!/nlsolve! do through the seams above
+ * Advance every member from t to t + dt by implicit Euler with NLNewton on the state resident
+ * in the handle ("u"): what OrdinaryDiffEq's perform_step!/nlsolve! do through the seams above
  * (core/src/model.jl:219-237), followed by limit_flow!, the negative-storage
- * check (core/src/util.jl:918-924) and the exact-forcing bookkeeping of
+ * check (isoutofdomain, core/src/util.jl:918-924) and the exact-forcing bookkeeping of
  * `update_cumulative_flows!` (core/src/callback.jl:125-182).
- * status_per_member (may be NULL): 0 converged, 1 Newton failure, |2 negative storage. */
+ * Each member runs its own sub-step sequence inside [t, t + dt]: an attempt whose Newton
+ * iteration fails or that ends with negative storage is rejected and retried with half the
+ * length, an accepted attempt that converged quickly doubles the nominal length again (what
+ * the reference's adaptive controller does on a failed nonlinear solve).  Members never
+ * influence each other, so results do not depend on how the ensemble is sharded.
+ * status_per_member (may be NULL): 0 ok, |1 a forced accept after Newton failure at the
+ * minimum sub-step, |2 negative storage accepted at the minimum sub-step. */
 int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member);
 /* Solver options: abstol, reltol (core/src/config.jl:187-188), max Newton iterations. */
 int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter);
-/* Counters since creation: [0] steps, [1] Newton iterations (sum over steps of the maximum
- * over members), [2] Jacobian/W refreshes, [3] member-steps that failed to converge. */
-int rbs_get_stats(rbs_handle* h, int64_t* out4);
+/* Stepper options.  full_newton: 0 = J and W evaluated once per attempt at (uprev, t + h) like
+ * the reference's nlsolve!, 1 = refreshed every Newton iteration.  predictor: 0 = z0 = 0
+ * (OrdinaryDiffEq `extrapolant = :constant`), 1 = last accepted increment rescaled to the new
+ * sub-step.  max_halvings: smallest sub-step is dt * 2^-max_halvings (0 = plain fixed-step
+ * implicit Euler).  grow_iters: double the sub-step after converging within this many
+ * iterations.  Defaults: 0, 1, 20, 4. */
+int rbs_set_stepper(rbs_handle* h, int32_t full_newton, int32_t predictor, int32_t max_halvings,
+                    int32_t grow_iters);
+/* Counters since creation: [0] outer steps, [1] kernel passes, [2] accepted sub-steps summed
+ * over members, [3] member-steps flagged |1, [4] Newton iterations summed over members,
+ * [5] rejected attempts summed over members. */
+int rbs_get_stats(rbs_handle* h, int64_t* out6);
 /* Refresh the basin caches (storage, level, area, factor) and du at the resident state. */
 int rbs_refresh(rbs_handle* h, double t);
+
+/* Per-launch timing with CUDA events on the handle's stream: rbs_profile(h, 1) starts
+ * recording every kernel launch, rbs_profile_report writes one line per kernel
+ * "name<TAB>launches<TAB>total_ms" (NUL terminated, truncated to len), rbs_profile(h, 0) stops. */
+int rbs_profile(rbs_handle* h, int32_t enable);
+int rbs_profile_report(rbs_handle* h, char* buf, int32_t len);
 
 /* Raw device pointer of a per-member array (for zero-copy interop, e.g. NCCL gathers or
  * torch tensors wrapping library memory); NULL if unknown. */

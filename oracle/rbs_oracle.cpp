@@ -1016,13 +1016,13 @@ static int newton_attempt(Model& m, NewtonWork& w, const double* uprev, double t
         }
         ndz_prev = ndz;
         ndz = std::sqrt(acc / n);
+        for (int i = 0; i < n; i++) w.z[i] -= w.dz[i];
         if (!std::isfinite(ndz)) { status = -1; break; }
         double theta = 0;
         if (iter > 1) {
             theta = ndz / ndz_prev;
             if (theta > 2) { status = -1; break; }
         }
-        for (int i = 0; i < n; i++) w.z[i] -= w.dz[i];
         if (iter > 1) eta = theta / (1 - theta);
         if ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0 && eta * ndz < kappa)) { status = 1; break; }
     }

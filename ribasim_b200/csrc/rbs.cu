@@ -59,8 +59,15 @@ struct rbs_handle {
     double tprev = 0.0;
     double abstol = 1e-5, reltol = 1e-5;
     int max_iter = 10;
+    // stepper options (rbs_set_stepper)
+    int full_newton = 0, predictor = 1, max_halvings = 20, grow_iters = 4;
+    int64_t max_passes = 100000;
     int64_t launches = 0;
-    int64_t stats[4] = {0, 0, 0, 0};
+    int64_t n_steps = 0, n_passes = 0, n_failed = 0;
+    // optional per-launch timing with CUDA events on the handle's stream (rbs_profile)
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
     // schedules (host)
     std::vector<int> lu_level_ptr, fwd_level_ptr, bwd_level_ptr;
     int *d_lu_level_ptr = nullptr, *d_fwd_level_ptr = nullptr, *d_bwd_level_ptr = nullptr;
@@ -159,84 +166,106 @@ void bind_net(rbs_handle* h) {
     M_D(infiltration); M_D(cum_precipitation); M_D(cum_surface_runoff); M_D(cum_drainage);
     M_D(exact); M_D(fb_rate); M_D(fb_cum); M_D(frp); M_D(fro); M_D(jv); M_D(wv); M_D(lu);
     M_D(norm_part); M_D(ndz); M_D(ndz_prev); M_D(eta); M_D(storage_prev); M_D(level_prev);
-    n.nstat = (int*)h->member["nstat"].p;
-    n.status = (int*)h->member["status"].p;
-    n.active_count = (int*)h->member["active_count"].p;
+    M_D(mh); M_D(mhnom); M_D(melapsed); M_D(mhlast); M_D(zlast);
+#define M_I(name) n.name = (int*)h->member[#name].p
+    M_I(nstat); M_I(status); M_I(active_count);
+    M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mlast); M_I(maction);
+    M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej);
+#undef M_I
 #undef S_D
 #undef S_I
 #undef M_D
 }
 
+inline void prof_begin(rbs_handle* h, const char* name) {
+    if (!h->profiling) return;
+    rbs_handle::ProfRec r{name, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, h->stream);
+    h->prof.push_back(r);
+}
+inline void prof_end(rbs_handle* h) {
+    if (h->profiling) cudaEventRecord(h->prof.back().b, h->stream);
+}
+
+#define LAUNCH_CFG(h, kernel, grid, block, ...)                                                \
+    do {                                                                                       \
+        prof_begin((h), #kernel);                                                              \
+        kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                              \
+        prof_end(h);                                                                           \
+        (h)->launches++;                                                                       \
+    } while (0)
+
 #define LAUNCH(h, kernel, total, ...)                                                          \
     do {                                                                                       \
         long long tot_ = (total);                                                              \
-        if (tot_ > 0) {                                                                        \
-            kernel<<<grid_for(tot_), 256, 0, (h)->stream>>>(__VA_ARGS__);                      \
-            (h)->launches++;                                                                   \
-        }                                                                                      \
+        if (tot_ > 0) LAUNCH_CFG(h, kernel, grid_for(tot_), 256, __VA_ARGS__);                 \
     } while (0)
 
-// RHS phases on the caches prepared by k_exact: ur -> du (and J values when JAC)
-template <bool JAC> void launch_rhs(rbs_handle* h, const double* ur) {
+// RHS phases on the caches prepared by k_exact / k_step_apply: ur -> du (and J values when JAC).
+// SRC 0 reads u_reduced from `ur`; SRC 1 fuses reduce_state!(uprev + z) into the basin kernel.
+template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
     long long B = n.B;
-    // controllers read du of flows that may not be formulated yet: those must read 0
-    // (water_balance! zeroes du first, core/src/solve.jl:54)
-    if (n.n_pid > 0 || n.n_cc > 0)
-        cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream);
-    LAUNCH(h, k_basin<JAC>, (long long)n.n_basin * B, n, ur, true);
-    LAUNCH(h, k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0);
+    LAUNCH(h, (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, false);
+    LAUNCH(h, k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0, pred);
     if (n.n_cc > 0) {
-        LAUNCH(h, k_continuous_control<JAC>, (long long)n.n_cc * B, n);
+        LAUNCH(h, k_continuous_control<JAC>, (long long)n.n_cc * B, n, pred);
         LAUNCH(h, k_links<JAC>, (long long)h->list_phase[1].size() * B, n, 1, h->d_list_phase[1],
-               (int)h->list_phase[1].size());
+               (int)h->list_phase[1].size(), pred);
     }
     if (n.n_pid > 0) {
-        LAUNCH(h, k_pid<JAC>, (long long)n.n_pid * B, n, ur);
+        LAUNCH(h, k_pid<JAC>, (long long)n.n_pid * B, n, n.ur, pred);
         LAUNCH(h, k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
-               (int)h->list_phase[2].size());
+               (int)h->list_phase[2].size(), pred);
     }
 }
+// controllers read du of flows that may not be formulated yet: those must read 0
+// (water_balance! zeroes du first, core/src/solve.jl:54)
+void zero_du_if_controlled(rbs_handle* h) {
+    Net& n = h->net;
+    if (n.n_pid > 0 || n.n_cc > 0)
+        cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream);
+}
 
-void launch_factor(rbs_handle* h, double inv_gamma) {
+// W = A J - I/gamma and its LU.  FROM_J: assembled on the fly (step path, per-member gamma = h).
+template <bool FROM_J> void launch_factor(rbs_handle* h, double inv_gamma, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
     long long B = n.B;
-    LAUNCH(h, k_assemble_w, (long long)n.nnz_w * B, n, inv_gamma);
+    if (!FROM_J) LAUNCH(h, k_assemble_w, (long long)n.nnz_w * B, n, inv_gamma);
     int n_levels = (int)h->lu_level_ptr.size() - 1;
     if (h->tile_mode) {
         int blocks = (n.B + h->tile - 1) / h->tile;
-        k_lu_tile<<<blocks, 256, 0, h->stream>>>(n, h->d_lu_level_ptr, n_levels, h->tile);
-        h->launches++;
+        LAUNCH_CFG(h, k_lu_tile<FROM_J>, blocks, 256, n, h->d_lu_level_ptr, n_levels, h->tile, inv_gamma, pred);
     } else {
         for (int lv = 0; lv < n_levels; lv++) {
             int e0 = h->lu_level_ptr[lv], e1 = h->lu_level_ptr[lv + 1];
-            LAUNCH(h, k_lu_level, (long long)(e1 - e0) * B, n, e0, e1);
+            LAUNCH(h, k_lu_level<FROM_J>, (long long)(e1 - e0) * B, n, e0, e1, inv_gamma, pred);
         }
     }
     h->factor_valid = true;
-    h->stats[2]++;
 }
 
-void launch_solve(rbs_handle* h, const double* b, double* x) {
+template <bool FROM_DU> void launch_solve(rbs_handle* h, const double* b, double* x, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
     long long B = n.B;
     int n_fwd = (int)h->fwd_level_ptr.size() - 1, n_bwd = (int)h->bwd_level_ptr.size() - 1;
     if (h->tile_mode) {
         int blocks = (n.B + h->tile - 1) / h->tile;
-        k_solve_tile<<<blocks, 256, 0, h->stream>>>(n, b, x, h->d_fwd_level_ptr, n_fwd,
-                                                    h->d_bwd_level_ptr, n_bwd, h->tile);
-        h->launches++;
+        LAUNCH_CFG(h, k_solve_tile<FROM_DU>, blocks, 256, n, b, x, h->d_fwd_level_ptr, n_fwd,
+                   h->d_bwd_level_ptr, n_bwd, h->tile, pred);
     } else {
-        LAUNCH(h, k_solve_load, (long long)n.n_reduced * B, n, b);
+        LAUNCH(h, k_solve_load<FROM_DU>, (long long)n.n_reduced * B, n, b, pred);
         for (int lv = 1; lv < n_fwd; lv++) {
             int p0 = h->fwd_level_ptr[lv], p1 = h->fwd_level_ptr[lv + 1];
-            LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 0);
+            LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 0, pred);
         }
         for (int lv = 0; lv < n_bwd; lv++) {
             int p0 = h->bwd_level_ptr[lv], p1 = h->bwd_level_ptr[lv + 1];
-            LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 1);
+            LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 1, pred);
         }
-        LAUNCH(h, k_solve_store, (long long)n.n_reduced * B, n, x);
+        LAUNCH(h, k_solve_store, (long long)n.n_reduced * B, n, x, pred);
     }
 }
 
@@ -367,9 +396,12 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         {"level_prev", n.n_basin}, {"fb_rate", n.n_fb}, {"fb_cum", n.n_fb}, {"frp", n.n_pump},
         {"fro", n.n_outlet}, {"jv", n.nnz_j}, {"wv", n.nnz_w}, {"lu", n.n_lu},
         {"norm_part", h->n_part}, {"ndz", 1}, {"ndz_prev", 1}, {"eta", 1},
+        {"zlast", n.n_state}, {"mh", 1}, {"mhnom", 1}, {"melapsed", 1}, {"mhlast", 1},
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
-    if (alloc_member(h, "nstat", 1, true) || alloc_member(h, "status", 1, true)) return bail("member alloc");
+    for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mlast",
+                          "maction", "cnt_iters", "cnt_sub", "cnt_rej"})
+        if (alloc_member(h, k, 1, true)) return bail("member alloc");
     {
         DevArr a; a.bytes = sizeof(int); a.is_int = true;
         if (cudaMalloc(&a.p, a.bytes) != cudaSuccess) return bail("active_count alloc");
@@ -420,6 +452,7 @@ void rbs_destroy(rbs_handle* h) {
     for (auto& kv : h->shared) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& kv : h->member) if (kv.second.p) cudaFree(kv.second.p);
     if (h->staging) cudaFree(h->staging);
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (h->h_active) cudaFreeHost(h->h_active);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -477,6 +510,17 @@ int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_e
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
+int rbs_copy_member_to_device(rbs_handle* h, const char* key, void* dst_device, int64_t n_entity) {
+    if (!h || !key || !dst_device) return fail("rbs_copy_member_to_device: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || it->second.is_int) return fail(std::string("unknown member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(dst_device, it->second.p, (size_t)n_entity * h->B * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
 int rbs_set_tprev(rbs_handle* h, double tprev) {
     if (!h) return fail("rbs_set_tprev: null handle");
     h->tprev = tprev;
@@ -488,9 +532,60 @@ int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter
     h->abstol = abstol; h->reltol = reltol; h->max_iter = max_iter;
     return 0;
 }
-int rbs_get_stats(rbs_handle* h, int64_t* out4) {
-    if (!h || !out4) return fail("rbs_get_stats: null argument");
-    for (int k = 0; k < 4; k++) out4[k] = h->stats[k];
+int rbs_set_stepper(rbs_handle* h, int32_t full_newton, int32_t predictor, int32_t max_halvings,
+                    int32_t grow_iters) {
+    if (!h) return fail("rbs_set_stepper: null handle");
+    if (max_halvings < 0 || max_halvings > 60 || grow_iters < 0) return fail("rbs_set_stepper: invalid option");
+    h->full_newton = full_newton != 0; h->predictor = predictor != 0;
+    h->max_halvings = max_halvings; h->grow_iters = grow_iters;
+    return 0;
+}
+int rbs_get_stats(rbs_handle* h, int64_t* out6) {
+    if (!h || !out6) return fail("rbs_get_stats: null argument");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    std::vector<int> buf((size_t)n.B * 3);
+    CUDA_TRY(cudaMemcpyAsync(buf.data(), n.cnt_iters, n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(buf.data() + n.B, n.cnt_sub, n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(buf.data() + 2 * n.B, n.cnt_rej, n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int64_t it = 0, sub = 0, rej = 0;
+    for (int m = 0; m < n.B; m++) { it += buf[m]; sub += buf[n.B + m]; rej += buf[2 * n.B + m]; }
+    out6[0] = h->n_steps; out6[1] = h->n_passes; out6[2] = sub; out6[3] = h->n_failed;
+    out6[4] = it; out6[5] = rej;
+    return 0;
+}
+
+int rbs_profile(rbs_handle* h, int32_t enable) {
+    if (!h) return fail("rbs_profile: null handle");
+    cudaSetDevice(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->prof.clear();
+    h->profiling = enable != 0;
+    return 0;
+}
+int rbs_profile_report(rbs_handle* h, char* buf, int32_t len) {
+    if (!h || !buf || len < 1) return fail("rbs_profile_report: null argument");
+    cudaSetDevice(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::map<std::string, std::pair<int64_t, double>> agg;
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& a = agg[r.name];
+            a.first++;
+            a.second += ms;
+        }
+    }
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+        out += line;
+    }
+    strncpy(buf, out.c_str(), (size_t)len - 1);
+    buf[len - 1] = 0;
     return 0;
 }
 
@@ -535,7 +630,7 @@ int rbs_rhs(rbs_handle* h, const double* u_reduced, double t, double* du, double
     CUDA_TRY(cudaMemcpyAsync(n.ur, u_reduced, (size_t)n.n_reduced * n.B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
     LAUNCH(h, k_exact, (long long)n.n_basin * n.B, n, t, h->tprev);
-    launch_rhs<false>(h, n.ur);
+    launch_rhs<false, 0>(h, n.ur);
     if (copy_out(h, du, n.du, n.n_state) || copy_out(h, storage, n.storage, n.n_basin) ||
         copy_out(h, level, n.level, n.n_basin) || copy_out(h, area, n.area, n.n_basin) ||
         copy_out(h, factor, n.factor, n.n_basin)) return 1;
@@ -552,8 +647,8 @@ int rbs_jac(rbs_handle* h, const double* u_reduced, double t, double gamma, doub
     CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
     CUDA_TRY(cudaMemsetAsync(n.jv, 0, (size_t)std::max(n.nnz_j, 1) * n.B * sizeof(double), h->stream));
     LAUNCH(h, k_exact, (long long)n.n_basin * n.B, n, t, h->tprev);
-    launch_rhs<true>(h, n.ur);
-    launch_factor(h, 1.0 / gamma);
+    launch_rhs<true, 0>(h, n.ur);
+    launch_factor<false>(h, 1.0 / gamma);
     if (copy_out(h, j_vals, n.jv, n.nnz_j) || copy_out(h, w_vals, n.wv, n.nnz_w)) return 1;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return check_async(h, "rbs_jac");
@@ -567,31 +662,24 @@ int rbs_solve(rbs_handle* h, const double* b, double* x) {
     size_t nb = (size_t)n.n_reduced * n.B * sizeof(double);
     CUDA_TRY(cudaMemcpyAsync(n.br, b, nb, cudaMemcpyHostToDevice, h->stream));
     double* c = mp(h, "cvec");
-    launch_solve(h, n.br, c);
+    launch_solve<false>(h, n.br, c);
     CUDA_TRY(cudaMemcpyAsync(x, c, nb, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return check_async(h, "rbs_solve");
-}
-
-static void launch_limit(rbs_handle* h, double* u, const double* uprev, double dt, double t) {
-    Net& n = h->net;
-    long long B = n.B;
-    LAUNCH(h, k_exact, (long long)n.n_basin * B, n, t, h->tprev);
-    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * B, n, u, nullptr, n.ur, 0.0, 0.0);
-    LAUNCH(h, k_basin<false>, (long long)n.n_basin * B, n, n.ur, false);
-    LAUNCH(h, k_limit_flow, (long long)n.off_integral * B, n, u, uprev, dt);
-    LAUNCH(h, k_limit_user_demand, (long long)n.n_ud_link * B, n, u, uprev, dt,
-           sp<int>(h, "ud_demand_from_timeseries"), sp<double>(h, "ud_alloc_total"));
 }
 
 int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, double t) {
     if (!h || !u || !uprev) return fail("rbs_limit_flow: null argument");
     cudaSetDevice(h->device);
     Net& n = h->net;
+    long long B = n.B;
     size_t nb = (size_t)n.n_state * n.B * sizeof(double);
     CUDA_TRY(cudaMemcpyAsync(n.u, u, nb, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(n.uprev, uprev, nb, cudaMemcpyHostToDevice, h->stream));
-    launch_limit(h, n.u, n.uprev, dt, t);
+    LAUNCH(h, k_exact, (long long)n.n_basin * B, n, t, h->tprev);
+    LAUNCH(h, (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, Pred{nullptr, 0, nullptr}, false);
+    LAUNCH(h, k_limit_flow, (long long)n.off_integral * B, n, n.u, n.uprev, dt,
+           sp<int>(h, "ud_demand_from_timeseries"), sp<double>(h, "ud_alloc_total"));
     CUDA_TRY(cudaMemcpyAsync(u, n.u, nb, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return check_async(h, "rbs_limit_flow");
@@ -604,10 +692,39 @@ int rbs_refresh(rbs_handle* h, double t) {
     long long B = n.B;
     CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
     LAUNCH(h, k_exact, (long long)n.n_basin * B, n, t, h->tprev);
-    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * B, n, n.u, nullptr, n.ur, 0.0, 0.0);
-    launch_rhs<false>(h, n.ur);
+    launch_rhs<false, 2>(h, nullptr);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return check_async(h, "rbs_refresh");
+}
+
+// One pass of the per-member state machine (see rbs_kernels.cuh, "sub-stepping state machine").
+static void launch_pass(rbs_handle* h, double dt, double h_min) {
+    Net& n = h->net;
+    long long B = n.B;
+    const int* from_ts = sp<int>(h, "ud_demand_from_timeseries");
+    const double* alloc_total = sp<double>(h, "ud_alloc_total");
+    // finalize half: members whose Newton iteration ended in the previous pass
+    Pred lim{n.mphase, PHASE_LIMIT, nullptr};
+    LAUNCH(h, (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, false);
+    LAUNCH(h, k_step_limit, (long long)n.n_state * B, n, from_ts, alloc_total);
+    LAUNCH(h, (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, true);
+    LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters);
+    LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
+    // Newton half
+    Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
+    zero_du_if_controlled(h);
+    launch_rhs<true, 1>(h, nullptr, nw);
+    if (!h->full_newton) launch_rhs<false, 1>(h, nullptr, nw);
+    launch_factor<true>(h, -1.0, nw);
+    double* c = mp(h, "cvec");
+    launch_solve<true>(h, nullptr, c, Pred{n.mphase, PHASE_NEWTON, nullptr});
+    {
+        dim3 block(32, RBS_DZ_ROWS), grid((n.B + 31) / 32, h->n_part);
+        LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
+    }
+    cudaMemsetAsync(n.active_count, 0, sizeof(int), h->stream);
+    LAUNCH(h, k_newton_converge, B, n, h->n_part, h->max_iter, 0.01, h->full_newton);
+    h->n_passes++;
 }
 
 int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member) {
@@ -616,51 +733,23 @@ int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_
     cudaSetDevice(h->device);
     Net& n = h->net;
     long long B = n.B;
-    double tn = t + dt;
-    double inv_dt = 1.0 / dt;
-    double* c = mp(h, "cvec");
-    CUDA_TRY(cudaMemsetAsync(n.status, 0, (size_t)n.B * sizeof(int), h->stream));
-    LAUNCH(h, k_exact, (long long)n.n_basin * B, n, tn, h->tprev);
-    LAUNCH(h, k_step_begin, std::max((long long)n.n_state * B, B), n);
-    int iters = 0;
-    for (int iter = 1; iter <= h->max_iter; iter++) {
-        iters = iter;
-        LAUNCH(h, k_reduce<1>, (long long)n.n_reduced * B, n, n.uprev, n.z, n.ur, 0.0, 0.0);
-        if (iter == 1) {
-            // Jacobian and W = J - I/dt at (uprev, t + dt): refreshed once per step
-            launch_rhs<true>(h, n.ur);
-            launch_factor(h, inv_dt);
-        } else {
-            launch_rhs<false>(h, n.ur);
-        }
-        LAUNCH(h, k_reduce<2>, (long long)n.n_reduced * B, n, n.du, n.z, n.br, dt, inv_dt);
-        launch_solve(h, n.br, c);
-        CUDA_TRY(cudaMemsetAsync(n.active_count, 0, sizeof(int), h->stream));
-        {
-            dim3 block(32, RBS_DZ_ROWS), grid((n.B + 31) / 32, h->n_part);
-            k_newton_update<<<grid, block, 0, h->stream>>>(n, c, dt, inv_dt, h->abstol, h->reltol,
-                                                           h->rows_per_block);
-            h->launches++;
-        }
-        LAUNCH(h, k_newton_converge, B, n, iter, h->n_part, h->max_iter, 0.01);
+    double h_min = std::ldexp(dt, -h->max_halvings);
+    LAUNCH(h, k_step_begin, (long long)(n.n_state + n.n_basin + 1) * B, n, dt, h->predictor);
+    // safety net only: every attempt either advances the member or halves its sub-step
+    const int64_t max_passes = h->max_passes;
+    for (int64_t pass = 0;; pass++) {
+        launch_pass(h, dt, h_min);
         CUDA_TRY(cudaMemcpyAsync(h->h_active, n.active_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         if (*h->h_active == 0) break;
+        if (pass > max_passes) return fail("rbs_step_implicit_euler: pass limit exceeded");
     }
-    LAUNCH(h, k_apply_z, (long long)n.n_state * B, n);
-    launch_limit(h, n.u, n.uprev, dt, tn);
-    // caches at the accepted state (check_negative_storage's water_balance! call)
-    CUDA_TRY(cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream));
-    LAUNCH(h, k_reduce<0>, (long long)n.n_reduced * B, n, n.u, nullptr, n.ur, 0.0, 0.0);
-    launch_rhs<false>(h, n.ur);
-    LAUNCH(h, k_step_end, std::max((long long)(n.n_basin + n.n_fb) * B, B), n, tn - h->tprev);
-    h->tprev = tn;
-    h->stats[0]++;
-    h->stats[1] += iters;
+    h->tprev = t + dt;
+    h->n_steps++;
     if (status_per_member) {
         CUDA_TRY(cudaMemcpyAsync(status_per_member, n.status, (size_t)n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        for (int m = 0; m < n.B; m++) if (status_per_member[m] & 1) h->stats[3]++;
+        for (int m = 0; m < n.B; m++) if (status_per_member[m] & 1) h->n_failed++;
     }
     return check_async(h, "rbs_step_implicit_euler");
 }

@@ -16,7 +16,8 @@
 enum { KIND_BASIN = 0, KIND_LEVEL_BOUNDARY = 1, KIND_TERMINAL = 2, KIND_NONE = 3 };
 enum { CT_TRC = 0, CT_PUMP = 1, CT_OUTLET = 2, CT_UD_IN = 3, CT_UD_OUT = 4, CT_LR = 5, CT_MANNING = 6 };
 enum { CONTROL_NONE = 0, CONTROL_CONTINUOUS = 1, CONTROL_PID = 2 };
-enum { NEWTON_ACTIVE = 0, NEWTON_CONVERGED = 1, NEWTON_FAILED = 2 };
+enum { PHASE_NEWTON = 0, PHASE_LIMIT = 1, PHASE_DONE = 2 };
+enum { ACTION_NONE = 0, ACTION_ACCEPT = 1, ACTION_REJECT = 2 };
 
 struct Net {
     // sizes
@@ -86,7 +87,25 @@ struct Net {
     int *nstat, *status, *active_count;
     double* storage_prev;  // limiter memory (basin.storage_prev, frozen: SURVEY row 22)
     double* level_prev;
+    // per-member sub-stepping state machine (rbs_step.cuh)
+    int *mphase, *mjac, *miter, *mconv, *mneg, *mlast, *maction;
+    int *cnt_iters, *cnt_sub, *cnt_rej;
+    double *mh, *mhnom, *melapsed, *mhlast, *zlast;
 };
+
+// Member predicate of the step path: a kernel launched with `mphase != nullptr` only works on
+// members whose phase equals `want`; with `mjac != nullptr` only on members whose Jacobian
+// flag equals the kernel's JAC template argument.  The seam entry points pass nullptr.
+struct Pred {
+    const int* mphase;
+    int want;
+    const int* mjac;
+};
+template <bool JAC> __device__ __forceinline__ bool rbs_skip(const Pred& p, int m) {
+    if (p.mphase && p.mphase[m] != p.want) return true;
+    if (p.mjac && (p.mjac[m] != 0) != JAC) return true;
+    return false;
+}
 
 #define RBS_TID (blockIdx.x * (long long)blockDim.x + threadIdx.x)
 
@@ -162,14 +181,39 @@ __global__ void k_reduce(Net n, const double* __restrict__ a, const double* __re
 }
 
 // ---- basin properties + vertical fluxes (solve.jl:120-227) -------------------------------------
-template <bool JAC>
-__global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du) {
+// SRC 0: u_reduced given in `ur`;  SRC 1: reduce_state! of (uprev + z) fused in;  SRC 2: of u.
+// Grid: n_reduced x B (rows >= n_basin only forward the PID integral state into n.ur).
+template <int SRC> __device__ __forceinline__ double rbs_state_in(const Net& n, long long o) {
+    return SRC == 1 ? n.uprev[o] + n.z[o] : n.u[o];
+}
+template <bool JAC, int SRC>
+__global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
+                        bool flag_negative) {
     long long tid = RBS_TID;
     int b = (int)(tid / n.B);
-    if (b >= n.n_basin) return;
+    if (b >= n.n_reduced) return;
     int m = (int)(tid - (long long)b * n.B);
+    if (rbs_skip<JAC>(pred, m)) return;
     long long o = (long long)b * n.B + m;
-    double S = (n.storage0[b] + ur[o]) + n.exact[o];
+    if (b >= n.n_basin) {
+        if (SRC != 0) n.ur[o] = rbs_state_in<SRC>(n, (long long)(n.off_integral + b - n.n_basin) * n.B + m);
+        return;
+    }
+    double urv;
+    if (SRC == 0) {
+        urv = ur[o];
+    } else {
+        double acc = 0.0;
+        for (int k = n.inc_ptr[b]; k < n.inc_ptr[b + 1]; k++) {
+            double v = rbs_state_in<SRC>(n, (long long)n.inc_state[k] * n.B + m);
+            acc = n.inc_sign[k] > 0.0 ? acc + v : acc - v;
+        }
+        acc -= rbs_state_in<SRC>(n, (long long)(n.off_evap + b) * n.B + m);
+        acc -= rbs_state_in<SRC>(n, (long long)(n.off_infil + b) * n.B + m);
+        urv = acc;
+        n.ur[o] = acc;
+    }
+    double S = (n.storage0[b] + urv) + n.exact[o];
     double dphi;
     double phi = rbs_reduction_factor(S, n.low_storage_threshold[b], dphi);
     int p0 = n.prof_ptr[b], np = n.prof_ptr[b + 1] - p0;
@@ -180,6 +224,7 @@ __global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du) {
     n.factor[o] = phi;
     n.level[o] = e.level;
     n.area[o] = e.area;
+    if (flag_negative && S < 0.0) atomicOr(&n.mneg[m], 1);  // integer flag only
     if (JAC) {
         n.dlevel[o] = e.dlevel;
         n.dfactor[o] = dphi;
@@ -216,12 +261,13 @@ __device__ __forceinline__ double rbs_ud_link(const Net& n, int k, int m, double
 // PHASE 0: every connector state whose flow does not depend on a controller;
 // PHASE 1/2: the pumps/outlets listed in `list` (controlled by ContinuousControl / PidControl).
 template <bool JAC>
-__global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_list) {
+__global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
     long long tid = RBS_TID;
     int li = (int)(tid / n.B);
     int count = phase == 0 ? n.n_conn : n_list;
     if (li >= count) return;
     int m = (int)(tid - (long long)li * n.B);
+    if (rbs_skip<JAC>(pred, m)) return;
     int s = phase == 0 ? li : list[li];
     int ct = n.conn_type[s], k = n.conn_idx[s];
     long long so = (long long)s * n.B + m;
@@ -301,11 +347,12 @@ __global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_li
 
 // ---- ContinuousControl (solve.jl:101-113, callback.jl:757-763) ----------------------------------
 template <bool JAC>
-__global__ void k_continuous_control(Net n) {
+__global__ void k_continuous_control(Net n, Pred pred) {
     long long tid = RBS_TID;
     int i = (int)(tid / n.B);
     if (i >= n.n_cc) return;
     int m = (int)(tid - (long long)i * n.B);
+    if (rbs_skip<JAC>(pred, m)) return;
     double value = 0.0;
     for (int j = n.cc_sv_ptr[i]; j < n.cc_sv_ptr[i + 1]; j++) {
         int kind = n.cc_sv_kind[j], idx = n.cc_sv_idx[j];
@@ -337,11 +384,12 @@ __global__ void k_continuous_control(Net n) {
 
 // ---- PidControl (solve.jl:229-346) ---------------------------------------------------------------
 template <bool JAC>
-__global__ void k_pid(Net n, const double* __restrict__ ur) {
+__global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred) {
     long long tid = RBS_TID;
     int i = (int)(tid / n.B);
     if (i >= n.n_pid) return;
     int m = (int)(tid - (long long)i * n.B);
+    if (rbs_skip<JAC>(pred, m)) return;
     int L = n.pid_listen_basin[i];
     long long lo = (long long)L * n.B + m;
     double err = n.pid_target[i] - n.level[lo];
@@ -409,24 +457,37 @@ __global__ void k_pid(Net n, const double* __restrict__ ur) {
 }
 
 // ---- W_inner = A*J_i - I/gamma (calc_J_inner! + jacobian2W!, differentiation.jl:153-271) --------
-__global__ void k_assemble_w(Net n, double inv_gamma) {
-    long long tid = RBS_TID;
-    int e = (int)(tid / n.B);
-    if (e >= n.nnz_w) return;
-    int m = (int)(tid - (long long)e * n.B);
+// One W entry: the ordered signed sum of the J_intermediate entries that land on it, minus
+// 1/gamma on the diagonal.
+__device__ __forceinline__ double rbs_w_entry(const Net& n, int e, int m, double inv_gamma) {
     double acc = 0.0;
     for (int k = n.wsrc_ptr[e]; k < n.wsrc_ptr[e + 1]; k++) {
         double v = n.jv[(long long)n.wsrc_pos[k] * n.B + m];
         acc = n.wsrc_sign[k] > 0.0 ? acc + v : acc - v;
     }
     if (n.wdiag_flag[e]) acc = acc - inv_gamma;
-    n.wv[(long long)e * n.B + m] = acc;
+    return acc;
+}
+__global__ void k_assemble_w(Net n, double inv_gamma) {
+    long long tid = RBS_TID;
+    int e = (int)(tid / n.B);
+    if (e >= n.nnz_w) return;
+    int m = (int)(tid - (long long)e * n.B);
+    n.wv[(long long)e * n.B + m] = rbs_w_entry(n, e, m, inv_gamma);
+}
+
+// gamma of member m: shared (seam calls) or 1/h of the member's current sub-step
+__device__ __forceinline__ double rbs_inv_gamma(const Net& n, int m, double inv_gamma) {
+    return inv_gamma > 0.0 ? inv_gamma : 1.0 / n.mh[m];
 }
 
 // ---- static-pattern LU: one entry of L or U (see ribasim_b200/symbolic.py) ----------------------
-__device__ __forceinline__ void rbs_lu_entry(const Net& n, int e, int m) {
+// FROM_J: W is assembled on the fly from J_intermediate (step path, no W array traffic).
+template <bool FROM_J>
+__device__ __forceinline__ void rbs_lu_entry(const Net& n, int e, int m, double inv_gamma) {
     int src = n.lu_wsrc[e];
-    double v = src >= 0 ? n.wv[(long long)src * n.B + m] : 0.0;
+    double v = 0.0;
+    if (src >= 0) v = FROM_J ? rbs_w_entry(n, src, m, inv_gamma) : n.wv[(long long)src * n.B + m];
     for (int q = n.lu_prod_ptr[e]; q < n.lu_prod_ptr[e + 1]; q++)
         v -= n.lu[(long long)n.lu_prod_l[q] * n.B + m] * n.lu[(long long)n.lu_prod_u[q] * n.B + m];
     int pv = n.lu_pivot[e];
@@ -435,17 +496,21 @@ __device__ __forceinline__ void rbs_lu_entry(const Net& n, int e, int m) {
 }
 
 // wide mode: one launch per dependency level, grid over (entries of the level) x members
-__global__ void k_lu_level(Net n, int e0, int e1) {
+template <bool FROM_J>
+__global__ void k_lu_level(Net n, int e0, int e1, double inv_gamma, Pred pred) {
     long long tid = RBS_TID;
     int e = e0 + (int)(tid / n.B);
     if (e >= e1) return;
     int m = (int)(tid - (long long)(e - e0) * n.B);
-    rbs_lu_entry(n, e, m);
+    if (rbs_skip<true>(pred, m)) return;
+    rbs_lu_entry<FROM_J>(n, e, m, FROM_J ? rbs_inv_gamma(n, m, inv_gamma) : 0.0);
 }
 
 // tile mode: a block owns a tile of members for the whole factorisation; levels are separated
 // by __syncthreads() only (no grid-wide dependency because members are independent).
-__global__ void k_lu_tile(Net n, const int* __restrict__ level_ptr, int n_levels, int tile) {
+template <bool FROM_J>
+__global__ void k_lu_tile(Net n, const int* __restrict__ level_ptr, int n_levels, int tile,
+                          double inv_gamma, Pred pred) {
     int m0 = blockIdx.x * tile;
     int tm = min(tile, n.B - m0);
     if (tm <= 0) return;
@@ -455,19 +520,40 @@ __global__ void k_lu_tile(Net n, const int* __restrict__ level_ptr, int n_levels
         for (int w = threadIdx.x; w < work; w += blockDim.x) {
             int e = e0 + w / tm;
             int m = m0 + w % tm;
-            rbs_lu_entry(n, e, m);
+            if (rbs_skip<true>(pred, m)) continue;
+            rbs_lu_entry<FROM_J>(n, e, m, FROM_J ? rbs_inv_gamma(n, m, inv_gamma) : 0.0);
         }
         __syncthreads();
     }
 }
 
 // ---- triangular solves ----------------------------------------------------------------------------
-__global__ void k_solve_load(Net n, const double* __restrict__ b) {  // xs = P b
+// Right-hand side of reduced row r: either b[r] (seam) or, on the step path, row r of
+// A * ((h*du - z)/h) computed on the fly (reduce_state!(b), differentiation.jl:321-325).
+template <bool FROM_DU>
+__device__ __forceinline__ double rbs_solve_rhs(const Net& n, const double* __restrict__ b, int r, int m) {
+    if (!FROM_DU) return b[(long long)r * n.B + m];
+    double h = n.mh[m], inv_h = 1.0 / h;
+    if (r < n.n_basin) {
+        double acc = 0.0;
+        for (int k = n.inc_ptr[r]; k < n.inc_ptr[r + 1]; k++) {
+            double v = rbs_red_in<2>(n.du, n.z, (long long)n.inc_state[k] * n.B + m, h, inv_h);
+            acc = n.inc_sign[k] > 0.0 ? acc + v : acc - v;
+        }
+        acc -= rbs_red_in<2>(n.du, n.z, (long long)(n.off_evap + r) * n.B + m, h, inv_h);
+        acc -= rbs_red_in<2>(n.du, n.z, (long long)(n.off_infil + r) * n.B + m, h, inv_h);
+        return acc;
+    }
+    return rbs_red_in<2>(n.du, n.z, (long long)(n.off_integral + r - n.n_basin) * n.B + m, h, inv_h);
+}
+template <bool FROM_DU>
+__global__ void k_solve_load(Net n, const double* __restrict__ b, Pred pred) {  // xs = P b
     long long tid = RBS_TID;
     int i = (int)(tid / n.B);
     if (i >= n.n_reduced) return;
     int m = (int)(tid - (long long)i * n.B);
-    n.xs[(long long)i * n.B + m] = b[(long long)n.perm[i] * n.B + m];
+    if (rbs_skip<true>(pred, m)) return;
+    n.xs[(long long)i * n.B + m] = rbs_solve_rhs<FROM_DU>(n, b, n.perm[i], m);
 }
 __device__ __forceinline__ void rbs_fwd_row(const Net& n, int pos, int m) {
     int i = n.fwd_row[pos];
@@ -483,60 +569,135 @@ __device__ __forceinline__ void rbs_bwd_row(const Net& n, int pos, int m) {
         v -= n.lu[(long long)n.bwd_u[q] * n.B + m] * n.xs[(long long)n.bwd_k[q] * n.B + m];
     n.xs[(long long)i * n.B + m] = v / n.lu[(long long)n.lu_diag[i] * n.B + m];
 }
-__global__ void k_solve_level(Net n, int p0, int p1, int backward) {
+__global__ void k_solve_level(Net n, int p0, int p1, int backward, Pred pred) {
     long long tid = RBS_TID;
     int pos = p0 + (int)(tid / n.B);
     if (pos >= p1) return;
     int m = (int)(tid - (long long)(pos - p0) * n.B);
+    if (rbs_skip<true>(pred, m)) return;
     if (backward) rbs_bwd_row(n, pos, m); else rbs_fwd_row(n, pos, m);
 }
+template <bool FROM_DU>
 __global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __restrict__ x,
                              const int* __restrict__ fwd_level_ptr, int n_fwd,
-                             const int* __restrict__ bwd_level_ptr, int n_bwd, int tile) {
+                             const int* __restrict__ bwd_level_ptr, int n_bwd, int tile, Pred pred) {
     int m0 = blockIdx.x * tile;
     int tm = min(tile, n.B - m0);
     if (tm <= 0) return;
     for (int w = threadIdx.x; w < n.n_reduced * tm; w += blockDim.x) {
         int i = w / tm, m = m0 + w % tm;
-        n.xs[(long long)i * n.B + m] = b[(long long)n.perm[i] * n.B + m];
+        if (rbs_skip<true>(pred, m)) continue;
+        n.xs[(long long)i * n.B + m] = rbs_solve_rhs<FROM_DU>(n, b, n.perm[i], m);
     }
     __syncthreads();
     for (int lv = 1; lv < n_fwd; lv++) {  // level 0 rows have no dependencies
         int p0 = fwd_level_ptr[lv], p1 = fwd_level_ptr[lv + 1];
-        for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x)
-            rbs_fwd_row(n, p0 + w / tm, m0 + w % tm);
+        for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x) {
+            int m = m0 + w % tm;
+            if (!rbs_skip<true>(pred, m)) rbs_fwd_row(n, p0 + w / tm, m);
+        }
         __syncthreads();
     }
     for (int lv = 0; lv < n_bwd; lv++) {
         int p0 = bwd_level_ptr[lv], p1 = bwd_level_ptr[lv + 1];
-        for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x)
-            rbs_bwd_row(n, p0 + w / tm, m0 + w % tm);
+        for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x) {
+            int m = m0 + w % tm;
+            if (!rbs_skip<true>(pred, m)) rbs_bwd_row(n, p0 + w / tm, m);
+        }
         __syncthreads();
     }
     for (int w = threadIdx.x; w < n.n_reduced * tm; w += blockDim.x) {
         int i = w / tm, m = m0 + w % tm;
+        if (rbs_skip<true>(pred, m)) continue;
         x[(long long)n.perm[i] * n.B + m] = n.xs[(long long)i * n.B + m];
     }
 }
-__global__ void k_solve_store(Net n, double* __restrict__ x) {  // x = P^T xs
+__global__ void k_solve_store(Net n, double* __restrict__ x, Pred pred) {  // x = P^T xs
     long long tid = RBS_TID;
     int i = (int)(tid / n.B);
     if (i >= n.n_reduced) return;
     int m = (int)(tid - (long long)i * n.B);
+    if (rbs_skip<true>(pred, m)) return;
     x[(long long)n.perm[i] * n.B + m] = n.xs[(long long)i * n.B + m];
 }
 
+// ---- limit_flow! (solve.jl:840-984); needs storage/level at the proposed u ------------------------
+__device__ __forceinline__ double rbs_min_low_storage_factor(const Net& n, int kind, int idx, int m) {
+    if (kind != KIND_BASIN) return 1.0;
+    long long o = (long long)idx * n.B + m;
+    double thr = n.low_storage_threshold[idx];
+    return rbs_reduction_factor(fmin(n.storage[o], n.storage_prev[o]) - 2 * thr, thr);
+}
+// flow-rate bounds of state s over the last step; false = unbounded (Manning, integral)
+__device__ __forceinline__ bool rbs_flow_bounds(const Net& n, int s, int m,
+                                                const int* __restrict__ from_ts,
+                                                const double* __restrict__ alloc_total, double& lo,
+                                                double& hi) {
+    if (s < n.n_conn) {
+        int ct = n.conn_type[s], k = n.conn_idx[s];
+        if (ct == CT_TRC) { lo = 0.0; hi = RBS_INF; return true; }
+        if (ct == CT_PUMP) { lo = n.pump_min_flow_rate[k]; hi = n.pump_max_flow_rate[k]; return true; }
+        if (ct == CT_OUTLET) { lo = n.outlet_min_flow_rate[k]; hi = n.outlet_max_flow_rate[k]; return true; }
+        if (ct == CT_LR) { hi = n.lr_max_flow_rate[k]; lo = -hi; return true; }
+        if (ct == CT_UD_IN) {
+            int i = n.ud_of_link[k];
+            if (from_ts[i]) { lo = 0.0; hi = RBS_INF; return true; }
+            int n_links = n.ud_link_ptr[i + 1] - n.ud_link_ptr[i];
+            double equal_split = n_links == 0 ? 0.0 : alloc_total[i] / n_links;
+            double alloc = n.ud_link_alloc[k];
+            double q_k_max = isinf(alloc) ? equal_split : alloc;
+            double fb = rbs_min_low_storage_factor(n, n.src_kind[s], n.src_idx[s], m);
+            double fl = 1.0;
+            if (n.src_kind[s] == KIND_BASIN) {
+                long long bo = (long long)n.src_idx[s] * n.B + m;
+                fl = rbs_reduction_factor(fmin(n.level[bo], n.level_prev[bo]) - n.ud_min_level[i] -
+                                              2 * n.ldt, n.ldt);
+            }
+            lo = fb * fl * q_k_max; hi = q_k_max;
+            return true;
+        }
+        return false;  // UserDemand outflow, ManningResistance: not limited
+    }
+    if (s < n.off_infil) { lo = 0.0; hi = RBS_INF; return true; }
+    if (s < n.off_integral) {
+        int b = s - n.off_infil;
+        double fmin_ = rbs_min_low_storage_factor(n, KIND_BASIN, b, m);
+        double infil = n.infiltration[(long long)b * n.B + m];
+        lo = fmin_ * infil; hi = infil;
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ double rbs_clamp_state(double v, double up, double lo, double hi, double dt) {
+    double a = up + lo * dt, b = up + hi * dt;
+    return v > b ? b : (v < a ? a : v);
+}
+// seam: clamp u in place against uprev over a shared dt
+__global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __restrict__ uprev,
+                             double dt, const int* __restrict__ from_ts,
+                             const double* __restrict__ alloc_total) {
+    long long tid = RBS_TID;
+    int s = (int)(tid / n.B);
+    if (s >= n.off_integral) return;
+    int m = (int)(tid - (long long)s * n.B);
+    long long o = (long long)s * n.B + m;
+    double lo, hi;
+    if (!rbs_flow_bounds(n, s, m, from_ts, alloc_total, lo, hi)) return;
+    u[o] = rbs_clamp_state(u[o], uprev[o], lo, hi, dt);
+}
+
 // ---- Newton update (dolinsolve tail + compute_step!/apply_step!) --------------------
-// dz = gamma*dt * (J_i c - b),  b = (dt k - z)/(gamma dt);  z <- z - dz;
+// dz = gamma*h * (J_i c - b),  b = (h k - z)/(gamma h);  z <- z - dz;
 // atmp = dz / (abstol + max(|uprev|, |uprev + z_old|) * reltol); partial sums of atmp^2.
 #define RBS_DZ_ROWS 8
-__global__ void k_newton_update(Net n, const double* __restrict__ c, double dt, double inv_dt,
-                                double abstol, double reltol, int rows_per_block) {
+__global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
+                                int rows_per_block) {
     int m = blockIdx.x * 32 + threadIdx.x;
     int r0 = blockIdx.y * rows_per_block;
     double acc = 0.0;
-    bool live = m < n.B && n.nstat[m] == NEWTON_ACTIVE;
+    bool live = m < n.B && n.mphase[m] == PHASE_NEWTON;
     if (live) {
+        double dt = n.mh[m], inv_dt = 1.0 / dt;
         int r1 = min(r0 + rows_per_block, n.n_state);
         for (int r = r0 + threadIdx.y; r < r1; r += RBS_DZ_ROWS) {
             long long o = (long long)r * n.B + m;
@@ -564,141 +725,184 @@ __global__ void k_newton_update(Net n, const double* __restrict__ c, double dt, 
     }
 }
 
-// per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve)
-__global__ void k_newton_converge(Net n, int iter, int n_part, int max_iter, double kappa) {
+// per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve);
+// a member whose iteration ends (converged or failed) moves to PHASE_LIMIT.  Also counts the
+// members that still have work after this pass.
+__global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa, int full_newton) {
     int m = (int)RBS_TID;
     if (m >= n.B) return;
-    if (n.nstat[m] != NEWTON_ACTIVE) return;
-    double s = 0.0;
-    for (int p = 0; p < n_part; p++) s += n.norm_part[(long long)p * n.B + m];
-    double ndz = sqrt(s / n.n_state);
-    double eta = n.eta[m];
-    int st = NEWTON_ACTIVE;
-    if (!isfinite(ndz)) st = NEWTON_FAILED;
-    else {
-        double theta = 0.0;
-        if (iter > 1) {
-            theta = ndz / n.ndz_prev[m];
-            if (theta > 2.0) st = NEWTON_FAILED;
-            else eta = theta / (1.0 - theta);
+    int ph = n.mphase[m];
+    if (ph == PHASE_NEWTON) {
+        int iter = n.miter[m];
+        double s = 0.0;
+        for (int p = 0; p < n_part; p++) s += n.norm_part[(long long)p * n.B + m];
+        double ndz = sqrt(s / n.n_state);
+        double eta = n.eta[m];
+        int st = 0;  // 0 continue, 1 converged, 2 failed
+        if (!isfinite(ndz)) st = 2;
+        else {
+            double theta = 0.0;
+            if (iter > 1) {
+                theta = ndz / n.ndz_prev[m];
+                if (theta > 2.0) st = 2;
+                else eta = theta / (1.0 - theta);
+            }
+            if (st == 0 && ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0.0 && eta * ndz < kappa)))
+                st = 1;
         }
-        if (st == NEWTON_ACTIVE &&
-            ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0.0 && eta * ndz < kappa)))
-            st = NEWTON_CONVERGED;
+        if (st == 0 && iter >= max_iter) st = 2;
+        n.ndz_prev[m] = ndz;
+        n.ndz[m] = ndz;
+        n.eta[m] = eta;
+        n.cnt_iters[m] += 1;
+        if (st == 0) {
+            n.miter[m] = iter + 1;
+            n.mjac[m] = full_newton;
+        } else {
+            n.mconv[m] = st == 1;
+            n.mphase[m] = PHASE_LIMIT;
+            ph = PHASE_LIMIT;
+        }
     }
-    if (st == NEWTON_ACTIVE && iter >= max_iter) st = NEWTON_FAILED;
-    n.ndz_prev[m] = ndz;
-    n.ndz[m] = ndz;
-    n.eta[m] = eta;
-    n.nstat[m] = st;
-    if (st == NEWTON_ACTIVE) atomicAdd(n.active_count, 1);  // integer counter only
+    if (ph != PHASE_DONE) atomicAdd(n.active_count, 1);  // integer counter only
 }
 
-__global__ void k_step_begin(Net n) {
-    // uprev <- u, z <- 0, Newton state reset; eta0 = max(eta_old, eps)^0.8 (initial_eta)
+// ---- sub-stepping state machine -------------------------------------------------------------------
+// Exact cumulative forcing at the end of the member's current attempt (solve.jl:137-150, 86-99);
+// on ACCEPT first advances the cumulatives by the accepted length (callback.jl:125-182).
+__device__ __forceinline__ void rbs_exact_update(const Net& n, int b, int m, bool accept, double h_acc,
+                                                 bool next, double h_next) {
+    long long o = (long long)b * n.B + m;
+    double P = n.fixed_area[b] * n.precipitation[o], R = n.surface_runoff[o], D = n.drainage[o];
+    double cp = n.cum_precipitation[o], cr = n.cum_surface_runoff[o], cd = n.cum_drainage[o];
+    if (accept) {
+        cp += P * h_acc; cr += h_acc * R; cd += h_acc * D;
+        n.cum_precipitation[o] = cp; n.cum_surface_runoff[o] = cr; n.cum_drainage[o] = cd;
+    }
+    double ex = ((cp + P * h_next) + (cr + h_next * R)) + (cd + h_next * D);
+    for (int k = n.bfb_ptr[b]; k < n.bfb_ptr[b + 1]; k++) {
+        long long f = (long long)n.bfb_idx[k] * n.B + m;
+        double fc = n.fb_cum[f], fr = n.fb_rate[f];
+        if (accept) { fc += fr * h_acc; n.fb_cum[f] = fc; }
+        ex += fc + fr * h_next;
+    }
+    if (next) n.exact[o] = ex;
+}
+
+// start of an outer step [t0, t0 + dt]: uprev <- u, first attempt length, predictor, exact
+__global__ void k_step_begin(Net n, double dt, int predictor) {
     long long tid = RBS_TID;
     long long total = (long long)n.n_state * n.B;
+    int m = (int)(tid % n.B);
+    double hnom = fmin(n.mhnom[m] > 0.0 ? n.mhnom[m] : dt, dt);
+    double h = hnom;  // elapsed = 0: the remainder is dt
     if (tid < total) {
+        double hl = n.mhlast[m];
         n.uprev[tid] = n.u[tid];
-        n.z[tid] = 0.0;
+        n.z[tid] = (predictor && hl > 0.0) ? n.zlast[tid] * (h / hl) : 0.0;
     }
-    if (tid < n.B) {
-        n.nstat[tid] = NEWTON_ACTIVE;
-        n.eta[tid] = pow(fmax(n.eta[tid], 2.220446049250313e-16), 0.8);
-        n.ndz_prev[tid] = 0.0;
+    long long bt = tid - total;
+    if (bt >= 0 && bt < (long long)n.n_basin * n.B)
+        rbs_exact_update(n, (int)(bt / n.B), m, false, 0.0, true, h);
+    long long mt = bt - (long long)n.n_basin * n.B;
+    if (mt >= 0 && mt < n.B) {
+        n.mhnom[m] = hnom;
+        n.mh[m] = h;
+        n.mlast[m] = 1 * (hnom >= dt);
+        n.melapsed[m] = 0.0;
+        n.mphase[m] = PHASE_NEWTON;
+        n.miter[m] = 1;
+        n.mjac[m] = 1;
+        n.mneg[m] = 0;
+        n.maction[m] = ACTION_NONE;
+        n.status[m] = 0;
+        n.eta[m] = pow(fmax(n.eta[m], 2.220446049250313e-16), 0.8);
+        n.ndz_prev[m] = 0.0;
     }
 }
 
-__global__ void k_apply_z(Net n) {  // u = uprev + z
-    long long tid = RBS_TID;
-    if (tid < (long long)n.n_state * n.B) n.u[tid] = n.uprev[tid] + n.z[tid];
-}
-
-// ---- limit_flow! (solve.jl:840-984); needs storage/level at the proposed u ------------------------
-__device__ __forceinline__ double rbs_min_low_storage_factor(const Net& n, int kind, int idx, int m) {
-    if (kind != KIND_BASIN) return 1.0;
-    long long o = (long long)idx * n.B + m;
-    double thr = n.low_storage_threshold[idx];
-    return rbs_reduction_factor(fmin(n.storage[o], n.storage_prev[o]) - 2 * thr, thr);
-}
-__global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __restrict__ uprev,
-                             double dt) {
+// PHASE_LIMIT members: u <- clamp(uprev + z) (limit_flow! on the proposed state)
+__global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
+                             const double* __restrict__ alloc_total) {
     long long tid = RBS_TID;
     int s = (int)(tid / n.B);
-    if (s >= n.off_integral) return;
+    if (s >= n.n_state) return;
     int m = (int)(tid - (long long)s * n.B);
+    if (n.mphase[m] != PHASE_LIMIT) return;
     long long o = (long long)s * n.B + m;
+    double up = n.uprev[o];
+    double v = up + n.z[o];
     double lo, hi;
-    if (s < n.n_conn) {
-        int ct = n.conn_type[s], k = n.conn_idx[s];
-        if (ct == CT_TRC) { lo = 0.0; hi = RBS_INF; }
-        else if (ct == CT_PUMP) { lo = n.pump_min_flow_rate[k]; hi = n.pump_max_flow_rate[k]; }
-        else if (ct == CT_OUTLET) { lo = n.outlet_min_flow_rate[k]; hi = n.outlet_max_flow_rate[k]; }
-        else if (ct == CT_LR) { hi = n.lr_max_flow_rate[k]; lo = -hi; }
-        else return;  // UserDemand: handled by k_limit_user_demand; Manning: unbounded
-    } else if (s < n.off_infil) {
-        lo = 0.0; hi = RBS_INF;
-    } else {
-        int b = s - n.off_infil;
-        double fmin_ = rbs_min_low_storage_factor(n, KIND_BASIN, b, m);
-        double infil = n.infiltration[(long long)b * n.B + m];
-        lo = fmin_ * infil; hi = infil;
-    }
-    double up = uprev[o];
-    double a = up + lo * dt, b = up + hi * dt;
-    double v = u[o];
-    u[o] = v > b ? b : (v < a ? a : v);
-}
-__global__ void k_limit_user_demand(Net n, double* __restrict__ u, const double* __restrict__ uprev,
-                                    double dt, const int* __restrict__ from_ts,
-                                    const double* __restrict__ alloc_total) {
-    long long tid = RBS_TID;
-    int k = (int)(tid / n.B);
-    if (k >= n.n_ud_link) return;
-    int m = (int)(tid - (long long)k * n.B);
-    int i = n.ud_of_link[k];
-    int s = n.off_ud_in + k;
-    long long o = (long long)s * n.B + m;
-    double lo, hi;
-    if (from_ts[i]) { lo = 0.0; hi = RBS_INF; }
-    else {
-        int n_links = n.ud_link_ptr[i + 1] - n.ud_link_ptr[i];
-        double equal_split = n_links == 0 ? 0.0 : alloc_total[i] / n_links;
-        double alloc = n.ud_link_alloc[k];
-        double q_k_max = isinf(alloc) ? equal_split : alloc;
-        double fb = rbs_min_low_storage_factor(n, n.src_kind[s], n.src_idx[s], m);
-        double fl = 1.0;
-        if (n.src_kind[s] == KIND_BASIN) {
-            long long bo = (long long)n.src_idx[s] * n.B + m;
-            fl = rbs_reduction_factor(fmin(n.level[bo], n.level_prev[bo]) - n.ud_min_level[i] -
-                                          2 * n.ldt, n.ldt);
-        }
-        lo = fb * fl * q_k_max; hi = q_k_max;
-    }
-    double up = uprev[o];
-    double a = up + lo * dt, b = up + hi * dt;
-    double v = u[o];
-    u[o] = v > b ? b : (v < a ? a : v);
+    if (rbs_flow_bounds(n, s, m, from_ts, alloc_total, lo, hi)) v = rbs_clamp_state(v, up, lo, hi, n.mh[m]);
+    n.u[o] = v;
 }
 
-// ---- end-of-step bookkeeping (callback.jl:125-182) + negative storage flag ------------------------
-__global__ void k_step_end(Net n, double dt_exact) {
+// PHASE_LIMIT members: accept or reject the attempt, choose the next attempt
+__global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters) {
+    int m = (int)RBS_TID;
+    if (m >= n.B) return;
+    if (n.mphase[m] != PHASE_LIMIT) { n.maction[m] = ACTION_NONE; return; }
+    bool conv = n.mconv[m] != 0, neg = n.mneg[m] != 0, last = n.mlast[m] != 0;
+    double h = n.mh[m], hnom = n.mhnom[m], elapsed = n.melapsed[m];
+    bool can_halve = max_halvings > 0 && 0.5 * h >= h_min * (1.0 - 1e-12);
+    n.mneg[m] = 0;
+    if ((conv && !neg) || !can_halve) {
+        elapsed = last ? dt : elapsed + h;
+        n.cnt_sub[m] += 1;
+        if (!conv) n.status[m] |= 1;
+        if (neg) n.status[m] |= 2;
+        n.mhlast[m] = h;
+        if (conv && n.miter[m] <= grow_iters) hnom = fmin(2.0 * hnom, dt);
+        n.maction[m] = ACTION_ACCEPT;
+    } else {
+        hnom = 0.5 * h;
+        n.eta[m] = 1.0;
+        n.cnt_rej[m] += 1;
+        n.maction[m] = ACTION_REJECT;
+    }
+    n.melapsed[m] = elapsed;
+    n.mhnom[m] = hnom;
+    if (elapsed >= dt) {
+        n.mphase[m] = PHASE_DONE;
+        return;
+    }
+    double rem = dt - elapsed;
+    bool nlast = hnom >= rem;
+    n.mlast[m] = nlast;
+    n.mh[m] = nlast ? rem : hnom;
+    n.mphase[m] = PHASE_NEWTON;
+    n.miter[m] = 1;
+    n.mjac[m] = 1;
+    n.eta[m] = pow(fmax(n.eta[m], 2.220446049250313e-16), 0.8);
+    n.ndz_prev[m] = 0.0;
+}
+
+// apply the decision to the states and the exact-forcing bookkeeping
+__global__ void k_step_apply(Net n, int predictor) {
     long long tid = RBS_TID;
-    int b = (int)(tid / n.B);
-    int m = (int)(tid - (long long)b * n.B);
-    if (b < n.n_basin) {
-        long long o = (long long)b * n.B + m;
-        n.cum_precipitation[o] += n.fixed_area[b] * n.precipitation[o] * dt_exact;
-        n.cum_surface_runoff[o] += dt_exact * n.surface_runoff[o];
-        n.cum_drainage[o] += dt_exact * n.drainage[o];
-        if (n.storage[o] < 0.0) atomicOr(&n.status[m], 2);
-    } else if (b < n.n_basin + n.n_fb) {
-        long long o = (long long)(b - n.n_basin) * n.B + m;
-        n.fb_cum[o] += n.fb_rate[o] * dt_exact;
+    long long total = (long long)n.n_state * n.B;
+    int m = (int)(tid % n.B);
+    int action = n.maction[m];
+    if (action == ACTION_NONE) return;
+    bool next = n.mphase[m] == PHASE_NEWTON;
+    double h_next = n.mh[m], hl = n.mhlast[m];
+    if (tid < total) {
+        double zl;
+        if (action == ACTION_ACCEPT) {
+            double un = n.u[tid];
+            zl = un - n.uprev[tid];
+            n.zlast[tid] = zl;
+            n.uprev[tid] = un;
+        } else {
+            n.u[tid] = n.uprev[tid];
+            zl = n.zlast[tid];
+        }
+        if (next) n.z[tid] = (predictor && hl > 0.0) ? zl * (h_next / hl) : 0.0;
+        return;
     }
-    if (tid < n.B) {
-        if (n.nstat[tid] != NEWTON_CONVERGED) atomicOr(&n.status[tid], 1);
-    }
+    long long bt = tid - total;
+    if (bt < (long long)n.n_basin * n.B)
+        rbs_exact_update(n, (int)(bt / n.B), m, action == ACTION_ACCEPT, hl, next, h_next);
 }
 
 __global__ void k_fill(double* p, long long nelem, double v) {

@@ -175,7 +175,7 @@ __device__ __forceinline__ double rbs_manning_flow(double h_a, double h_b, doubl
     bool up = q0 > 0.0;
     double f = up ? f_a : f_b;
     if (want_jac) {
-        if (!(A > 0.0) || !(R > 0.0)) {
+        if (A == 0.0 || R == 0.0) {  // 0 * inf in the formal derivative: exactly dry reach
             dq_a = 0.0;
             dq_b = 0.0;
         } else {

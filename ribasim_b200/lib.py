@@ -80,6 +80,7 @@ def load() -> ctypes.CDLL:
         "rbs_set_param_i32": (ctypes.c_int, [vp, cp, ip, i64]),
         "rbs_set_member_f64": (ctypes.c_int, [vp, cp, dp, i64, i32]),
         "rbs_get_member_f64": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
         "rbs_set_tprev": (ctypes.c_int, [vp, f64]),
         "rbs_reduce": (ctypes.c_int, [vp, dp, dp]),
         "rbs_rhs": (ctypes.c_int, [vp, dp, f64, dp, dp, dp, dp, dp]),
@@ -88,8 +89,11 @@ def load() -> ctypes.CDLL:
         "rbs_limit_flow": (ctypes.c_int, [vp, dp, dp, f64, f64]),
         "rbs_step_implicit_euler": (ctypes.c_int, [vp, f64, f64, ip]),
         "rbs_set_solver": (ctypes.c_int, [vp, f64, f64, i32]),
+        "rbs_set_stepper": (ctypes.c_int, [vp, i32, i32, i32, i32]),
         "rbs_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(i64)]),
         "rbs_refresh": (ctypes.c_int, [vp, f64]),
+        "rbs_profile": (ctypes.c_int, [vp, i32]),
+        "rbs_profile_report": (ctypes.c_int, [vp, cp, i32]),
         "rbs_device_ptr": (vp, [vp, cp]),
         "rbs_stream": (vp, [vp]),
         "rbs_synchronize": (ctypes.c_int, [vp]),
@@ -106,9 +110,9 @@ EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64",
-    "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
-    "rbs_step_implicit_euler", "rbs_set_solver", "rbs_get_stats", "rbs_refresh",
-    "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
+    "rbs_copy_member_to_device", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
+    "rbs_step_implicit_euler", "rbs_set_solver", "rbs_set_stepper", "rbs_get_stats", "rbs_refresh",
+    "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
 ]
 
 
@@ -239,6 +243,24 @@ class Handle:
         _check(self.L.rbs_get_member_f64(self.h, key.encode(), _dp(out.reshape(-1)), n_entity))
         return out
 
+    def set_member_ptr(self, key: str, host_ptr: int, n_entity: int) -> None:
+        """Like set_member but from a raw host pointer (e.g. a pinned staging buffer)."""
+        _check(self.L.rbs_set_member_f64(self.h, key.encode(),
+                                         ctypes.cast(host_ptr, ctypes.POINTER(ctypes.c_double)),
+                                         n_entity, 0))
+
+    def get_member_ptr(self, key: str, host_ptr: int, n_entity: int) -> None:
+        _check(self.L.rbs_get_member_f64(self.h, key.encode(),
+                                         ctypes.cast(host_ptr, ctypes.POINTER(ctypes.c_double)),
+                                         n_entity))
+
+    def copy_member_to_device(self, key: str, device_ptr: int, n_entity: int) -> None:
+        _check(self.L.rbs_copy_member_to_device(self.h, key.encode(), ctypes.c_void_p(device_ptr),
+                                                n_entity))
+
+    def stream_ptr(self) -> int:
+        return int(self.L.rbs_stream(self.h) or 0)
+
     def set_tprev(self, t: float) -> None:
         _check(self.L.rbs_set_tprev(self.h, float(t)))
 
@@ -296,10 +318,29 @@ class Handle:
     def refresh(self, t: float) -> None:
         _check(self.L.rbs_refresh(self.h, t))
 
+    def set_stepper(self, full_newton: bool = False, predictor: bool = True, max_halvings: int = 20,
+                    grow_iters: int = 4) -> None:
+        _check(self.L.rbs_set_stepper(self.h, int(full_newton), int(predictor), int(max_halvings),
+                                      int(grow_iters)))
+
     def stats(self) -> dict[str, int]:
-        out = (ctypes.c_int64 * 4)()
+        out = (ctypes.c_int64 * 6)()
         _check(self.L.rbs_get_stats(self.h, out))
-        return dict(steps=out[0], newton_iters=out[1], jac_refreshes=out[2], failed=out[3])
+        return dict(steps=out[0], passes=out[1], substeps=out[2], failed=out[3],
+                    newton_iters=out[4], rejects=out[5])
+
+    def profile(self, enable: bool) -> None:
+        _check(self.L.rbs_profile(self.h, int(enable)))
+
+    def profile_report(self) -> dict[str, tuple[int, float]]:
+        """{kernel name: (launches, total milliseconds)} since profiling was enabled."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _check(self.L.rbs_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split("\t")
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def kernel_launches(self) -> int:
         return int(self.L.rbs_kernel_launches(self.h))

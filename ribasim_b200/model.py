@@ -36,7 +36,9 @@ class Model:
 
     def __init__(self, model: str | Path | ModelTables | Params, n_members: int = 1,
                  device: int = 0, dt: float | None = None, flat: Flat | None = None,
-                 sym: Symbolic | None = None, lu_mode: int = -1, lu_tile: int = 0):
+                 sym: Symbolic | None = None, lu_mode: int = -1, lu_tile: int = 0,
+                 full_newton: bool = False, predictor: bool = True, max_halvings: int = 20,
+                 grow_iters: int = 4):
         if isinstance(model, Params):
             self.p = model
         else:
@@ -57,6 +59,7 @@ class Model:
         self.h = lib.Handle(self.flat, self.sym, n_members=self.B, device=device, lu_mode=lu_mode,
                             lu_tile=lu_tile)
         self.h.set_solver(self.tables.solver_option("abstol"), self.tables.solver_option("reltol"))
+        self.h.set_stepper(full_newton, predictor, max_halvings, grow_iters)
         n = self.p.nodes
         ud = n["user_demand"]
         self.h.set_param("ud_demand_from_timeseries",

@@ -298,11 +298,12 @@ def pump_discrete_control_model() -> ModelTables:
 
 
 # ----------------------------------------------------------------------------- synthetic networks
-def _random_profile(rng: np.random.Generator, n_points: int, mu: float, sigma: float):
+def _random_profile(rng: np.random.Generator, n_points: int, mu: float, sigma: float,
+                    bottom: float | None = None):
     level = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 2.0, size=n_points - 1))])
     area = np.sort(rng.lognormal(mu, sigma, size=n_points))
     area = np.maximum.accumulate(area + np.arange(n_points) * 1e-3)
-    return level + rng.uniform(-2.0, 2.0), area
+    return level + (rng.uniform(-2.0, 2.0) if bottom is None else bottom), area
 
 
 def _rating_curve(rng: np.random.Generator, bottom: float, n_points: int = 4):
@@ -314,8 +315,8 @@ def _rating_curve(rng: np.random.Generator, bottom: float, n_points: int = 4):
 def _add_connector(m: ModelTables, rng, kind: str, node_id: int, bottom_src: float) -> None:
     if kind == "ManningResistance":
         m.add_node(kind, node_id, static=dict(
-            length=float(rng.uniform(200.0, 2000.0)), manning_n=float(rng.uniform(0.02, 0.06)),
-            profile_width=float(rng.uniform(2.0, 30.0)), profile_slope=0.0))
+            length=float(rng.uniform(500.0, 5000.0)), manning_n=float(rng.uniform(0.02, 0.05)),
+            profile_width=float(rng.uniform(5.0, 50.0)), profile_slope=0.0))
     elif kind == "LinearResistance":
         m.add_node(kind, node_id, static=dict(resistance=float(rng.uniform(50.0, 5000.0)),
                                               max_flow_rate=float(rng.uniform(5.0, 50.0))))
@@ -341,16 +342,21 @@ def hws_like_model(n_basins: int = 500, seed: int = 20260119, n_days: int = 30,
                     endtime=datetime(2023, 1, 20) + timedelta(days=n_days),
                     solver=dict(algorithm="ImplicitEuler", dt=3600.0))
     days = [m.starttime + timedelta(days=k) for k in range(n_days + 1)]
+    # river-like tree: parent close in index, degree bounded; bed levels rise away from the
+    # outlet (basin 0) so that the initial state is near a physically meaningful flow regime
+    parents = np.zeros(n_basins, dtype=np.int64)
     bottoms = np.zeros(n_basins)
+    for b in range(1, n_basins):
+        parents[b] = int(rng.integers(max(0, b - 6), b))
+        bottoms[b] = bottoms[parents[b]] + rng.uniform(0.02, 0.3)
     nid = 1
     basin_id = []
     basin_rows_time = []
     for b in range(n_basins):
         k = int(rng.integers(2, 9))
-        level, area = _random_profile(rng, k, 13.0, 1.5)
-        bottoms[b] = level[0]
+        level, area = _random_profile(rng, k, 13.0, 1.5, bottom=float(bottoms[b]))
         m.add_node("Basin", nid, profile=dict(level=level, area=area),
-                   state=dict(level=float(level[0] + rng.uniform(0.5, 1.5))))
+                   state=dict(level=float(level[0] + rng.uniform(0.8, 1.2))))
         P = rng.lognormal(-1.0, 1.0, size=len(days)) * 0.002 / 86400
         E = (1.0 + 0.5 * np.sin(np.arange(len(days)) / 58.0)) * 0.001 / 86400
         D = rng.lognormal(0.0, 0.5, size=len(days)) * 1e-2
@@ -367,8 +373,8 @@ def hws_like_model(n_basins: int = 500, seed: int = 20260119, n_days: int = 30,
     probs = np.array([0.35, 0.15, 0.20, 0.15, 0.10, 0.05])
     pairs: set[tuple[int, int]] = set()
     edges: list[tuple[int, int]] = []
-    for b in range(1, n_basins):  # river-like tree: parent close in index, degree bounded
-        parent = int(rng.integers(max(0, b - 6), b))
+    for b in range(1, n_basins):
+        parent = int(parents[b])
         edges.append((b, parent))
         pairs.add((min(b, parent), max(b, parent)))
     n_chords = n_basins // 10
@@ -378,7 +384,7 @@ def hws_like_model(n_basins: int = 500, seed: int = 20260119, n_days: int = 30,
         if a == c or (min(a, c), max(a, c)) in pairs:
             continue
         pairs.add((min(a, c), max(a, c)))
-        edges.append((a, c))
+        edges.append((a, c) if bottoms[a] >= bottoms[c] else (c, a))  # downhill
         n_chords -= 1
     outlets_for_pid = []
     for (a, c) in edges:

@@ -16,7 +16,7 @@ FORCING = ("precipitation", "surface_runoff", "potential_evaporation", "drainage
 
 def make_case(name: str, B: int, seed: int = 0, t: float = 3600.0, **kw):
     """Params, flat arrays and per-member random reduced states / forcing for model `name`."""
-    tables = MODELS[name](**kw) if name in MODELS else name
+    tables = MODELS[name](**kw) if isinstance(name, str) else name
     p = build_params(tables)
     flat = flatten(p)
     rng = np.random.default_rng(seed)

@@ -121,23 +121,32 @@ def test_reduce_and_limit_flow_parity(name):
         h.close()
 
 
-@pytest.mark.parametrize("name,dt,n_steps", [("basic", 3600.0, 24), ("trivial", 21600.0, 12),
-                                             ("user_demand", 3600.0, 12),
-                                             ("outlet_continuous_control", 3600.0, 12),
-                                             ("pid_control", 3600.0, 12),
-                                             ("backwater", 1.0, 40)])
-def test_implicit_euler_steps_parity(name, dt, n_steps):
-    """Device-resident Newton steps against the oracle's NLNewton restatement: same iteration
-    counts, states equal within Newton round-off."""
-    from oracle.oracle import _dp
+STEP_CASES = [("basic", 3600.0, 24), ("trivial", 21600.0, 12), ("user_demand", 3600.0, 12),
+              ("outlet_continuous_control", 3600.0, 12), ("pid_control", 3600.0, 12),
+              ("backwater", 3600.0, 6), ("hws_like", 3600.0, 6)]
+
+
+@pytest.mark.parametrize("name,dt,n_steps", STEP_CASES)
+@pytest.mark.parametrize("full_newton", [0, 1])
+def test_implicit_euler_steps_parity(name, dt, n_steps, full_newton):
+    """Device-resident sub-stepping Newton against the oracle's restatement of the same
+    algorithm: same accept/reject sequence and iteration counts, states equal within Newton
+    round-off (a small fraction of the solver tolerance)."""
+    from oracle.oracle import _dp, advance_opts
 
     B = 4
-    case = make_case(name, B, seed=7, t=0.0)
+    if name == "hws_like":
+        from ribasim_b200.testmodels import hws_like_model
+        case = make_case(hws_like_model(n_basins=60, n_days=2), B, seed=7, t=0.0)
+    else:
+        case = make_case(name, B, seed=7, t=0.0)
     flat = case["flat"]
     n = flat["n_state"]
     h = gpu_handle_for(case)
     try:
         h.set_solver(1e-5, 1e-5, 10)
+        h.set_stepper(full_newton=bool(full_newton), predictor=True, max_halvings=20, grow_iters=4)
+        opts = advance_opts(1e-5, 1e-5, 10, full_newton, 4, 20, 1)
         h.refresh(0.0)
         h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
         oms = []
@@ -146,27 +155,35 @@ def test_implicit_euler_steps_parity(name, dt, n_steps):
             _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
             lv = np.ascontiguousarray(c0["level"])
             om.L.orc_set_level_prev(om.h, _dp(lv))
+            om.set_f64("fb_rate_step", case["fb_rate"][:, m])
             oms.append(om)
         us = [np.zeros(n) for _ in range(B)]
         etas = [1.0] * B
+        htry = [dt] * B
+        tot = dict(iters=0, substeps=0, rejects=0)
         t = 0.0
         for s in range(n_steps):
             st = h.step(t, dt)
             for m, om in enumerate(oms):
-                om.set_f64("fb_incr", case["fb_rate"][:, m] * dt)
-                rc, it, cv, ng, etas[m] = om.step(us[m], t, dt, 1e-5, 1e-5, etas[m])
-                assert (st[m] & 1) == (0 if cv else 1), (name, s, m)
+                rc, so, htry[m], etas[m] = om.advance(us[m], t, dt, opts, htry[m], etas[m])
+                for k in tot:
+                    tot[k] += so[k]
+                assert (st[m] & 1) == (0 if so["converged"] else 1), (name, s, m)
             t += dt
         ug = h.get_member("u", n)
         Sg = h.get_member("storage", flat["n_basin"])
         for m, om in enumerate(oms):
             scale = 1e-5 + np.abs(us[m]) * 1e-5  # the solver's own abstol/reltol
             assert np.max(np.abs(ug[:, m] - us[m]) / scale) <= 1e-3, name
+            om.set_f64("fb_incr", np.zeros(flat["n_fb"]))
             _, co = om.rhs(om.reduce(us[m]), t, with_cache=True)
             assert np.max(np.abs(Sg[:, m] - co["storage"]) /
                           (1e-5 + np.abs(co["storage"]) * 1e-5)) <= 1e-2, name
         stats = h.stats()
         assert stats["steps"] == n_steps
+        assert stats["failed"] == 0
+        assert (stats["substeps"], stats["newton_iters"], stats["rejects"]) == \
+            (tot["substeps"], tot["iters"], tot["rejects"]), name
     finally:
         h.close()
 
@@ -181,7 +198,8 @@ def test_model_driver_matches_oracle_run():
     t_end = 10 * 86400.0
     p = build_params(MODELS["basic"]())
     u_o, S_o, lv_o, st_o = run_oracle(p, 3600.0, t_end=t_end)
-    model = Model(build_params(MODELS["basic"]()), n_members=3, dt=3600.0)
+    model = Model(build_params(MODELS["basic"]()), n_members=3, dt=3600.0, max_halvings=0,
+                  predictor=False)
     try:
         model.update_until(t_end)
         S_g, u_g = model.storage(), model.u()
