@@ -112,6 +112,13 @@ int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, dou
  * status_per_member (may be NULL): 0 ok, |1 a forced accept after Newton failure at the
  * minimum sub-step, |2 negative storage accepted at the minimum sub-step. */
 int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member);
+/* The same for a window of n_steps consecutive outer steps of length dt during which forcing
+ * and shared parameters do not change (e.g. the hourly steps between two daily forcing updates,
+ * the solver's tstops: core/src/model.jl:166,194-196).  Every member walks through its own
+ * n_steps outer steps without waiting for the others at the step boundaries; the per-member
+ * result is identical to n_steps calls of rbs_step_implicit_euler.  status bits are OR-ed over
+ * the window. */
+int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member);
 /* Solver options: abstol, reltol (core/src/config.jl:187-188), max Newton iterations. */
 int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter);
 /* Stepper options.  full_newton: 0 = J and W evaluated once per attempt at (uprev, t + h) like
@@ -134,6 +141,11 @@ int rbs_refresh(rbs_handle* h, double t);
  * "name<TAB>launches<TAB>total_ms" (NUL terminated, truncated to len), rbs_profile(h, 0) stops. */
 int rbs_profile(rbs_handle* h, int32_t enable);
 int rbs_profile_report(rbs_handle* h, char* buf, int32_t len);
+
+/* Tuning aid: average duration (ms) of the Newton linear-solve kernel (W assembly from the
+ * current J values, factorisation, substitution) on the first n_active members, `reps` back to
+ * back launches on the handle's stream.  Leaves the stepping state machine reset. */
+int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_per_launch);
 
 /* Raw device pointer of a per-member array (for zero-copy interop, e.g. NCCL gathers or
  * torch tensors wrapping library memory); NULL if unknown. */

@@ -82,8 +82,8 @@ def lib() -> ctypes.CDLL:
         L.orc_pchip_eval.argtypes = [vp, ctypes.c_int, ctypes.c_double]
         L.orc_pchip_eval.restype = ctypes.c_double
         L.orc_run_batch.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(dp), ctypes.c_int,
-                                    ctypes.c_double, ctypes.c_double, ctypes.c_int,
-                                    ctypes.c_double, ctypes.c_double, ctypes.c_int, ip]
+                                    ctypes.c_double, ctypes.c_double, ctypes.c_int, dp, dp, dp,
+                                    ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
         _lib = L
     return _lib
 
@@ -339,6 +339,31 @@ def advance_opts(abstol=1e-5, reltol=1e-5, max_iter=10, full_newton=0, grow_iter
                  max_halvings=0, predictor=0) -> np.ndarray:
     return np.array([abstol, reltol, max_iter, full_newton, grow_iters, max_halvings, predictor],
                     dtype=np.float64)
+
+
+class OracleBatch:
+    """Independent oracle instances (one per ensemble member) advanced on host threads: the
+    CPU baseline of bench.py."""
+
+    def __init__(self, members: list[OracleModel], opts: np.ndarray, n_threads: int):
+        self.members = members
+        self.opts = np.ascontiguousarray(opts, dtype=np.float64)
+        self.n_threads = int(n_threads)
+        n = len(members)
+        self.us = [np.zeros(m.n_state) for m in members]
+        self.h_try = np.zeros(n)
+        self.eta = np.ones(n)
+        self._hs = (ctypes.c_void_p * n)(*[m.h for m in members])
+        self._us = (ctypes.POINTER(ctypes.c_double) * n)(*[_dp(u) for u in self.us])
+        self.L = lib()
+
+    def run(self, t0: float, dt: float, n_steps: int) -> dict[str, int]:
+        if not np.any(self.h_try):
+            self.h_try[:] = dt
+        out = (ctypes.c_int64 * 3)()
+        self.L.orc_run_batch(self._hs, self._us, len(self.members), t0, dt, n_steps,
+                             _dp(self.opts), _dp(self.h_try), _dp(self.eta), self.n_threads, out)
+        return dict(failed=out[0], substeps=out[1], iters=out[2])
 
 
 def run_oracle(p, dt: float, t_end: float | None = None, flat=None, abstol: float | None = None,

@@ -1210,29 +1210,35 @@ double orc_storage_to_level(void* h, int b, double S) { return storage_to_level(
 double orc_level_to_area(void* h, int b, double level) { return level_to_area(*(Model*)h, b, level); }
 double orc_pchip_eval(void* h, int table, double x) { return ((Model*)h)->tabs[table].eval(x); }
 
-// Advance `n` independent instances by `n_steps` fixed steps each on `n_threads` threads
-// (CPU baseline: one instance per ensemble member; the reference core is single-threaded
-// per model).
-int orc_run_batch(void** hs, double** us, int n, double t0, double dt, int n_steps, double abstol,
-                  double reltol, int n_threads, int* failures) {
+// Advance `n` independent instances by `n_steps` outer steps each on `n_threads` threads with
+// the same stepping algorithm as the device (CPU baseline: one instance per ensemble member; the
+// reference core is single-threaded per model).  opts7 as in orc_advance;
+// h_try / eta: per-instance carry; out3 = {failed member-steps, sub-steps, Newton iterations}.
+int orc_run_batch(void** hs, double** us, int n, double t0, double dt, int n_steps,
+                  const double* opts7, double* h_try, double* eta, int n_threads, int64_t* out3) {
+    AdvanceOpts o;
+    o.abstol = opts7[0]; o.reltol = opts7[1]; o.max_iter = (int)opts7[2]; o.full_newton = (int)opts7[3];
+    o.grow_iters = (int)opts7[4]; o.max_halvings = (int)opts7[5]; o.predictor = (int)opts7[6];
     std::vector<std::thread> th;
-    std::vector<int> fails(n_threads, 0);
+    std::vector<int64_t> fails(n_threads, 0), subs(n_threads, 0), its(n_threads, 0);
     for (int w = 0; w < n_threads; w++)
         th.emplace_back([&, w]() {
             for (int i = w; i < n; i += n_threads) {
-                double eta = 1.0;
                 double t = t0;
                 for (int s = 0; s < n_steps; s++) {
-                    fails[w] += newton_step(*(Model*)hs[i], us[i], t, dt, abstol, reltol, 10, &eta,
-                                            nullptr, true);
+                    StepStats st;
+                    fails[w] += advance(*(Model*)hs[i], us[i], t, dt, o, &h_try[i], &eta[i], &st);
+                    subs[w] += st.substeps;
+                    its[w] += st.iters;
                     t += dt;
                 }
             }
         });
     for (auto& x : th) x.join();
-    int total = 0;
-    for (int f : fails) total += f;
-    if (failures) *failures = total;
+    if (out3) {
+        out3[0] = out3[1] = out3[2] = 0;
+        for (int w = 0; w < n_threads; w++) { out3[0] += fails[w]; out3[1] += subs[w]; out3[2] += its[w]; }
+    }
     return 0;
 }
 

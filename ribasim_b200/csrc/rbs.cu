@@ -55,7 +55,8 @@ struct rbs_handle {
     std::map<std::string, int64_t> member_entities;
     double* staging = nullptr;  // device scratch for host<->device seam calls
     size_t staging_bytes = 0;
-    int* h_active = nullptr;  // pinned
+    int* h_active = nullptr;  // pinned: {n_active, n_limit}
+    int *d_alist = nullptr, *d_llist = nullptr, *d_counts = nullptr;
     double tprev = 0.0;
     double abstol = 1e-5, reltol = 1e-5;
     int max_iter = 10;
@@ -73,6 +74,12 @@ struct rbs_handle {
     int *d_lu_level_ptr = nullptr, *d_fwd_level_ptr = nullptr, *d_bwd_level_ptr = nullptr;
     bool tile_mode = true;
     int tile = 8;
+    int smem_tile = 0, smem_threads = 1024;  // shared-memory factor+solve kernel (0 = does not fit)
+    LinSched sched{};
+    bool sched16 = false;
+    void* d_blob = nullptr;
+    size_t smem_bytes = 0;
+    int *d_lsrc_ptr = nullptr, *d_lsrc_code = nullptr;
     std::vector<int> list_phase[3];
     int* d_list_phase[3] = {nullptr, nullptr, nullptr};
     int n_part = 1, rows_per_block = 64;
@@ -170,7 +177,7 @@ void bind_net(rbs_handle* h) {
 #define M_I(name) n.name = (int*)h->member[#name].p
     M_I(nstat); M_I(status); M_I(active_count);
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mlast); M_I(maction);
-    M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej);
+    M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep);
 #undef M_I
 #undef S_D
 #undef S_I
@@ -189,36 +196,39 @@ inline void prof_end(rbs_handle* h) {
     if (h->profiling) cudaEventRecord(h->prof.back().b, h->stream);
 }
 
-#define LAUNCH_CFG(h, kernel, grid, block, ...)                                                \
+#define LAUNCH_CFG_AS(h, label, kernel, grid, block, ...)                                      \
     do {                                                                                       \
-        prof_begin((h), #kernel);                                                              \
+        prof_begin((h), label);                                                                \
         kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                              \
         prof_end(h);                                                                           \
         (h)->launches++;                                                                       \
     } while (0)
+#define LAUNCH_CFG(h, kernel, grid, block, ...) LAUNCH_CFG_AS(h, #kernel, kernel, grid, block, __VA_ARGS__)
 
-#define LAUNCH(h, kernel, total, ...)                                                          \
+// grid over (entities x launch domain), profile label = kernel name or an explicit one
+#define LAUNCH_AS(h, label, kernel, total, ...)                                                \
     do {                                                                                       \
         long long tot_ = (total);                                                              \
-        if (tot_ > 0) LAUNCH_CFG(h, kernel, grid_for(tot_), 256, __VA_ARGS__);                 \
+        if (tot_ > 0) LAUNCH_CFG_AS(h, label, kernel, grid_for(tot_), 256, __VA_ARGS__);       \
     } while (0)
+#define LAUNCH(h, kernel, total, ...) LAUNCH_AS(h, #kernel, kernel, total, __VA_ARGS__)
 
 // RHS phases on the caches prepared by k_exact / k_step_apply: ur -> du (and J values when JAC).
 // SRC 0 reads u_reduced from `ur`; SRC 1 fuses reduce_state!(uprev + z) into the basin kernel.
 template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
-    long long B = n.B;
-    LAUNCH(h, (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, false);
-    LAUNCH(h, k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0, pred);
+    long long B = n.NA;
+    LAUNCH_AS(h, JAC ? "k_basin<jac>" : "k_basin<rhs>", (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, false);
+    LAUNCH_AS(h, JAC ? "k_links<jac>" : "k_links<rhs>", k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0, pred);
     if (n.n_cc > 0) {
-        LAUNCH(h, k_continuous_control<JAC>, (long long)n.n_cc * B, n, pred);
-        LAUNCH(h, k_links<JAC>, (long long)h->list_phase[1].size() * B, n, 1, h->d_list_phase[1],
-               (int)h->list_phase[1].size(), pred);
+        LAUNCH_AS(h, JAC ? "k_continuous_control<jac>" : "k_continuous_control<rhs>", k_continuous_control<JAC>, (long long)n.n_cc * B, n, pred);
+        LAUNCH_AS(h, JAC ? "k_links_cc<jac>" : "k_links_cc<rhs>", k_links<JAC>, (long long)h->list_phase[1].size() * B, n, 1, h->d_list_phase[1],
+                  (int)h->list_phase[1].size(), pred);
     }
     if (n.n_pid > 0) {
-        LAUNCH(h, k_pid<JAC>, (long long)n.n_pid * B, n, n.ur, pred);
-        LAUNCH(h, k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
-               (int)h->list_phase[2].size(), pred);
+        LAUNCH_AS(h, JAC ? "k_pid<jac>" : "k_pid<rhs>", k_pid<JAC>, (long long)n.n_pid * B, n, n.ur, pred);
+        LAUNCH_AS(h, JAC ? "k_links_pid<jac>" : "k_links_pid<rhs>", k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
+                  (int)h->list_phase[2].size(), pred);
     }
 }
 // controllers read du of flows that may not be formulated yet: those must read 0
@@ -232,16 +242,16 @@ void zero_du_if_controlled(rbs_handle* h) {
 // W = A J - I/gamma and its LU.  FROM_J: assembled on the fly (step path, per-member gamma = h).
 template <bool FROM_J> void launch_factor(rbs_handle* h, double inv_gamma, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
-    long long B = n.B;
+    long long B = n.NA;
     if (!FROM_J) LAUNCH(h, k_assemble_w, (long long)n.nnz_w * B, n, inv_gamma);
     int n_levels = (int)h->lu_level_ptr.size() - 1;
     if (h->tile_mode) {
-        int blocks = (n.B + h->tile - 1) / h->tile;
-        LAUNCH_CFG(h, k_lu_tile<FROM_J>, blocks, 256, n, h->d_lu_level_ptr, n_levels, h->tile, inv_gamma, pred);
+        int blocks = (n.NA + h->tile - 1) / h->tile;
+        LAUNCH_CFG_AS(h, "k_lu_tile", k_lu_tile<FROM_J>, blocks, 256, n, h->d_lu_level_ptr, n_levels, h->tile, inv_gamma, pred);
     } else {
         for (int lv = 0; lv < n_levels; lv++) {
             int e0 = h->lu_level_ptr[lv], e1 = h->lu_level_ptr[lv + 1];
-            LAUNCH(h, k_lu_level<FROM_J>, (long long)(e1 - e0) * B, n, e0, e1, inv_gamma, pred);
+            LAUNCH_AS(h, "k_lu_level", k_lu_level<FROM_J>, (long long)(e1 - e0) * B, n, e0, e1, inv_gamma, pred);
         }
     }
     h->factor_valid = true;
@@ -249,14 +259,14 @@ template <bool FROM_J> void launch_factor(rbs_handle* h, double inv_gamma, Pred 
 
 template <bool FROM_DU> void launch_solve(rbs_handle* h, const double* b, double* x, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
-    long long B = n.B;
+    long long B = n.NA;
     int n_fwd = (int)h->fwd_level_ptr.size() - 1, n_bwd = (int)h->bwd_level_ptr.size() - 1;
     if (h->tile_mode) {
-        int blocks = (n.B + h->tile - 1) / h->tile;
-        LAUNCH_CFG(h, k_solve_tile<FROM_DU>, blocks, 256, n, b, x, h->d_fwd_level_ptr, n_fwd,
+        int blocks = (n.NA + h->tile - 1) / h->tile;
+        LAUNCH_CFG_AS(h, "k_solve_tile", k_solve_tile<FROM_DU>, blocks, 256, n, b, x, h->d_fwd_level_ptr, n_fwd,
                    h->d_bwd_level_ptr, n_bwd, h->tile, pred);
     } else {
-        LAUNCH(h, k_solve_load<FROM_DU>, (long long)n.n_reduced * B, n, b, pred);
+        LAUNCH_AS(h, "k_solve_load", k_solve_load<FROM_DU>, (long long)n.n_reduced * B, n, b, pred);
         for (int lv = 1; lv < n_fwd; lv++) {
             int p0 = h->fwd_level_ptr[lv], p1 = h->fwd_level_ptr[lv + 1];
             LAUNCH(h, k_solve_level, (long long)(p1 - p0) * B, n, p0, p1, 0, pred);
@@ -334,11 +344,16 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail("rbs_create: stream creation failed");
-    if (cudaMallocHost(&h->h_active, sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
+    if (cudaMallocHost(&h->h_active, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
+    if (cudaMalloc(&h->d_alist, sizeof(int) * n_members) != cudaSuccess ||
+        cudaMalloc(&h->d_llist, sizeof(int) * n_members) != cudaSuccess ||
+        cudaMalloc(&h->d_counts, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: list alloc failed");
     for (auto& kv : b->i) { h->hi[kv.first] = kv.second; if (upload(h, kv.first, kv.second, true)) return bail("upload"); }
     for (auto& kv : b->d) if (upload(h, kv.first, kv.second, false)) return bail("upload");
     Net& n = h->net;
     n.B = n_members;
+    n.NA = n_members;
+    n.alist = nullptr;
     const char* required[] = {"n_basin", "n_state", "n_conn", "n_reduced", "nnz_j", "nnz_w", "n_lu"};
     for (const char* k : required)
         if (b->i.find(k) == b->i.end()) { fail(std::string("rbs_create: missing descriptor key ") + k); return bail(""); }
@@ -400,7 +415,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
     for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mlast",
-                          "maction", "cnt_iters", "cnt_sub", "cnt_rej"})
+                          "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep"})
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
     {
         DevArr a; a.bytes = sizeof(int); a.is_int = true;
@@ -439,6 +454,85 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     int mode = geti(b, "lu_mode", -1);  // 0 wide, 1 tile, -1 auto
     if (mode < 0) h->tile_mode = (n.B / tile) >= 64 || n.n_lu < 4096;
     else h->tile_mode = mode == 1;
+    {
+        // ---- shared-memory factor+solve kernel: packed schedule + member tile size
+        auto geta = [&](const char* k) -> const std::vector<int32_t>& {
+            static const std::vector<int32_t> empty;
+            auto it = b->i.find(k);
+            return it == b->i.end() ? empty : it->second;
+        };
+        std::vector<int32_t> blob;
+        LinSched& sc = h->sched;
+        auto put = [&](const std::vector<int32_t>& v) { int off = (int)blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return off; };
+        sc.prod_ptr = put(geta("lu_prod_ptr")); sc.pivot = put(geta("lu_pivot"));
+        sc.prod_l = put(geta("lu_prod_l")); sc.prod_u = put(geta("lu_prod_u"));
+        sc.diag = put(geta("lu_diag")); sc.perm = put(geta("perm"));
+        sc.fwd_row = put(geta("fwd_row")); sc.fwd_ptr = put(geta("fwd_ptr"));
+        sc.fwd_l = put(geta("fwd_l")); sc.fwd_k = put(geta("fwd_k"));
+        sc.bwd_row = put(geta("bwd_row")); sc.bwd_ptr = put(geta("bwd_ptr"));
+        sc.bwd_u = put(geta("bwd_u")); sc.bwd_k = put(geta("bwd_k"));
+        sc.lvl_lu = put(geta("lu_level_ptr")); sc.lvl_fwd = put(geta("fwd_level_ptr"));
+        sc.lvl_bwd = put(geta("bwd_level_ptr"));
+        sc.total = (int)blob.size();
+        sc.n_levels = (int)h->lu_level_ptr.size() - 1;
+        sc.n_fwd = (int)h->fwd_level_ptr.size() - 1;
+        sc.n_bwd = (int)h->bwd_level_ptr.size() - 1;
+        int32_t vmax = 0;
+        for (int32_t v : blob) vmax = std::max(vmax, v);
+        h->sched16 = vmax < 65535;
+        size_t idx_bytes;
+        if (h->sched16) {
+            std::vector<uint16_t> b16(blob.size());
+            for (size_t k = 0; k < blob.size(); k++) b16[k] = blob[k] < 0 ? (uint16_t)0xFFFF : (uint16_t)blob[k];
+            idx_bytes = b16.size() * sizeof(uint16_t);
+            if (cudaMalloc(&h->d_blob, std::max<size_t>(idx_bytes, 2)) != cudaSuccess) return bail("schedule alloc");
+            cudaMemcpyAsync(h->d_blob, b16.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);
+        } else {
+            idx_bytes = blob.size() * sizeof(int32_t);
+            if (cudaMalloc(&h->d_blob, std::max<size_t>(idx_bytes, 4)) != cudaSuccess) return bail("schedule alloc");
+            cudaMemcpyAsync(h->d_blob, blob.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
+        // per LU slot: the J entries that land on it (lu_wsrc composed with the W assembly lists)
+        {
+            auto &lw = geta("lu_wsrc"), &wp = geta("wsrc_ptr"), &wpos = geta("wsrc_pos"), &wd = geta("wdiag_flag");
+            auto itd = b->d.find("wsrc_sign");
+            std::vector<int32_t> lptr(1, 0), lcode;
+            for (int e = 0; e < n.n_lu; e++) {
+                int src = e < (int)lw.size() ? lw[e] : -1;
+                if (src >= 0) {
+                    for (int k = wp[src]; k < wp[src + 1]; k++)
+                        lcode.push_back((wpos[k] << 1) | (itd->second[k] > 0.0 ? 0 : 1));
+                    if (wd[src]) lcode.push_back(-1);
+                }
+                lptr.push_back((int32_t)lcode.size());
+            }
+            if (upload(h, "lsrc_ptr", lptr, true) || upload(h, "lsrc_code", lcode, true)) return bail("lsrc upload");
+            h->d_lsrc_ptr = sp<int>(h, "lsrc_ptr");
+            h->d_lsrc_code = sp<int>(h, "lsrc_code");
+        }
+        int want = geti(b, "smem_tile", -1);  // -1 auto (32), 0 off, else 8 / 16 / 32
+        int dev_smem = 0;
+        cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        int t = want < 0 ? 32 : want;
+        if (t != 0 && t != 8 && t != 16 && t != 32) t = 32;
+        auto bytes_for = [&](int tile) { return (size_t)n.n_reduced * tile * sizeof(double) + idx_bytes + 16; };
+        while (t >= 8 && bytes_for(t) + 2048 > (size_t)dev_smem) t >>= 1;
+        if (t < 8) t = 0;  // schedule + solution vectors do not fit: level-per-launch fallback
+        h->smem_tile = t;
+        h->smem_threads = geti(b, "smem_threads", 1024);
+        if (t > 0) {
+            int bytes = (int)bytes_for(t);
+            cudaError_t e1 = cudaSuccess;
+#define SET_ATTR(T, IT) e1 = cudaFuncSetAttribute(k_newton_linear<T, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+            if (h->sched16) { if (t == 32) SET_ATTR(32, uint16_t); else if (t == 16) SET_ATTR(16, uint16_t); else SET_ATTR(8, uint16_t); }
+            else { if (t == 32) SET_ATTR(32, int32_t); else if (t == 16) SET_ATTR(16, int32_t); else SET_ATTR(8, int32_t); }
+#undef SET_ATTR
+            if (e1 != cudaSuccess) { cudaGetLastError(); h->smem_tile = 0; }
+            h->smem_bytes = bytes;
+        }
+    }
     bind_net(h);
     n.cc_tab_offset = geti(b, "cc_tab_offset");
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -454,6 +548,10 @@ void rbs_destroy(rbs_handle* h) {
     if (h->staging) cudaFree(h->staging);
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (h->h_active) cudaFreeHost(h->h_active);
+    if (h->d_blob) cudaFree(h->d_blob);
+    if (h->d_alist) cudaFree(h->d_alist);
+    if (h->d_llist) cudaFree(h->d_llist);
+    if (h->d_counts) cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -697,61 +795,128 @@ int rbs_refresh(rbs_handle* h, double t) {
     return check_async(h, "rbs_refresh");
 }
 
-// One pass of the per-member state machine (see rbs_kernels.cuh, "sub-stepping state machine").
-static void launch_pass(rbs_handle* h, double dt, double h_min) {
+// Newton linear solve of the members in the launch domain: fused factor+solve kernel, or the
+// level-per-launch kernels when the schedule does not fit in shared memory.
+static void launch_linear(rbs_handle* h, double* c, Pred nw) {
     Net& n = h->net;
-    long long B = n.B;
+    if (h->smem_tile > 0) {
+        int blocks = (n.NA + h->smem_tile - 1) / h->smem_tile;
+        prof_begin(h, "k_newton_linear");
+#define RUN_LIN(T, IT) k_newton_linear<T, IT><<<blocks, h->smem_threads, h->smem_bytes, h->stream>>>( \
+            n, h->sched, (const IT*)h->d_blob, h->d_lsrc_ptr, h->d_lsrc_code, c)
+        if (h->sched16) { if (h->smem_tile == 32) RUN_LIN(32, uint16_t); else if (h->smem_tile == 16) RUN_LIN(16, uint16_t); else RUN_LIN(8, uint16_t); }
+        else { if (h->smem_tile == 32) RUN_LIN(32, int32_t); else if (h->smem_tile == 16) RUN_LIN(16, int32_t); else RUN_LIN(8, int32_t); }
+#undef RUN_LIN
+        prof_end(h);
+        h->launches++;
+    } else {
+        launch_factor<true>(h, -1.0, nw);
+        launch_solve<true>(h, nullptr, c, Pred{n.mphase, PHASE_NEWTON, nullptr});
+    }
+}
+
+// One pass of the per-member state machine (see rbs_kernels.cuh, "sub-stepping state machine").
+// The finalize half runs on the compacted list of members in PHASE_LIMIT, the Newton half on
+// the compacted list of members that are not DONE, so a pass costs what its active members cost.
+static void launch_pass(rbs_handle* h, double dt, double h_min, int n_active, int n_limit, bool first,
+                        int n_steps) {
+    Net& n = h->net;
     const int* from_ts = sp<int>(h, "ud_demand_from_timeseries");
     const double* alloc_total = sp<double>(h, "ud_alloc_total");
-    // finalize half: members whose Newton iteration ended in the previous pass
-    Pred lim{n.mphase, PHASE_LIMIT, nullptr};
-    LAUNCH(h, (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, false);
-    LAUNCH(h, k_step_limit, (long long)n.n_state * B, n, from_ts, alloc_total);
-    LAUNCH(h, (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, true);
-    LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters);
-    LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
+    if (n_limit > 0) {
+        // finalize half: members whose Newton iteration ended in the previous pass
+        n.NA = n_limit;
+        n.alist = h->d_llist;
+        long long B = n.NA;
+        Pred lim{n.mphase, PHASE_LIMIT, nullptr};
+        LAUNCH_AS(h, "k_basin_limit_pre", (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, false);
+        LAUNCH(h, k_step_limit, (long long)n.n_state * B, n, from_ts, alloc_total);
+        LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, true);
+        LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps);
+        LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
+    }
     // Newton half
+    n.NA = n_active;
+    n.alist = first ? nullptr : h->d_alist;
     Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
     zero_du_if_controlled(h);
     launch_rhs<true, 1>(h, nullptr, nw);
     if (!h->full_newton) launch_rhs<false, 1>(h, nullptr, nw);
-    launch_factor<true>(h, -1.0, nw);
     double* c = mp(h, "cvec");
-    launch_solve<true>(h, nullptr, c, Pred{n.mphase, PHASE_NEWTON, nullptr});
+    launch_linear(h, c, nw);
     {
-        dim3 block(32, RBS_DZ_ROWS), grid((n.B + 31) / 32, h->n_part);
+        dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 31) / 32, h->n_part);
         LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
     }
-    cudaMemsetAsync(n.active_count, 0, sizeof(int), h->stream);
-    LAUNCH(h, k_newton_converge, B, n, h->n_part, h->max_iter, 0.01, h->full_newton);
+    LAUNCH(h, k_newton_converge, (long long)n.NA, n, h->n_part, h->max_iter, 0.01, h->full_newton);
+    n.NA = n.B;
+    n.alist = nullptr;
+    LAUNCH_CFG(h, k_compact, 1, 1024, n, h->d_alist, h->d_llist, h->d_counts);
     h->n_passes++;
 }
 
-int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member) {
-    if (!h) return fail("rbs_step_implicit_euler: null handle");
-    if (!(dt > 0)) return fail("rbs_step_implicit_euler: dt must be positive");
+int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_per_launch) {
+    if (!h || !ms_per_launch) return fail("rbs_time_linear: null argument");
+    if (n_active < 1 || n_active > h->B || reps < 1) return fail("rbs_time_linear: invalid argument");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    // all members in the Newton phase with a Jacobian refresh, sub-step of 1 hour
+    std::vector<int> ph(n.B, PHASE_NEWTON), one(n.B, 1);
+    std::vector<double> hh(n.B, 3600.0);
+    CUDA_TRY(cudaMemcpyAsync(n.mphase, ph.data(), n.B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(n.mjac, one.data(), n.B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(n.mh, hh.data(), n.B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    n.NA = n_active;
+    n.alist = nullptr;
+    Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
+    double* c = mp(h, "cvec");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    launch_linear(h, c, nw);  // warm-up
+    cudaEventRecord(a, h->stream);
+    for (int r = 0; r < reps; r++) launch_linear(h, c, nw);
+    cudaEventRecord(b, h->stream);
+    n.NA = n.B;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_per_launch = ms / reps;
+    return check_async(h, "rbs_time_linear");
+}
+
+int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
+    if (!h) return fail("rbs_advance: null handle");
+    if (!(dt > 0) || n_steps < 1) return fail("rbs_advance: dt must be positive and n_steps >= 1");
     cudaSetDevice(h->device);
     Net& n = h->net;
     long long B = n.B;
     double h_min = std::ldexp(dt, -h->max_halvings);
     LAUNCH(h, k_step_begin, (long long)(n.n_state + n.n_basin + 1) * B, n, dt, h->predictor);
     // safety net only: every attempt either advances the member or halves its sub-step
-    const int64_t max_passes = h->max_passes;
-    for (int64_t pass = 0;; pass++) {
-        launch_pass(h, dt, h_min);
-        CUDA_TRY(cudaMemcpyAsync(h->h_active, n.active_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    const int64_t max_passes = h->max_passes * n_steps;
+    int n_active = n.B, n_limit = 0;
+    for (int64_t pass = 0; n_active > 0; pass++) {
+        if (pass > max_passes) return fail("rbs_advance: pass limit exceeded");
+        launch_pass(h, dt, h_min, n_active, n_limit, pass == 0, n_steps);
+        CUDA_TRY(cudaMemcpyAsync(h->h_active, h->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        if (*h->h_active == 0) break;
-        if (pass > max_passes) return fail("rbs_step_implicit_euler: pass limit exceeded");
+        n_active = h->h_active[0];
+        n_limit = h->h_active[1];
     }
-    h->tprev = t + dt;
-    h->n_steps++;
+    h->tprev = t + dt * n_steps;
+    h->n_steps += n_steps;
     if (status_per_member) {
         CUDA_TRY(cudaMemcpyAsync(status_per_member, n.status, (size_t)n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         for (int m = 0; m < n.B; m++) if (status_per_member[m] & 1) h->n_failed++;
     }
-    return check_async(h, "rbs_step_implicit_euler");
+    return check_async(h, "rbs_advance");
+}
+
+int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member) {
+    return rbs_advance(h, t, dt, 1, status_per_member);
 }
 
 }  // extern "C"

@@ -22,6 +22,9 @@ enum { ACTION_NONE = 0, ACTION_ACCEPT = 1, ACTION_REJECT = 2 };
 struct Net {
     // sizes
     int B;  // members on this device
+    // launch domain: the first NA entries of `alist` (nullptr = identity); set per launch
+    int NA;
+    const int* alist;
     int n_basin, n_pid, n_state, n_conn, n_reduced;
     int n_trc, n_pump, n_outlet, n_ud, n_ud_link, n_lr, n_manning, n_lb, n_fb, n_cc, n_tab;
     int off_trc, off_pump, off_outlet, off_ud_in, off_ud_out, off_lr, off_manning, off_evap,
@@ -90,6 +93,7 @@ struct Net {
     // per-member sub-stepping state machine (rbs_step.cuh)
     int *mphase, *mjac, *miter, *mconv, *mneg, *mlast, *maction;
     int *cnt_iters, *cnt_sub, *cnt_rej;
+    int* mstep;  // outer steps completed in the current window
     double *mh, *mhnom, *melapsed, *mhlast, *zlast;
 };
 
@@ -108,6 +112,8 @@ template <bool JAC> __device__ __forceinline__ bool rbs_skip(const Pred& p, int 
 }
 
 #define RBS_TID (blockIdx.x * (long long)blockDim.x + threadIdx.x)
+// member index of position j in the launch domain (compacted list of active members)
+#define RBS_MEMBER(n, j) ((n).alist ? (n).alist[(j)] : (j))
 
 struct RbsEnd { double h, f, dh, df; };
 
@@ -131,9 +137,9 @@ __device__ __forceinline__ RbsEnd rbs_fetch_end(const Net& n, int kind, int idx,
 // ---- exact cumulative forcing up to the RHS time (solve.jl:137-150, 86-99) -------------------
 __global__ void k_exact(Net n, double t, double tprev) {
     long long tid = RBS_TID;
-    int b = (int)(tid / n.B);
+    int b = (int)(tid / n.NA);
     if (b >= n.n_basin) return;
-    int m = (int)(tid - (long long)b * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)b * n.NA));
     long long o = (long long)b * n.B + m;
     double dt = t - tprev;
     double ccp = n.cum_precipitation[o] + n.fixed_area[b] * n.precipitation[o] * dt;
@@ -161,9 +167,9 @@ template <int MODE>
 __global__ void k_reduce(Net n, const double* __restrict__ a, const double* __restrict__ b,
                          double* __restrict__ out, double dt, double inv_dt) {
     long long tid = RBS_TID;
-    int r = (int)(tid / n.B);
+    int r = (int)(tid / n.NA);
     if (r >= n.n_reduced) return;
-    int m = (int)(tid - (long long)r * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)r * n.NA));
     if (r < n.n_basin) {
         double acc = 0.0;
         for (int k = n.inc_ptr[r]; k < n.inc_ptr[r + 1]; k++) {
@@ -190,9 +196,9 @@ template <bool JAC, int SRC>
 __global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
                         bool flag_negative) {
     long long tid = RBS_TID;
-    int b = (int)(tid / n.B);
+    int b = (int)(tid / n.NA);
     if (b >= n.n_reduced) return;
-    int m = (int)(tid - (long long)b * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)b * n.NA));
     if (rbs_skip<JAC>(pred, m)) return;
     long long o = (long long)b * n.B + m;
     if (b >= n.n_basin) {
@@ -263,10 +269,10 @@ __device__ __forceinline__ double rbs_ud_link(const Net& n, int k, int m, double
 template <bool JAC>
 __global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
     long long tid = RBS_TID;
-    int li = (int)(tid / n.B);
+    int li = (int)(tid / n.NA);
     int count = phase == 0 ? n.n_conn : n_list;
     if (li >= count) return;
-    int m = (int)(tid - (long long)li * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)li * n.NA));
     if (rbs_skip<JAC>(pred, m)) return;
     int s = phase == 0 ? li : list[li];
     int ct = n.conn_type[s], k = n.conn_idx[s];
@@ -349,9 +355,9 @@ __global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_li
 template <bool JAC>
 __global__ void k_continuous_control(Net n, Pred pred) {
     long long tid = RBS_TID;
-    int i = (int)(tid / n.B);
+    int i = (int)(tid / n.NA);
     if (i >= n.n_cc) return;
-    int m = (int)(tid - (long long)i * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
     if (rbs_skip<JAC>(pred, m)) return;
     double value = 0.0;
     for (int j = n.cc_sv_ptr[i]; j < n.cc_sv_ptr[i + 1]; j++) {
@@ -386,9 +392,9 @@ __global__ void k_continuous_control(Net n, Pred pred) {
 template <bool JAC>
 __global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred) {
     long long tid = RBS_TID;
-    int i = (int)(tid / n.B);
+    int i = (int)(tid / n.NA);
     if (i >= n.n_pid) return;
-    int m = (int)(tid - (long long)i * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
     if (rbs_skip<JAC>(pred, m)) return;
     int L = n.pid_listen_basin[i];
     long long lo = (long long)L * n.B + m;
@@ -470,9 +476,9 @@ __device__ __forceinline__ double rbs_w_entry(const Net& n, int e, int m, double
 }
 __global__ void k_assemble_w(Net n, double inv_gamma) {
     long long tid = RBS_TID;
-    int e = (int)(tid / n.B);
+    int e = (int)(tid / n.NA);
     if (e >= n.nnz_w) return;
-    int m = (int)(tid - (long long)e * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)e * n.NA));
     n.wv[(long long)e * n.B + m] = rbs_w_entry(n, e, m, inv_gamma);
 }
 
@@ -499,9 +505,9 @@ __device__ __forceinline__ void rbs_lu_entry(const Net& n, int e, int m, double 
 template <bool FROM_J>
 __global__ void k_lu_level(Net n, int e0, int e1, double inv_gamma, Pred pred) {
     long long tid = RBS_TID;
-    int e = e0 + (int)(tid / n.B);
+    int e = e0 + (int)(tid / n.NA);
     if (e >= e1) return;
-    int m = (int)(tid - (long long)(e - e0) * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)(e - e0) * n.NA));
     if (rbs_skip<true>(pred, m)) return;
     rbs_lu_entry<FROM_J>(n, e, m, FROM_J ? rbs_inv_gamma(n, m, inv_gamma) : 0.0);
 }
@@ -512,14 +518,14 @@ template <bool FROM_J>
 __global__ void k_lu_tile(Net n, const int* __restrict__ level_ptr, int n_levels, int tile,
                           double inv_gamma, Pred pred) {
     int m0 = blockIdx.x * tile;
-    int tm = min(tile, n.B - m0);
+    int tm = min(tile, n.NA - m0);
     if (tm <= 0) return;
     for (int lv = 0; lv < n_levels; lv++) {
         int e0 = level_ptr[lv], e1 = level_ptr[lv + 1];
         int work = (e1 - e0) * tm;
         for (int w = threadIdx.x; w < work; w += blockDim.x) {
             int e = e0 + w / tm;
-            int m = m0 + w % tm;
+            int m = RBS_MEMBER(n, m0 + w % tm);
             if (rbs_skip<true>(pred, m)) continue;
             rbs_lu_entry<FROM_J>(n, e, m, FROM_J ? rbs_inv_gamma(n, m, inv_gamma) : 0.0);
         }
@@ -549,9 +555,9 @@ __device__ __forceinline__ double rbs_solve_rhs(const Net& n, const double* __re
 template <bool FROM_DU>
 __global__ void k_solve_load(Net n, const double* __restrict__ b, Pred pred) {  // xs = P b
     long long tid = RBS_TID;
-    int i = (int)(tid / n.B);
+    int i = (int)(tid / n.NA);
     if (i >= n.n_reduced) return;
-    int m = (int)(tid - (long long)i * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
     if (rbs_skip<true>(pred, m)) return;
     n.xs[(long long)i * n.B + m] = rbs_solve_rhs<FROM_DU>(n, b, n.perm[i], m);
 }
@@ -571,9 +577,9 @@ __device__ __forceinline__ void rbs_bwd_row(const Net& n, int pos, int m) {
 }
 __global__ void k_solve_level(Net n, int p0, int p1, int backward, Pred pred) {
     long long tid = RBS_TID;
-    int pos = p0 + (int)(tid / n.B);
+    int pos = p0 + (int)(tid / n.NA);
     if (pos >= p1) return;
-    int m = (int)(tid - (long long)(pos - p0) * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)(pos - p0) * n.NA));
     if (rbs_skip<true>(pred, m)) return;
     if (backward) rbs_bwd_row(n, pos, m); else rbs_fwd_row(n, pos, m);
 }
@@ -582,10 +588,10 @@ __global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __rest
                              const int* __restrict__ fwd_level_ptr, int n_fwd,
                              const int* __restrict__ bwd_level_ptr, int n_bwd, int tile, Pred pred) {
     int m0 = blockIdx.x * tile;
-    int tm = min(tile, n.B - m0);
+    int tm = min(tile, n.NA - m0);
     if (tm <= 0) return;
     for (int w = threadIdx.x; w < n.n_reduced * tm; w += blockDim.x) {
-        int i = w / tm, m = m0 + w % tm;
+        int i = w / tm, m = RBS_MEMBER(n, m0 + w % tm);
         if (rbs_skip<true>(pred, m)) continue;
         n.xs[(long long)i * n.B + m] = rbs_solve_rhs<FROM_DU>(n, b, n.perm[i], m);
     }
@@ -593,7 +599,7 @@ __global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __rest
     for (int lv = 1; lv < n_fwd; lv++) {  // level 0 rows have no dependencies
         int p0 = fwd_level_ptr[lv], p1 = fwd_level_ptr[lv + 1];
         for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x) {
-            int m = m0 + w % tm;
+            int m = RBS_MEMBER(n, m0 + w % tm);
             if (!rbs_skip<true>(pred, m)) rbs_fwd_row(n, p0 + w / tm, m);
         }
         __syncthreads();
@@ -601,24 +607,179 @@ __global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __rest
     for (int lv = 0; lv < n_bwd; lv++) {
         int p0 = bwd_level_ptr[lv], p1 = bwd_level_ptr[lv + 1];
         for (int w = threadIdx.x; w < (p1 - p0) * tm; w += blockDim.x) {
-            int m = m0 + w % tm;
+            int m = RBS_MEMBER(n, m0 + w % tm);
             if (!rbs_skip<true>(pred, m)) rbs_bwd_row(n, p0 + w / tm, m);
         }
         __syncthreads();
     }
     for (int w = threadIdx.x; w < n.n_reduced * tm; w += blockDim.x) {
-        int i = w / tm, m = m0 + w % tm;
+        int i = w / tm, m = RBS_MEMBER(n, m0 + w % tm);
         if (rbs_skip<true>(pred, m)) continue;
         x[(long long)n.perm[i] * n.B + m] = n.xs[(long long)i * n.B + m];
     }
 }
 __global__ void k_solve_store(Net n, double* __restrict__ x, Pred pred) {  // x = P^T xs
     long long tid = RBS_TID;
-    int i = (int)(tid / n.B);
+    int i = (int)(tid / n.NA);
     if (i >= n.n_reduced) return;
-    int m = (int)(tid - (long long)i * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
     if (rbs_skip<true>(pred, m)) return;
     x[(long long)n.perm[i] * n.B + m] = n.xs[(long long)i * n.B + m];
+}
+
+// ---- step path: fused factorisation + substitution of one member tile -----------------------------
+// A block owns TILE members of the launch domain (TILE = 32: a warp handles one L/U entry or one
+// solution row for 32 consecutive members, every global access is one coalesced 256 B request).
+//   * the whole elimination / substitution schedule (index arrays, packed to 16 bit when the
+//     network allows) is staged in shared memory once per block, so the ~100 dependent levels
+//     never wait on an index load;
+//   * the L/U factors stay in the global `lu` array: each block touches n_lu*TILE*8 B of it,
+//     written and re-read within microseconds, i.e. it lives in the 126 MB L2; all operands of
+//     an entry (its own slot, the pivot, the product pairs) are independent loads issued together;
+//   * the solution vectors live in shared memory ([n_reduced][TILE]);
+//   * W = A J - I/h is assembled on the fly from J_intermediate (no W array), the right-hand side
+//     A*((h du - z)/h) is gathered on the fly (no b array).
+// Members that reuse their factors (frozen-Newton iterations >= 2) skip the elimination.
+struct LinSched {          // offsets (in index elements) into the packed schedule blob
+    int prod_ptr, pivot, prod_l, prod_u, diag, perm;
+    int fwd_row, fwd_ptr, fwd_l, fwd_k, bwd_row, bwd_ptr, bwd_u, bwd_k;
+    int lvl_lu, lvl_fwd, lvl_bwd;  // level pointers
+    int total;             // number of index elements
+    int n_levels, n_fwd, n_bwd;
+};
+
+template <int TILE, class IT>
+__global__ void __launch_bounds__(1024)
+k_newton_linear(Net n, LinSched sc, const IT* __restrict__ blob, const int* __restrict__ lsrc_ptr,
+                const int* __restrict__ lsrc_code, double* __restrict__ x) {
+    extern __shared__ double smem[];
+    double* xs_s = smem;                               // [n_reduced][TILE]
+    IT* ix = (IT*)(xs_s + (size_t)n.n_reduced * TILE);
+    __shared__ int mem_s[TILE], fac_s[TILE];           // member index (-1 = idle), refresh flag
+    __shared__ double invh_s[TILE];
+    __shared__ int any_fac;
+    const IT NONE = (IT)~(IT)0;
+    constexpr int LOG = TILE == 32 ? 5 : (TILE == 16 ? 4 : (TILE == 8 ? 3 : (TILE == 4 ? 2 : (TILE == 2 ? 1 : 0))));
+    int m0 = blockIdx.x * TILE;
+    int tm = min(TILE, n.NA - m0);
+    if (tm <= 0) return;
+    if (threadIdx.x == 0) any_fac = 0;
+    __syncthreads();
+    if (threadIdx.x < TILE) {
+        int j = threadIdx.x;
+        int m = j < tm ? RBS_MEMBER(n, m0 + j) : -1;
+        if (m >= 0 && n.mphase[m] != PHASE_NEWTON) m = -1;
+        mem_s[j] = m;
+        int f = m >= 0 && n.mjac[m] != 0;
+        fac_s[j] = f;
+        if (f) any_fac = 1;
+        invh_s[j] = m >= 0 ? 1.0 / n.mh[m] : 0.0;
+    }
+    for (int w = threadIdx.x; w < sc.total; w += blockDim.x) ix[w] = blob[w];
+    __syncthreads();
+    const int j = threadIdx.x & (TILE - 1);
+    const int lane_e = threadIdx.x >> LOG, stride_e = blockDim.x >> LOG;
+    const int m = mem_s[j];
+    const bool fac = fac_s[j] != 0;
+    double* lu = n.lu + (m >= 0 ? m : 0);
+    const long long B = n.B;
+    if (any_fac) {
+        // 1. initialise the factor slots from J (ordered signed sums; code < 0 = "- 1/h")
+        if (fac) {
+            double invh = invh_s[j];
+            for (int e = lane_e; e < n.n_lu; e += stride_e) {
+                double v = 0.0;
+                for (int k = lsrc_ptr[e]; k < lsrc_ptr[e + 1]; k++) {
+                    int code = lsrc_code[k];
+                    if (code < 0) { v = v - invh; continue; }
+                    double jvv = n.jv[(long long)(code >> 1) * B + m];
+                    v = (code & 1) ? v - jvv : v + jvv;
+                }
+                lu[(long long)e * B] = v;
+            }
+        }
+        __syncthreads();
+        // 2. elimination, level by level
+        const IT *pp = ix + sc.prod_ptr, *pv_ = ix + sc.pivot, *pl = ix + sc.prod_l, *pu = ix + sc.prod_u;
+        const IT* lvl = ix + sc.lvl_lu;
+        for (int lv = 0; lv < sc.n_levels; lv++) {
+            int e0 = lvl[lv], e1 = lvl[lv + 1];
+            if (fac) {
+                for (int e = e0 + lane_e; e < e1; e += stride_e) {
+                    int q0 = pp[e], q1 = pp[e + 1];
+                    IT pv = pv_[e];
+                    if (q1 == q0 && pv == NONE) continue;  // plain copy of W: already in place
+                    // all operands are independent loads: issue them before the arithmetic
+                    double v = lu[(long long)e * B];
+                    double piv = pv != NONE ? lu[(long long)(int)pv * B] : 1.0;
+                    int q = q0;
+                    for (; q + 1 < q1; q += 2) {
+                        double a0 = lu[(long long)(int)pl[q] * B], b0 = lu[(long long)(int)pu[q] * B];
+                        double a1 = lu[(long long)(int)pl[q + 1] * B], b1 = lu[(long long)(int)pu[q + 1] * B];
+                        v -= a0 * b0;
+                        v -= a1 * b1;
+                    }
+                    if (q < q1) v -= lu[(long long)(int)pl[q] * B] * lu[(long long)(int)pu[q] * B];
+                    if (pv != NONE) v /= piv;
+                    lu[(long long)e * B] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // 3. right-hand side, forward and backward substitution
+    const IT* perm = ix + sc.perm;
+    for (int i = lane_e; i < n.n_reduced; i += stride_e)
+        xs_s[i * TILE + j] = m >= 0 ? rbs_solve_rhs<true>(n, nullptr, (int)perm[i], m) : 0.0;
+    __syncthreads();
+    {
+        const IT *lvf = ix + sc.lvl_fwd, *lvb = ix + sc.lvl_bwd;
+        const IT *fr = ix + sc.fwd_row, *fp = ix + sc.fwd_ptr, *fl = ix + sc.fwd_l, *fk = ix + sc.fwd_k;
+        for (int lv = 1; lv < sc.n_fwd; lv++) {  // level 0 rows have no dependencies
+            int p0 = lvf[lv], p1 = lvf[lv + 1];
+            if (m >= 0) {
+                for (int pos = p0 + lane_e; pos < p1; pos += stride_e) {
+                    int i = fr[pos];
+                    int q0 = fp[pos], q1 = fp[pos + 1];
+                    double v = xs_s[i * TILE + j];
+                    int q = q0;
+                    for (; q + 1 < q1; q += 2) {
+                        double a0 = lu[(long long)(int)fl[q] * B], a1 = lu[(long long)(int)fl[q + 1] * B];
+                        v -= a0 * xs_s[(int)fk[q] * TILE + j];
+                        v -= a1 * xs_s[(int)fk[q + 1] * TILE + j];
+                    }
+                    if (q < q1) v -= lu[(long long)(int)fl[q] * B] * xs_s[(int)fk[q] * TILE + j];
+                    xs_s[i * TILE + j] = v;
+                }
+            }
+            __syncthreads();
+        }
+        const IT *br = ix + sc.bwd_row, *bp = ix + sc.bwd_ptr, *bu = ix + sc.bwd_u, *bk = ix + sc.bwd_k;
+        const IT* dg = ix + sc.diag;
+        for (int lv = 0; lv < sc.n_bwd; lv++) {
+            int p0 = lvb[lv], p1 = lvb[lv + 1];
+            if (m >= 0) {
+                for (int pos = p0 + lane_e; pos < p1; pos += stride_e) {
+                    int i = br[pos];
+                    int q0 = bp[pos], q1 = bp[pos + 1];
+                    double d = lu[(long long)(int)dg[i] * B];
+                    double v = xs_s[i * TILE + j];
+                    int q = q0;
+                    for (; q + 1 < q1; q += 2) {
+                        double a0 = lu[(long long)(int)bu[q] * B], a1 = lu[(long long)(int)bu[q + 1] * B];
+                        v -= a0 * xs_s[(int)bk[q] * TILE + j];
+                        v -= a1 * xs_s[(int)bk[q + 1] * TILE + j];
+                    }
+                    if (q < q1) v -= lu[(long long)(int)bu[q] * B] * xs_s[(int)bk[q] * TILE + j];
+                    xs_s[i * TILE + j] = v / d;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (m >= 0)
+        for (int i = lane_e; i < n.n_reduced; i += stride_e)
+            x[(long long)(int)perm[i] * B + m] = xs_s[i * TILE + j];
 }
 
 // ---- limit_flow! (solve.jl:840-984); needs storage/level at the proposed u ------------------------
@@ -677,9 +838,9 @@ __global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __rest
                              double dt, const int* __restrict__ from_ts,
                              const double* __restrict__ alloc_total) {
     long long tid = RBS_TID;
-    int s = (int)(tid / n.B);
+    int s = (int)(tid / n.NA);
     if (s >= n.off_integral) return;
-    int m = (int)(tid - (long long)s * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)s * n.NA));
     long long o = (long long)s * n.B + m;
     double lo, hi;
     if (!rbs_flow_bounds(n, s, m, from_ts, alloc_total, lo, hi)) return;
@@ -692,10 +853,11 @@ __global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __rest
 #define RBS_DZ_ROWS 8
 __global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
                                 int rows_per_block) {
-    int m = blockIdx.x * 32 + threadIdx.x;
+    int j = blockIdx.x * 32 + threadIdx.x;
+    int m = j < n.NA ? RBS_MEMBER(n, j) : 0;
     int r0 = blockIdx.y * rows_per_block;
     double acc = 0.0;
-    bool live = m < n.B && n.mphase[m] == PHASE_NEWTON;
+    bool live = j < n.NA && n.mphase[m] == PHASE_NEWTON;
     if (live) {
         double dt = n.mh[m], inv_dt = 1.0 / dt;
         int r1 = min(r0 + rows_per_block, n.n_state);
@@ -718,7 +880,7 @@ __global__ void k_newton_update(Net n, const double* __restrict__ c, double abst
     __shared__ double sh[RBS_DZ_ROWS][33];
     sh[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.y == 0 && m < n.B) {
+    if (threadIdx.y == 0 && j < n.NA) {
         double s = 0.0;
         for (int y = 0; y < RBS_DZ_ROWS; y++) s += sh[y][threadIdx.x];
         n.norm_part[(long long)blockIdx.y * n.B + m] = s;
@@ -726,11 +888,11 @@ __global__ void k_newton_update(Net n, const double* __restrict__ c, double abst
 }
 
 // per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve);
-// a member whose iteration ends (converged or failed) moves to PHASE_LIMIT.  Also counts the
-// members that still have work after this pass.
+// a member whose iteration ends (converged or failed) moves to PHASE_LIMIT.
 __global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa, int full_newton) {
-    int m = (int)RBS_TID;
-    if (m >= n.B) return;
+    int j = (int)RBS_TID;
+    if (j >= n.NA) return;
+    int m = RBS_MEMBER(n, j);
     int ph = n.mphase[m];
     if (ph == PHASE_NEWTON) {
         int iter = n.miter[m];
@@ -761,10 +923,40 @@ __global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa,
         } else {
             n.mconv[m] = st == 1;
             n.mphase[m] = PHASE_LIMIT;
-            ph = PHASE_LIMIT;
         }
     }
-    if (ph != PHASE_DONE) atomicAdd(n.active_count, 1);  // integer counter only
+}
+
+// Ordered compaction of the members that still have work: `alist_out` = members not DONE,
+// `llist_out` = members in PHASE_LIMIT, counts[0..1] their lengths.  One block; order is kept
+// so that a mostly-active ensemble stays coalesced.  Integer work only.
+__global__ void k_compact(Net n, int* __restrict__ alist_out, int* __restrict__ llist_out,
+                          int* __restrict__ counts) {
+    __shared__ int sa[1024], sl[1024];
+    int t = threadIdx.x, T = blockDim.x;
+    int per = (n.B + T - 1) / T;
+    int lo = min(t * per, n.B), hi = min(lo + per, n.B);
+    int ca = 0, cl = 0;
+    for (int m = lo; m < hi; m++) {
+        int ph = n.mphase[m];
+        ca += ph != PHASE_DONE;
+        cl += ph == PHASE_LIMIT;
+    }
+    sa[t] = ca; sl[t] = cl;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {  // inclusive Hillis-Steele scan
+        int va = t >= off ? sa[t - off] : 0, vl = t >= off ? sl[t - off] : 0;
+        __syncthreads();
+        sa[t] += va; sl[t] += vl;
+        __syncthreads();
+    }
+    int pa = sa[t] - ca, pl = sl[t] - cl;
+    for (int m = lo; m < hi; m++) {
+        int ph = n.mphase[m];
+        if (ph != PHASE_DONE) alist_out[pa++] = m;
+        if (ph == PHASE_LIMIT) llist_out[pl++] = m;
+    }
+    if (t == T - 1) { counts[0] = sa[t]; counts[1] = sl[t]; }
 }
 
 // ---- sub-stepping state machine -------------------------------------------------------------------
@@ -816,6 +1008,7 @@ __global__ void k_step_begin(Net n, double dt, int predictor) {
         n.mneg[m] = 0;
         n.maction[m] = ACTION_NONE;
         n.status[m] = 0;
+        n.mstep[m] = 0;
         n.eta[m] = pow(fmax(n.eta[m], 2.220446049250313e-16), 0.8);
         n.ndz_prev[m] = 0.0;
     }
@@ -825,9 +1018,9 @@ __global__ void k_step_begin(Net n, double dt, int predictor) {
 __global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
                              const double* __restrict__ alloc_total) {
     long long tid = RBS_TID;
-    int s = (int)(tid / n.B);
+    int s = (int)(tid / n.NA);
     if (s >= n.n_state) return;
-    int m = (int)(tid - (long long)s * n.B);
+    int m = RBS_MEMBER(n, (int)(tid - (long long)s * n.NA));
     if (n.mphase[m] != PHASE_LIMIT) return;
     long long o = (long long)s * n.B + m;
     double up = n.uprev[o];
@@ -838,9 +1031,11 @@ __global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
 }
 
 // PHASE_LIMIT members: accept or reject the attempt, choose the next attempt
-__global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters) {
-    int m = (int)RBS_TID;
-    if (m >= n.B) return;
+__global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters,
+                              int n_steps) {
+    int j = (int)RBS_TID;
+    if (j >= n.NA) return;
+    int m = RBS_MEMBER(n, j);
     if (n.mphase[m] != PHASE_LIMIT) { n.maction[m] = ACTION_NONE; return; }
     bool conv = n.mconv[m] != 0, neg = n.mneg[m] != 0, last = n.mlast[m] != 0;
     double h = n.mh[m], hnom = n.mhnom[m], elapsed = n.melapsed[m];
@@ -860,12 +1055,21 @@ __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, 
         n.cnt_rej[m] += 1;
         n.maction[m] = ACTION_REJECT;
     }
+    if (elapsed >= dt) {
+        // outer step finished: the member goes straight on to its next outer step of the
+        // window (members never wait for each other), or is done
+        int ks = n.mstep[m] + 1;
+        n.mstep[m] = ks;
+        if (ks >= n_steps) {
+            n.melapsed[m] = elapsed;
+            n.mhnom[m] = hnom;
+            n.mphase[m] = PHASE_DONE;
+            return;
+        }
+        elapsed = 0.0;
+    }
     n.melapsed[m] = elapsed;
     n.mhnom[m] = hnom;
-    if (elapsed >= dt) {
-        n.mphase[m] = PHASE_DONE;
-        return;
-    }
     double rem = dt - elapsed;
     bool nlast = hnom >= rem;
     n.mlast[m] = nlast;
@@ -880,29 +1084,29 @@ __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, 
 // apply the decision to the states and the exact-forcing bookkeeping
 __global__ void k_step_apply(Net n, int predictor) {
     long long tid = RBS_TID;
-    long long total = (long long)n.n_state * n.B;
-    int m = (int)(tid % n.B);
+    int ent = (int)(tid / n.NA);
+    if (ent >= n.n_state + n.n_basin) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)ent * n.NA));
     int action = n.maction[m];
     if (action == ACTION_NONE) return;
     bool next = n.mphase[m] == PHASE_NEWTON;
     double h_next = n.mh[m], hl = n.mhlast[m];
-    if (tid < total) {
+    if (ent < n.n_state) {
+        long long o = (long long)ent * n.B + m;
         double zl;
         if (action == ACTION_ACCEPT) {
-            double un = n.u[tid];
-            zl = un - n.uprev[tid];
-            n.zlast[tid] = zl;
-            n.uprev[tid] = un;
+            double un = n.u[o];
+            zl = un - n.uprev[o];
+            n.zlast[o] = zl;
+            n.uprev[o] = un;
         } else {
-            n.u[tid] = n.uprev[tid];
-            zl = n.zlast[tid];
+            n.u[o] = n.uprev[o];
+            zl = n.zlast[o];
         }
-        if (next) n.z[tid] = (predictor && hl > 0.0) ? zl * (h_next / hl) : 0.0;
+        if (next) n.z[o] = (predictor && hl > 0.0) ? zl * (h_next / hl) : 0.0;
         return;
     }
-    long long bt = tid - total;
-    if (bt < (long long)n.n_basin * n.B)
-        rbs_exact_update(n, (int)(bt / n.B), m, action == ACTION_ACCEPT, hl, next, h_next);
+    rbs_exact_update(n, ent - n.n_state, m, action == ACTION_ACCEPT, hl, next, h_next);
 }
 
 __global__ void k_fill(double* p, long long nelem, double v) {

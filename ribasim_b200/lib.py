@@ -88,10 +88,12 @@ def load() -> ctypes.CDLL:
         "rbs_solve": (ctypes.c_int, [vp, dp, dp]),
         "rbs_limit_flow": (ctypes.c_int, [vp, dp, dp, f64, f64]),
         "rbs_step_implicit_euler": (ctypes.c_int, [vp, f64, f64, ip]),
+        "rbs_advance": (ctypes.c_int, [vp, f64, f64, i32, ip]),
         "rbs_set_solver": (ctypes.c_int, [vp, f64, f64, i32]),
         "rbs_set_stepper": (ctypes.c_int, [vp, i32, i32, i32, i32]),
         "rbs_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(i64)]),
         "rbs_refresh": (ctypes.c_int, [vp, f64]),
+        "rbs_time_linear": (ctypes.c_int, [vp, i32, i32, dp]),
         "rbs_profile": (ctypes.c_int, [vp, i32]),
         "rbs_profile_report": (ctypes.c_int, [vp, cp, i32]),
         "rbs_device_ptr": (vp, [vp, cp]),
@@ -111,8 +113,8 @@ EXPORTED_SYMBOLS = [
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64",
     "rbs_copy_member_to_device", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
-    "rbs_step_implicit_euler", "rbs_set_solver", "rbs_set_stepper", "rbs_get_stats", "rbs_refresh",
-    "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
+    "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_get_stats", "rbs_refresh",
+    "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
 ]
 
 
@@ -157,7 +159,8 @@ class Handle:
     """One ensemble shard on one GPU (`rbs_handle`)."""
 
     def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
-                 device: int = 0, lu_mode: int = -1, lu_tile: int = 0):
+                 device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
+                 smem_threads: int = 1024):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -196,6 +199,8 @@ class Handle:
                 set_i(name, getattr(sym, name))
             set_i("lu_mode", [lu_mode])
             set_i("lu_tile", [lu_tile])
+            set_i("smem_tile", [smem_tile])
+            set_i("smem_threads", [smem_threads])
             self.h = self.L.rbs_create(b, self.B, int(device))
         finally:
             self.L.rbs_builder_destroy(b)
@@ -315,6 +320,12 @@ class Handle:
         _check(self.L.rbs_step_implicit_euler(self.h, t, dt, _ip(st)))
         return st
 
+    def advance(self, t: float, dt: float, n_steps: int, want_status: bool = True):
+        """A window of `n_steps` outer steps with constant forcing (rbs_advance)."""
+        st = np.zeros(self.B, dtype=np.int32) if want_status else None
+        _check(self.L.rbs_advance(self.h, t, dt, int(n_steps), _ip(st)))
+        return st
+
     def refresh(self, t: float) -> None:
         _check(self.L.rbs_refresh(self.h, t))
 
@@ -328,6 +339,11 @@ class Handle:
         _check(self.L.rbs_get_stats(self.h, out))
         return dict(steps=out[0], passes=out[1], substeps=out[2], failed=out[3],
                     newton_iters=out[4], rejects=out[5])
+
+    def time_linear(self, n_active: int, reps: int = 10) -> float:
+        out = ctypes.c_double(0.0)
+        _check(self.L.rbs_time_linear(self.h, int(n_active), int(reps), ctypes.byref(out)))
+        return out.value
 
     def profile(self, enable: bool) -> None:
         _check(self.L.rbs_profile(self.h, int(enable)))

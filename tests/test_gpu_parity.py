@@ -248,6 +248,37 @@ def test_member_independence_and_determinism():
     assert np.array_equal(S_sub, S_all[:, pick])
 
 
+def test_advance_window_equals_single_steps():
+    """rbs_advance over a window = the same number of rbs_step_implicit_euler calls, bitwise,
+    although members cross the outer step boundaries at different passes."""
+    from ribasim_b200.testmodels import hws_like_model
+    case = make_case(hws_like_model(n_basins=60, n_days=2), 48, seed=11, t=0.0)
+    flat = case["flat"]
+    n = flat["n_state"]
+    out = []
+    for windowed in (False, True):
+        h = gpu_handle_for(case)
+        try:
+            h.set_stepper(full_newton=True)
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
+            if windowed:
+                st = h.advance(0.0, 1800.0, 8)
+            else:
+                st = np.zeros(48, dtype=np.int32)
+                for k in range(8):
+                    st |= h.step(k * 1800.0, 1800.0)
+            out.append((h.get_member("u", n), h.get_member("storage", flat["n_basin"]), st, h.stats()))
+        finally:
+            h.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
+    for k in ("substeps", "newton_iters", "rejects"):
+        assert out[0][3][k] == out[1][3][k]
+    assert out[1][3]["passes"] <= out[0][3]["passes"]
+
+
 def test_water_balance_closes_at_full_size():
     """Size-independent property on a large ensemble: after k steps every basin satisfies
     S = S0 + A u + exact inflows (the identity reduce_state! + formulate_storages! encode)."""
