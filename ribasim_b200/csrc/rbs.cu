@@ -57,6 +57,19 @@ struct rbs_handle {
     size_t staging_bytes = 0;
     int* h_active = nullptr;  // pinned: {n_active, n_limit}
     int *d_alist = nullptr, *d_llist = nullptr, *d_counts = nullptr;
+    cudaStream_t cur = nullptr;  // stream the launch helpers use (the handle's, or a group's)
+    // member groups: independent state machines on their own streams, so the latency-bound
+    // kernels of one group overlap with the kernels of the others
+    struct Group {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev = nullptr;
+        int lo = 0, hi = 0;
+        int *d_alist = nullptr, *d_llist = nullptr, *d_counts = nullptr;
+        int* h_counts = nullptr;  // pinned {n_active, n_limit}
+        int n_active = 0, n_limit = 0;
+        bool pending = false, done = false;
+    };
+    std::vector<Group> groups;
     double tprev = 0.0;
     double abstol = 1e-5, reltol = 1e-5;
     int max_iter = 10;
@@ -76,6 +89,11 @@ struct rbs_handle {
     int tile = 8;
     int smem_tile = 0, smem_threads = 1024;  // shared-memory factor+solve kernel (0 = does not fit)
     LinSched sched{};
+    LduSched dsched{};
+    void* d_blob2 = nullptr;
+    bool lin_smem16 = false;
+    bool lin_smem = false;   // factors in shared memory (tile 8) instead of L2 (tile 8/16/32)
+    size_t lin_smem_bytes = 0;
     bool sched16 = false;
     void* d_blob = nullptr;
     size_t smem_bytes = 0;
@@ -189,17 +207,17 @@ inline void prof_begin(rbs_handle* h, const char* name) {
     rbs_handle::ProfRec r{name, nullptr, nullptr};
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
-    cudaEventRecord(r.a, h->stream);
+    cudaEventRecord(r.a, h->cur);
     h->prof.push_back(r);
 }
 inline void prof_end(rbs_handle* h) {
-    if (h->profiling) cudaEventRecord(h->prof.back().b, h->stream);
+    if (h->profiling) cudaEventRecord(h->prof.back().b, h->cur);
 }
 
 #define LAUNCH_CFG_AS(h, label, kernel, grid, block, ...)                                      \
     do {                                                                                       \
         prof_begin((h), label);                                                                \
-        kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                              \
+        kernel<<<(grid), (block), 0, (h)->cur>>>(__VA_ARGS__);                              \
         prof_end(h);                                                                           \
         (h)->launches++;                                                                       \
     } while (0)
@@ -235,8 +253,7 @@ template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pr
 // (water_balance! zeroes du first, core/src/solve.jl:54)
 void zero_du_if_controlled(rbs_handle* h) {
     Net& n = h->net;
-    if (n.n_pid > 0 || n.n_cc > 0)
-        cudaMemsetAsync(n.du, 0, (size_t)n.n_state * n.B * sizeof(double), h->stream);
+    if (n.n_pid > 0 || n.n_cc > 0) LAUNCH(h, k_zero_du, (long long)n.n_state * n.NA, n);
 }
 
 // W = A J - I/gamma and its LU.  FROM_J: assembled on the fly (step path, per-member gamma = h).
@@ -344,7 +361,28 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail("rbs_create: stream creation failed");
+    h->cur = h->stream;
     if (cudaMallocHost(&h->h_active, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
+    {
+        int ng = geti(b, "n_groups", 0);
+        if (ng <= 0) ng = n_members >= 2048 ? 4 : (n_members >= 512 ? 2 : 1);
+        ng = std::min(ng, std::max(1, n_members / 32));
+        h->groups.resize(ng);
+        for (int g = 0; g < ng; g++) {
+            auto& G = h->groups[g];
+            // group boundaries on multiples of 32 members keep every group's accesses aligned
+            int per = ((n_members + ng - 1) / ng + 31) / 32 * 32;
+            G.lo = std::min(g * per, n_members);
+            G.hi = std::min(G.lo + per, n_members);
+            if (g == 0) G.stream = h->stream;
+            else if (cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess) return bail("group stream");
+            if (cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming) != cudaSuccess) return bail("group event");
+            size_t nb_ = sizeof(int) * std::max(G.hi - G.lo, 1);
+            if (cudaMalloc(&G.d_alist, nb_) != cudaSuccess || cudaMalloc(&G.d_llist, nb_) != cudaSuccess ||
+                cudaMalloc(&G.d_counts, 2 * sizeof(int)) != cudaSuccess ||
+                cudaMallocHost(&G.h_counts, 2 * sizeof(int)) != cudaSuccess) return bail("group alloc");
+        }
+    }
     if (cudaMalloc(&h->d_alist, sizeof(int) * n_members) != cudaSuccess ||
         cudaMalloc(&h->d_llist, sizeof(int) * n_members) != cudaSuccess ||
         cudaMalloc(&h->d_counts, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: list alloc failed");
@@ -474,6 +512,24 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         sc.lvl_lu = put(geta("lu_level_ptr")); sc.lvl_fwd = put(geta("fwd_level_ptr"));
         sc.lvl_bwd = put(geta("bwd_level_ptr"));
         sc.total = (int)blob.size();
+        {
+            // per LU slot (LU order): the J entries that land on it, for the L2 tile kernel
+            auto &lw = geta("lu_wsrc"), &wp = geta("wsrc_ptr"), &wpos = geta("wsrc_pos"), &wd = geta("wdiag_flag");
+            auto itd = b->d.find("wsrc_sign");
+            std::vector<int32_t> lptr(1, 0), lcode;
+            for (int e = 0; e < n.n_lu; e++) {
+                int src = e < (int)lw.size() ? lw[e] : -1;
+                if (src >= 0) {
+                    for (int k = wp[src]; k < wp[src + 1]; k++)
+                        lcode.push_back((wpos[k] << 1) | (itd->second[k] > 0.0 ? 0 : 1));
+                    if (wd[src]) lcode.push_back(-1);
+                }
+                lptr.push_back((int32_t)lcode.size());
+            }
+            if (upload(h, "lsrc_ptr", lptr, true) || upload(h, "lsrc_code", lcode, true)) return bail("lsrc upload");
+            h->d_lsrc_ptr = sp<int>(h, "lsrc_ptr");
+            h->d_lsrc_code = sp<int>(h, "lsrc_code");
+        }
         sc.n_levels = (int)h->lu_level_ptr.size() - 1;
         sc.n_fwd = (int)h->fwd_level_ptr.size() - 1;
         sc.n_bwd = (int)h->bwd_level_ptr.size() - 1;
@@ -494,30 +550,13 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             cudaMemcpyAsync(h->d_blob, blob.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
         }
-        // per LU slot: the J entries that land on it (lu_wsrc composed with the W assembly lists)
-        {
-            auto &lw = geta("lu_wsrc"), &wp = geta("wsrc_ptr"), &wpos = geta("wsrc_pos"), &wd = geta("wdiag_flag");
-            auto itd = b->d.find("wsrc_sign");
-            std::vector<int32_t> lptr(1, 0), lcode;
-            for (int e = 0; e < n.n_lu; e++) {
-                int src = e < (int)lw.size() ? lw[e] : -1;
-                if (src >= 0) {
-                    for (int k = wp[src]; k < wp[src + 1]; k++)
-                        lcode.push_back((wpos[k] << 1) | (itd->second[k] > 0.0 ? 0 : 1));
-                    if (wd[src]) lcode.push_back(-1);
-                }
-                lptr.push_back((int32_t)lcode.size());
-            }
-            if (upload(h, "lsrc_ptr", lptr, true) || upload(h, "lsrc_code", lcode, true)) return bail("lsrc upload");
-            h->d_lsrc_ptr = sp<int>(h, "lsrc_ptr");
-            h->d_lsrc_code = sp<int>(h, "lsrc_code");
-        }
         int want = geti(b, "smem_tile", -1);  // -1 auto (32), 0 off, else 8 / 16 / 32
         int dev_smem = 0;
         cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         int t = want < 0 ? 32 : want;
         if (t != 0 && t != 8 && t != 16 && t != 32) t = 32;
-        auto bytes_for = [&](int tile) { return (size_t)n.n_reduced * tile * sizeof(double) + idx_bytes + 16; };
+        size_t isz = h->sched16 ? sizeof(uint16_t) : sizeof(int32_t);
+        auto bytes_for = [&](int tile) { return (size_t)n.n_reduced * tile * sizeof(double) + (size_t)sc.total * isz + 16; };
         while (t >= 8 && bytes_for(t) + 2048 > (size_t)dev_smem) t >>= 1;
         if (t < 8) t = 0;  // schedule + solution vectors do not fit: level-per-launch fallback
         h->smem_tile = t;
@@ -532,6 +571,82 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             if (e1 != cudaSuccess) { cudaGetLastError(); h->smem_tile = 0; }
             h->smem_bytes = bytes;
         }
+        // ---- shared-memory kernel (LDU schedule): second packed blob
+        int lin_mode = geti(b, "lin_mode", -1);  // -1 auto, 0 wide, 1 L2 tile kernel, 2 shared-memory kernel
+        if (b->i.count("ldu_prod_ptr") && want != 0 && (lin_mode < 0 || lin_mode == 2)) {
+            std::vector<int32_t> blob2;
+            LduSched& ds = h->dsched;
+            auto put2 = [&](const std::vector<int32_t>& v) { int off = (int)blob2.size(); blob2.insert(blob2.end(), v.begin(), v.end()); return off; };
+            ds.prod_ptr = put2(geta("ldu_prod_ptr")); ds.flag = put2(geta("ldu_flag"));
+            ds.prod_l = put2(geta("ldu_prod_l")); ds.prod_u = put2(geta("ldu_prod_u"));
+            ds.prod_p = put2(geta("ldu_prod_p")); ds.diag = put2(geta("ldu_diag")); ds.perm = put2(geta("perm"));
+            ds.fwd_row = put2(geta("ldu_fwd_row")); ds.fwd_ptr = put2(geta("ldu_fwd_ptr"));
+            ds.fwd_l = put2(geta("ldu_fwd_l")); ds.fwd_k = put2(geta("ldu_fwd_k"));
+            ds.bwd_row = put2(geta("ldu_bwd_row")); ds.bwd_ptr = put2(geta("ldu_bwd_ptr"));
+            ds.bwd_u = put2(geta("ldu_bwd_u")); ds.bwd_k = put2(geta("ldu_bwd_k"));
+            ds.lvl = put2(geta("ldu_level_ptr")); ds.lvl_fwd = put2(geta("ldu_fwd_level_ptr"));
+            ds.lvl_bwd = put2(geta("ldu_bwd_level_ptr"));
+            {
+                // per level: split the product lists over 4 lanes (warp per slot) when that shortens
+                // the level's critical path, else one thread per (slot, member)
+                auto wide_of = [&](const std::vector<int32_t>& lvlp, const std::vector<int32_t>& ptr) {
+                    std::vector<int32_t> w;
+                    for (size_t l = 0; l + 1 < lvlp.size(); l++) {
+                        int cnt = lvlp[l + 1] - lvlp[l], mx = 0;
+                        for (int e = lvlp[l]; e < lvlp[l + 1]; e++) mx = std::max(mx, ptr[e + 1] - ptr[e]);
+                        int thin = (cnt + 127) / 128 * (2 + mx), wide = (cnt + 31) / 32 * (3 + (mx + 3) / 4);
+                        w.push_back(wide < thin ? 1 : 0);
+                    }
+                    if (w.empty()) w.push_back(0);
+                    return w;
+                };
+                ds.wide = put2(wide_of(geta("ldu_level_ptr"), geta("ldu_prod_ptr")));
+                ds.wide_fwd = put2(wide_of(geta("ldu_fwd_level_ptr"), geta("ldu_fwd_ptr")));
+                ds.wide_bwd = put2(wide_of(geta("ldu_bwd_level_ptr"), geta("ldu_bwd_ptr")));
+            }
+            ds.n_levels = (int)geta("ldu_level_ptr").size() - 1;
+            ds.n_fwd = (int)geta("ldu_fwd_level_ptr").size() - 1;
+            ds.n_bwd = (int)geta("ldu_bwd_level_ptr").size() - 1;
+            {
+                auto &lw = geta("ldu_wsrc"), &wp = geta("wsrc_ptr"), &wpos = geta("wsrc_pos"), &wd = geta("wdiag_flag");
+                auto itd = b->d.find("wsrc_sign");
+                std::vector<int32_t> lptr(1, 0), lcode;
+                for (int e = 0; e < n.n_lu; e++) {
+                    int src = e < (int)lw.size() ? lw[e] : -1;
+                    if (src >= 0) {
+                        for (int k = wp[src]; k < wp[src + 1]; k++)
+                            lcode.push_back((wpos[k] << 1) | (itd->second[k] > 0.0 ? 0 : 1));
+                        if (wd[src]) lcode.push_back(-1);
+                    }
+                    lptr.push_back((int32_t)lcode.size());
+                }
+                if (upload(h, "dsrc_ptr", lptr, true) || upload(h, "dsrc_code", lcode, true)) return bail("dsrc upload");
+            }
+            ds.total = (int)blob2.size();
+            int32_t vmax2 = 0;
+            for (int32_t v : blob2) vmax2 = std::max(vmax2, v);
+            bool s16 = vmax2 < 65535;
+            size_t isz2 = s16 ? sizeof(uint16_t) : sizeof(int32_t);
+            size_t sb = (size_t)(n.n_lu + n.n_reduced) * 8 * sizeof(double) + (size_t)ds.total * isz2 + 16;
+            if (sb + 1024 <= (size_t)dev_smem) {
+                if (cudaMalloc(&h->d_blob2, std::max<size_t>(blob2.size() * isz2, 4)) != cudaSuccess) return bail("schedule alloc");
+                if (s16) {
+                    std::vector<uint16_t> b16(blob2.size());
+                    for (size_t k = 0; k < blob2.size(); k++) b16[k] = blob2[k] < 0 ? (uint16_t)0xFFFF : (uint16_t)blob2[k];
+                    cudaMemcpyAsync(h->d_blob2, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice, h->stream);
+                    cudaStreamSynchronize(h->stream);
+                } else {
+                    cudaMemcpyAsync(h->d_blob2, blob2.data(), blob2.size() * 4, cudaMemcpyHostToDevice, h->stream);
+                    cudaStreamSynchronize(h->stream);
+                }
+                cudaError_t e2 = s16
+                    ? cudaFuncSetAttribute(k_newton_linear_smem<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
+                    : cudaFuncSetAttribute(k_newton_linear_smem<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+                if (e2 == cudaSuccess) { h->lin_smem = true; h->lin_smem_bytes = sb; h->lin_smem16 = s16; }
+                else cudaGetLastError();
+            }
+        }
+        if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; }
     }
     bind_net(h);
     n.cc_tab_offset = geti(b, "cc_tab_offset");
@@ -548,7 +663,16 @@ void rbs_destroy(rbs_handle* h) {
     if (h->staging) cudaFree(h->staging);
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (h->h_active) cudaFreeHost(h->h_active);
+    for (auto& G : h->groups) {
+        if (G.d_alist) cudaFree(G.d_alist);
+        if (G.d_llist) cudaFree(G.d_llist);
+        if (G.d_counts) cudaFree(G.d_counts);
+        if (G.h_counts) cudaFreeHost(G.h_counts);
+        if (G.ev) cudaEventDestroy(G.ev);
+        if (G.stream && G.stream != h->stream) cudaStreamDestroy(G.stream);
+    }
     if (h->d_blob) cudaFree(h->d_blob);
+    if (h->d_blob2) cudaFree(h->d_blob2);
     if (h->d_alist) cudaFree(h->d_alist);
     if (h->d_llist) cudaFree(h->d_llist);
     if (h->d_counts) cudaFree(h->d_counts);
@@ -799,10 +923,23 @@ int rbs_refresh(rbs_handle* h, double t) {
 // level-per-launch kernels when the schedule does not fit in shared memory.
 static void launch_linear(rbs_handle* h, double* c, Pred nw) {
     Net& n = h->net;
-    if (h->smem_tile > 0) {
+    if (h->lin_smem) {
+        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * n.NA, n, sp<int>(h, "dsrc_ptr"),
+               sp<int>(h, "dsrc_code"));
+        int blocks = (n.NA + 7) / 8;
+        prof_begin(h, "k_newton_linear_smem");
+        if (h->lin_smem16)
+            k_newton_linear_smem<uint16_t><<<blocks, h->smem_threads, h->lin_smem_bytes, h->cur>>>(
+                n, h->dsched, (const uint16_t*)h->d_blob2, h->full_newton ? 0 : 1, c);
+        else
+            k_newton_linear_smem<int32_t><<<blocks, h->smem_threads, h->lin_smem_bytes, h->cur>>>(
+                n, h->dsched, (const int32_t*)h->d_blob2, h->full_newton ? 0 : 1, c);
+        prof_end(h);
+        h->launches++;
+    } else if (h->smem_tile > 0) {
         int blocks = (n.NA + h->smem_tile - 1) / h->smem_tile;
         prof_begin(h, "k_newton_linear");
-#define RUN_LIN(T, IT) k_newton_linear<T, IT><<<blocks, h->smem_threads, h->smem_bytes, h->stream>>>( \
+#define RUN_LIN(T, IT) k_newton_linear<T, IT><<<blocks, h->smem_threads, h->smem_bytes, h->cur>>>( \
             n, h->sched, (const IT*)h->d_blob, h->d_lsrc_ptr, h->d_lsrc_code, c)
         if (h->sched16) { if (h->smem_tile == 32) RUN_LIN(32, uint16_t); else if (h->smem_tile == 16) RUN_LIN(16, uint16_t); else RUN_LIN(8, uint16_t); }
         else { if (h->smem_tile == 32) RUN_LIN(32, int32_t); else if (h->smem_tile == 16) RUN_LIN(16, int32_t); else RUN_LIN(8, int32_t); }
@@ -818,15 +955,15 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
 // One pass of the per-member state machine (see rbs_kernels.cuh, "sub-stepping state machine").
 // The finalize half runs on the compacted list of members in PHASE_LIMIT, the Newton half on
 // the compacted list of members that are not DONE, so a pass costs what its active members cost.
-static void launch_pass(rbs_handle* h, double dt, double h_min, int n_active, int n_limit, bool first,
-                        int n_steps) {
+static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h_min, int n_steps) {
     Net& n = h->net;
+    h->cur = G.stream;
     const int* from_ts = sp<int>(h, "ud_demand_from_timeseries");
     const double* alloc_total = sp<double>(h, "ud_alloc_total");
-    if (n_limit > 0) {
+    if (G.n_limit > 0) {
         // finalize half: members whose Newton iteration ended in the previous pass
-        n.NA = n_limit;
-        n.alist = h->d_llist;
+        n.NA = G.n_limit;
+        n.alist = G.d_llist;
         long long B = n.NA;
         Pred lim{n.mphase, PHASE_LIMIT, nullptr};
         LAUNCH_AS(h, "k_basin_limit_pre", (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, false);
@@ -836,8 +973,8 @@ static void launch_pass(rbs_handle* h, double dt, double h_min, int n_active, in
         LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
     }
     // Newton half
-    n.NA = n_active;
-    n.alist = first ? nullptr : h->d_alist;
+    n.NA = G.n_active;
+    n.alist = G.d_alist;
     Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
     zero_du_if_controlled(h);
     launch_rhs<true, 1>(h, nullptr, nw);
@@ -851,7 +988,8 @@ static void launch_pass(rbs_handle* h, double dt, double h_min, int n_active, in
     LAUNCH(h, k_newton_converge, (long long)n.NA, n, h->n_part, h->max_iter, 0.01, h->full_newton);
     n.NA = n.B;
     n.alist = nullptr;
-    LAUNCH_CFG(h, k_compact, 1, 1024, n, h->d_alist, h->d_llist, h->d_counts);
+    LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
+    h->cur = h->stream;
     h->n_passes++;
 }
 
@@ -883,6 +1021,15 @@ int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_pe
     cudaEventElapsedTime(&ms, a, b);
     cudaEventDestroy(a); cudaEventDestroy(b);
     *ms_per_launch = ms / reps;
+#ifdef RBS_LIN_PROFILE
+    if (h->lin_smem) {
+        long long clk[8];
+        cudaMemcpyFromSymbol(clk, g_lin_clk, sizeof clk);
+        fprintf(stderr, "lin phases (cycles): blob %lld init %lld elim %lld rhs %lld fwd %lld bwd %lld out %lld total %lld\n",
+                clk[1] - clk[0], clk[2] - clk[1], clk[3] - clk[2], clk[4] - clk[3], clk[5] - clk[4],
+                clk[6] - clk[5], clk[7] - clk[6], clk[7] - clk[0]);
+    }
+#endif
     return check_async(h, "rbs_time_linear");
 }
 
@@ -893,18 +1040,50 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
     Net& n = h->net;
     long long B = n.B;
     double h_min = std::ldexp(dt, -h->max_halvings);
+    h->cur = h->stream;
     LAUNCH(h, k_step_begin, (long long)(n.n_state + n.n_basin + 1) * B, n, dt, h->predictor);
-    // safety net only: every attempt either advances the member or halves its sub-step
-    const int64_t max_passes = h->max_passes * n_steps;
-    int n_active = n.B, n_limit = 0;
-    for (int64_t pass = 0; n_active > 0; pass++) {
-        if (pass > max_passes) return fail("rbs_advance: pass limit exceeded");
-        launch_pass(h, dt, h_min, n_active, n_limit, pass == 0, n_steps);
-        CUDA_TRY(cudaMemcpyAsync(h->h_active, h->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-        n_active = h->h_active[0];
-        n_limit = h->h_active[1];
+    // fork: every group starts from the common begin on its own stream
+    cudaEvent_t ev_begin = h->groups[0].ev;
+    CUDA_TRY(cudaEventRecord(ev_begin, h->stream));
+    for (auto& G : h->groups) {
+        if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, ev_begin, 0));
+        h->cur = G.stream;
+        LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
+        G.n_active = G.hi - G.lo;
+        G.n_limit = 0;
+        G.pending = false;
+        G.done = G.n_active == 0;
     }
+    h->cur = h->stream;
+    // safety net only: every attempt either advances the member or halves its sub-step
+    const int64_t max_passes = h->max_passes * n_steps * (int64_t)h->groups.size();
+    int64_t passes = 0;
+    size_t n_done = 0;
+    for (auto& G : h->groups) n_done += G.done;
+    while (n_done < h->groups.size()) {
+        bool progressed = false;
+        for (auto& G : h->groups) {
+            if (G.done) continue;
+            if (G.pending) {
+                cudaError_t q = cudaEventQuery(G.ev);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) return fail(std::string("rbs_advance: ") + cudaGetErrorString(q));
+                G.pending = false;
+                G.n_active = G.h_counts[0];
+                G.n_limit = G.h_counts[1];
+                if (G.n_active == 0) { G.done = true; n_done++; progressed = true; continue; }
+            }
+            if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
+            launch_pass(h, G, dt, h_min, n_steps);
+            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+            CUDA_TRY(cudaEventRecord(G.ev, G.stream));
+            G.pending = true;
+            progressed = true;
+        }
+        if (!progressed && h->groups.size() == 1) cudaEventSynchronize(h->groups[0].ev);
+    }
+    // join: every group's last event has been observed complete by the host, so all group
+    // streams are idle and later work enqueued on the handle's stream is ordered after them
     h->tprev = t + dt * n_steps;
     h->n_steps += n_steps;
     if (status_per_member) {

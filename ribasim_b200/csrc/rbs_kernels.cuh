@@ -782,6 +782,222 @@ k_newton_linear(Net n, LinSched sc, const IT* __restrict__ blob, const int* __re
             x[(long long)(int)perm[i] * B + m] = xs_s[i * TILE + j];
 }
 
+// ---- step path, small and medium networks: factors in shared memory, LDU schedule ----------------
+// TILE = 8 members per block.  L/U factors ([n_lu][8] doubles), solution vectors, the schedule and
+// the assembly lists (which J entries land on which slot, which states reduce into which row) are
+// all resident in shared memory, so every dependent level costs shared-memory latency only.
+// The schedule is the "LDU" variant of ribasim_b200/symbolic.py: L is kept unscaled and the
+// diagonal slots hold the pivot reciprocals r_k, so a slot depends only on pivots of earlier
+// elimination rounds — one level per round and no division on the critical path:
+//   slot(i,j) -= (slot(i,k) * r_k) * slot(k,j);   diagonal: r_i = 1 / slot(i,i)
+//   forward   yhat_i = r_i * (b_i - sum_k L~[i,k] yhat_k)
+//   backward  x_i = yhat_i - r_i * sum_j U[i,j] x_j
+// Global traffic is the compulsory one: J values and du/z in, c out (plus the factors once when
+// frozen-Newton iterations will reuse them).
+struct LduSched {          // offsets (in index elements) into the packed schedule blob
+    int prod_ptr, flag, prod_l, prod_u, prod_p, diag, perm;
+    int fwd_row, fwd_ptr, fwd_l, fwd_k, bwd_row, bwd_ptr, bwd_u, bwd_k;
+    int lvl, lvl_fwd, lvl_bwd;
+    int wide, wide_fwd, wide_bwd;  // per level: 1 = split each product list over 4 lanes
+    int total;
+    int n_levels, n_fwd, n_bwd;
+};
+
+// Input of the shared-memory kernel, produced at full occupancy: the initial value of every
+// factor slot (W = A J - I/h scattered into the LU pattern; ordered signed sums, code < 0 is the
+// "- 1/h" of a diagonal entry) for members that refresh their Jacobian, and the reduced
+// right-hand side b_r = A*((h du - z)/h) for every member in the Newton phase.
+__global__ void k_assemble_linear(Net n, const int* __restrict__ dsrc_ptr,
+                                  const int* __restrict__ dsrc_code) {
+    long long tid = RBS_TID;
+    int e = (int)(tid / n.NA);
+    if (e >= n.n_lu + n.n_reduced) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)e * n.NA));
+    if (n.mphase[m] != PHASE_NEWTON) return;
+    if (e < n.n_lu) {
+        if (n.mjac[m] == 0) return;
+        double invh = 1.0 / n.mh[m];
+        double v = 0.0;
+        for (int k = dsrc_ptr[e]; k < dsrc_ptr[e + 1]; k++) {
+            int code = dsrc_code[k];
+            if (code < 0) { v = v - invh; continue; }
+            double jvv = n.jv[(long long)(code >> 1) * n.B + m];
+            v = (code & 1) ? v - jvv : v + jvv;
+        }
+        n.lu[(long long)e * n.B + m] = v;
+    } else {
+        int r = e - n.n_lu;
+        n.br[(long long)r * n.B + m] = rbs_solve_rhs<true>(n, nullptr, r, m);
+    }
+}
+
+// phase clocks of block 0 (tuning aid, compiled in with -DRBS_LIN_PROFILE; see rbs_time_linear)
+#ifdef RBS_LIN_PROFILE
+__device__ long long g_lin_clk[8];
+#define LIN_CLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_lin_clk[k] = clock64(); } while (0)
+#else
+#define LIN_CLK(k) do { } while (0)
+#endif
+
+template <class IT>
+__global__ void __launch_bounds__(1024)
+k_newton_linear_smem(Net n, LduSched sc, const IT* __restrict__ blob, int write_lu,
+                     double* __restrict__ x) {
+    constexpr int TILE = 8;
+    extern __shared__ double smem[];
+    double* lu_s = smem;                               // [n_lu][TILE]
+    double* xs_s = lu_s + (size_t)n.n_lu * TILE;       // [n_reduced][TILE]
+    IT* ix = (IT*)(xs_s + (size_t)n.n_reduced * TILE);
+    __shared__ int mem_s[TILE], fac_s[TILE];
+    __shared__ int any_fac;
+    int m0 = blockIdx.x * TILE;
+    int tm = min(TILE, n.NA - m0);
+    if (tm <= 0) return;
+    LIN_CLK(0);
+    if (threadIdx.x == 0) any_fac = 0;
+    __syncthreads();
+    if (threadIdx.x < TILE) {
+        int jj = threadIdx.x;
+        int mm = jj < tm ? RBS_MEMBER(n, m0 + jj) : -1;
+        if (mm >= 0 && n.mphase[mm] != PHASE_NEWTON) mm = -1;
+        mem_s[jj] = mm;
+        int f = mm >= 0 && n.mjac[mm] != 0;
+        fac_s[jj] = f;
+        if (f) any_fac = 1;
+    }
+    for (int w = threadIdx.x; w < sc.total; w += blockDim.x) ix[w] = blob[w];
+    __syncthreads();
+    LIN_CLK(1);
+    const int j = threadIdx.x & (TILE - 1);
+    const int slot = threadIdx.x >> 3, n_slot = blockDim.x >> 3;
+    // in the level loops a warp owns one slot: 8 members x 4 lanes that share the slot's product
+    // list (partial sums are combined with a fixed shuffle tree, so results are reproducible)
+    const int g = (threadIdx.x >> 3) & 3;
+    const int wslot = threadIdx.x >> 5, n_wslot = blockDim.x >> 5;
+    const int m = mem_s[j];
+    const bool fac = fac_s[j] != 0;
+    const long long B = n.B;
+    // 1. factor slots (initial values from k_assemble_linear, or the stored factors)
+    if (m >= 0) {
+        const double* lug = n.lu + m;
+#pragma unroll 8
+        for (int e = slot; e < n.n_lu; e += n_slot) lu_s[e * TILE + j] = lug[(long long)e * B];
+    }
+    __syncthreads();
+    LIN_CLK(2);
+    // 2. elimination: one level per round
+    if (any_fac) {
+        const IT *pp = ix + sc.prod_ptr, *fl_ = ix + sc.flag, *pl = ix + sc.prod_l, *pu = ix + sc.prod_u,
+                 *ppv = ix + sc.prod_p;
+        const IT *lvl = ix + sc.lvl, *wd = ix + sc.wide;
+        for (int lv = 0; lv < sc.n_levels; lv++) {
+            int e0 = lvl[lv], e1 = lvl[lv + 1];
+            if (wd[lv]) {
+                for (int e = e0 + wslot; e < e1; e += n_wslot) {  // warp-uniform
+                    int q0 = pp[e], q1 = pp[e + 1];
+                    bool isd = fl_[e] != 0;
+                    if (q1 == q0 && !isd) continue;
+                    double s = 0.0;
+                    for (int q = q0 + g; q < q1; q += 4)
+                        s += (lu_s[(int)pl[q] * TILE + j] * lu_s[(int)ppv[q] * TILE + j]) *
+                             lu_s[(int)pu[q] * TILE + j];
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (g == 0 && fac) {
+                        double v = lu_s[e * TILE + j] - s;
+                        lu_s[e * TILE + j] = isd ? 1.0 / v : v;
+                    }
+                }
+            } else if (fac) {
+                for (int e = e0 + slot; e < e1; e += n_slot) {
+                    int q0 = pp[e], q1 = pp[e + 1];
+                    bool isd = fl_[e] != 0;
+                    if (q1 == q0 && !isd) continue;
+                    double s = 0.0;
+                    for (int q = q0; q < q1; q++)
+                        s += (lu_s[(int)pl[q] * TILE + j] * lu_s[(int)ppv[q] * TILE + j]) *
+                             lu_s[(int)pu[q] * TILE + j];
+                    double v = lu_s[e * TILE + j] - s;
+                    lu_s[e * TILE + j] = isd ? 1.0 / v : v;
+                }
+            }
+            __syncthreads();
+        }
+        // keep the factors for the iterations that reuse them
+        if (write_lu && fac)
+            for (int e = slot; e < n.n_lu; e += n_slot) n.lu[(long long)e * B + m] = lu_s[e * TILE + j];
+    }
+    LIN_CLK(3);
+    // 3. right-hand side in elimination order
+    const IT* perm = ix + sc.perm;
+    if (m >= 0) {
+        const double* br = n.br + m;
+#pragma unroll 4
+        for (int i = slot; i < n.n_reduced; i += n_slot) xs_s[i * TILE + j] = br[(long long)(int)perm[i] * B];
+    }
+    __syncthreads();
+    LIN_CLK(4);
+    // 4. forward and backward substitution
+    {
+        const IT *lvf = ix + sc.lvl_fwd, *lvb = ix + sc.lvl_bwd, *dg = ix + sc.diag;
+        const IT *fr = ix + sc.fwd_row, *fp = ix + sc.fwd_ptr, *fl = ix + sc.fwd_l, *fk = ix + sc.fwd_k;
+        const IT *wdf = ix + sc.wide_fwd, *wdb = ix + sc.wide_bwd;
+        for (int lv = 0; lv < sc.n_fwd; lv++) {
+            int p0 = lvf[lv], p1 = lvf[lv + 1];
+            if (wdf[lv]) {
+                for (int pos = p0 + wslot; pos < p1; pos += n_wslot) {  // warp-uniform
+                    int i = fr[pos];
+                    double s = 0.0;
+                    for (int q = fp[pos] + g; q < (int)fp[pos + 1]; q += 4)
+                        s += lu_s[(int)fl[q] * TILE + j] * xs_s[(int)fk[q] * TILE + j];
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (g == 0) xs_s[i * TILE + j] = (xs_s[i * TILE + j] - s) * lu_s[(int)dg[i] * TILE + j];
+                }
+            } else {
+                for (int pos = p0 + slot; pos < p1; pos += n_slot) {
+                    int i = fr[pos];
+                    double s = 0.0;
+                    for (int q = fp[pos]; q < (int)fp[pos + 1]; q++)
+                        s += lu_s[(int)fl[q] * TILE + j] * xs_s[(int)fk[q] * TILE + j];
+                    xs_s[i * TILE + j] = (xs_s[i * TILE + j] - s) * lu_s[(int)dg[i] * TILE + j];
+                }
+            }
+            __syncthreads();
+        }
+        LIN_CLK(5);
+        const IT *br = ix + sc.bwd_row, *bp = ix + sc.bwd_ptr, *bu = ix + sc.bwd_u, *bk = ix + sc.bwd_k;
+        for (int lv = 1; lv < sc.n_bwd; lv++) {  // level 0 rows have no U entries: x = yhat
+            int p0 = lvb[lv], p1 = lvb[lv + 1];
+            if (wdb[lv]) {
+                for (int pos = p0 + wslot; pos < p1; pos += n_wslot) {
+                    int i = br[pos];
+                    double s = 0.0;
+                    for (int q = bp[pos] + g; q < (int)bp[pos + 1]; q += 4)
+                        s += lu_s[(int)bu[q] * TILE + j] * xs_s[(int)bk[q] * TILE + j];
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (g == 0) xs_s[i * TILE + j] = xs_s[i * TILE + j] - lu_s[(int)dg[i] * TILE + j] * s;
+                }
+            } else {
+                for (int pos = p0 + slot; pos < p1; pos += n_slot) {
+                    int i = br[pos];
+                    double s = 0.0;
+                    for (int q = bp[pos]; q < (int)bp[pos + 1]; q++)
+                        s += lu_s[(int)bu[q] * TILE + j] * xs_s[(int)bk[q] * TILE + j];
+                    xs_s[i * TILE + j] = xs_s[i * TILE + j] - lu_s[(int)dg[i] * TILE + j] * s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    LIN_CLK(6);
+    if (m >= 0)
+        for (int i = slot; i < n.n_reduced; i += n_slot)
+            x[(long long)(int)perm[i] * B + m] = xs_s[i * TILE + j];
+    LIN_CLK(7);
+}
+
 // ---- limit_flow! (solve.jl:840-984); needs storage/level at the proposed u ------------------------
 __device__ __forceinline__ double rbs_min_low_storage_factor(const Net& n, int kind, int idx, int m) {
     if (kind != KIND_BASIN) return 1.0;
@@ -927,15 +1143,16 @@ __global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa,
     }
 }
 
-// Ordered compaction of the members that still have work: `alist_out` = members not DONE,
-// `llist_out` = members in PHASE_LIMIT, counts[0..1] their lengths.  One block; order is kept
-// so that a mostly-active ensemble stays coalesced.  Integer work only.
-__global__ void k_compact(Net n, int* __restrict__ alist_out, int* __restrict__ llist_out,
-                          int* __restrict__ counts) {
+// Ordered compaction of the members [m_lo, m_hi) that still have work: `alist_out` = members not
+// DONE, `llist_out` = members in PHASE_LIMIT, counts[0..1] their lengths.  One block; order is
+// kept so that a mostly-active ensemble stays coalesced.  Integer work only.
+__global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out,
+                          int* __restrict__ llist_out, int* __restrict__ counts) {
     __shared__ int sa[1024], sl[1024];
     int t = threadIdx.x, T = blockDim.x;
-    int per = (n.B + T - 1) / T;
-    int lo = min(t * per, n.B), hi = min(lo + per, n.B);
+    int nm = m_hi - m_lo;
+    int per = (nm + T - 1) / T;
+    int lo = m_lo + min(t * per, nm), hi = min(lo + per, m_hi);
     int ca = 0, cl = 0;
     for (int m = lo; m < hi; m++) {
         int ph = n.mphase[m];
@@ -957,6 +1174,15 @@ __global__ void k_compact(Net n, int* __restrict__ alist_out, int* __restrict__ 
         if (ph == PHASE_LIMIT) llist_out[pl++] = m;
     }
     if (t == T - 1) { counts[0] = sa[t]; counts[1] = sl[t]; }
+}
+
+// du <- 0 for the members of the launch domain (controllers read flows not yet formulated)
+__global__ void k_zero_du(Net n) {
+    long long tid = RBS_TID;
+    int s = (int)(tid / n.NA);
+    if (s >= n.n_state) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)s * n.NA));
+    n.du[(long long)s * n.B + m] = 0.0;
 }
 
 // ---- sub-stepping state machine -------------------------------------------------------------------

@@ -160,7 +160,7 @@ class Handle:
 
     def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
                  device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
-                 smem_threads: int = 1024):
+                 smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -195,12 +195,19 @@ class Handle:
             set_i("n_lu", [sym.n_lu])
             for name in ("perm", "lu_wsrc", "lu_pivot", "lu_prod_ptr", "lu_prod_l", "lu_prod_u",
                          "lu_level_ptr", "lu_diag", "fwd_level_ptr", "fwd_row", "fwd_ptr", "fwd_l",
-                         "fwd_k", "bwd_level_ptr", "bwd_row", "bwd_ptr", "bwd_u", "bwd_k"):
+                         "fwd_k", "bwd_level_ptr", "bwd_row", "bwd_ptr", "bwd_u", "bwd_k",
+                         "ldu_wsrc", "ldu_flag", "ldu_prod_ptr", "ldu_prod_l", "ldu_prod_u",
+                         "ldu_prod_p", "ldu_level_ptr", "ldu_diag", "ldu_fwd_level_ptr",
+                         "ldu_fwd_row", "ldu_fwd_ptr", "ldu_fwd_l", "ldu_fwd_k",
+                         "ldu_bwd_level_ptr", "ldu_bwd_row", "ldu_bwd_ptr", "ldu_bwd_u",
+                         "ldu_bwd_k"):
                 set_i(name, getattr(sym, name))
             set_i("lu_mode", [lu_mode])
             set_i("lu_tile", [lu_tile])
             set_i("smem_tile", [smem_tile])
             set_i("smem_threads", [smem_threads])
+            set_i("lin_mode", [lin_mode])
+            set_i("n_groups", [n_groups])
             self.h = self.L.rbs_create(b, self.B, int(device))
         finally:
             self.L.rbs_builder_destroy(b)

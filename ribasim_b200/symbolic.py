@@ -6,7 +6,7 @@ Here the pattern is fixed for all ensemble members, so everything that depends o
 pattern is computed once on the host:
 
 * a fill-reducing ordering by *rake-and-compress rounds*: every round eliminates an
-  independent set of minimum-degree vertices (degree <= 2 whenever possible).  Leaves are
+  independent set of low-degree vertices (lowest degree first).  Leaves are
   raked, chain vertices are compressed, so trees and chains finish in O(log n) rounds with
   O(n) fill (a tridiagonal chain becomes cyclic reduction);
 * the static fill pattern of L+U on the symmetrised pattern (no pivoting — `-W_inner` is
@@ -51,27 +51,55 @@ class Symbolic:
     bwd_u: np.ndarray
     bwd_k: np.ndarray
     n_rounds: int
+    # "LDU" variant used by the shared-memory kernel: the same L/U slots, but L is kept unscaled
+    # and the pivot reciprocals r_k = 1/U[k,k] are stored in the diagonal slots, so an entry only
+    # depends on pivots of earlier rounds: one level per round, no division on the critical path.
+    # slot(i,j) -= slot(i,k) * r_k * slot(k,j);  forward: yhat_i = r_i (b_i - sum L~[i,k] yhat_k);
+    # backward: x_i = yhat_i - r_i sum U[i,j] x_j.
+    ldu_wsrc: np.ndarray = None      # W entry feeding each slot (-1 fill); slots sorted by round
+    ldu_flag: np.ndarray = None      # 1 for diagonal slots
+    ldu_prod_ptr: np.ndarray = None
+    ldu_prod_l: np.ndarray = None
+    ldu_prod_u: np.ndarray = None
+    ldu_prod_p: np.ndarray = None    # slot of r_k of the product's pivot
+    ldu_level_ptr: np.ndarray = None
+    ldu_diag: np.ndarray = None      # slot of r_i per permuted row
+    ldu_fwd_level_ptr: np.ndarray = None
+    ldu_fwd_row: np.ndarray = None
+    ldu_fwd_ptr: np.ndarray = None
+    ldu_fwd_l: np.ndarray = None
+    ldu_fwd_k: np.ndarray = None
+    ldu_bwd_level_ptr: np.ndarray = None
+    ldu_bwd_row: np.ndarray = None
+    ldu_bwd_ptr: np.ndarray = None
+    ldu_bwd_u: np.ndarray = None
+    ldu_bwd_k: np.ndarray = None
 
     @property
     def n_lu(self) -> int:
         return len(self.lu_row)
 
 
-def rake_compress_order(n: int, adj: list[set[int]]) -> tuple[list[int], list[list[int]], int]:
-    """Return (elimination order, higher-ordered neighbour set of each pivot, #rounds).
+def rake_compress_order(n: int, adj: list[set[int]]):
+    """Return (elimination order, higher-ordered neighbour set of each pivot, #rounds,
+    round of each vertex).
 
     `adj` is consumed (it becomes the quotient graph)."""
     alive = np.ones(n, dtype=bool)
     order: list[int] = []
     struct: list[list[int]] = [[] for _ in range(n)]
     deg = np.array([len(a) for a in adj], dtype=np.int64)
+    round_of = np.zeros(n, dtype=np.int64)
     rounds = 0
     remaining = n
     while remaining:
         rounds += 1
         live = np.flatnonzero(alive)
         d = deg[live]
-        thr = max(int(d.min()), 2)
+        # candidates: degree up to 2*min + 2.  The slack lets the dense-ish core that chords
+        # leave behind be eliminated in a handful of rounds (independent sets of several
+        # vertices) instead of one vertex per round, for a few percent more fill.
+        thr = max(2 * int(d.min()) + 2, 2)
         cand = live[d <= thr]
         cand = cand[np.argsort(deg[cand], kind="stable")]
         blocked: set[int] = set()
@@ -92,9 +120,10 @@ def rake_compress_order(n: int, adj: list[set[int]]) -> tuple[list[int], list[li
                 deg[a] = len(s)
             adj[v] = set()
             alive[v] = False
+            round_of[v] = rounds - 1
             order.append(v)
         remaining -= len(picked)
-    return order, struct, rounds
+    return order, struct, rounds, round_of
 
 
 def analyse(n: int, wrow_ptr: np.ndarray, wcol: np.ndarray) -> Symbolic:
@@ -108,7 +137,7 @@ def analyse(n: int, wrow_ptr: np.ndarray, wcol: np.ndarray) -> Symbolic:
             if i != j:
                 adj[i].add(j)
                 adj[j].add(i)
-    order, struct_old, rounds = rake_compress_order(n, adj)
+    order, struct_old, rounds, round_old = rake_compress_order(n, adj)
     perm = np.array(order, dtype=np.int64)
     iperm = np.empty(n, dtype=np.int64)
     iperm[perm] = np.arange(n)
@@ -214,7 +243,54 @@ def analyse(n: int, wrow_ptr: np.ndarray, wcol: np.ndarray) -> Symbolic:
 
     f_lptr, f_row, f_ptr, f_l, f_k = schedule(lvl_y, Lrow)
     b_lptr, b_row, b_ptr, b_u, b_k = schedule(lvl_x, Urow)
+
+    # ---- LDU variant: slots sorted by the round of their pivot min(i, j)
+    rnd = np.array([round_old[order[min(r, c)]] for r, c in zip(ent_row, ent_col)], dtype=np.int64)
+    order_d = np.argsort(rnd, kind="stable")
+    new_d = np.empty(n_lu, dtype=np.int64)
+    new_d[order_d] = np.arange(n_lu)
+    d_level_ptr = np.searchsorted(rnd[order_d], np.arange(rounds + 1), side="left")
+    d_wsrc = np.full(n_lu, -1, dtype=np.int64)
+    d_flag = np.zeros(n_lu, dtype=np.int64)
+    dp_ptr = [0]
+    dp_l: list[int] = []
+    dp_u: list[int] = []
+    dp_p: list[int] = []
+    for e_new, e_old in enumerate(order_d.tolist()):
+        i_old, j_old = order[ent_row[e_old]], order[ent_col[e_old]]
+        d_wsrc[e_new] = wpos.get((i_old, j_old), -1)
+        d_flag[e_new] = int(ent_row[e_old] == ent_col[e_old])
+        for (el, eu) in prods[e_old]:
+            kpiv = ent_col[el]  # L[i,k] sits in column k
+            dp_l.append(int(new_d[el]))
+            dp_u.append(int(new_d[eu]))
+            dp_p.append(int(new_d[diag[kpiv]]))
+        dp_ptr.append(len(dp_l))
+    d_diag = new_d[diag]
+
+    def schedule_d(lvl, rows):
+        idx = np.argsort(lvl, kind="stable")
+        nl = int(lvl.max()) + 1 if n else 0
+        lptr = np.searchsorted(lvl[idx], np.arange(nl + 1), side="left")
+        ptr = [0]
+        ent: list[int] = []
+        col: list[int] = []
+        for i in idx.tolist():
+            for k, e in sorted(rows[i]):
+                ent.append(int(new_d[order_e[e]]))  # rows[] hold LU-sorted slot ids
+                col.append(k)
+            ptr.append(len(ent))
+        return as_i32(lptr), as_i32(idx), as_i32(ptr), as_i32(ent), as_i32(col)
+
+    df_lptr, df_row, df_ptr, df_l, df_k = schedule_d(lvl_y, Lrow)
+    db_lptr, db_row, db_ptr, db_u, db_k = schedule_d(lvl_x, Urow)
     return Symbolic(
+        ldu_wsrc=as_i32(d_wsrc), ldu_flag=as_i32(d_flag), ldu_prod_ptr=as_i32(dp_ptr),
+        ldu_prod_l=as_i32(dp_l), ldu_prod_u=as_i32(dp_u), ldu_prod_p=as_i32(dp_p),
+        ldu_level_ptr=as_i32(d_level_ptr), ldu_diag=as_i32(d_diag),
+        ldu_fwd_level_ptr=df_lptr, ldu_fwd_row=df_row, ldu_fwd_ptr=df_ptr, ldu_fwd_l=df_l,
+        ldu_fwd_k=df_k, ldu_bwd_level_ptr=db_lptr, ldu_bwd_row=db_row, ldu_bwd_ptr=db_ptr,
+        ldu_bwd_u=db_u, ldu_bwd_k=db_k,
         n=n, perm=as_i32(perm), iperm=as_i32(iperm),
         lu_row=as_i32(lu_row), lu_col=as_i32(lu_col), lu_wsrc=as_i32(lu_wsrc),
         lu_pivot=as_i32(lu_pivot), lu_prod_ptr=as_i32(prod_ptr), lu_prod_l=as_i32(prod_l),
@@ -256,6 +332,43 @@ def numeric_solve(sym: Symbolic, lu: np.ndarray, b: np.ndarray) -> np.ndarray:
             for q in range(sym.bwd_ptr[pos], sym.bwd_ptr[pos + 1]):
                 v -= lu[sym.bwd_u[q]] * x[sym.bwd_k[q]]
             x[i] = v / lu[sym.lu_diag[i]]
+    out = np.empty_like(x)
+    out[sym.perm] = x
+    return out
+
+
+def numeric_factor_ldu(sym: Symbolic, wvals: np.ndarray) -> np.ndarray:
+    """NumPy restatement of the LDU numeric phase of the shared-memory kernel."""
+    lu = np.zeros(sym.n_lu)
+    for lv in range(len(sym.ldu_level_ptr) - 1):
+        lo, hi = sym.ldu_level_ptr[lv], sym.ldu_level_ptr[lv + 1]
+        new = {}
+        for e in range(lo, hi):
+            v = wvals[sym.ldu_wsrc[e]] if sym.ldu_wsrc[e] >= 0 else 0.0
+            for q in range(sym.ldu_prod_ptr[e], sym.ldu_prod_ptr[e + 1]):
+                v -= (lu[sym.ldu_prod_l[q]] * lu[sym.ldu_prod_p[q]]) * lu[sym.ldu_prod_u[q]]
+            new[e] = 1.0 / v if sym.ldu_flag[e] else v
+        for e, v in new.items():  # a level only reads earlier levels
+            lu[e] = v
+    return lu
+
+
+def numeric_solve_ldu(sym: Symbolic, lu: np.ndarray, b: np.ndarray) -> np.ndarray:
+    x = b[sym.perm].astype(np.float64).copy()
+    for lv in range(len(sym.ldu_fwd_level_ptr) - 1):
+        for pos in range(sym.ldu_fwd_level_ptr[lv], sym.ldu_fwd_level_ptr[lv + 1]):
+            i = sym.ldu_fwd_row[pos]
+            v = x[i]
+            for q in range(sym.ldu_fwd_ptr[pos], sym.ldu_fwd_ptr[pos + 1]):
+                v -= lu[sym.ldu_fwd_l[q]] * x[sym.ldu_fwd_k[q]]
+            x[i] = v * lu[sym.ldu_diag[i]]
+    for lv in range(1, len(sym.ldu_bwd_level_ptr) - 1):
+        for pos in range(sym.ldu_bwd_level_ptr[lv], sym.ldu_bwd_level_ptr[lv + 1]):
+            i = sym.ldu_bwd_row[pos]
+            v = 0.0
+            for q in range(sym.ldu_bwd_ptr[pos], sym.ldu_bwd_ptr[pos + 1]):
+                v += lu[sym.ldu_bwd_u[q]] * x[sym.ldu_bwd_k[q]]
+            x[i] = x[i] - lu[sym.ldu_diag[i]] * v
     out = np.empty_like(x)
     out[sym.perm] = x
     return out

@@ -11,7 +11,8 @@ import pytest
 
 from ribasim_b200.flatten import flatten
 from ribasim_b200.network import build_params
-from ribasim_b200.symbolic import analyse, numeric_factor, numeric_solve
+from ribasim_b200.symbolic import (analyse, numeric_factor, numeric_factor_ldu, numeric_solve,
+                                   numeric_solve_ldu)
 from ribasim_b200.tables import ModelTables
 from ribasim_b200.testmodels import MODELS
 
@@ -189,6 +190,11 @@ def test_symbolic_lu_solves(name, kw):
     lu = numeric_factor(sym, wv)
     x = numeric_solve(sym, lu, b)
     assert np.allclose(W @ x, b, rtol=1e-10, atol=1e-10)
+    # LDU variant (one level per elimination round, reciprocal pivots)
+    lud = numeric_factor_ldu(sym, wv)
+    xd = numeric_solve_ldu(sym, lud, b)
+    assert np.allclose(W @ xd, b, rtol=1e-10, atol=1e-10)
+    assert len(sym.ldu_level_ptr) - 1 == sym.n_rounds
 
 
 def test_symbolic_lu_chain_is_logarithmic():
