@@ -1,0 +1,78 @@
+"""Turn the ncu artefacts brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+    python profiles/summarize.py r1
+"""
+import collections
+import csv
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+OUT = ROOT / "gpurun_out"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+]
+
+
+def launch_list():
+    src = OUT / f"launches_{tag}.csv"
+    if not src.exists():
+        return
+    lines = [l for l in src.read_text().splitlines(True) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        name = row["Kernel Name"].split("(")[0].replace("void ", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        us = v / 1e3 if unit == "ns" else (v * 1e3 if unit == "ms" else v)
+        a = agg.setdefault(name, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += us
+        a[2] = max(a[2], us)
+    tot = sum(a[1] for a in agg.values())
+    with open(ROOT / "profiles" / f"launches_{tag}.txt", "w") as f:
+        f.write("# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none\n"
+                "# python profiles/run_profile.py --steps 4   (window of 4 steady-state steps, 4096 members,\n"
+                "# 500 basins, one member group; per-launch times are cold-cache and serialised)\n")
+        f.write(f"{'kernel':34s} {'launches':>8s} {'total_us':>10s} {'mean_us':>9s} {'max_us':>9s} {'share':>6s}\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k:34s} {a[0]:8d} {a[1]:10.1f} {a[1] / a[0]:9.1f} {a[2]:9.1f} {a[1] / tot:6.3f}\n")
+        f.write(f"{'TOTAL':34s} {sum(a[0] for a in agg.values()):8d} {tot:10.1f}\n")
+
+
+def full_reports():
+    for rep in sorted(OUT.glob(f"{tag}_k_*.ncu-rep")):
+        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        d = dict(zip(hdr, zip(units, vals)))
+        with open(ROOT / "profiles" / f"{rep.stem}.txt", "w") as f:
+            f.write(f"# ncu --set full --clock-control none --import-source on, one launch of {d.get('Kernel Name', ('', '?'))[1]}\n")
+            for k in KEYS:
+                if k in d:
+                    f.write(f"{k:90s} {d[k][1]:>16s} {d[k][0]}\n")
+            rd = float(d["dram__bytes_read.sum"][1].replace(",", "")) if "dram__bytes_read.sum" in d else 0
+            wr = float(d["dram__bytes_write.sum"][1].replace(",", "")) if "dram__bytes_write.sum" in d else 0
+            f.write(f"# dram traffic (read+write): {rd + wr:.3f} {d['dram__bytes_read.sum'][0]}\n")
+
+
+launch_list()
+full_reports()
+print("written:", sorted(p.name for p in (ROOT / "profiles").glob(f"*{tag}*")))

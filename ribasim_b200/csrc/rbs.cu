@@ -74,7 +74,7 @@ struct rbs_handle {
     double abstol = 1e-5, reltol = 1e-5;
     int max_iter = 10;
     // stepper options (rbs_set_stepper)
-    int full_newton = 0, predictor = 1, max_halvings = 20, grow_iters = 4;
+    int full_newton = 1, predictor = 1, max_halvings = 20, grow_iters = 4;
     int64_t max_passes = 100000;
     int64_t launches = 0;
     int64_t n_steps = 0, n_passes = 0, n_failed = 0;
@@ -306,6 +306,43 @@ int ensure_staging(rbs_handle* h, size_t bytes) {
     return 0;
 }
 
+void free_groups(rbs_handle* h) {
+    for (auto& G : h->groups) {
+        if (G.d_alist) cudaFree(G.d_alist);
+        if (G.d_llist) cudaFree(G.d_llist);
+        if (G.d_counts) cudaFree(G.d_counts);
+        if (G.h_counts) cudaFreeHost(G.h_counts);
+        if (G.ev) cudaEventDestroy(G.ev);
+        if (G.stream && G.stream != h->stream) cudaStreamDestroy(G.stream);
+    }
+    h->groups.clear();
+}
+
+// Partition the members into `ng` groups (0 = auto) with their own streams and work lists.
+int make_groups(rbs_handle* h, int ng) {
+    free_groups(h);
+    int n_members = h->B;
+    if (ng <= 0) ng = n_members >= 2048 ? 4 : (n_members >= 512 ? 2 : 1);
+    ng = std::min(ng, std::max(1, n_members / 32));
+    h->groups.resize(ng);
+    // group boundaries on multiples of 32 members keep every group's accesses aligned
+    int per = ((n_members + ng - 1) / ng + 31) / 32 * 32;
+    for (int g = 0; g < ng; g++) {
+        auto& G = h->groups[g];
+        G.lo = std::min(g * per, n_members);
+        G.hi = std::min(G.lo + per, n_members);
+        if (g == 0) G.stream = h->stream;
+        else CUDA_TRY(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming));
+        size_t nb_ = sizeof(int) * std::max(G.hi - G.lo, 1);
+        CUDA_TRY(cudaMalloc(&G.d_alist, nb_));
+        CUDA_TRY(cudaMalloc(&G.d_llist, nb_));
+        CUDA_TRY(cudaMalloc(&G.d_counts, 2 * sizeof(int)));
+        CUDA_TRY(cudaMallocHost(&G.h_counts, 2 * sizeof(int)));
+    }
+    return 0;
+}
+
 int check_async(rbs_handle* h, const char* where) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(std::string(where) + ": " + cudaGetErrorString(e));
@@ -363,29 +400,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         return bail("rbs_create: stream creation failed");
     h->cur = h->stream;
     if (cudaMallocHost(&h->h_active, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
-    {
-        int ng = geti(b, "n_groups", 0);
-        if (ng <= 0) ng = n_members >= 2048 ? 4 : (n_members >= 512 ? 2 : 1);
-        ng = std::min(ng, std::max(1, n_members / 32));
-        h->groups.resize(ng);
-        for (int g = 0; g < ng; g++) {
-            auto& G = h->groups[g];
-            // group boundaries on multiples of 32 members keep every group's accesses aligned
-            int per = ((n_members + ng - 1) / ng + 31) / 32 * 32;
-            G.lo = std::min(g * per, n_members);
-            G.hi = std::min(G.lo + per, n_members);
-            if (g == 0) G.stream = h->stream;
-            else if (cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess) return bail("group stream");
-            if (cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming) != cudaSuccess) return bail("group event");
-            size_t nb_ = sizeof(int) * std::max(G.hi - G.lo, 1);
-            if (cudaMalloc(&G.d_alist, nb_) != cudaSuccess || cudaMalloc(&G.d_llist, nb_) != cudaSuccess ||
-                cudaMalloc(&G.d_counts, 2 * sizeof(int)) != cudaSuccess ||
-                cudaMallocHost(&G.h_counts, 2 * sizeof(int)) != cudaSuccess) return bail("group alloc");
-        }
-    }
-    if (cudaMalloc(&h->d_alist, sizeof(int) * n_members) != cudaSuccess ||
-        cudaMalloc(&h->d_llist, sizeof(int) * n_members) != cudaSuccess ||
-        cudaMalloc(&h->d_counts, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: list alloc failed");
+    if (make_groups(h, geti(b, "n_groups", 0))) return bail("rbs_create: group setup failed");
     for (auto& kv : b->i) { h->hi[kv.first] = kv.second; if (upload(h, kv.first, kv.second, true)) return bail("upload"); }
     for (auto& kv : b->d) if (upload(h, kv.first, kv.second, false)) return bail("upload");
     Net& n = h->net;
@@ -663,14 +678,7 @@ void rbs_destroy(rbs_handle* h) {
     if (h->staging) cudaFree(h->staging);
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (h->h_active) cudaFreeHost(h->h_active);
-    for (auto& G : h->groups) {
-        if (G.d_alist) cudaFree(G.d_alist);
-        if (G.d_llist) cudaFree(G.d_llist);
-        if (G.d_counts) cudaFree(G.d_counts);
-        if (G.h_counts) cudaFreeHost(G.h_counts);
-        if (G.ev) cudaEventDestroy(G.ev);
-        if (G.stream && G.stream != h->stream) cudaStreamDestroy(G.stream);
-    }
+    free_groups(h);
     if (h->d_blob) cudaFree(h->d_blob);
     if (h->d_blob2) cudaFree(h->d_blob2);
     if (h->d_alist) cudaFree(h->d_alist);
@@ -761,6 +769,13 @@ int rbs_set_stepper(rbs_handle* h, int32_t full_newton, int32_t predictor, int32
     h->full_newton = full_newton != 0; h->predictor = predictor != 0;
     h->max_halvings = max_halvings; h->grow_iters = grow_iters;
     return 0;
+}
+int rbs_set_groups(rbs_handle* h, int32_t n_groups) {
+    if (!h) return fail("rbs_set_groups: null handle");
+    if (n_groups < 0 || n_groups > 64) return fail("rbs_set_groups: invalid group count");
+    cudaSetDevice(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return make_groups(h, n_groups);
 }
 int rbs_get_stats(rbs_handle* h, int64_t* out6) {
     if (!h || !out6) return fail("rbs_get_stats: null argument");

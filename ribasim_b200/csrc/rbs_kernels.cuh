@@ -267,7 +267,7 @@ __device__ __forceinline__ double rbs_ud_link(const Net& n, int k, int m, double
 // PHASE 0: every connector state whose flow does not depend on a controller;
 // PHASE 1/2: the pumps/outlets listed in `list` (controlled by ContinuousControl / PidControl).
 template <bool JAC>
-__global__ void k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
+__global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
     long long tid = RBS_TID;
     int li = (int)(tid / n.NA);
     int count = phase == 0 ? n.n_conn : n_list;

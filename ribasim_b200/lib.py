@@ -91,6 +91,7 @@ def load() -> ctypes.CDLL:
         "rbs_advance": (ctypes.c_int, [vp, f64, f64, i32, ip]),
         "rbs_set_solver": (ctypes.c_int, [vp, f64, f64, i32]),
         "rbs_set_stepper": (ctypes.c_int, [vp, i32, i32, i32, i32]),
+        "rbs_set_groups": (ctypes.c_int, [vp, i32]),
         "rbs_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(i64)]),
         "rbs_refresh": (ctypes.c_int, [vp, f64]),
         "rbs_time_linear": (ctypes.c_int, [vp, i32, i32, dp]),
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64",
     "rbs_copy_member_to_device", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
-    "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_get_stats", "rbs_refresh",
+    "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
     "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
 ]
 
@@ -336,10 +337,13 @@ class Handle:
     def refresh(self, t: float) -> None:
         _check(self.L.rbs_refresh(self.h, t))
 
-    def set_stepper(self, full_newton: bool = False, predictor: bool = True, max_halvings: int = 20,
+    def set_stepper(self, full_newton: bool = True, predictor: bool = True, max_halvings: int = 20,
                     grow_iters: int = 4) -> None:
         _check(self.L.rbs_set_stepper(self.h, int(full_newton), int(predictor), int(max_halvings),
                                       int(grow_iters)))
+
+    def set_groups(self, n_groups: int) -> None:
+        _check(self.L.rbs_set_groups(self.h, int(n_groups)))
 
     def stats(self) -> dict[str, int]:
         out = (ctypes.c_int64 * 6)()

@@ -37,7 +37,7 @@ class Model:
     def __init__(self, model: str | Path | ModelTables | Params, n_members: int = 1,
                  device: int = 0, dt: float | None = None, flat: Flat | None = None,
                  sym: Symbolic | None = None, lu_mode: int = -1, lu_tile: int = 0,
-                 full_newton: bool = False, predictor: bool = True, max_halvings: int = 20,
+                 full_newton: bool = True, predictor: bool = True, max_halvings: int = 20,
                  grow_iters: int = 4, smem_tile: int = -1, smem_threads: int = 1024,
                  lin_mode: int = -1, n_groups: int = 0):
         if isinstance(model, Params):

@@ -199,7 +199,7 @@ def test_model_driver_matches_oracle_run():
     p = build_params(MODELS["basic"]())
     u_o, S_o, lv_o, st_o = run_oracle(p, 3600.0, t_end=t_end)
     model = Model(build_params(MODELS["basic"]()), n_members=3, dt=3600.0, max_halvings=0,
-                  predictor=False)
+                  predictor=False, full_newton=False)
     try:
         model.update_until(t_end)
         S_g, u_g = model.storage(), model.u()
