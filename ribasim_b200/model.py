@@ -70,8 +70,10 @@ class Model:
             if len(ud["node_id"]) else np.zeros(0)
         self.h.set_param("ud_alloc_total", alloc_total)
         # forcing at t0 is the same for all members until the caller perturbs it
+        self._uploaded = {}
         for name in FORCING_NAMES:
             self.h.set_member(name, self.p.basin.vertical_flux[name], broadcast=True)
+            self._uploaded[name] = self.p.basin.vertical_flux[name].copy()
         self._fb_rate_members: np.ndarray | None = None
         self._push_time_params(0.0)
         self._push_fb_rate(0.0, min(self.dt, self.t_end))
@@ -117,15 +119,42 @@ class Model:
             self.h.set_member("fb_rate", self._fb_rate_members)
 
     # ------------------------------------------------------------------ time stepping
-    def _next_time(self, limit: float) -> float:
+    def _next_stop(self, limit: float) -> float:
         while self._k_stop < len(self.tstops) and self.tstops[self._k_stop] <= self.t:
             self._k_stop += 1
         nxt = self.tstops[self._k_stop] if self._k_stop < len(self.tstops) else self.t_end
-        return min(self.t + self.dt, nxt, limit)
+        return min(nxt, limit)
+
+    def _next_time(self, limit: float) -> float:
+        return min(self.t + self.dt, self._next_stop(limit))
 
     def update(self, want_status: bool = True):
         """One solver step (BMI.update, core/src/bmi.jl:36-39)."""
+        self._sync_inputs()
         return self._step_to(self._next_time(self.t_end), want_status)
+
+    def _sync_inputs(self) -> None:
+        """Upload the BMI-writable host arrays the caller changed since the last step
+        (`basin.infiltration` etc. are written through `get_value_ptr` in the reference,
+        core/src/bmi.jl:64-88; here the host arrays are mirrors synced at update boundaries)."""
+        if getattr(self, "_member_forcing", False):
+            return
+        for name in FORCING_NAMES:
+            arr = self.p.basin.vertical_flux[name]
+            if not np.array_equal(arr, self._uploaded[name], equal_nan=True):
+                self.h.set_member(name, arr, broadcast=True)
+                self._uploaded[name] = arr.copy()
+
+    def _count_status(self, st) -> None:
+        if st is not None:
+            self.status_counts["newton_failed"] += int(np.count_nonzero(st & 1))
+            self.status_counts["negative_storage"] += int(np.count_nonzero(st & 2))
+
+    def _after_step(self) -> None:
+        """`update_basin!` at forcing tstops (core/src/callback.jl:846-866)."""
+        if self.t in self._ftstops and not getattr(self, "_member_forcing", False):
+            update_vertical_flux(self.p, self.t)
+            self._sync_inputs()
 
     def _step_to(self, t_next: float, want_status: bool = True):
         t0 = self.t
@@ -133,21 +162,38 @@ class Model:
         self._push_fb_rate(t0, t_next)
         st = self.h.step(t0, t_next - t0, want_status)
         self.t = t_next
-        if st is not None:
-            self.status_counts["newton_failed"] += int(np.count_nonzero(st & 1))
-            self.status_counts["negative_storage"] += int(np.count_nonzero(st & 2))
-        if self.t in self._ftstops and not getattr(self, "_member_forcing", False):
-            if update_vertical_flux(self.p, self.t):
-                for name in FORCING_NAMES:
-                    self.h.set_member(name, self.p.basin.vertical_flux[name], broadcast=True)
+        self._count_status(st)
+        self._after_step()
         return st
 
+    def _params_constant(self, t_a: float, t_b: float) -> bool:
+        """True when the shared time-dependent parameters are the same at both times (block
+        interpolation between tstops), so the steps in between can run as one device window."""
+        a, b = eval_time_params(self.p, t_a), eval_time_params(self.p, t_b)
+        return all(np.array_equal(a[k], b[k], equal_nan=True) for k in a)
+
     def update_until(self, time: float, want_status: bool = True) -> None:
-        """BMI.update_until (core/src/bmi.jl:41-52)."""
+        """BMI.update_until (core/src/bmi.jl:41-52).  Whole `dt` steps that end before the next
+        tstop run as one `rbs_advance` window; the step that lands on a tstop (or on `time`)
+        is taken on its own with the parameters of that instant, like the reference's RHS."""
         if time < self.t:
             raise ValueError("The model has already passed the given timestamp.")
         while self.t < time:
-            self._step_to(self._next_time(time), want_status)
+            self._sync_inputs()
+            t_stop = self._next_stop(time)
+            n_full = int(math.floor((t_stop - self.t) / self.dt + 1e-9))
+            if n_full >= 1 and self.t + n_full * self.dt >= t_stop - 1e-9 * self.dt:
+                n_full -= 1  # the step that ends on the stop is taken separately
+            if n_full >= 2 and self._params_constant(self.t + self.dt, self.t + n_full * self.dt):
+                t0 = self.t
+                self._push_time_params(t0 + self.dt)
+                self._push_fb_rate(t0, t0 + n_full * self.dt)
+                st = self.h.advance(t0, self.dt, n_full, want_status)
+                self.t = t0 + n_full * self.dt
+                self._count_status(st)
+                self._after_step()
+            else:
+                self._step_to(self._next_time(time), want_status)
 
     def run(self) -> None:
         self.update_until(self.t_end)

@@ -1,0 +1,101 @@
+"""BMI surface on the GPU path, after core/test/bmi_test.jl and
+python/ribasim_api/tests/test_bmi.py (fixed time stepping: the adaptive QNDF is out of scope)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from ribasim_b200.testmodels import MODELS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def basic_toml(tmp_path):
+    m = MODELS["basic"]()
+    m.solver.update(algorithm="ImplicitEuler", dt=3600.0)
+    return m.write(tmp_path / "basic")
+
+
+def _bmi(toml):
+    from ribasim_b200.bmi import RibasimBmi
+    b = RibasimBmi()
+    b.initialize(toml)
+    return b
+
+
+def test_fixed_timestepping(basic_toml):
+    # core/test/bmi_test.jl:30-50
+    b = _bmi(basic_toml)
+    try:
+        dt = 3600.0
+        assert b.get_time_units() == "s"
+        assert b.get_time_step() == dt
+        assert b.get_start_time() == 0.0 and b.get_current_time() == 0.0
+        assert b.get_end_time() == pytest.approx(3.16224e7)
+        b.update()
+        assert b.get_current_time() == dt
+        with pytest.raises(RuntimeError, match="already passed"):
+            b.update_until(dt - 60)
+        b.update_until(dt + 60)
+        assert b.get_current_time() == dt + 60
+        b.update()
+        assert b.get_current_time() == 2 * dt + 60
+        b.update_until(86400.0)
+        assert b.get_current_time() == 86400.0
+    finally:
+        b.finalize()
+    with pytest.raises(RuntimeError, match="Model not initialized"):
+        b.update()  # core/test/libribasim_test.jl: error path
+
+
+def test_get_value_ptr(basic_toml):
+    # core/test/bmi_test.jl:52-90, python/ribasim_api/tests/test_bmi.py:95-110
+    b = _bmi(basic_toml)
+    try:
+        storage0 = b.get_value_ptr("basin.storage")
+        assert np.allclose(storage0, np.ones(4))
+        assert np.allclose(b.get_value_ptr("basin.level"), 4 * [0.04471158417652035], atol=1e-6)
+        with pytest.raises(KeyError, match="Unknown variable foo"):
+            b.get_value_ptr("foo")
+        names = ["basin.storage", "basin.level", "basin.infiltration", "basin.surface_runoff",
+                 "basin.drainage", "basin.cumulative_infiltration",
+                 "basin.cumulative_surface_runoff", "basin.cumulative_drainage",
+                 "basin.subgrid_level", "user_demand.demand", "user_demand.cumulative_inflow"]
+        first = {n: b.get_value_ptr(n) for n in names}
+        b.update_until(86400.0)
+        for n in names:  # get_value_ptr does not copy
+            assert b.get_value_ptr(n) is first[n]
+            assert b.get_var_type(n) == "double"
+        assert not np.allclose(storage0, np.ones(4))
+        assert b.get_component_name() == "Ribasim"
+    finally:
+        b.finalize()
+
+
+def test_vertical_basin_flux(basic_toml):
+    # core/test/bmi_test.jl:112-127: forcing written through the pointer is used by the solver
+    b = _bmi(basic_toml)
+    try:
+        drainage = b.get_value_ptr("basin.drainage")
+        flux = np.array([1.0, 2.0, 3.0, 4.0])
+        drainage[:] = flux
+        dt = 5 * 86400.0
+        b.update_until(dt)
+        assert np.allclose(b.get_value_ptr("basin.cumulative_drainage"), dt * flux, rtol=1e-12)
+    finally:
+        b.finalize()
+
+
+def test_windowed_update_matches_stepwise(basic_toml):
+    """update_until in one call (device windows) == hour by hour."""
+    a, b = _bmi(basic_toml), _bmi(basic_toml)
+    try:
+        a.update_until(3 * 86400.0)
+        for k in range(1, 73):
+            b.update_until(k * 3600.0)
+        assert np.array_equal(a.get_value_ptr("basin.storage"), b.get_value_ptr("basin.storage"))
+    finally:
+        a.finalize()
+        b.finalize()

@@ -248,6 +248,68 @@ def test_member_independence_and_determinism():
     assert np.array_equal(S_sub, S_all[:, pick])
 
 
+@pytest.mark.parametrize("lin_mode,n_groups", [(0, 1), (1, 1), (2, 1), (2, 3)])
+def test_linear_solver_tiers_agree(lin_mode, n_groups):
+    """The three execution tiers of the Newton linear solve (level-per-launch, factors in L2,
+    factors in shared memory with the LDU schedule) and any member grouping give the same
+    trajectories up to the rounding of their different elimination arithmetic."""
+    from ribasim_b200.testmodels import hws_like_model
+    case = make_case(hws_like_model(n_basins=60, n_days=2), 40, seed=13, t=0.0)
+    flat = case["flat"]
+    n = flat["n_state"]
+
+    def run(**kw):
+        h = gpu_handle_for(case, **kw)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
+            st = h.advance(0.0, 3600.0, 4)
+            return h.get_member("u", n), st, h.stats()
+        finally:
+            h.close()
+
+    u_ref, st_ref, stats_ref = run(lin_mode=0, n_groups=1)
+    u, st, stats = run(lin_mode=lin_mode, n_groups=n_groups)
+    assert np.array_equal(st, st_ref) and not np.any(st & 1)
+    scale = 1e-5 + np.abs(u_ref) * 1e-5
+    assert np.max(np.abs(u - u_ref) / scale) <= 1e-3
+    if lin_mode == 0:
+        assert np.array_equal(u, u_ref)
+
+
+def test_random_tree_wide_mode_matches_oracle():
+    """Config-5-like network (random tree, here 1500 basins) on the level-per-launch tier that
+    the 100k-basin network uses, against the oracle."""
+    from oracle.oracle import _dp, advance_opts
+    from ribasim_b200.testmodels import random_tree_model
+    B = 3
+    case = make_case(random_tree_model(n_basins=1500, n_hours=6), B, seed=17, t=0.0)
+    flat = case["flat"]
+    n = flat["n_state"]
+    h = gpu_handle_for(case, lin_mode=0)
+    try:
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
+        st = h.advance(0.0, 3600.0, 2)
+        ug = h.get_member("u", n)
+    finally:
+        h.close()
+    assert not np.any(st & 1)
+    opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1)
+    for m in range(B):
+        om = oracle_for_member(case, m)
+        _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
+        lv = np.ascontiguousarray(c0["level"])
+        om.L.orc_set_level_prev(om.h, _dp(lv))
+        om.set_f64("fb_rate_step", case["fb_rate"][:, m])
+        u = np.zeros(n)
+        eta, htry = 1.0, 3600.0
+        for k in range(2):
+            _, _, htry, eta = om.advance(u, k * 3600.0, 3600.0, opts, htry, eta)
+        scale = 1e-5 + np.abs(u) * 1e-5
+        assert np.max(np.abs(ug[:, m] - u) / scale) <= 1e-2
+
+
 def test_advance_window_equals_single_steps():
     """rbs_advance over a window = the same number of rbs_step_implicit_euler calls, bitwise,
     although members cross the outer step boundaries at different passes."""
