@@ -156,7 +156,7 @@ def cpu_arm(p, flat, n_members: int, n_steps: int, spinup: int, full_newton: int
     # The CPU arm always runs the reference's own Newton variant (J and W evaluated once per
     # attempt, OrdinaryDiffEq NLNewton) — it is also the faster one on the CPU.
     del full_newton
-    batch = OracleBatch(members, advance_opts(1e-5, 1e-5, 10, 0, 4, 20, 1), threads)
+    batch = OracleBatch(members, advance_opts(1e-5, 1e-5, 10, 0, 4, 20, 1, 1, 2), threads)
 
     def set_day(day):
         base, fb = base_forcing(p, day)

@@ -126,11 +126,14 @@ int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter
  * (OrdinaryDiffEq `extrapolant = :constant`), 1 = last accepted increment rescaled to the new
  * sub-step.  max_halvings: smallest sub-step is dt * 2^-max_halvings (0 = plain fixed-step
  * implicit Euler).  grow_iters: double the sub-step after converging within this many
- * iterations.  Defaults: 1, 1, 20, 4 (with the analytic Jacobian a refresh costs about as
- * much as an RHS evaluation, and full Newton needs fewer iterations and far fewer rejected
- * sub-steps than the frozen variant on stiff networks). */
+ * iterations.  early_exit: give up an attempt as soon as the contraction rate theta predicts
+ * that eta*|dz| cannot fall below kappa within max_iter (Hairer-Wanner) instead of iterating to
+ * max_iter.  shrink_log2: a rejected attempt is retried with h / 2^shrink_log2.
+ * Defaults: 1, 1, 20, 4, 1, 2 (with the analytic Jacobian a refresh costs about as much as an
+ * RHS evaluation, and full Newton needs fewer iterations and far fewer rejected sub-steps than
+ * the frozen variant on stiff networks). */
 int rbs_set_stepper(rbs_handle* h, int32_t full_newton, int32_t predictor, int32_t max_halvings,
-                    int32_t grow_iters);
+                    int32_t grow_iters, int32_t early_exit, int32_t shrink_log2);
 /* Number of member groups (0 = automatic).  Each group runs its own state machine on its own
  * CUDA stream so that the latency-bound kernels of one group overlap with the others'; results
  * do not depend on the grouping. */

@@ -336,9 +336,9 @@ class OracleModel:
 
 
 def advance_opts(abstol=1e-5, reltol=1e-5, max_iter=10, full_newton=0, grow_iters=4,
-                 max_halvings=0, predictor=0) -> np.ndarray:
-    return np.array([abstol, reltol, max_iter, full_newton, grow_iters, max_halvings, predictor],
-                    dtype=np.float64)
+                 max_halvings=0, predictor=0, early_exit=0, shrink_log2=1) -> np.ndarray:
+    return np.array([abstol, reltol, max_iter, full_newton, grow_iters, max_halvings, predictor,
+                     early_exit, shrink_log2], dtype=np.float64)
 
 
 class OracleBatch:

@@ -943,6 +943,8 @@ void limit_flow(const Model& m, double* u, const double* uprev, double dt, doubl
 struct AdvanceOpts {
     double abstol = 1e-5, reltol = 1e-5;
     int max_iter = 10, full_newton = 0, grow_iters = 4, max_halvings = 0, predictor = 0;
+    int early_exit = 0;   // 1: give up an attempt predicted not to converge within max_iter
+    int shrink_log2 = 1;  // a rejected attempt is retried with h / 2^shrink_log2
 };
 struct StepStats { int iters = 0, converged = 0, negative_storage = 0, substeps = 0, rejects = 0; double ndz = 0; };
 
@@ -1022,6 +1024,9 @@ static int newton_attempt(Model& m, NewtonWork& w, const double* uprev, double t
         if (iter > 1) {
             theta = ndz / ndz_prev;
             if (theta > 2) { status = -1; break; }
+            // Hairer-Wanner: the remaining iterations cannot bring eta*ndz below kappa
+            if (o.early_exit && (theta >= 1.0 ||
+                ndz * std::pow(theta, o.max_iter - iter) > kappa * (1.0 - theta))) { status = -1; break; }
         }
         if (iter > 1) eta = theta / (1 - theta);
         if ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0 && eta * ndz < kappa)) { status = 1; break; }
@@ -1087,7 +1092,8 @@ int advance(Model& m, double* u, double t0, double dt, const AdvanceOpts& o, dou
             if (!conv) failed_members_steps++;
             if (conv && iters <= o.grow_iters) h_nom = std::min(2.0 * h_nom, dt);
         } else {
-            h_nom = 0.5 * h;
+            h_nom = std::ldexp(h, -o.shrink_log2);
+            if (h_nom < h_min) h_nom = h_min;
             *eta_old = 1.0;
             st.rejects++;
         }
@@ -1196,6 +1202,7 @@ int orc_advance(void* h, double* u, double t0, double dt, const double* opts, do
     AdvanceOpts o;
     o.abstol = opts[0]; o.reltol = opts[1]; o.max_iter = (int)opts[2]; o.full_newton = (int)opts[3];
     o.grow_iters = (int)opts[4]; o.max_halvings = (int)opts[5]; o.predictor = (int)opts[6];
+    o.early_exit = (int)opts[7]; o.shrink_log2 = (int)opts[8];
     StepStats st;
     int rc = advance(*(Model*)h, u, t0, dt, o, h_try, eta_old, &st);
     if (out5) { out5[0] = st.iters; out5[1] = st.substeps; out5[2] = st.rejects;
@@ -1219,6 +1226,7 @@ int orc_run_batch(void** hs, double** us, int n, double t0, double dt, int n_ste
     AdvanceOpts o;
     o.abstol = opts7[0]; o.reltol = opts7[1]; o.max_iter = (int)opts7[2]; o.full_newton = (int)opts7[3];
     o.grow_iters = (int)opts7[4]; o.max_halvings = (int)opts7[5]; o.predictor = (int)opts7[6];
+    o.early_exit = (int)opts7[7]; o.shrink_log2 = (int)opts7[8];
     std::vector<std::thread> th;
     std::vector<int64_t> fails(n_threads, 0), subs(n_threads, 0), its(n_threads, 0);
     for (int w = 0; w < n_threads; w++)

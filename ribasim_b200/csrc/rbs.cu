@@ -75,6 +75,7 @@ struct rbs_handle {
     int max_iter = 10;
     // stepper options (rbs_set_stepper)
     int full_newton = 1, predictor = 1, max_halvings = 20, grow_iters = 4;
+    int early_exit = 1, shrink_log2 = 2;
     int64_t max_passes = 100000;
     int64_t launches = 0;
     int64_t n_steps = 0, n_passes = 0, n_failed = 0;
@@ -763,11 +764,13 @@ int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter
     return 0;
 }
 int rbs_set_stepper(rbs_handle* h, int32_t full_newton, int32_t predictor, int32_t max_halvings,
-                    int32_t grow_iters) {
+                    int32_t grow_iters, int32_t early_exit, int32_t shrink_log2) {
     if (!h) return fail("rbs_set_stepper: null handle");
-    if (max_halvings < 0 || max_halvings > 60 || grow_iters < 0) return fail("rbs_set_stepper: invalid option");
+    if (max_halvings < 0 || max_halvings > 60 || grow_iters < 0 || shrink_log2 < 1 || shrink_log2 > 8)
+        return fail("rbs_set_stepper: invalid option");
     h->full_newton = full_newton != 0; h->predictor = predictor != 0;
     h->max_halvings = max_halvings; h->grow_iters = grow_iters;
+    h->early_exit = early_exit != 0; h->shrink_log2 = shrink_log2;
     return 0;
 }
 int rbs_set_groups(rbs_handle* h, int32_t n_groups) {
@@ -984,7 +987,7 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         LAUNCH_AS(h, "k_basin_limit_pre", (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, false);
         LAUNCH(h, k_step_limit, (long long)n.n_state * B, n, from_ts, alloc_total);
         LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, true);
-        LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps);
+        LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps, h->shrink_log2);
         LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
     }
     // Newton half
@@ -1000,7 +1003,7 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 31) / 32, h->n_part);
         LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
     }
-    LAUNCH(h, k_newton_converge, (long long)n.NA, n, h->n_part, h->max_iter, 0.01, h->full_newton);
+    LAUNCH(h, k_newton_converge, (long long)n.NA, n, h->n_part, h->max_iter, 0.01, h->full_newton, h->early_exit);
     n.NA = n.B;
     n.alist = nullptr;
     LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);

@@ -1105,7 +1105,8 @@ __global__ void k_newton_update(Net n, const double* __restrict__ c, double abst
 
 // per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve);
 // a member whose iteration ends (converged or failed) moves to PHASE_LIMIT.
-__global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa, int full_newton) {
+__global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa, int full_newton,
+                                  int early_exit) {
     int j = (int)RBS_TID;
     if (j >= n.NA) return;
     int m = RBS_MEMBER(n, j);
@@ -1123,6 +1124,9 @@ __global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa,
             if (iter > 1) {
                 theta = ndz / n.ndz_prev[m];
                 if (theta > 2.0) st = 2;
+                // Hairer-Wanner: the remaining iterations cannot bring eta*ndz below kappa
+                else if (early_exit && (theta >= 1.0 ||
+                         ndz * pow(theta, (double)(max_iter - iter)) > kappa * (1.0 - theta))) st = 2;
                 else eta = theta / (1.0 - theta);
             }
             if (st == 0 && ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0.0 && eta * ndz < kappa)))
@@ -1258,7 +1262,7 @@ __global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
 
 // PHASE_LIMIT members: accept or reject the attempt, choose the next attempt
 __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters,
-                              int n_steps) {
+                              int n_steps, int shrink_log2) {
     int j = (int)RBS_TID;
     if (j >= n.NA) return;
     int m = RBS_MEMBER(n, j);
@@ -1276,7 +1280,7 @@ __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, 
         if (conv && n.miter[m] <= grow_iters) hnom = fmin(2.0 * hnom, dt);
         n.maction[m] = ACTION_ACCEPT;
     } else {
-        hnom = 0.5 * h;
+        hnom = fmax(ldexp(h, -shrink_log2), h_min);
         n.eta[m] = 1.0;
         n.cnt_rej[m] += 1;
         n.maction[m] = ACTION_REJECT;

@@ -90,7 +90,7 @@ def load() -> ctypes.CDLL:
         "rbs_step_implicit_euler": (ctypes.c_int, [vp, f64, f64, ip]),
         "rbs_advance": (ctypes.c_int, [vp, f64, f64, i32, ip]),
         "rbs_set_solver": (ctypes.c_int, [vp, f64, f64, i32]),
-        "rbs_set_stepper": (ctypes.c_int, [vp, i32, i32, i32, i32]),
+        "rbs_set_stepper": (ctypes.c_int, [vp, i32, i32, i32, i32, i32, i32]),
         "rbs_set_groups": (ctypes.c_int, [vp, i32]),
         "rbs_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(i64)]),
         "rbs_refresh": (ctypes.c_int, [vp, f64]),
@@ -338,9 +338,9 @@ class Handle:
         _check(self.L.rbs_refresh(self.h, t))
 
     def set_stepper(self, full_newton: bool = True, predictor: bool = True, max_halvings: int = 20,
-                    grow_iters: int = 4) -> None:
+                    grow_iters: int = 4, early_exit: bool = True, shrink_log2: int = 2) -> None:
         _check(self.L.rbs_set_stepper(self.h, int(full_newton), int(predictor), int(max_halvings),
-                                      int(grow_iters)))
+                                      int(grow_iters), int(early_exit), int(shrink_log2)))
 
     def set_groups(self, n_groups: int) -> None:
         _check(self.L.rbs_set_groups(self.h, int(n_groups)))

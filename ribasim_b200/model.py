@@ -38,7 +38,8 @@ class Model:
                  device: int = 0, dt: float | None = None, flat: Flat | None = None,
                  sym: Symbolic | None = None, lu_mode: int = -1, lu_tile: int = 0,
                  full_newton: bool = True, predictor: bool = True, max_halvings: int = 20,
-                 grow_iters: int = 4, smem_tile: int = -1, smem_threads: int = 1024,
+                 grow_iters: int = 4, early_exit: bool = True, shrink_log2: int = 2,
+                 smem_tile: int = -1, smem_threads: int = 1024,
                  lin_mode: int = -1, n_groups: int = 0):
         if isinstance(model, Params):
             self.p = model
@@ -61,7 +62,7 @@ class Model:
                             lu_tile=lu_tile, smem_tile=smem_tile, smem_threads=smem_threads,
                             lin_mode=lin_mode, n_groups=n_groups)
         self.h.set_solver(self.tables.solver_option("abstol"), self.tables.solver_option("reltol"))
-        self.h.set_stepper(full_newton, predictor, max_halvings, grow_iters)
+        self.h.set_stepper(full_newton, predictor, max_halvings, grow_iters, early_exit, shrink_log2)
         n = self.p.nodes
         ud = n["user_demand"]
         self.h.set_param("ud_demand_from_timeseries",

@@ -146,7 +146,7 @@ def test_implicit_euler_steps_parity(name, dt, n_steps, full_newton):
     try:
         h.set_solver(1e-5, 1e-5, 10)
         h.set_stepper(full_newton=bool(full_newton), predictor=True, max_halvings=20, grow_iters=4)
-        opts = advance_opts(1e-5, 1e-5, 10, full_newton, 4, 20, 1)
+        opts = advance_opts(1e-5, 1e-5, 10, full_newton, 4, 20, 1, 1, 2)
         h.refresh(0.0)
         h.set_member("level_prev", h.get_member("level", flat["n_basin"]))
         oms = []
@@ -199,7 +199,7 @@ def test_model_driver_matches_oracle_run():
     p = build_params(MODELS["basic"]())
     u_o, S_o, lv_o, st_o = run_oracle(p, 3600.0, t_end=t_end)
     model = Model(build_params(MODELS["basic"]()), n_members=3, dt=3600.0, max_halvings=0,
-                  predictor=False, full_newton=False)
+                  predictor=False, full_newton=False, early_exit=False)
     try:
         model.update_until(t_end)
         S_g, u_g = model.storage(), model.u()
@@ -295,7 +295,7 @@ def test_random_tree_wide_mode_matches_oracle():
     finally:
         h.close()
     assert not np.any(st & 1)
-    opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1)
+    opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1, 1, 2)
     for m in range(B):
         om = oracle_for_member(case, m)
         _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
