@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--members", type=int, default=4096, help="ensemble members per GPU")
     ap.add_argument("--basins", type=int, default=500)
+    ap.add_argument("--workload", default="hws", choices=["hws", "tree"],
+                    help="hws: HWS-like network (BASELINE config 4); tree: random tree (config 5)")
     ap.add_argument("--spinup", type=int, default=48, help="untimed steps from the initial state")
     ap.add_argument("--full-newton", type=int, default=1)
     ap.add_argument("--lu-tile", type=int, default=0)
@@ -57,13 +59,16 @@ def parse_args():
 
 
 # ----------------------------------------------------------------------------- workload
-def build_workload(n_basins: int):
+def build_workload(n_basins: int, workload: str = "hws"):
     from ribasim_b200.flatten import flatten
     from ribasim_b200.network import build_params
     from ribasim_b200.symbolic import analyse
-    from ribasim_b200.testmodels import hws_like_model
+    from ribasim_b200.testmodels import hws_like_model, random_tree_model
 
-    tables = hws_like_model(n_basins=n_basins, n_days=30)
+    if workload == "tree":
+        tables = random_tree_model(n_basins=n_basins, n_hours=24 * 30)
+    else:
+        tables = hws_like_model(n_basins=n_basins, n_days=30)
     p = build_params(tables)
     flat = flatten(p)
     sym = analyse(flat["n_reduced"], flat["wrow_ptr"], flat["wcol"])
@@ -200,7 +205,7 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    p, flat, sym = build_workload(args.basins)
+    p, flat, sym = build_workload(args.basins, args.workload)
     sample = args.cpu_members or 32 * cores
     # warm-up steps are part of the (untimed) spin-up of the sample
     val, el, stats = cpu_arm(p, flat, sample, args.steps, args.spinup + args.warmup,
@@ -224,7 +229,7 @@ def reference_arm(args):
 
 def workload_config(args, flat, sym, members_local, world):
     return {
-        "workload": f"hws_like synthetic network, {flat['n_basin']} basins x "
+        "workload": f"{'random-tree' if args.workload == 'tree' else 'hws_like'} synthetic network, {flat['n_basin']} basins x "
                     f"{members_local} members per GPU, dt=3600 s implicit Euler",
         "n_basin": flat["n_basin"], "n_state": flat["n_state"], "n_reduced": flat["n_reduced"],
         "nnz_j": flat["nnz_j"], "nnz_w": flat["nnz_w"], "n_lu": sym.n_lu,
@@ -257,7 +262,7 @@ def main():
     from ribasim_b200.ensemble import gather_members, member_range, perturbed_forcing
     from ribasim_b200.model import Model
 
-    p, flat, sym = build_workload(args.basins)
+    p, flat, sym = build_workload(args.basins, args.workload)
     if args.strong:
         lo, hi = member_range(args.members, rank, world)
         total_members = args.members
@@ -421,6 +426,21 @@ def main():
         dist.destroy_process_group()
 
 
+def ncu_traffic(group: str):
+    """dram read+write bytes per launch of the group's main kernel from the committed
+    `ncu --set full` capture (profiles/r1_*.txt; full 4096-member launch), or None."""
+    main = {"linear_solve": "k_newton_linear_smem", "rhs_jacobian": "k_links",
+            "newton_update": "k_newton_update", "limiter_accept": "k_step_apply"}.get(group)
+    f = ROOT / "profiles" / f"r1_{main}.txt"
+    if main is None or not f.exists():
+        return None
+    for line in f.read_text().splitlines():
+        if line.startswith("# dram traffic"):
+            val, unit = line.split(":")[1].split()[:2]
+            return float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+    return None
+
+
 def roofline(flat, sym, report, s0, s1, nm, args):
     """HBM roofline of the dominant kernel group: algorithmic bytes (SURVEY §8(d) per-member
     figures x member-launches actually executed) / summed CUDA-event duration."""
@@ -455,7 +475,7 @@ def roofline(flat, sym, report, s0, s1, nm, args):
     step_bytes = sum(b for _, b in groups.values())
     return {
         "bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": ncu_traffic(name), "peak_source": peak_src,
         "share_of_step": gms / total_ms if total_ms else None,
         "step_achieved": step_bytes / (total_ms * 1e-3) / 1e9 if total_ms else None,
         "groups_ms": {k: round(v[0], 3) for k, v in groups.items()},

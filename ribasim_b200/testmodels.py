@@ -297,6 +297,41 @@ def pump_discrete_control_model() -> ModelTables:
     return m
 
 
+def junction_combined_model() -> ModelTables:
+    """Confluence and bifurcation through Junction nodes (junction.py:13-98)."""
+    m = _model()
+    prof = dict(area=[1000.0, 1000.0], level=[0.0, 1.0])
+    m.add_node("Basin", 1, profile=prof, static=dict(infiltration=2.5), state=dict(level=1.0))
+    m.add_node("Junction", 2)
+    m.add_node("LinearResistance", 3, static=dict(resistance=1.0))
+    m.add_node("LinearResistance", 4, static=dict(resistance=1.0))
+    m.add_node("Basin", 5, profile=prof, static=dict(surface_runoff=1.0), state=dict(level=1.0))
+    m.add_node("Basin", 6, profile=prof, static=dict(drainage=4.0), state=dict(level=1.0))
+    m.add_node("LinearResistance", 7, static=dict(resistance=1.0))
+    m.add_node("LinearResistance", 8, static=dict(resistance=1.0))
+    m.add_node("Junction", 9)
+    m.add_node("Basin", 10, profile=prof, static=dict(infiltration=2.5), state=dict(level=1.0))
+    for a, b in ((1, 2), (2, 3), (2, 4), (3, 5), (4, 6), (5, 7), (6, 8), (7, 9), (8, 9), (9, 10)):
+        m.add_link(a, b)
+    return m
+
+
+def junction_chained_model() -> ModelTables:
+    """Basin 1 -> Junction 2 -> Junction 3 -> LR 4/5 -> Basin 6/7 (junction.py:101-165)."""
+    m = _model()
+    prof = dict(area=[1000.0, 1000.0], level=[0.0, 1.0])
+    m.add_node("Basin", 1, profile=prof, static=dict(drainage=1.0), state=dict(level=1.0))
+    m.add_node("Junction", 2)
+    m.add_node("Junction", 3)
+    m.add_node("LinearResistance", 4, static=dict(resistance=1.0))
+    m.add_node("LinearResistance", 5, static=dict(resistance=1.0))
+    m.add_node("Basin", 6, profile=prof, state=dict(level=0.0))
+    m.add_node("Basin", 7, profile=prof, state=dict(level=0.0))
+    for a, b in ((1, 2), (2, 3), (3, 4), (3, 5), (4, 6), (5, 7)):
+        m.add_link(a, b)
+    return m
+
+
 # ----------------------------------------------------------------------------- synthetic networks
 def _random_profile(rng: np.random.Generator, n_points: int, mu: float, sigma: float,
                     bottom: float | None = None):
@@ -523,6 +558,8 @@ def _add_connector_fast(m: ModelTables, rng, kind: str, node_id: int, bottom_src
 
 
 MODELS = dict(
+    junction_combined=junction_combined_model,
+    junction_chained=junction_chained_model,
     basic=basic_model,
     basic_transient=basic_transient_model,
     backwater=backwater_model,

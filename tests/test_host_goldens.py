@@ -224,3 +224,17 @@ def test_pump_discrete_control_compiles():
     p = build_params(MODELS["pump_discrete_control"]())
     flat = flatten(p)
     assert flat["n_pump"] >= 1
+
+
+def test_junction_elimination_link_counts():
+    # core/test/run_models_test.jl:672-701
+    p = build_params(MODELS["junction_combined"]())
+    assert len(p.internal_flow_links) == 8 and len(p.external_flow_links) == 10
+    assert all(v.type != "Junction" for v in p.graph.code_of)
+    p = build_params(MODELS["junction_chained"]())
+    assert len(p.internal_flow_links) == 4 and len(p.external_flow_links) == 6
+    assert all(v.type != "Junction" for v in p.graph.code_of)
+    # both LinearResistance nodes flow out of Basin #1 through the eliminated junction chain
+    lr = p.nodes["linear_resistance"]
+    assert [l.link[0].value for l in lr["inflow_link"]] == [1, 1]
+    assert [l.link[1].value for l in lr["outflow_link"]] == [6, 7]
