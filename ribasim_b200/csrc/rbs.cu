@@ -195,7 +195,7 @@ void bind_net(rbs_handle* h) {
     M_D(mh); M_D(mhnom); M_D(melapsed); M_D(mhlast); M_D(zlast);
 #define M_I(name) n.name = (int*)h->member[#name].p
     M_I(nstat); M_I(status); M_I(active_count);
-    M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mlast); M_I(maction);
+    M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
     M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep);
 #undef M_I
 #undef S_D
@@ -237,7 +237,7 @@ inline void prof_end(rbs_handle* h) {
 template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
     long long B = n.NA;
-    LAUNCH_AS(h, JAC ? "k_basin<jac>" : "k_basin<rhs>", (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, false);
+    LAUNCH_AS(h, JAC ? "k_basin<jac>" : "k_basin<rhs>", (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, 0);
     LAUNCH_AS(h, JAC ? "k_links<jac>" : "k_links<rhs>", k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0, pred);
     if (n.n_cc > 0) {
         LAUNCH_AS(h, JAC ? "k_continuous_control<jac>" : "k_continuous_control<rhs>", k_continuous_control<JAC>, (long long)n.n_cc * B, n, pred);
@@ -250,13 +250,6 @@ template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pr
                   (int)h->list_phase[2].size(), pred);
     }
 }
-// controllers read du of flows that may not be formulated yet: those must read 0
-// (water_balance! zeroes du first, core/src/solve.jl:54)
-void zero_du_if_controlled(rbs_handle* h) {
-    Net& n = h->net;
-    if (n.n_pid > 0 || n.n_cc > 0) LAUNCH(h, k_zero_du, (long long)n.n_state * n.NA, n);
-}
-
 // W = A J - I/gamma and its LU.  FROM_J: assembled on the fly (step path, per-member gamma = h).
 template <bool FROM_J> void launch_factor(rbs_handle* h, double inv_gamma, Pred pred = Pred{nullptr, 0, nullptr}) {
     Net& n = h->net;
@@ -468,7 +461,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         {"zlast", n.n_state}, {"mh", 1}, {"mhnom", 1}, {"melapsed", 1}, {"mhlast", 1},
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
-    for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mlast",
+    for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mneg2", "mclamp", "mlast",
                           "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep"})
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
     {
@@ -917,7 +910,7 @@ int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, dou
     CUDA_TRY(cudaMemcpyAsync(n.u, u, nb, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(n.uprev, uprev, nb, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(h, k_exact, (long long)n.n_basin * B, n, t, h->tprev);
-    LAUNCH(h, (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, Pred{nullptr, 0, nullptr}, false);
+    LAUNCH(h, (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, Pred{nullptr, 0, nullptr}, 0);
     LAUNCH(h, k_limit_flow, (long long)n.off_integral * B, n, n.u, n.uprev, dt,
            sp<int>(h, "ud_demand_from_timeseries"), sp<double>(h, "ud_alloc_total"));
     CUDA_TRY(cudaMemcpyAsync(u, n.u, nb, cudaMemcpyDeviceToHost, h->stream));
@@ -984,9 +977,9 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         n.alist = G.d_llist;
         long long B = n.NA;
         Pred lim{n.mphase, PHASE_LIMIT, nullptr};
-        LAUNCH_AS(h, "k_basin_limit_pre", (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, false);
+        LAUNCH_AS(h, "k_basin_limit_pre", (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, 1);
         LAUNCH(h, k_step_limit, (long long)n.n_state * B, n, from_ts, alloc_total);
-        LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, true);
+        LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, 2);
         LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps, h->shrink_log2);
         LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
     }
@@ -994,7 +987,6 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
     n.NA = G.n_active;
     n.alist = G.d_alist;
     Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
-    zero_du_if_controlled(h);
     launch_rhs<true, 1>(h, nullptr, nw);
     if (!h->full_newton) launch_rhs<false, 1>(h, nullptr, nw);
     double* c = mp(h, "cvec");
@@ -1003,10 +995,10 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 31) / 32, h->n_part);
         LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
     }
-    LAUNCH(h, k_newton_converge, (long long)n.NA, n, h->n_part, h->max_iter, 0.01, h->full_newton, h->early_exit);
     n.NA = n.B;
     n.alist = nullptr;
-    LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
+    LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts, 1, h->n_part,
+               h->max_iter, 0.01, h->full_newton, h->early_exit);
     h->cur = h->stream;
     h->n_passes++;
 }
@@ -1066,7 +1058,7 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
     for (auto& G : h->groups) {
         if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, ev_begin, 0));
         h->cur = G.stream;
-        LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
+        LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts, 0, 0, 0, 0.0, 0, 0);
         G.n_active = G.hi - G.lo;
         G.n_limit = 0;
         G.pending = false;

@@ -91,7 +91,7 @@ struct Net {
     double* storage_prev;  // limiter memory (basin.storage_prev, frozen: SURVEY row 22)
     double* level_prev;
     // per-member sub-stepping state machine (rbs_step.cuh)
-    int *mphase, *mjac, *miter, *mconv, *mneg, *mlast, *maction;
+    int *mphase, *mjac, *miter, *mconv, *mneg, *mneg2, *mclamp, *mlast, *maction;
     int *cnt_iters, *cnt_sub, *cnt_rej;
     int* mstep;  // outer steps completed in the current window
     double *mh, *mhnom, *melapsed, *mhlast, *zlast;
@@ -194,12 +194,15 @@ template <int SRC> __device__ __forceinline__ double rbs_state_in(const Net& n, 
 }
 template <bool JAC, int SRC>
 __global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
-                        bool flag_negative) {
+                        int flag_negative) {
+    // flag_negative: 0 none; 1 = proposed state (sets mneg); 2 = clamped state (only members the
+    // limiter changed, sets mneg2)
     long long tid = RBS_TID;
     int b = (int)(tid / n.NA);
     if (b >= n.n_reduced) return;
     int m = RBS_MEMBER(n, (int)(tid - (long long)b * n.NA));
     if (rbs_skip<JAC>(pred, m)) return;
+    if (flag_negative == 2 && n.mclamp[m] == 0) return;
     long long o = (long long)b * n.B + m;
     if (b >= n.n_basin) {
         if (SRC != 0) n.ur[o] = rbs_state_in<SRC>(n, (long long)(n.off_integral + b - n.n_basin) * n.B + m);
@@ -230,7 +233,7 @@ __global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pre
     n.factor[o] = phi;
     n.level[o] = e.level;
     n.area[o] = e.area;
-    if (flag_negative && S < 0.0) atomicOr(&n.mneg[m], 1);  // integer flag only
+    if (flag_negative && S < 0.0) atomicOr(flag_negative == 2 ? &n.mneg2[m] : &n.mneg[m], 1);  // integer flag only
     if (JAC) {
         n.dlevel[o] = e.dlevel;
         n.dfactor[o] = dphi;
@@ -302,7 +305,12 @@ __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* _
     if (ct == CT_PUMP || ct == CT_OUTLET) {
         bool outlet = ct == CT_OUTLET;
         int control = outlet ? n.outlet_control_type[k] : n.pump_control_type[k];
-        if (control != phase) return;
+        if (control != phase) {
+            // controllers read du of flows that are not formulated yet: those must read 0
+            // (water_balance! zeroes du first, core/src/solve.jl:54)
+            if (phase == 0) n.du[so] = 0.0;
+            return;
+        }
         controlled = control != CONTROL_NONE;
         RbsEnd a = rbs_fetch_end<JAC>(n, n.src_kind[s], n.src_idx[s], m);
         RbsEnd b = rbs_fetch_end<JAC>(n, n.dst_kind[s], n.dst_idx[s], m);
@@ -1105,53 +1113,50 @@ __global__ void k_newton_update(Net n, const double* __restrict__ c, double abst
 
 // per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve);
 // a member whose iteration ends (converged or failed) moves to PHASE_LIMIT.
-__global__ void k_newton_converge(Net n, int n_part, int max_iter, double kappa, int full_newton,
-                                  int early_exit) {
-    int j = (int)RBS_TID;
-    if (j >= n.NA) return;
-    int m = RBS_MEMBER(n, j);
-    int ph = n.mphase[m];
-    if (ph == PHASE_NEWTON) {
-        int iter = n.miter[m];
-        double s = 0.0;
-        for (int p = 0; p < n_part; p++) s += n.norm_part[(long long)p * n.B + m];
-        double ndz = sqrt(s / n.n_state);
-        double eta = n.eta[m];
-        int st = 0;  // 0 continue, 1 converged, 2 failed
-        if (!isfinite(ndz)) st = 2;
-        else {
-            double theta = 0.0;
-            if (iter > 1) {
-                theta = ndz / n.ndz_prev[m];
-                if (theta > 2.0) st = 2;
-                // Hairer-Wanner: the remaining iterations cannot bring eta*ndz below kappa
-                else if (early_exit && (theta >= 1.0 ||
-                         ndz * pow(theta, (double)(max_iter - iter)) > kappa * (1.0 - theta))) st = 2;
-                else eta = theta / (1.0 - theta);
-            }
-            if (st == 0 && ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0.0 && eta * ndz < kappa)))
-                st = 1;
+__device__ __forceinline__ void rbs_newton_converge(const Net& n, int m, int n_part, int max_iter,
+                                                    double kappa, int full_newton, int early_exit) {
+    int iter = n.miter[m];
+    double s = 0.0;
+    for (int p = 0; p < n_part; p++) s += n.norm_part[(long long)p * n.B + m];
+    double ndz = sqrt(s / n.n_state);
+    double eta = n.eta[m];
+    int st = 0;  // 0 continue, 1 converged, 2 failed
+    if (!isfinite(ndz)) st = 2;
+    else {
+        double theta = 0.0;
+        if (iter > 1) {
+            theta = ndz / n.ndz_prev[m];
+            if (theta > 2.0) st = 2;
+            // Hairer-Wanner: the remaining iterations cannot bring eta*ndz below kappa
+            else if (early_exit && (theta >= 1.0 ||
+                     ndz * pow(theta, (double)(max_iter - iter)) > kappa * (1.0 - theta))) st = 2;
+            else eta = theta / (1.0 - theta);
         }
-        if (st == 0 && iter >= max_iter) st = 2;
-        n.ndz_prev[m] = ndz;
-        n.ndz[m] = ndz;
-        n.eta[m] = eta;
-        n.cnt_iters[m] += 1;
-        if (st == 0) {
-            n.miter[m] = iter + 1;
-            n.mjac[m] = full_newton;
-        } else {
-            n.mconv[m] = st == 1;
-            n.mphase[m] = PHASE_LIMIT;
-        }
+        if (st == 0 && ((iter == 1 && ndz < 1e-5) || (iter > 1 && eta >= 0.0 && eta * ndz < kappa)))
+            st = 1;
+    }
+    if (st == 0 && iter >= max_iter) st = 2;
+    n.ndz_prev[m] = ndz;
+    n.ndz[m] = ndz;
+    n.eta[m] = eta;
+    n.cnt_iters[m] += 1;
+    if (st == 0) {
+        n.miter[m] = iter + 1;
+        n.mjac[m] = full_newton;
+    } else {
+        n.mconv[m] = st == 1;
+        n.mphase[m] = PHASE_LIMIT;
     }
 }
 
 // Ordered compaction of the members [m_lo, m_hi) that still have work: `alist_out` = members not
 // DONE, `llist_out` = members in PHASE_LIMIT, counts[0..1] their lengths.  One block; order is
 // kept so that a mostly-active ensemble stays coalesced.  Integer work only.
+// With converge != 0 the members in the Newton phase first get the convergence test of the
+// iteration they just finished (all of them iterated in this pass).
 __global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out,
-                          int* __restrict__ llist_out, int* __restrict__ counts) {
+                          int* __restrict__ llist_out, int* __restrict__ counts, int converge,
+                          int n_part, int max_iter, double kappa, int full_newton, int early_exit) {
     __shared__ int sa[1024], sl[1024];
     int t = threadIdx.x, T = blockDim.x;
     int nm = m_hi - m_lo;
@@ -1159,6 +1164,8 @@ __global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out
     int lo = m_lo + min(t * per, nm), hi = min(lo + per, m_hi);
     int ca = 0, cl = 0;
     for (int m = lo; m < hi; m++) {
+        if (converge && n.mphase[m] == PHASE_NEWTON)
+            rbs_newton_converge(n, m, n_part, max_iter, kappa, full_newton, early_exit);
         int ph = n.mphase[m];
         ca += ph != PHASE_DONE;
         cl += ph == PHASE_LIMIT;
@@ -1178,15 +1185,6 @@ __global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out
         if (ph == PHASE_LIMIT) llist_out[pl++] = m;
     }
     if (t == T - 1) { counts[0] = sa[t]; counts[1] = sl[t]; }
-}
-
-// du <- 0 for the members of the launch domain (controllers read flows not yet formulated)
-__global__ void k_zero_du(Net n) {
-    long long tid = RBS_TID;
-    int s = (int)(tid / n.NA);
-    if (s >= n.n_state) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)s * n.NA));
-    n.du[(long long)s * n.B + m] = 0.0;
 }
 
 // ---- sub-stepping state machine -------------------------------------------------------------------
@@ -1236,6 +1234,8 @@ __global__ void k_step_begin(Net n, double dt, int predictor) {
         n.miter[m] = 1;
         n.mjac[m] = 1;
         n.mneg[m] = 0;
+        n.mneg2[m] = 0;
+        n.mclamp[m] = 0;
         n.maction[m] = ACTION_NONE;
         n.status[m] = 0;
         n.mstep[m] = 0;
@@ -1256,7 +1256,11 @@ __global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
     double up = n.uprev[o];
     double v = up + n.z[o];
     double lo, hi;
-    if (rbs_flow_bounds(n, s, m, from_ts, alloc_total, lo, hi)) v = rbs_clamp_state(v, up, lo, hi, n.mh[m]);
+    if (rbs_flow_bounds(n, s, m, from_ts, alloc_total, lo, hi)) {
+        double vc = rbs_clamp_state(v, up, lo, hi, n.mh[m]);
+        if (vc != v) n.mclamp[m] = 1;  // every writer stores the same value
+        v = vc;
+    }
     n.u[o] = v;
 }
 
@@ -1267,7 +1271,10 @@ __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, 
     if (j >= n.NA) return;
     int m = RBS_MEMBER(n, j);
     if (n.mphase[m] != PHASE_LIMIT) { n.maction[m] = ACTION_NONE; return; }
-    bool conv = n.mconv[m] != 0, neg = n.mneg[m] != 0, last = n.mlast[m] != 0;
+    bool conv = n.mconv[m] != 0, last = n.mlast[m] != 0;
+    bool neg = (n.mclamp[m] ? n.mneg2[m] : n.mneg[m]) != 0;
+    n.mneg2[m] = 0;
+    n.mclamp[m] = 0;
     double h = n.mh[m], hnom = n.mhnom[m], elapsed = n.melapsed[m];
     bool can_halve = max_halvings > 0 && 0.5 * h >= h_min * (1.0 - 1e-12);
     n.mneg[m] = 0;
