@@ -75,6 +75,16 @@ int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_e
 /* Device-to-device copy of a per-member array into caller-owned device memory (e.g. the send
  * buffer of the final NCCL gather of an ensemble sharded over GPUs). */
 int rbs_copy_member_to_device(rbs_handle* h, const char* key, void* dst_device, int64_t n_entity);
+/* Integer per-member arrays: "status", "dc_state" (control state index per DiscreteControl
+ * node, -1 = none yet), "dc_truth" (per condition), counters "cnt_iters", "cnt_sub", "cnt_rej",
+ * "cnt_dc" (control state changes). */
+int rbs_get_member_i32(rbs_handle* h, const char* key, int32_t* host, int64_t n_entity);
+/* DiscreteControl at the initial time (`apply_discrete_control!` with t == 0,
+ * core/src/callback.jl:608-661): evaluates every condition on the caches of the last
+ * rbs_refresh and sets the control state of every member.  During stepping the evaluation runs on
+ * the device after every accepted (sub-)step of a member; per-member control states select the
+ * row of the control-state parameter tables ("pump_cs_flow_rate", ...). */
+int rbs_apply_discrete_control(rbs_handle* h);
 /* Previous accepted time `tprev` (core/src/parameter.jl:1126-1130). */
 int rbs_set_tprev(rbs_handle* h, double tprev);
 

@@ -70,6 +70,9 @@ def lib() -> ctypes.CDLL:
         L.orc_limit_flow.argtypes = [vp, dp, dp, ctypes.c_double, ctypes.c_double]
         L.orc_step.argtypes = [vp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                ctypes.c_double, ctypes.c_int, dp, ip, ip, ip]
+        L.orc_apply_discrete_control.argtypes = [vp, dp, ctypes.c_double]
+        L.orc_get_dc.argtypes = [vp, ip, ip, ip]
+        L.orc_get_dc_record.argtypes = [vp, ip, ctypes.c_int]
         L.orc_advance.argtypes = [vp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, ip]
         L.orc_reduction_factor.argtypes = [ctypes.c_double, ctypes.c_double]
         L.orc_reduction_factor.restype = ctypes.c_double
@@ -243,6 +246,15 @@ class OracleModel:
         self.set_i32("cc_table_idx", [len(trc["interpolations"]) + i for i in range(len(cc["func"]))])
         self.set_i32("cc_target_is_outlet", [t.type == "Outlet" for t in cc["target_node"]])
         self.set_i32("cc_target_idx", [t.idx - 1 for t in cc["target_node"]])
+        # DiscreteControl: shared description (index layout of flatten._flatten_discrete_control)
+        from ribasim_b200.flatten import flatten
+        flat = flatten(p)
+        self.set_i32("n_dc", [flat.ints["n_dc"]])
+        for k, v in flat.arrays.items():
+            if k.startswith("dc_") or "_cs_" in k or k.endswith("_dc"):
+                (self.set_i32 if v.dtype == np.int32 else self.set_f64)(k, v)
+        self.n_dc = flat.ints["n_dc"]
+        self.n_dc_cond = flat.ints["n_dc_cond"]
 
     # ------------------------------------------------------------------ time cache
     def set_time_params(self, tp: dict[str, np.ndarray]) -> None:
@@ -253,6 +265,23 @@ class OracleModel:
                 continue
             else:
                 self.set_f64(k, v)
+
+    def apply_discrete_control(self, u_reduced, t: float) -> None:
+        ur = _f64(u_reduced)
+        self.L.orc_apply_discrete_control(self.h, _dp(ur), t)
+
+    def discrete_control_state(self):
+        st = np.zeros(max(self.n_dc, 1), dtype=np.int32)
+        tr = np.zeros(max(self.n_dc_cond, 1), dtype=np.int32)
+        cnt = np.zeros(2, dtype=np.int32)
+        self.L.orc_get_dc(self.h, _ip(st), _ip(tr), _ip(cnt))
+        return st[: self.n_dc], tr[: self.n_dc_cond], int(cnt[0]), int(cnt[1])
+
+    def discrete_control_record(self) -> list[tuple[int, int, int]]:
+        """(DiscreteControl index, truth bits, new control state index) per change."""
+        buf = np.zeros(3 * 4096, dtype=np.int32)
+        n = self.L.orc_get_dc_record(self.h, _ip(buf), buf.size)
+        return [tuple(int(x) for x in buf[i:i + 3]) for i in range(0, min(n, buf.size), 3)]
 
     def set_pattern(self, rows_1based, cols_1based) -> None:
         r = _i32(np.asarray(rows_1based) - 1)
@@ -389,6 +418,7 @@ def run_oracle(p, dt: float, t_end: float | None = None, flat=None, abstol: floa
     _, cache = om.rhs(om.reduce(u), 0.0, with_cache=True)
     lv = np.ascontiguousarray(cache["level"])
     om.L.orc_set_level_prev(om.h, _dp(lv))
+    om.apply_discrete_control(om.reduce(u), 0.0)  # callbacks are initialised at t = 0
     tstops = [x for x in p.tstops if x <= t_end]
     ftstops = set(forcing_tstops(p, t_end))
     t = 0.0
@@ -419,4 +449,5 @@ def run_oracle(p, dt: float, t_end: float | None = None, flat=None, abstol: floa
     om.set_time_params(eval_time_params(p, t))
     om.set_f64("fb_incr", np.zeros(len(p.nodes["flow_boundary"]["node_id"])))
     _, cache = om.rhs(om.reduce(u), t, with_cache=True)
+    stats["oracle"] = om
     return u, cache["storage"], cache["level"], stats

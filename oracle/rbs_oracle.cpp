@@ -274,6 +274,11 @@ struct Model {
     double tprev = 0.0;
     double h_override = -1.0;  // >= 0: exact forcing integrates over this sub-step length
     std::vector<double> zlast; double hlast = 0.0;  // last accepted increment (predictor)
+    // DiscreteControl state (core/src/callback.jl:608-696)
+    int n_dc = 0;
+    std::vector<int> dc_truth, dc_state;
+    int dc_changes = 0, dc_undefined = 0;
+    std::vector<int> dc_record;  // (node index, truth bits, new control state) per change
     int merged_exact = 0;  // 1: sum the exact forcing terms first (device association)
     std::vector<Pchip> tabs;
     // colouring of J_intermediate columns
@@ -283,8 +288,8 @@ struct Model {
     std::vector<double> storage_prev, level_prev;
 
     // bound views of the named arrays (rebound by bind() after every set/clone)
-#define RBS_D_FIELDS(X) X(cc_sv_const) X(cc_sv_weight) X(cumulative_drainage) X(cumulative_precipitation) X(cumulative_surface_runoff) X(drainage) X(fb_cumulative_flow) X(fb_incr) X(fb_rate_now) X(fb_rate_step) X(fixed_area) X(infiltration) X(lb_level) X(low_storage_threshold) X(lr_max_flow_rate) X(lr_resistance) X(mn_downstream_bottom) X(mn_length) X(mn_manning_n) X(mn_profile_slope) X(mn_profile_width) X(mn_upstream_bottom) X(pid_derivative) X(pid_integral) X(pid_proportional) X(pid_target) X(potential_evaporation) X(precipitation) X(prof_area) X(prof_cumS) X(prof_dSdh) X(prof_level) X(storage0) X(surface_runoff) X(tab_t) X(tab_u) X(trc_max_downstream_level) X(ud_allocated) X(ud_demand) X(ud_demand_static) X(ud_link_alloc) X(ud_min_level) X(ud_return_factor) X(pump_flow_rate) X(pump_min_flow_rate) X(pump_max_flow_rate) X(pump_min_upstream_level) X(pump_max_downstream_level) X(pump_flow_demand) X(outlet_flow_rate) X(outlet_min_flow_rate) X(outlet_max_flow_rate) X(outlet_min_upstream_level) X(outlet_max_downstream_level) X(outlet_flow_demand)
-#define RBS_I_FIELDS(X) X(bin_idx) X(bin_ptr) X(bin_type) X(bout_idx) X(bout_ptr) X(bout_type) X(cc_sv_idx) X(cc_sv_kind) X(cc_sv_ptr) X(cc_table_idx) X(cc_target_idx) X(cc_target_is_outlet) X(fb_dst_idx) X(fb_dst_type) X(lr_dst_idx) X(lr_dst_type) X(lr_src_idx) X(lr_src_type) X(mn_dst_idx) X(mn_dst_type) X(mn_src_idx) X(mn_src_type) X(pid_listen_basin) X(pid_target_idx) X(pid_target_is_outlet) X(prof_ptr) X(tab_left_linear) X(tab_ptr) X(tab_right_linear) X(trc_dst_idx) X(trc_dst_type) X(trc_src_idx) X(trc_src_type) X(trc_table_idx) X(ud_demand_from_timeseries) X(ud_dst_idx) X(ud_dst_type) X(ud_has_priority) X(ud_link_ptr) X(ud_link_src_idx) X(ud_link_src_type) X(pump_control_type) X(pump_src_type) X(pump_src_idx) X(pump_dst_type) X(pump_dst_idx) X(outlet_control_type) X(outlet_src_type) X(outlet_src_idx) X(outlet_dst_type) X(outlet_dst_idx)
+#define RBS_D_FIELDS(X) X(dc_sv_weight) X(dc_thr_hi) X(dc_thr_lo) X(dc_sv_const) X(pump_cs_flow_rate) X(pump_cs_min_flow_rate) X(pump_cs_max_flow_rate) X(pump_cs_min_upstream_level) X(pump_cs_max_downstream_level) X(outlet_cs_flow_rate) X(outlet_cs_min_flow_rate) X(outlet_cs_max_flow_rate) X(outlet_cs_min_upstream_level) X(outlet_cs_max_downstream_level) X(lr_cs_resistance) X(lr_cs_max_flow_rate) X(cc_sv_const) X(cc_sv_weight) X(cumulative_drainage) X(cumulative_precipitation) X(cumulative_surface_runoff) X(drainage) X(fb_cumulative_flow) X(fb_incr) X(fb_rate_now) X(fb_rate_step) X(fixed_area) X(infiltration) X(lb_level) X(low_storage_threshold) X(lr_max_flow_rate) X(lr_resistance) X(mn_downstream_bottom) X(mn_length) X(mn_manning_n) X(mn_profile_slope) X(mn_profile_width) X(mn_upstream_bottom) X(pid_derivative) X(pid_integral) X(pid_proportional) X(pid_target) X(potential_evaporation) X(precipitation) X(prof_area) X(prof_cumS) X(prof_dSdh) X(prof_level) X(storage0) X(surface_runoff) X(tab_t) X(tab_u) X(trc_max_downstream_level) X(ud_allocated) X(ud_demand) X(ud_demand_static) X(ud_link_alloc) X(ud_min_level) X(ud_return_factor) X(pump_flow_rate) X(pump_min_flow_rate) X(pump_max_flow_rate) X(pump_min_upstream_level) X(pump_max_downstream_level) X(pump_flow_demand) X(outlet_flow_rate) X(outlet_min_flow_rate) X(outlet_max_flow_rate) X(outlet_min_upstream_level) X(outlet_max_downstream_level) X(outlet_flow_demand)
+#define RBS_I_FIELDS(X) X(dc_cond_ptr) X(dc_csv_ptr) X(dc_sv_kind) X(dc_sv_idx) X(dc_logic_ptr) X(dc_logic) X(pump_dc) X(pump_cs_ptr) X(outlet_dc) X(outlet_cs_ptr) X(lr_dc) X(lr_cs_ptr) X(trc_dc) X(trc_cs_ptr) X(trc_cs_table) X(bin_idx) X(bin_ptr) X(bin_type) X(bout_idx) X(bout_ptr) X(bout_type) X(cc_sv_idx) X(cc_sv_kind) X(cc_sv_ptr) X(cc_table_idx) X(cc_target_idx) X(cc_target_is_outlet) X(fb_dst_idx) X(fb_dst_type) X(lr_dst_idx) X(lr_dst_type) X(lr_src_idx) X(lr_src_type) X(mn_dst_idx) X(mn_dst_type) X(mn_src_idx) X(mn_src_type) X(pid_listen_basin) X(pid_target_idx) X(pid_target_is_outlet) X(prof_ptr) X(tab_left_linear) X(tab_ptr) X(tab_right_linear) X(trc_dst_idx) X(trc_dst_type) X(trc_src_idx) X(trc_src_type) X(trc_table_idx) X(ud_demand_from_timeseries) X(ud_dst_idx) X(ud_dst_type) X(ud_has_priority) X(ud_link_ptr) X(ud_link_src_idx) X(ud_link_src_type) X(pump_control_type) X(pump_src_type) X(pump_src_idx) X(pump_dst_type) X(pump_dst_idx) X(outlet_control_type) X(outlet_src_type) X(outlet_src_idx) X(outlet_dst_type) X(outlet_dst_idx)
 #define X(name) double* name = nullptr;
     RBS_D_FIELDS(X)
 #undef X
@@ -309,7 +314,8 @@ struct Model {
         off_trc = o.off_trc; off_pump = o.off_pump; off_outlet = o.off_outlet; off_ud_in = o.off_ud_in;
         off_ud_out = o.off_ud_out; off_lr = o.off_lr; off_manning = o.off_manning; off_evap = o.off_evap;
         off_infil = o.off_infil; off_integral = o.off_integral; n_state = o.n_state; n_reduced = o.n_reduced;
-        level_difference_threshold = o.level_difference_threshold; tprev = o.tprev; h_override = o.h_override; zlast = o.zlast; hlast = o.hlast;
+        level_difference_threshold = o.level_difference_threshold; tprev = o.tprev; h_override = o.h_override; zlast = o.zlast; hlast = o.hlast; n_dc = o.n_dc; dc_truth = o.dc_truth; dc_state = o.dc_state;
+        dc_changes = o.dc_changes; dc_undefined = o.dc_undefined; dc_record = o.dc_record;
         merged_exact = o.merged_exact; tabs = o.tabs; color_of_col = o.color_of_col; n_colors = o.n_colors;
         pat_rows = o.pat_rows; pat_cols = o.pat_cols; storage_prev = o.storage_prev; level_prev = o.level_prev;
         lu = o.lu; lu_ready = o.lu_ready;
@@ -335,6 +341,9 @@ struct Model {
         n_outlet = cnt("n_outlet"); n_ud = cnt("n_ud"); n_lr = cnt("n_lr");
         n_manning = cnt("n_manning"); n_pid = cnt("n_pid"); n_cc = cnt("n_cc");
         n_lb = cnt("n_lb"); n_fb = cnt("n_fb"); n_prio = cnt("n_prio");
+        n_dc = cnt("n_dc");
+        dc_truth.assign(n_dc ? I("dc_cond_ptr")[n_dc] : 0, 0);
+        dc_state.assign(n_dc, -1);
         n_ud_link = n_ud ? I("ud_link_ptr")[n_ud] : 0;
         // state_components order, core/src/parameter.jl:11-22
         off_trc = 0; off_pump = off_trc + n_trc; off_outlet = off_pump + n_pump;
@@ -927,6 +936,80 @@ void limit_flow(const Model& m, double* u, const double* uprev, double dt, doubl
 }
 
 // ------------------------------------------------------------------------------------------
+// DiscreteControl — apply_discrete_control! / set_new_control_state! / set_control_params!
+// (core/src/callback.jl:608-786).  `flow` holds du-like values per state (the RHS at t = 0, the
+// mean flow (u - uprev)/h after an accepted implicit-Euler step: what get_du returns).
+// ------------------------------------------------------------------------------------------
+void dc_write_params(Model& m) {
+    for (int k = 0; k < m.n_pump; k++) {
+        int d = m.pump_dc ? m.pump_dc[k] : -1;
+        if (d < 0 || m.dc_state[d] < 0) continue;
+        int row = m.pump_cs_ptr[k] + m.dc_state[d];
+        m.pump_flow_rate[k] = m.pump_cs_flow_rate[row];
+        m.pump_min_flow_rate[k] = m.pump_cs_min_flow_rate[row];
+        m.pump_max_flow_rate[k] = m.pump_cs_max_flow_rate[row];
+        m.pump_min_upstream_level[k] = m.pump_cs_min_upstream_level[row];
+        m.pump_max_downstream_level[k] = m.pump_cs_max_downstream_level[row];
+    }
+    for (int k = 0; k < m.n_outlet; k++) {
+        int d = m.outlet_dc ? m.outlet_dc[k] : -1;
+        if (d < 0 || m.dc_state[d] < 0) continue;
+        int row = m.outlet_cs_ptr[k] + m.dc_state[d];
+        m.outlet_flow_rate[k] = m.outlet_cs_flow_rate[row];
+        m.outlet_min_flow_rate[k] = m.outlet_cs_min_flow_rate[row];
+        m.outlet_max_flow_rate[k] = m.outlet_cs_max_flow_rate[row];
+        m.outlet_min_upstream_level[k] = m.outlet_cs_min_upstream_level[row];
+        m.outlet_max_downstream_level[k] = m.outlet_cs_max_downstream_level[row];
+    }
+    for (int k = 0; k < m.n_lr; k++) {
+        int d = m.lr_dc ? m.lr_dc[k] : -1;
+        if (d < 0 || m.dc_state[d] < 0) continue;
+        int row = m.lr_cs_ptr[k] + m.dc_state[d];
+        m.lr_resistance[k] = m.lr_cs_resistance[row];
+        m.lr_max_flow_rate[k] = m.lr_cs_max_flow_rate[row];
+    }
+    for (int k = 0; k < m.n_trc; k++) {
+        int d = m.trc_dc ? m.trc_dc[k] : -1;
+        if (d < 0 || m.dc_state[d] < 0) continue;
+        const_cast<int32_t*>(m.trc_table_idx)[k] = m.trc_cs_table[m.trc_cs_ptr[k] + m.dc_state[d]];
+    }
+}
+
+void apply_discrete_control(Model& m, const Cache<double>& c, const double* flow, bool initial) {
+    bool any = false;
+    for (int i = 0; i < m.n_dc; i++) {
+        int c0 = m.dc_cond_ptr[i], c1 = m.dc_cond_ptr[i + 1];
+        int bits = 0;
+        bool change = false;
+        for (int cd = c0; cd < c1; cd++) {
+            double value = 0.0;
+            for (int j = m.dc_csv_ptr[cd]; j < m.dc_csv_ptr[cd + 1]; j++) {
+                int kind = m.dc_sv_kind[j], idx = m.dc_sv_idx[j];
+                double x;
+                if (kind == SV_BASIN_LEVEL) x = c.level[idx];
+                else if (kind == SV_BASIN_STORAGE) x = c.storage[idx];
+                else if (kind == SV_DU_STATE) x = flow[idx];
+                else x = m.dc_sv_const[j];
+                value += m.dc_sv_weight[j] * x;
+            }
+            int told = m.dc_truth[cd];
+            int tnew = told ? (value >= m.dc_thr_lo[cd]) : (value > m.dc_thr_hi[cd]);
+            if (tnew != told) { change = true; m.dc_truth[cd] = tnew; }
+            bits |= tnew << (cd - c0);
+        }
+        if (initial || change) {
+            int snew = m.dc_logic[m.dc_logic_ptr[i] + bits];
+            if (snew < 0) m.dc_undefined++;
+            else if (snew != m.dc_state[i]) {
+                m.dc_state[i] = snew; m.dc_changes++; any = true;
+                m.dc_record.push_back(i); m.dc_record.push_back(bits); m.dc_record.push_back(snew);
+            }
+        }
+    }
+    if (any) dc_write_params(m);
+}
+
+// ------------------------------------------------------------------------------------------
 // Implicit Euler with NLNewton (OrdinaryDiffEq, third-party; semantics as recalled in SURVEY
 // §8(c)): z0 = 0, gamma = 1, W = J - I/h, solve W dz = (h f(uprev+z) - z)/h, z <- z - dz,
 // kappa = 1/100, max_iter = 10.  `full_newton = 0` evaluates J and W once per (sub-)step at
@@ -1047,6 +1130,7 @@ int advance(Model& m, double* u, double t0, double dt, const AdvanceOpts& o, dou
     std::vector<double> uprev(n), uprop(n);
     std::vector<double> fb_full(m.fb_incr, m.fb_incr + m.n_fb);
     bool have_rate = m.fb_rate_step != nullptr && m.n_fb > 0;
+    if (m.n_dc > 0) dc_write_params(m);  // the host may have refreshed the shared parameters
     double h_min = std::ldexp(dt, -o.max_halvings);
     double h_nom = std::min(*h_try > 0 ? *h_try : dt, dt);
     double elapsed = 0.0;
@@ -1077,6 +1161,11 @@ int advance(Model& m, double* u, double t0, double dt, const AdvanceOpts& o, dou
             m.zlast.resize(n);
             for (int i = 0; i < n; i++) m.zlast[i] = uprop[i] - uprev[i];
             m.hlast = h;
+            if (m.n_dc > 0) {
+                std::vector<double> flow(n);
+                for (int i = 0; i < n; i++) flow[i] = m.zlast[i] / h;
+                apply_discrete_control(m, w.c, flow.data(), false);
+            }
             // update_cumulative_flows! — core/src/callback.jl:125-182
             auto& fa = m.fixed_area;
             for (int i = 0; i < m.n_basin; i++) {
@@ -1193,6 +1282,28 @@ int orc_step(void* h, double* u, double t, double dt, double abstol, double relt
     if (converged) *converged = st.converged;
     if (negative_storage) *negative_storage = st.negative_storage;
     return rc;
+}
+
+// DiscreteControl at t = 0 on the state `ur` (RHS flows of that state); out: control states
+void orc_apply_discrete_control(void* h, const double* ur, double t) {
+    Model& m = *(Model*)h;
+    Cache<double> c; c.resize(m);
+    std::vector<double> du(m.n_state);
+    water_balance(m, c, ur, t, du.data());
+    apply_discrete_control(m, c, du.data(), true);
+}
+void orc_get_dc(void* h, int32_t* state, int32_t* truth, int32_t* counts2) {
+    Model& m = *(Model*)h;
+    for (int i = 0; i < m.n_dc; i++) state[i] = m.dc_state[i];
+    for (size_t i = 0; i < m.dc_truth.size(); i++) truth[i] = m.dc_truth[i];
+    counts2[0] = m.dc_changes; counts2[1] = m.dc_undefined;
+}
+
+int orc_get_dc_record(void* h, int32_t* out, int max_entries) {
+    Model& m = *(Model*)h;
+    int n = std::min((int)m.dc_record.size(), max_entries);
+    for (int i = 0; i < n; i++) out[i] = m.dc_record[i];
+    return (int)m.dc_record.size();
 }
 
 // sub-stepping implicit Euler: opts = {abstol, reltol, max_iter, full_newton, grow_iters,

@@ -181,6 +181,15 @@ void bind_net(rbs_handle* h) {
     S_I(cc_target_is_outlet); S_I(cc_target_idx); S_I(cc_target_state); S_I(cc_sv_ptr);
     S_I(cc_sv_kind); S_I(cc_sv_idx); S_D(cc_sv_weight);
     S_I(cc_term_ptr); S_I(cc_term_kind); S_I(cc_term_sv); S_I(cc_term_src); S_I(cc_term_dst);
+    S_I(dc_cond_ptr); S_I(dc_csv_ptr); S_I(dc_sv_kind); S_I(dc_sv_idx); S_I(dc_logic_ptr); S_I(dc_logic);
+    S_D(dc_sv_weight); S_D(dc_thr_hi); S_D(dc_thr_lo); S_D(dc_sv_const);
+    S_I(pump_dc); S_I(pump_cs_ptr); S_I(outlet_dc); S_I(outlet_cs_ptr); S_I(lr_dc); S_I(lr_cs_ptr);
+    S_I(trc_dc); S_I(trc_cs_ptr); S_I(trc_cs_table);
+    S_D(pump_cs_flow_rate); S_D(pump_cs_min_flow_rate); S_D(pump_cs_max_flow_rate);
+    S_D(pump_cs_min_upstream_level); S_D(pump_cs_max_downstream_level);
+    S_D(outlet_cs_flow_rate); S_D(outlet_cs_min_flow_rate); S_D(outlet_cs_max_flow_rate);
+    S_D(outlet_cs_min_upstream_level); S_D(outlet_cs_max_downstream_level);
+    S_D(lr_cs_resistance); S_D(lr_cs_max_flow_rate);
     S_I(jrow_ptr); S_I(jcol); S_I(jpos_src); S_I(jpos_dst); S_I(ud_out_jpos);
     S_I(wsrc_ptr); S_I(wsrc_pos); S_I(wdiag_flag); S_D(wsrc_sign);
     S_I(lu_wsrc); S_I(lu_pivot); S_I(lu_prod_ptr); S_I(lu_prod_l); S_I(lu_prod_u); S_I(lu_diag);
@@ -197,6 +206,7 @@ void bind_net(rbs_handle* h) {
     M_I(nstat); M_I(status); M_I(active_count);
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
     M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep);
+    M_I(dc_truth); M_I(dc_state); M_I(cnt_dc);
 #undef M_I
 #undef S_D
 #undef S_I
@@ -409,7 +419,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     GI(n_outlet); GI(n_ud); GI(n_ud_link); GI(n_lr); GI(n_manning); GI(n_lb); GI(n_fb); GI(n_cc);
     GI(n_tab); GI(off_trc); GI(off_pump); GI(off_outlet); GI(off_ud_in); GI(off_ud_out); GI(off_lr);
     GI(off_manning); GI(off_evap); GI(off_infil); GI(off_integral); GI(nnz_j); GI(nnz_w); GI(n_lu);
-    GI(cc_tab_offset);
+    GI(cc_tab_offset); GI(n_dc); GI(n_dc_cond);
 #undef GI
     {
         auto it = b->d.find("level_difference_threshold");
@@ -430,6 +440,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         {"ud_alloc_total", n.n_ud, 0},
         {"pid_target", n.n_pid, 0}, {"pid_proportional", n.n_pid, 0}, {"pid_integral", n.n_pid, 0},
         {"pid_derivative", n.n_pid, 0},
+        {"dc_thr_hi", n.n_dc_cond, inf}, {"dc_thr_lo", n.n_dc_cond, inf},
     };
     for (auto& pd : pds)
         if (h->shared.find(pd.key) == h->shared.end())
@@ -438,6 +449,10 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         if (upload(h, "trc_table_idx", std::vector<int32_t>((size_t)n.n_trc, 0), true)) return bail("param alloc");
     if (h->shared.find("ud_demand_from_timeseries") == h->shared.end())
         if (upload(h, "ud_demand_from_timeseries", std::vector<int32_t>((size_t)n.n_ud, 0), true)) return bail("param alloc");
+    if (h->shared.find("dc_sv_const") == h->shared.end()) {
+        size_t nsv = h->hi.count("dc_sv_kind") ? h->hi["dc_sv_kind"].size() : 0;
+        if (upload(h, "dc_sv_const", std::vector<double>(nsv, 0.0), false)) return bail("param alloc");
+    }
     if (h->shared.find("cc_sv_const") == h->shared.end()) {
         size_t nsv = h->hi.count("cc_sv_kind") ? h->hi["cc_sv_kind"].size() : 0;
         if (upload(h, "cc_sv_const", std::vector<double>(nsv, 0.0), false)) return bail("param alloc");
@@ -462,8 +477,12 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
     for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mneg2", "mclamp", "mlast",
-                          "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep"})
+                          "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep", "cnt_dc"})
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
+    if (alloc_member(h, "dc_truth", n.n_dc_cond, true) || alloc_member(h, "dc_state", n.n_dc, true))
+        return bail("member alloc");
+    // no control state set yet
+    cudaMemsetAsync(h->member["dc_state"].p, 0xFF, h->member["dc_state"].bytes, h->stream);
     {
         DevArr a; a.bytes = sizeof(int); a.is_int = true;
         if (cudaMalloc(&a.p, a.bytes) != cudaSuccess) return bail("active_count alloc");
@@ -745,6 +764,25 @@ int rbs_copy_member_to_device(rbs_handle* h, const char* key, void* dst_device, 
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
+int rbs_get_member_i32(rbs_handle* h, const char* key, int32_t* host, int64_t n_entity) {
+    if (!h || !key || !host) return fail("rbs_get_member_i32: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || !it->second.is_int) return fail(std::string("unknown int member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(host, it->second.p, (size_t)n_entity * h->B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int rbs_apply_discrete_control(rbs_handle* h) {
+    if (!h) return fail("rbs_apply_discrete_control: null handle");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    if (n.n_dc > 0) LAUNCH(h, k_discrete_control, (long long)n.n_dc * n.B, n, 1);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_apply_discrete_control");
+}
 int rbs_set_tprev(rbs_handle* h, double tprev) {
     if (!h) return fail("rbs_set_tprev: null handle");
     h->tprev = tprev;
@@ -982,6 +1020,7 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, 2);
         LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps, h->shrink_log2);
         LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
+        if (n.n_dc > 0) LAUNCH(h, k_discrete_control, (long long)n.n_dc * B, n, 0);
     }
     // Newton half
     n.NA = G.n_active;

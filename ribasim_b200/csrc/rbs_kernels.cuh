@@ -30,6 +30,7 @@ struct Net {
     int off_trc, off_pump, off_outlet, off_ud_in, off_ud_out, off_lr, off_manning, off_evap,
         off_infil, off_integral;
     int nnz_j, nnz_w, n_lu;
+    int n_dc, n_dc_cond;
     double ldt;  // level_difference_threshold
     // basins (shared)
     const double *storage0, *low_storage_threshold, *fixed_area;
@@ -90,6 +91,17 @@ struct Net {
     int *nstat, *status, *active_count;
     double* storage_prev;  // limiter memory (basin.storage_prev, frozen: SURVEY row 22)
     double* level_prev;
+    // DiscreteControl (shared structure, per-member truth and control states)
+    const int *dc_cond_ptr, *dc_csv_ptr, *dc_sv_kind, *dc_sv_idx, *dc_logic_ptr, *dc_logic;
+    const double *dc_sv_weight, *dc_thr_hi, *dc_thr_lo, *dc_sv_const;
+    const int *pump_dc, *pump_cs_ptr, *outlet_dc, *outlet_cs_ptr, *lr_dc, *lr_cs_ptr, *trc_dc,
+        *trc_cs_ptr, *trc_cs_table;
+    const double *pump_cs_flow_rate, *pump_cs_min_flow_rate, *pump_cs_max_flow_rate,
+        *pump_cs_min_upstream_level, *pump_cs_max_downstream_level;
+    const double *outlet_cs_flow_rate, *outlet_cs_min_flow_rate, *outlet_cs_max_flow_rate,
+        *outlet_cs_min_upstream_level, *outlet_cs_max_downstream_level;
+    const double *lr_cs_resistance, *lr_cs_max_flow_rate;
+    int *dc_truth, *dc_state, *cnt_dc;
     // per-member sub-stepping state machine (rbs_step.cuh)
     int *mphase, *mjac, *miter, *mconv, *mneg, *mneg2, *mclamp, *mlast, *maction;
     int *cnt_iters, *cnt_sub, *cnt_rej;
@@ -116,6 +128,20 @@ template <bool JAC> __device__ __forceinline__ bool rbs_skip(const Pred& p, int 
 #define RBS_MEMBER(n, j) ((n).alist ? (n).alist[(j)] : (j))
 
 struct RbsEnd { double h, f, dh, df; };
+
+// Row of the control-state parameter table that applies to node k for member m, or -1 when the
+// node is not under DiscreteControl (or no control state has been set yet): the shared static /
+// time-dependent parameter applies.  Replaces the reference's in-place parameter swap
+// (`set_control_params!`, core/src/callback.jl:765-786), which cannot be per ensemble member.
+__device__ __forceinline__ int rbs_dc_row(const Net& n, const int* __restrict__ dc_of,
+                                          const int* __restrict__ cs_ptr, int k, int m) {
+    if (n.n_dc == 0) return -1;
+    int d = dc_of[k];
+    if (d < 0) return -1;
+    int st = n.dc_state[(long long)d * n.B + m];
+    return st < 0 ? -1 : cs_ptr[k] + st;
+}
+#define RBS_P(row, cs_arr, shared_arr, k) ((row) >= 0 ? (cs_arr)[(row)] : (shared_arr)[(k)])
 
 template <bool JAC>
 __device__ __forceinline__ RbsEnd rbs_fetch_end(const Net& n, int kind, int idx, int m) {
@@ -314,28 +340,38 @@ __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* _
         controlled = control != CONTROL_NONE;
         RbsEnd a = rbs_fetch_end<JAC>(n, n.src_kind[s], n.src_idx[s], m);
         RbsEnd b = rbs_fetch_end<JAC>(n, n.dst_kind[s], n.dst_idx[s], m);
+        int row = outlet ? rbs_dc_row(n, n.outlet_dc, n.outlet_cs_ptr, k, m)
+                         : rbs_dc_row(n, n.pump_dc, n.pump_cs_ptr, k, m);
         double fr = controlled ? (outlet ? n.fro : n.frp)[(long long)k * n.B + m]
-                               : (outlet ? n.outlet_flow_rate : n.pump_flow_rate)[k];
+                               : (outlet ? RBS_P(row, n.outlet_cs_flow_rate, n.outlet_flow_rate, k)
+                                         : RBS_P(row, n.pump_cs_flow_rate, n.pump_flow_rate, k));
         q = rbs_pump_outlet_flow(
             fr, a.h, b.h, a.f, a.dh, b.dh, a.df,
-            (outlet ? n.outlet_min_flow_rate : n.pump_min_flow_rate)[k],
-            (outlet ? n.outlet_max_flow_rate : n.pump_max_flow_rate)[k],
+            outlet ? RBS_P(row, n.outlet_cs_min_flow_rate, n.outlet_min_flow_rate, k)
+                   : RBS_P(row, n.pump_cs_min_flow_rate, n.pump_min_flow_rate, k),
+            outlet ? RBS_P(row, n.outlet_cs_max_flow_rate, n.outlet_max_flow_rate, k)
+                   : RBS_P(row, n.pump_cs_max_flow_rate, n.pump_max_flow_rate, k),
             (outlet ? n.outlet_flow_demand : n.pump_flow_demand)[k],
-            (outlet ? n.outlet_min_upstream_level : n.pump_min_upstream_level)[k],
-            (outlet ? n.outlet_max_downstream_level : n.pump_max_downstream_level)[k], n.ldt,
-            outlet, g_fr, dq_a, dq_b);
+            outlet ? RBS_P(row, n.outlet_cs_min_upstream_level, n.outlet_min_upstream_level, k)
+                   : RBS_P(row, n.pump_cs_min_upstream_level, n.pump_min_upstream_level, k),
+            outlet ? RBS_P(row, n.outlet_cs_max_downstream_level, n.outlet_max_downstream_level, k)
+                   : RBS_P(row, n.pump_cs_max_downstream_level, n.pump_max_downstream_level, k),
+            n.ldt, outlet, g_fr, dq_a, dq_b);
     } else {
         RbsEnd a = rbs_fetch_end<JAC>(n, n.src_kind[s], n.src_idx[s], m);
         RbsEnd b = rbs_fetch_end<JAC>(n, n.dst_kind[s], n.dst_idx[s], m);
         if (ct == CT_LR) {
-            q = rbs_lr_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df, n.lr_resistance[k],
-                            n.lr_max_flow_rate[k], dq_a, dq_b);
+            int row = rbs_dc_row(n, n.lr_dc, n.lr_cs_ptr, k, m);
+            q = rbs_lr_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df,
+                            RBS_P(row, n.lr_cs_resistance, n.lr_resistance, k),
+                            RBS_P(row, n.lr_cs_max_flow_rate, n.lr_max_flow_rate, k), dq_a, dq_b);
         } else if (ct == CT_MANNING) {
             q = rbs_manning_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df, n.mn_length[k],
                                  n.mn_manning_n[k], n.mn_profile_width[k], n.mn_profile_slope[k],
                                  n.mn_upstream_bottom[k], n.mn_downstream_bottom[k], dq_a, dq_b, JAC);
         } else {  // CT_TRC
-            int tb = n.trc_table_idx[k];
+            int row = rbs_dc_row(n, n.trc_dc, n.trc_cs_ptr, k, m);
+            int tb = row >= 0 ? n.trc_cs_table[row] : n.trc_table_idx[k];
             int t0 = n.tab_ptr[tb], tn = n.tab_ptr[tb + 1] - t0;
             double dQ;
             double Q = rbs_pchip_eval(a.h, tn, n.tab_t + t0, n.tab_u + t0, n.tab_du + t0,
@@ -1021,9 +1057,24 @@ __device__ __forceinline__ bool rbs_flow_bounds(const Net& n, int s, int m,
     if (s < n.n_conn) {
         int ct = n.conn_type[s], k = n.conn_idx[s];
         if (ct == CT_TRC) { lo = 0.0; hi = RBS_INF; return true; }
-        if (ct == CT_PUMP) { lo = n.pump_min_flow_rate[k]; hi = n.pump_max_flow_rate[k]; return true; }
-        if (ct == CT_OUTLET) { lo = n.outlet_min_flow_rate[k]; hi = n.outlet_max_flow_rate[k]; return true; }
-        if (ct == CT_LR) { hi = n.lr_max_flow_rate[k]; lo = -hi; return true; }
+        if (ct == CT_PUMP) {
+            int row = rbs_dc_row(n, n.pump_dc, n.pump_cs_ptr, k, m);
+            lo = RBS_P(row, n.pump_cs_min_flow_rate, n.pump_min_flow_rate, k);
+            hi = RBS_P(row, n.pump_cs_max_flow_rate, n.pump_max_flow_rate, k);
+            return true;
+        }
+        if (ct == CT_OUTLET) {
+            int row = rbs_dc_row(n, n.outlet_dc, n.outlet_cs_ptr, k, m);
+            lo = RBS_P(row, n.outlet_cs_min_flow_rate, n.outlet_min_flow_rate, k);
+            hi = RBS_P(row, n.outlet_cs_max_flow_rate, n.outlet_max_flow_rate, k);
+            return true;
+        }
+        if (ct == CT_LR) {
+            int row = rbs_dc_row(n, n.lr_dc, n.lr_cs_ptr, k, m);
+            hi = RBS_P(row, n.lr_cs_max_flow_rate, n.lr_max_flow_rate, k);
+            lo = -hi;
+            return true;
+        }
         if (ct == CT_UD_IN) {
             int i = n.ud_of_link[k];
             if (from_ts[i]) { lo = 0.0; hi = RBS_INF; return true; }
@@ -1344,6 +1395,48 @@ __global__ void k_step_apply(Net n, int predictor) {
         return;
     }
     rbs_exact_update(n, ent - n.n_state, m, action == ACTION_ACCEPT, hl, next, h_next);
+}
+
+// ---- DiscreteControl (apply_discrete_control!, core/src/callback.jl:608-661) ----------------------
+// One thread per (DiscreteControl node, member), after an accepted (sub-)step of that member:
+// compound variables -> hysteresis conditions -> truth state -> control state.  Flows are the
+// mean flows of the accepted step (u - uprev)/h, which is what get_du holds after an implicit
+// Euler step; with `initial` (t = 0) the RHS du of the initial state is used and the control
+// state is set even without a truth-state change.
+__global__ void k_discrete_control(Net n, int initial) {
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.NA);
+    if (i >= n.n_dc) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
+    if (!initial && n.maction[m] != ACTION_ACCEPT) return;
+    double inv_h = (!initial && n.mhlast[m] > 0.0) ? 1.0 / n.mhlast[m] : 0.0;
+    int c0 = n.dc_cond_ptr[i], c1 = n.dc_cond_ptr[i + 1];
+    int bits = 0;
+    bool change = false;
+    for (int c = c0; c < c1; c++) {
+        double value = 0.0;
+        for (int j = n.dc_csv_ptr[c]; j < n.dc_csv_ptr[c + 1]; j++) {
+            int kind = n.dc_sv_kind[j], idx = n.dc_sv_idx[j];
+            double x;
+            if (kind == 0) x = n.level[(long long)idx * n.B + m];
+            else if (kind == 1) x = n.storage[(long long)idx * n.B + m];
+            else if (kind == 2) x = initial ? n.du[(long long)idx * n.B + m]
+                                            : n.zlast[(long long)idx * n.B + m] * inv_h;
+            else x = n.dc_sv_const[j];
+            value += n.dc_sv_weight[j] * x;
+        }
+        long long o = (long long)c * n.B + m;
+        int told = n.dc_truth[o];
+        int tnew = told ? (value >= n.dc_thr_lo[c]) : (value > n.dc_thr_hi[c]);
+        if (tnew != told) { change = true; n.dc_truth[o] = tnew; }
+        bits |= tnew << (c - c0);
+    }
+    if (initial || change) {
+        int snew = n.dc_logic[n.dc_logic_ptr[i] + bits];
+        long long so = (long long)i * n.B + m;
+        if (snew < 0) atomicOr(&n.status[m], 4);  // no control state specified for this truth state
+        else if (snew != n.dc_state[so]) { n.dc_state[so] = snew; atomicAdd(&n.cnt_dc[m], 1); }
+    }
 }
 
 __global__ void k_fill(double* p, long long nelem, double v) {

@@ -54,6 +54,7 @@ class Flat:
     # J_intermediate pattern in CSR (row = state) and CSC order (for golden tests)
     jac_rows_csc: np.ndarray | None = None
     jac_cols_csc: np.ndarray | None = None
+    dc_state_names: list | None = None
 
     def __getitem__(self, k: str):
         if k in self.arrays:
@@ -242,8 +243,110 @@ def flatten(p: Params) -> Flat:
     _, A["cc_sv_idx"] = _ragged(sv_idx, np.int32)
     _, A["cc_sv_weight"] = _ragged(sv_w, np.float64)
 
+    _flatten_discrete_control(p, f)
     _build_patterns(p, f)
     return f
+
+
+def _flatten_discrete_control(p: Params, f: Flat) -> None:
+    """DiscreteControl (core/src/callback.jl:596-696) for per-member evaluation on the device.
+
+    Conditions are numbered DC node by DC node in truth-state order (compound variable, then
+    condition); a truth state is the bit pattern `sum(truth[j] << j)`; `dc_logic` maps it to the
+    index of the control state in the node's own list of state names (-1: undefined).  Every
+    controlled node gets one parameter row per control state of its DiscreteControl node."""
+    n = p.nodes
+    A = f.arrays
+    dc = n["discrete_control"]
+    n_dc = len(dc["node_id"])
+    f.ints["n_dc"] = n_dc
+    cond_ptr = [0]
+    csv_ptr = [0]
+    sv_kind: list[int] = []
+    sv_idx: list[int] = []
+    sv_w: list[float] = []
+    logic_ptr = [0]
+    logic: list[int] = []
+    state_names: list[list[str]] = []
+    for i in range(n_dc):
+        n_cond = 0
+        for cv in dc["compound_variables"][i]:
+            for _ in cv["threshold_high"]:
+                for sv in cv["subvariables"]:
+                    sv_kind.append(sv["kind"])
+                    sv_idx.append(sv["idx"])
+                    sv_w.append(sv["weight"])
+                csv_ptr.append(len(sv_kind))
+                n_cond += 1
+        cond_ptr.append(cond_ptr[-1] + n_cond)
+        lm = dc["logic_mapping"][i]
+        names = sorted(set(lm.values()))
+        state_names.append(names)
+        table = [-1] * (1 << n_cond)
+        for truth, cs in lm.items():
+            bits = sum(1 << j for j, b in enumerate(truth) if b)
+            table[bits] = names.index(cs)
+        logic.extend(table)
+        logic_ptr.append(len(logic))
+    f.ints["n_dc_cond"] = cond_ptr[-1]
+    A["dc_cond_ptr"] = as_i32(cond_ptr)
+    A["dc_csv_ptr"] = as_i32(csv_ptr)
+    A["dc_sv_kind"] = as_i32(sv_kind)
+    A["dc_sv_idx"] = as_i32(sv_idx)
+    A["dc_sv_weight"] = as_f64(sv_w)
+    A["dc_logic_ptr"] = as_i32(logic_ptr)
+    A["dc_logic"] = as_i32(logic)
+    A["dc_n_states"] = as_i32([len(x) for x in state_names])
+    f.dc_state_names = state_names
+
+    dc_of: dict[int, int] = {}
+    for i, targets in enumerate(dc["controlled_nodes"]):
+        for tnode in targets:
+            dc_of[tnode.value] = i
+
+    def rows(key: str, fields: list[str], base: dict[str, np.ndarray]):
+        d = n[key]
+        ctrl, ptr = [], [0]
+        vals = {fl: [] for fl in fields}
+        cm = d.get("control_mapping", {})
+        for k, nid in enumerate(d["node_id"]):
+            i = dc_of.get(nid.value, -1)
+            ctrl.append(i)
+            if i >= 0:
+                for cs in state_names[i]:
+                    upd = cm.get((nid.value, cs), {})
+                    for fl in fields:
+                        vals[fl].append(float(upd[fl]) if fl in upd else float(base[fl][k]))
+            ptr.append(len(vals[fields[0]]))
+        return as_i32(ctrl), as_i32(ptr), {fl: as_f64(v) for fl, v in vals.items()}
+
+    for key, pre in (("pump", "pump"), ("outlet", "outlet")):
+        d = n[key]
+        base = dict(
+            flow_rate=np.asarray(d["flow_rate"], dtype=np.float64),
+            min_flow_rate=np.array([s(0.0) for s in d["min_flow_rate"]]),
+            max_flow_rate=np.array([s(0.0) for s in d["max_flow_rate"]]),
+            min_upstream_level=np.array([s(0.0) for s in d["min_upstream_level"]]),
+            max_downstream_level=np.array([s(0.0) for s in d["max_downstream_level"]]),
+        )
+        ctrl, ptr, vals = rows(key, list(base), base)
+        A[f"{pre}_dc"], A[f"{pre}_cs_ptr"] = ctrl, ptr
+        for fl, v in vals.items():
+            A[f"{pre}_cs_{fl}"] = v
+    lr = n["linear_resistance"]
+    ctrl, ptr, vals = rows("linear_resistance", ["resistance", "max_flow_rate"],
+                           dict(resistance=lr["resistance"], max_flow_rate=lr["max_flow_rate"]))
+    A["lr_dc"], A["lr_cs_ptr"] = ctrl, ptr
+    A["lr_cs_resistance"], A["lr_cs_max_flow_rate"] = vals["resistance"], vals["max_flow_rate"]
+    trc = n["tabulated_rating_curve"]
+    base_tab = np.array([float(s(0.0)) for s in trc["current_interpolation_index"]])
+    ctrl, ptr, vals = rows("tabulated_rating_curve", ["table"], dict(table=base_tab))
+    A["trc_dc"], A["trc_cs_ptr"] = ctrl, ptr
+    A["trc_cs_table"] = as_i32(vals["table"] - 1)  # 0-based table index
+    for key in ("manning_resistance", "pid_control"):
+        for nid in n[key]["node_id"]:
+            if nid.value in dc_of:
+                raise NotImplementedError(f"DiscreteControl of {nid} is not supported yet")
 
 
 def _node_state(p: Params, nid: NodeID, inflow: bool) -> int | None:

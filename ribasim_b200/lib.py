@@ -81,6 +81,8 @@ def load() -> ctypes.CDLL:
         "rbs_set_member_f64": (ctypes.c_int, [vp, cp, dp, i64, i32]),
         "rbs_get_member_f64": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
+        "rbs_get_member_i32": (ctypes.c_int, [vp, cp, ip, i64]),
+        "rbs_apply_discrete_control": (ctypes.c_int, [vp]),
         "rbs_set_tprev": (ctypes.c_int, [vp, f64]),
         "rbs_reduce": (ctypes.c_int, [vp, dp, dp]),
         "rbs_rhs": (ctypes.c_int, [vp, dp, f64, dp, dp, dp, dp, dp]),
@@ -113,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64",
-    "rbs_copy_member_to_device", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
+    "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
     "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
 ]
@@ -151,7 +153,7 @@ PARAM_F64 = [
     "outlet_flow_rate", "outlet_min_flow_rate", "outlet_max_flow_rate",
     "outlet_min_upstream_level", "outlet_max_downstream_level", "outlet_flow_demand",
     "ud_total_demand", "ud_return_factor", "pid_target", "pid_proportional", "pid_integral",
-    "pid_derivative", "cc_sv_const",
+    "pid_derivative", "cc_sv_const", "dc_thr_hi", "dc_thr_lo", "dc_sv_const",
 ]
 PARAM_I32 = ["trc_table_idx"]
 
@@ -273,6 +275,14 @@ class Handle:
 
     def stream_ptr(self) -> int:
         return int(self.L.rbs_stream(self.h) or 0)
+
+    def get_member_i32(self, key: str, n_entity: int) -> np.ndarray:
+        out = np.empty((n_entity, self.B), dtype=np.int32)
+        _check(self.L.rbs_get_member_i32(self.h, key.encode(), _ip(out.reshape(-1)), n_entity))
+        return out
+
+    def apply_discrete_control(self) -> None:
+        _check(self.L.rbs_apply_discrete_control(self.h))
 
     def set_tprev(self, t: float) -> None:
         _check(self.L.rbs_set_tprev(self.h, float(t)))

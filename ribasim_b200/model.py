@@ -83,6 +83,11 @@ class Model:
         self.h.refresh(0.0)
         nb = self.flat.ints["n_basin"]
         self.h.set_member("level_prev", self.h.get_member("level", nb))
+        # callbacks are initialised at t = 0: DiscreteControl sets the first control states
+        # (core/src/callback.jl:631-634), then the caches are refreshed with them
+        if self.flat.ints["n_dc"] > 0:
+            self.h.apply_discrete_control()
+            self.h.refresh(0.0)
         self.status_counts = dict(newton_failed=0, negative_storage=0)
 
     # ------------------------------------------------------------------ forcing / parameters
@@ -208,6 +213,11 @@ class Model:
 
     def u(self) -> np.ndarray:
         return self.h.get_member("u", self.flat.ints["n_state"])
+
+    def control_state(self) -> np.ndarray:
+        """Control state index per DiscreteControl node and member (-1 = none); the names are
+        `flat.dc_state_names[i]`."""
+        return self.h.get_member_i32("dc_state", self.flat.ints["n_dc"])
 
     def flow(self) -> np.ndarray:
         return self.h.get_member("du", self.flat.ints["n_state"])

@@ -88,6 +88,20 @@ def eval_time_params(p: Params, t: float) -> dict[str, np.ndarray]:
         for sv in cvars:
             consts.append(sv["series"](t + sv["look_ahead"]) if sv["kind"] == SV_CONSTANT else 0.0)
     out["cc_sv_const"] = np.array(consts, dtype=np.float64)
+
+    # DiscreteControl: thresholds at t and boundary sub-variables at t + look_ahead, in the
+    # condition order of flatten._flatten_discrete_control
+    hi, lo, dconst = [], [], []
+    for cvars in n["discrete_control"]["compound_variables"]:
+        for cv in cvars:
+            for th, tl in zip(cv["threshold_high"], cv["threshold_low"]):
+                hi.append(th(t))
+                lo.append(tl(t))
+                for sv in cv["subvariables"]:
+                    dconst.append(sv["series"](t + sv["look_ahead"]) if sv["kind"] == SV_CONSTANT else 0.0)
+    out["dc_thr_hi"] = np.array(hi, dtype=np.float64)
+    out["dc_thr_lo"] = np.array(lo, dtype=np.float64)
+    out["dc_sv_const"] = np.array(dconst, dtype=np.float64)
     return out
 
 

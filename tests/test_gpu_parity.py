@@ -310,6 +310,65 @@ def test_random_tree_wide_mode_matches_oracle():
         assert np.max(np.abs(ug[:, m] - u) / scale) <= 1e-2
 
 
+def test_discrete_control_per_member():
+    """DiscreteControl evaluated on the device per ensemble member: members with different forcing
+    switch control states at different times; states, truth values and trajectories match the
+    oracle member by member."""
+    from oracle.oracle import _dp, advance_opts
+    B = 6
+    case = make_case("pump_discrete_control", B, seed=21, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    # spread the members: different precipitation on the receiving basin
+    case["forcing"]["precipitation"][1, :] = np.linspace(0.0, 4e-8, B)
+    h = gpu_handle_for(case)
+    opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1, 1, 2)
+    try:
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        h.apply_discrete_control()
+        h.refresh(0.0)
+        dt, n_win, win = 86400.0, 12, 10
+        oms, us, etas, htry = [], [], [1.0] * B, [dt] * B
+        for m in range(B):
+            om = oracle_for_member(case, m)
+            _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
+            lv = np.ascontiguousarray(c0["level"])
+            om.L.orc_set_level_prev(om.h, _dp(lv))
+            om.set_f64("fb_rate_step", case["fb_rate"][:, m])
+            om.apply_discrete_control(np.zeros(flat["n_reduced"]), 0.0)
+            oms.append(om)
+            us.append(np.zeros(n))
+        st0 = h.get_member_i32("dc_state", flat["n_dc"])
+        for m, om in enumerate(oms):
+            assert np.array_equal(st0[:, m], om.discrete_control_state()[0])
+        t = 0.0
+        for k in range(n_win):
+            st = h.advance(t, dt, win)
+            assert not np.any(st)
+            for m, om in enumerate(oms):
+                for j in range(win):
+                    _, _, htry[m], etas[m] = om.advance(us[m], t + j * dt, dt, opts, htry[m], etas[m])
+            t += win * dt
+            dcs = h.get_member_i32("dc_state", flat["n_dc"])
+            dct = h.get_member_i32("dc_truth", flat["n_dc_cond"])
+            for m, om in enumerate(oms):
+                so, to, _, undefined = om.discrete_control_state()
+                assert undefined == 0
+                assert np.array_equal(dcs[:, m], so), (k, m)
+                assert np.array_equal(dct[:, m], to), (k, m)
+        ug = h.get_member("u", n)
+        changes = h.get_member_i32("cnt_dc", 1)[0]
+        for m, om in enumerate(oms):
+            scale = 1e-5 + np.abs(us[m]) * 1e-5
+            assert np.max(np.abs(ug[:, m] - us[m]) / scale) <= 1e-2
+            assert changes[m] == om.discrete_control_state()[2]
+        assert len(set(changes.tolist())) > 1 or len({tuple(c) for c in dcs.T}) > 1, \
+            "members were meant to diverge"
+    finally:
+        h.close()
+
+
 def test_advance_window_equals_single_steps():
     """rbs_advance over a window = the same number of rbs_step_implicit_euler calls, bitwise,
     although members cross the outer step boundaries at different passes."""

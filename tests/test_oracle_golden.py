@@ -256,3 +256,21 @@ def test_backwater_against_standard_step_method():
     du = om.rhs(om.reduce(u) * 0 + (S - p.basin.storage0), p.tables.t_end)
     assert du[flat["off_manning"] + 49] == pytest.approx(5.0, abs=1e-3)
     assert du[flat["off_manning"]] == pytest.approx(5.0, abs=1e-3)
+
+
+def test_pump_discrete_control_record():
+    # core/test/control_test.jl:33-44: the sequence of control state changes over the year
+    p = build_params(MODELS["pump_discrete_control"]())
+    flat = flatten(p)
+    u, S, lv, st = run_oracle(p, 3600.0, full_newton=1, max_halvings=20, predictor=1)
+    om = st["oracle"]
+    rec = om.discrete_control_record()
+    ids = [n.value for n in p.nodes["discrete_control"]["node_id"]]
+    names = flat.dc_state_names
+    assert [ids[i] for i, _, _ in rec] == [5, 6, 5, 5, 6]
+    assert [names[i][s_] for i, _, s_ in rec] == ["off", "active", "on", "off", "inactive"]
+    truth = ["".join("T" if (b >> j) & 1 else "F" for j in range(2 if i == 0 else 1)) for i, b, _ in rec]
+    assert truth == ["TF", "F", "FF", "FT", "T"]
+    # end of run: pump off and resistance inactive -> no flow (control_test.jl:62-64)
+    om.set_time_params(eval_time_params(p, p.tables.t_end))
+    assert st["failed"] == 0
