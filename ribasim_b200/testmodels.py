@@ -297,6 +297,26 @@ def pump_discrete_control_model() -> ModelTables:
     return m
 
 
+def tabulated_rating_curve_model() -> ModelTables:
+    """One static and one time-varying (cyclic) rating curve between two basins
+    (basic.py:276-361)."""
+    m = _model()
+    prof = dict(area=[0.01, 1000.0], level=[0.0, 1.0])
+    m.add_node("Basin", 1, profile=prof, static=dict(precipitation=0.002 / 86400),
+               state=dict(level=0.04471158417652035))
+    m.add_node("TabulatedRatingCurve", 2, static=dict(level=[0.0, 1.0], flow_rate=[0.0, 10 / 86400]))
+    m.add_node("TabulatedRatingCurve", 3, cyclic_time=True, time=dict(
+        time=["2020-01-01 00:00:00.000", "2020-01-01 00:00:00.000", "2020-02-01 00:00:00.001",
+              "2020-02-01 00:00:00.001", "2020-03-01 00:00:00.000", "2020-03-01 00:00:00.000",
+              "2020-04-01 00:00:00.000", "2020-04-01 00:00:00.000"],
+        level=[0.0, 1.0, 0.0, 1.1, 0.0, 1.2, 0.0, 1.0], flow_rate=4 * [0.0, 10 / 86400]))
+    m.add_node("Basin", 4, profile=prof, static=dict(precipitation=0.0),
+               state=dict(level=0.04471158417652035))
+    for a, b in ((1, 2), (1, 3), (2, 4), (3, 4)):
+        m.add_link(a, b)
+    return m
+
+
 def junction_combined_model() -> ModelTables:
     """Confluence and bifurcation through Junction nodes (junction.py:13-98)."""
     m = _model()
@@ -558,6 +578,7 @@ def _add_connector_fast(m: ModelTables, rng, kind: str, node_id: int, bottom_src
 
 
 MODELS = dict(
+    tabulated_rating_curve=tabulated_rating_curve_model,
     junction_combined=junction_combined_model,
     junction_chained=junction_chained_model,
     basic=basic_model,

@@ -19,7 +19,8 @@ RTOL_ENTRY = 1e-12
 MODELS_RHS = ["basic", "basic_transient", "backwater", "trivial", "bucket", "linear_resistance",
               "rating_curve", "rating_curve_between_basins", "manning_resistance", "misc_nodes",
               "user_demand", "pid_control", "pid_control_equation", "outlet_continuous_control",
-              "pump_discrete_control", "junction_combined", "junction_chained"]
+              "pump_discrete_control", "junction_combined", "junction_chained",
+              "tabulated_rating_curve"]
 
 
 def _scaled_err(a: np.ndarray, b: np.ndarray, axis_scale: np.ndarray) -> float:

@@ -274,3 +274,20 @@ def test_pump_discrete_control_record():
     # end of run: pump off and resistance inactive -> no flow (control_test.jl:62-64)
     om.set_time_params(eval_time_params(p, p.tables.t_end))
     assert st["failed"] == 0
+
+
+def test_tabulated_rating_curve_model():
+    # core/test/run_models_test.jl:326-352: time-varying (cyclic) rating curves
+    p = build_params(MODELS["tabulated_rating_curve"]())
+    trc = p.nodes["tabulated_rating_curve"]
+    idx1, idx2 = trc["current_interpolation_index"]
+    assert set(idx1.u) == {1}
+    assert list(idx2.u) == [2, 3, 4, 2]
+    assert np.allclose(idx2.t, [0.0, 2.6784e6, 5.184e6, 7.8624e6], rtol=1e-6)
+    assert idx2.periodic
+    assert len(trc["interpolations"]) == 5
+    assert trc["interpolations"][3].t[-1] == 1.2
+    u, S, lv, st = run_oracle(p, 3600.0, full_newton=1, max_halvings=20, predictor=1)
+    # `≈` on Float32 goldens: rtol = sqrt(eps(Float32))
+    assert np.allclose(S, [368.31558, 365.68442], rtol=3.5e-4, atol=0)
+    assert st["failed"] == 0
