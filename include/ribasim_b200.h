@@ -72,6 +72,15 @@ int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64
 int rbs_set_member_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity,
                        int32_t broadcast);
 int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_entity);
+/* Asynchronous variants for PINNED host buffers, to overlap transfers with stepping.
+ * rbs_set_member_f64_async stages the upload on a copy stream into a shadow buffer while the
+ * next rbs_step_implicit_euler / rbs_advance call computes with the current values; the staged
+ * values become live when that call returns, i.e. they are the input of the step after it
+ * (stage step k+1's forcing, then run step k).  The host buffer may be reused after that call.
+ * rbs_get_member_f64_async snapshots the array on the device (ordered after the work enqueued so
+ * far) and transfers it in the background; the host buffer is valid after rbs_synchronize. */
+int rbs_set_member_f64_async(rbs_handle* h, const char* key, const double* pinned_host, int64_t n_entity);
+int rbs_get_member_f64_async(rbs_handle* h, const char* key, double* pinned_host, int64_t n_entity);
 /* Device-to-device copy of a per-member array into caller-owned device memory (e.g. the send
  * buffer of the final NCCL gather of an ensemble sharded over GPUs). */
 int rbs_copy_member_to_device(rbs_handle* h, const char* key, void* dst_device, int64_t n_entity);

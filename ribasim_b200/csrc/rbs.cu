@@ -58,6 +58,12 @@ struct rbs_handle {
     int* h_active = nullptr;  // pinned: {n_active, n_limit}
     int *d_alist = nullptr, *d_llist = nullptr, *d_counts = nullptr;
     cudaStream_t cur = nullptr;  // stream the launch helpers use (the handle's, or a group's)
+    // asynchronous host<->device staging: uploads land in shadow buffers on the copy stream and
+    // become live at the start of the next step; downloads read a device-side snapshot
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
+    std::map<std::string, void*> shadow_in, shadow_out;
+    std::vector<std::string> staged;
     // member groups: independent state machines on their own streams, so the latency-bound
     // kernels of one group overlap with the kernels of the others
     struct Group {
@@ -403,6 +409,10 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail("rbs_create: stream creation failed");
     h->cur = h->stream;
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess)
+        return bail("rbs_create: copy stream creation failed");
     if (cudaMallocHost(&h->h_active, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
     if (make_groups(h, geti(b, "n_groups", 0))) return bail("rbs_create: group setup failed");
     for (auto& kv : b->i) { h->hi[kv.first] = kv.second; if (upload(h, kv.first, kv.second, true)) return bail("upload"); }
@@ -692,6 +702,11 @@ void rbs_destroy(rbs_handle* h) {
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (h->h_active) cudaFreeHost(h->h_active);
     free_groups(h);
+    for (auto& kv : h->shadow_in) if (kv.second) cudaFree(kv.second);
+    for (auto& kv : h->shadow_out) if (kv.second) cudaFree(kv.second);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d_blob) cudaFree(h->d_blob);
     if (h->d_blob2) cudaFree(h->d_blob2);
     if (h->d_alist) cudaFree(h->d_alist);
@@ -741,6 +756,50 @@ int rbs_set_member_f64(rbs_handle* h, const char* key, const double* host, int64
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return check_async(h, "rbs_set_member_f64");
+}
+// make staged uploads live: swap shadow and live buffers once the copy stream has delivered them
+static int commit_staged(rbs_handle* h) {
+    if (h->staged.empty()) return 0;
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    for (auto& key : h->staged) std::swap(h->member[key].p, h->shadow_in[key]);
+    h->staged.clear();
+    bind_net(h);
+    return 0;
+}
+int rbs_set_member_f64_async(rbs_handle* h, const char* key, const double* pinned_host, int64_t n_entity) {
+    if (!h || !key || !pinned_host) return fail("rbs_set_member_f64_async: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || it->second.is_int) return fail(std::string("unknown member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    void*& sh = h->shadow_in[key];
+    if (!sh) CUDA_TRY(cudaMalloc(&sh, it->second.bytes));
+    for (auto& k : h->staged) if (k == key) return fail(std::string("already staged: ") + key);
+    CUDA_TRY(cudaMemcpyAsync(sh, pinned_host, (size_t)n_entity * h->B * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_copy, h->copy_stream));
+    h->staged.push_back(key);
+    return 0;
+}
+int rbs_get_member_f64_async(rbs_handle* h, const char* key, double* pinned_host, int64_t n_entity) {
+    if (!h || !key || !pinned_host) return fail("rbs_get_member_f64_async: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || it->second.is_int) return fail(std::string("unknown member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    void*& sh = h->shadow_out[key];
+    if (!sh) CUDA_TRY(cudaMalloc(&sh, it->second.bytes));
+    size_t nb = (size_t)n_entity * h->B * sizeof(double);
+    // snapshot on the compute stream (ordered after the step), transfer on the copy stream; the
+    // previous transfer out of this snapshot buffer must have left first
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    CUDA_TRY(cudaMemcpyAsync(sh, it->second.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev_main, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
+    CUDA_TRY(cudaMemcpyAsync(pinned_host, sh, nb, cudaMemcpyDeviceToHost, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_copy, h->copy_stream));
+    return 0;
 }
 int rbs_get_member_f64(rbs_handle* h, const char* key, double* host, int64_t n_entity) {
     if (!h || !key || !host) return fail("rbs_get_member_f64: null argument");
@@ -870,6 +929,7 @@ int rbs_synchronize(rbs_handle* h) {
     if (!h) return fail("rbs_synchronize: null handle");
     cudaSetDevice(h->device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
     return check_async(h, "rbs_synchronize");
 }
 
@@ -1135,6 +1195,8 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
     // streams are idle and later work enqueued on the handle's stream is ordered after them
     h->tprev = t + dt * n_steps;
     h->n_steps += n_steps;
+    // uploads staged while this window was running apply from the next window on
+    if (commit_staged(h)) return 1;
     if (status_per_member) {
         CUDA_TRY(cudaMemcpyAsync(status_per_member, n.status, (size_t)n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));

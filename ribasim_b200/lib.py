@@ -19,7 +19,8 @@ from .symbolic import Symbolic, analyse
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "librbs.so"
+# RBS_LIB selects another build of the same sources (e.g. the -DRBS_LIN_PROFILE tuning build)
+LIB_PATH = Path(os.environ["RBS_LIB"]) if os.environ.get("RBS_LIB") else PKG_DIR / "librbs.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -80,6 +81,8 @@ def load() -> ctypes.CDLL:
         "rbs_set_param_i32": (ctypes.c_int, [vp, cp, ip, i64]),
         "rbs_set_member_f64": (ctypes.c_int, [vp, cp, dp, i64, i32]),
         "rbs_get_member_f64": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_set_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_get_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
         "rbs_get_member_i32": (ctypes.c_int, [vp, cp, ip, i64]),
         "rbs_apply_discrete_control": (ctypes.c_int, [vp]),
@@ -114,7 +117,8 @@ def load() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
-    "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64",
+    "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64", "rbs_set_member_f64_async",
+    "rbs_get_member_f64_async",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
     "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
@@ -268,6 +272,16 @@ class Handle:
         _check(self.L.rbs_get_member_f64(self.h, key.encode(),
                                          ctypes.cast(host_ptr, ctypes.POINTER(ctypes.c_double)),
                                          n_entity))
+
+    def set_member_ptr_async(self, key: str, pinned_ptr: int, n_entity: int) -> None:
+        """Stage an upload from pinned memory; live at the start of the next step."""
+        _check(self.L.rbs_set_member_f64_async(
+            self.h, key.encode(), ctypes.cast(pinned_ptr, ctypes.POINTER(ctypes.c_double)), n_entity))
+
+    def get_member_ptr_async(self, key: str, pinned_ptr: int, n_entity: int) -> None:
+        """Background download into pinned memory; valid after synchronize()."""
+        _check(self.L.rbs_get_member_f64_async(
+            self.h, key.encode(), ctypes.cast(pinned_ptr, ctypes.POINTER(ctypes.c_double)), n_entity))
 
     def copy_member_to_device(self, key: str, device_ptr: int, n_entity: int) -> None:
         _check(self.L.rbs_copy_member_to_device(self.h, key.encode(), ctypes.c_void_p(device_ptr),
