@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -102,6 +103,12 @@ struct rbs_handle {
     bool lin_smem = false;   // factors in shared memory (tile 8) instead of L2 (tile 8/16/32)
     size_t lin_smem_bytes = 0;
     bool sched16 = false;
+    // entry schedule (factorisation with fused forward substitution), see symbolic.build_entries
+    EntSched esched{};
+    void* d_ent_blob = nullptr;
+    bool lin_ent = false;
+    int ent_tile = 2;
+    size_t ent_smem_bytes = 0;
     void* d_blob = nullptr;
     size_t smem_bytes = 0;
     int *d_lsrc_ptr = nullptr, *d_lsrc_code = nullptr;
@@ -611,7 +618,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         }
         // ---- shared-memory kernel (LDU schedule): second packed blob
         int lin_mode = geti(b, "lin_mode", -1);  // -1 auto, 0 wide, 1 L2 tile kernel, 2 shared-memory kernel
-        if (b->i.count("ldu_prod_ptr") && want != 0 && (lin_mode < 0 || lin_mode == 2)) {
+        if (b->i.count("ldu_prod_ptr") && want != 0 && (lin_mode < 0 || lin_mode == 2 || lin_mode == 3)) {
             std::vector<int32_t> blob2;
             LduSched& ds = h->dsched;
             auto put2 = [&](const std::vector<int32_t>& v) { int off = (int)blob2.size(); blob2.insert(blob2.end(), v.begin(), v.end()); return off; };
@@ -684,7 +691,51 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 else cudaGetLastError();
             }
         }
-        if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; }
+        // ---- entry schedule kernel (preferred when the tile's slots + schedule fit)
+        if (b->i.count("ent_e") && want != 0 && (lin_mode < 0 || lin_mode == 3)) {
+            EntSched& es = h->esched;
+            es.n_elim = geti(b, "ent_n_elim"); es.n_bwd = geti(b, "ent_n_bwd");
+            es.n_slots = n.n_lu + n.n_reduced; es.y0 = n.n_lu;
+            es.dbg = getenv("RBS_ENT_DBG") ? atoi(getenv("RBS_ENT_DBG")) : 0;
+            std::vector<uint16_t> hb;
+            auto put16 = [&](const std::vector<int32_t>& v) {
+                int off = (int)hb.size();
+                for (int32_t x : v) hb.push_back((uint16_t)x);
+                return off;
+            };
+            put16(geta("ent_e"));
+            es.off_q0 = put16(geta("ent_q0")); es.off_cf = put16(geta("ent_cf"));
+            es.off_pl = put16(geta("ent_prod_l")); es.off_pp = put16(geta("ent_prod_p"));
+            es.off_pu = put16(geta("ent_prod_u")); es.off_lvl = put16(geta("ent_lvl_ptr"));
+            es.off_team = put16(geta("ent_team_log")); es.off_perm = put16(geta("perm"));
+            while (hb.size() % 8) hb.push_back(0);
+            es.total = (int)hb.size();
+            bool ok = n.n_lu + n.n_reduced < 65536 && geta("ent_prod_l").size() < 65536 &&
+                      (int)geta("ent_lvl_ptr").size() == es.n_elim + es.n_bwd + 1;
+            // member tile: small tiles let several blocks share an SM (the level loop is latency
+            // bound); the largest of 2 / 4 / 8 members that still leaves room for 4 blocks per SM,
+            // else whatever fits
+            int et = geti(b, "ent_tile", 0);
+            if (et != 2 && et != 4 && et != 8) {
+                et = 0;
+                for (int cand : {2, 4, 8})
+                    if (((size_t)es.n_slots * cand * sizeof(double) + 1024) * 4 <= (size_t)228 * 1024) et = cand;
+                if (et == 0) et = 2;
+            }
+            size_t sb = (size_t)es.n_slots * et * sizeof(double);
+            if (ok && sb + 256 <= (size_t)dev_smem) {
+                if (cudaMalloc(&h->d_ent_blob, hb.size() * 2) != cudaSuccess) return bail("schedule alloc");
+                cudaMemcpyAsync(h->d_ent_blob, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice, h->stream);
+                cudaStreamSynchronize(h->stream);
+                cudaError_t e3 =
+                    et == 2 ? cudaFuncSetAttribute(k_newton_linear_ent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
+                    : et == 4 ? cudaFuncSetAttribute(k_newton_linear_ent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
+                              : cudaFuncSetAttribute(k_newton_linear_ent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+                if (e3 == cudaSuccess) { h->lin_ent = true; h->ent_smem_bytes = sb; h->ent_tile = et; }
+                else cudaGetLastError();
+            }
+        }
+        if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; h->lin_ent = false; }
     }
     bind_net(h);
     n.cc_tab_offset = geti(b, "cc_tab_offset");
@@ -709,6 +760,7 @@ void rbs_destroy(rbs_handle* h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d_blob) cudaFree(h->d_blob);
     if (h->d_blob2) cudaFree(h->d_blob2);
+    if (h->d_ent_blob) cudaFree(h->d_ent_blob);
     if (h->d_alist) cudaFree(h->d_alist);
     if (h->d_llist) cudaFree(h->d_llist);
     if (h->d_counts) cudaFree(h->d_counts);
@@ -1032,7 +1084,19 @@ int rbs_refresh(rbs_handle* h, double t) {
 // level-per-launch kernels when the schedule does not fit in shared memory.
 static void launch_linear(rbs_handle* h, double* c, Pred nw) {
     Net& n = h->net;
-    if (h->lin_smem) {
+    if (h->lin_ent) {
+        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * n.NA, n, sp<int>(h, "dsrc_ptr"),
+               sp<int>(h, "dsrc_code"));
+        int et = h->ent_tile, blocks = (n.NA + et - 1) / et, nt = RBS_ENT_LANES * et / 2;
+        const uint16_t* ixd = (const uint16_t*)h->d_ent_blob;
+        int wl = h->full_newton ? 0 : 1;
+        prof_begin(h, "k_newton_linear_ent");
+        if (et == 2) k_newton_linear_ent<2><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, ixd, wl, c);
+        else if (et == 4) k_newton_linear_ent<4><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, ixd, wl, c);
+        else k_newton_linear_ent<8><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, ixd, wl, c);
+        prof_end(h);
+        h->launches++;
+    } else if (h->lin_smem) {
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * n.NA, n, sp<int>(h, "dsrc_ptr"),
                sp<int>(h, "dsrc_code"));
         int blocks = (n.NA + 7) / 8;
@@ -1131,6 +1195,15 @@ int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_pe
     cudaEventDestroy(a); cudaEventDestroy(b);
     *ms_per_launch = ms / reps;
 #ifdef RBS_LIN_PROFILE
+    if (h->lin_ent) {
+        long long lv[64], clk[8];
+        cudaMemcpyFromSymbol(lv, g_lin_lvl, sizeof lv);
+        cudaMemcpyFromSymbol(clk, g_lin_clk, sizeof clk);
+        int nl = h->esched.n_elim + h->esched.n_bwd;
+        fprintf(stderr, "levels (cycles):");
+        for (int l = 0; l < nl && l < 64; l++) fprintf(stderr, " %lld", lv[l] - (l ? lv[l - 1] : clk[2]));
+        fprintf(stderr, "\n");
+    }
     if (h->lin_smem) {
         long long clk[8];
         cudaMemcpyFromSymbol(clk, g_lin_clk, sizeof clk);

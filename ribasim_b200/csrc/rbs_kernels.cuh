@@ -878,6 +878,7 @@ __global__ void k_assemble_linear(Net n, const int* __restrict__ dsrc_ptr,
 // phase clocks of block 0 (tuning aid, compiled in with -DRBS_LIN_PROFILE; see rbs_time_linear)
 #ifdef RBS_LIN_PROFILE
 __device__ long long g_lin_clk[8];
+__device__ long long g_lin_lvl[64];
 #define LIN_CLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_lin_clk[k] = clock64(); } while (0)
 #else
 #define LIN_CLK(k) do { } while (0)
@@ -1039,6 +1040,158 @@ k_newton_linear_smem(Net n, LduSched sc, const IT* __restrict__ blob, int write_
     if (m >= 0)
         for (int i = slot; i < n.n_reduced; i += n_slot)
             x[(long long)(int)perm[i] * B + m] = xs_s[i * TILE + j];
+    LIN_CLK(7);
+}
+
+// ---- entry schedule: factorisation with fused forward substitution + backward substitution -------
+// See ribasim_b200/symbolic.py (build_entries).  A block keeps the slots of a tile of TILE members
+// in shared memory as S[slot][TILE].  TILE/2 threads own one entry of a level, each thread two
+// members (one 128-bit shared-memory access per operand), and accumulate the entry's products
+//     acc = sum_q (S[l_q] * S[p_q]) * S[u_q];  v = S[e] (* S[r] if SCALE) - acc;  S[e] = RCP ? 1/v : v
+// In levels with few entries and long lists a team of 2^team_log lanes shares an entry (products
+// strided over the team, partial sums combined by a fixed shuffle butterfly: reproducible).
+// Levels only read slots of earlier levels and are separated by block barriers.
+//
+// The level loop is a chain of dependent shared-memory loads and fp64 operations: a block on its
+// own keeps an SM's schedulers ~20% busy.  So the tile is small (TILE = 2: 46 KB of slots for the
+// 500-basin network) and the schedule is read through L1 from global memory instead of being
+// copied into every block's shared memory: four or more blocks share an SM and fill each other's
+// barrier and latency gaps.
+// Members that reuse stored factors (`fac` bit clear) only update the right-hand-side column.
+#define RBS_ENT_RCP 0x100
+#define RBS_ENT_SCALE 0x200
+#define RBS_ENT_LANES 256
+struct EntSched {
+    // offsets (uint16 elements) into the schedule blob; ent_e starts at 0
+    int off_q0, off_cf, off_pl, off_pp, off_pu, off_lvl, off_team, off_perm;
+    int total;                // uint16 elements, multiple of 8
+    int n_elim, n_bwd, n_slots, y0;
+    int dbg;
+};
+
+__device__ __forceinline__ void rbs_cp_async8(void* smem_dst, const void* gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void rbs_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// facmask: bit 0 / 1 set = first / second member of this thread's pair refreshes its factors
+template <int TILE>
+__device__ __forceinline__ void rbs_ent_levels(double* S, const uint16_t* __restrict__ ix, const EntSched& es,
+                                               int lv0, int lv1, unsigned facmask) {
+    constexpr int TPL = TILE / 2;            // threads per entry lane
+    constexpr int EL = RBS_ENT_LANES;
+    const int lane_e = threadIdx.x / TPL;
+    const double* Sc = S + (threadIdx.x % TPL) * 2;  // this thread's member pair
+    const uint16_t *ent_e = ix, *ent_q0 = ix + es.off_q0, *ent_cf = ix + es.off_cf;
+    const uint16_t *pl = ix + es.off_pl, *pp = ix + es.off_pp, *pu = ix + es.off_pu;
+    const uint16_t *lvl = ix + es.off_lvl, *team = ix + es.off_team;
+    for (int lv = lv0; lv < lv1; lv++) {
+        const int e0 = lvl[lv], e1 = lvl[lv + 1], tl = team[lv];
+        const int ts = 1 << tl, t = lane_e & (ts - 1), stride = EL >> tl;
+        // warps whose lanes get no entry in the first pass have none in the later ones either:
+        // they go straight to the barrier
+        if ((int)(threadIdx.x >> 5) * (32 / TPL) < min((e1 - e0) << tl, EL))
+        for (int base = e0; base < e1; base += stride) {  // warp-uniform trip count
+            const int k = base + (lane_e >> tl);
+            const bool valid = k < e1;
+            double a0 = 0.0, a1 = 0.0;
+            int e = 0, q0 = 0, cf = 0;
+            if (valid) {
+                e = ent_e[k]; q0 = ent_q0[k]; cf = ent_cf[k];
+                const int q1 = q0 + (cf & 0xFF);
+#pragma unroll 2
+                for (int q = q0 + t; q < q1; q += ts) {
+                    double2 l = *(const double2*)(Sc + (int)pl[q] * TILE);
+                    double2 p = *(const double2*)(Sc + (int)pp[q] * TILE);
+                    double2 u = *(const double2*)(Sc + (int)pu[q] * TILE);
+                    a0 += (l.x * p.x) * u.x;
+                    a1 += (l.y * p.y) * u.y;
+                }
+            }
+            for (int sft = 0; sft < tl; sft++) {  // uniform; teams are aligned groups of lanes
+                a0 += __shfl_xor_sync(0xffffffffu, a0, TPL << sft);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, TPL << sft);
+            }
+            if (valid && t == 0) {
+                double2* T = (double2*)(const_cast<double*>(Sc) + e * TILE);
+                const double2 o = *T;
+                double2 v = o;
+                if (cf & RBS_ENT_SCALE) {
+                    const double2 r = *(const double2*)(Sc + (int)((cf & 0xFF) ? pp[q0] : q0) * TILE);
+                    v.x *= r.x; v.y *= r.y;
+                }
+                v.x -= a0; v.y -= a1;
+                if (cf & RBS_ENT_RCP) { v.x = 1.0 / v.x; v.y = 1.0 / v.y; }
+                if (e < es.y0 && facmask != 3u) {
+                    if (!(facmask & 1u)) v.x = o.x;
+                    if (!(facmask & 2u)) v.y = o.y;
+                }
+                *T = v;
+            }
+        }
+        __syncthreads();
+#ifdef RBS_LVL_PROFILE
+        if (blockIdx.x == 0 && threadIdx.x == 0 && lv < 64) g_lin_lvl[lv] = clock64();
+#endif
+    }
+}
+
+// Newton linear solve of one member tile per block on the entry schedule; input as for
+// k_newton_linear_smem: the initial slot values / stored factors in `lu`, the reduced right-hand
+// side in `br` (k_assemble_linear).
+template <int TILE>
+__global__ void __launch_bounds__(RBS_ENT_LANES * TILE / 2)
+k_newton_linear_ent(Net n, EntSched es, const uint16_t* __restrict__ ix, int write_lu,
+                    double* __restrict__ x) {
+    constexpr int NT = RBS_ENT_LANES * TILE / 2;
+    extern __shared__ double smem[];
+    double* S = smem;                                    // [n_slots][TILE]
+    const uint16_t* perm = ix + es.off_perm;
+    __shared__ int mem_s[TILE], fac_s[TILE];
+    int m0 = blockIdx.x * TILE;
+    int tm = min(TILE, n.NA - m0);
+    if (tm <= 0) return;
+    LIN_CLK(0);
+    if (threadIdx.x < TILE) {
+        int jj = threadIdx.x;
+        int mm = jj < tm ? RBS_MEMBER(n, m0 + jj) : -1;
+        if (mm >= 0 && n.mphase[mm] != PHASE_NEWTON) mm = -1;
+        mem_s[jj] = mm;
+        fac_s[jj] = mm >= 0 && n.mjac[mm] != 0;
+    }
+    __syncthreads();
+    LIN_CLK(1);
+    const int j = threadIdx.x % TILE;
+    const int slot = threadIdx.x / TILE, n_slot = NT / TILE;
+    const int m = mem_s[j];
+    const long long B = n.B;
+    if (m >= 0) {
+        const double* lug = n.lu + m;
+        for (int e = slot; e < n.n_lu; e += n_slot) rbs_cp_async8(S + e * TILE + j, lug + (long long)e * B);
+        const double* br = n.br + m;
+        for (int i = slot; i < n.n_reduced; i += n_slot)
+            rbs_cp_async8(S + (es.y0 + i) * TILE + j, br + (long long)(int)perm[i] * B);
+    }
+    rbs_cp_async_wait_all();
+    __syncthreads();
+    LIN_CLK(2);
+    const int c2 = (threadIdx.x % (TILE / 2)) * 2;
+    const unsigned facmask = (fac_s[c2] ? 1u : 0u) | (fac_s[c2 + 1] ? 2u : 0u);
+    rbs_ent_levels<TILE>(S, ix, es, 0, es.n_elim, facmask);
+    LIN_CLK(3);
+    LIN_CLK(4);
+    LIN_CLK(5);
+    rbs_ent_levels<TILE>(S, ix, es, es.n_elim, es.n_elim + es.n_bwd, facmask);
+    LIN_CLK(6);
+    if (m >= 0) {
+        for (int i = slot; i < n.n_reduced; i += n_slot)
+            x[(long long)(int)perm[i] * B + m] = S[(es.y0 + i) * TILE + j];
+        if (write_lu && fac_s[j])
+            for (int e = slot; e < n.n_lu; e += n_slot) n.lu[(long long)e * B + m] = S[e * TILE + j];
+    }
     LIN_CLK(7);
 }
 

@@ -15,7 +15,7 @@ from pathlib import Path
 import numpy as np
 
 from .flatten import Flat
-from .symbolic import Symbolic, analyse
+from .symbolic import Symbolic, analyse, build_entries
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
@@ -209,6 +209,21 @@ class Handle:
                          "ldu_bwd_level_ptr", "ldu_bwd_row", "ldu_bwd_ptr", "ldu_bwd_u",
                          "ldu_bwd_k"):
                 set_i(name, getattr(sym, name))
+            # entry schedule of the tile kernels (slots + schedule must fit the 227 KB of shared
+            # memory of an sm_100 SM; the library checks and falls back to the other tiers)
+            ent = build_entries(sym)
+            if ent is not None:
+                set_i("ent_e", ent.ent_e)
+                set_i("ent_q0", ent.ent_q0)
+                set_i("ent_cf", ent.ent_cf)
+                set_i("ent_prod_l", ent.prod_l)
+                set_i("ent_prod_p", ent.prod_p)
+                set_i("ent_prod_u", ent.prod_u)
+                set_i("ent_lvl_ptr", ent.lvl_ptr)
+                set_i("ent_team_log", ent.team_log)
+                set_i("ent_n_elim", [ent.n_elim])
+                set_i("ent_n_bwd", [ent.n_bwd])
+                set_i("ent_tile", [int(os.environ.get("RBS_ENT_TILE", "0"))])
             set_i("lu_mode", [lu_mode])
             set_i("lu_tile", [lu_tile])
             set_i("smem_tile", [smem_tile])

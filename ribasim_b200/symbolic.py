@@ -372,3 +372,163 @@ def numeric_solve_ldu(sym: Symbolic, lu: np.ndarray, b: np.ndarray) -> np.ndarra
     out = np.empty_like(x)
     out[sym.perm] = x
     return out
+
+
+# ------------------------------------------------------------------ entry schedule (tile kernels)
+# The tile kernels (`rbs_ent_levels` in csrc/rbs_kernels.cuh) keep one member tile's factor slots
+# in shared memory as S[slot][8 members] and run the whole solve as a sequence of *levels*
+# separated by block barriers.  Four threads own one entry of the level (each thread two of the
+# tile's eight members, one 128-bit shared-memory access per operand) and accumulate its products:
+#
+#     acc = sum_q (S[l_q] * S[p_q]) * S[u_q];   v = S[e] (* S[r] if SCALE) - acc;   S[e] = 1/v if RCP else v
+#
+# In levels with few entries and long product lists a *team* of 2^team_log entry lanes shares one
+# entry (products strided over the team, partial sums combined by a fixed shuffle butterfly).
+# Slots: [0, n_lu) the LDU factor slots; [n_lu, n_lu + n) the right-hand side column y (permuted
+# rows), which is eliminated together with the matrix (forward substitution fused into the
+# factorisation) and holds the solution after the backward levels.
+#   elimination level r : slot(i,j) -= (slot(i,k) r_k) slot(k,j), diagonal -> reciprocal,
+#                         y_i -= (slot(i,k) r_k) y_k
+#   backward level      : x_i = y_i r_i - sum_j (slot(i,j) r_i) x_j
+ENT_RCP = 1 << 8
+ENT_SCALE = 1 << 9
+ENT_LANES = 256  # entry lanes per block (1024 threads, four per entry: two members each)
+
+
+@dataclass
+class EntrySched:
+    ent_e: np.ndarray      # target slot per entry, entries sorted by level
+    ent_q0: np.ndarray     # first product (or, for a SCALE entry without products, the r slot)
+    ent_cf: np.ndarray     # product count (low 8 bits) | ENT_RCP | ENT_SCALE
+    prod_l: np.ndarray
+    prod_p: np.ndarray
+    prod_u: np.ndarray
+    lvl_ptr: np.ndarray    # entries of level lv: [lvl_ptr[lv], lvl_ptr[lv + 1])
+    team_log: np.ndarray   # per level: log2 of the lanes that share one entry
+    n_elim: int
+    n_bwd: int
+    n_slots: int
+    y0: int
+
+    def smem_bytes(self, tile: int = 8) -> int:
+        idx = 2 * (self.ent_e.size * 3 + self.prod_l.size * 3 + self.lvl_ptr.size + self.team_log.size)
+        return self.n_slots * tile * 8 + idx + 64
+
+
+def build_entries(sym: Symbolic) -> EntrySched | None:
+    """Entry schedule of the LDU elimination (+ fused forward substitution) and the backward
+    substitution.  None when an index does not fit 16 bits."""
+    n, n_lu = sym.n, sym.n_lu
+    y0 = n_lu
+    n_slots = n_lu + n
+    diag = sym.ldu_diag
+    n_elim = len(sym.ldu_level_ptr) - 1
+    levels: list[list] = [[] for _ in range(n_elim)]
+    lvl_of_slot = np.empty(max(n_lu, 1), dtype=np.int64)
+    for lv in range(n_elim):
+        lo, hi = int(sym.ldu_level_ptr[lv]), int(sym.ldu_level_ptr[lv + 1])
+        lvl_of_slot[lo:hi] = lv
+        for e in range(lo, hi):
+            q0, q1 = int(sym.ldu_prod_ptr[e]), int(sym.ldu_prod_ptr[e + 1])
+            is_d = bool(sym.ldu_flag[e])
+            if q1 == q0 and not is_d:
+                continue  # plain copy of W: already in place
+            prods = [(int(sym.ldu_prod_l[q]), int(sym.ldu_prod_p[q]), int(sym.ldu_prod_u[q]))
+                     for q in range(q0, q1)]
+            levels[lv].append((e, prods, ENT_RCP if is_d else 0, 0))
+    for pos in range(n):
+        i = int(sym.ldu_fwd_row[pos])
+        q0, q1 = int(sym.ldu_fwd_ptr[pos]), int(sym.ldu_fwd_ptr[pos + 1])
+        if q1 == q0:
+            continue
+        prods = [(int(sym.ldu_fwd_l[q]), int(diag[int(sym.ldu_fwd_k[q])]), y0 + int(sym.ldu_fwd_k[q]))
+                 for q in range(q0, q1)]
+        levels[int(lvl_of_slot[diag[i]])].append((y0 + i, prods, 0, 0))
+    n_bwd = len(sym.ldu_bwd_level_ptr) - 1
+    blevels: list[list] = [[] for _ in range(n_bwd)]
+    for lv in range(n_bwd):
+        for pos in range(int(sym.ldu_bwd_level_ptr[lv]), int(sym.ldu_bwd_level_ptr[lv + 1])):
+            i = int(sym.ldu_bwd_row[pos])
+            q0, q1 = int(sym.ldu_bwd_ptr[pos]), int(sym.ldu_bwd_ptr[pos + 1])
+            r_i = int(diag[i])
+            prods = [(int(sym.ldu_bwd_u[q]), r_i, y0 + int(sym.ldu_bwd_k[q])) for q in range(q0, q1)]
+            blevels[lv].append((y0 + i, prods, ENT_SCALE, r_i))
+    ent_e, ent_q0, ent_cf, pl, pp, pu, lvl_ptr, team = [], [], [], [], [], [], [0], []
+    def assign(lvl, tl):
+        """Lane k of the block takes entries k, k + L, k + 2L, ... of the level (L lanes, or teams
+        of 2^tl lanes).  Pass by pass the biggest entry goes to the least loaded lane; lanes are
+        then ordered by entry count so that every pass is a prefix.  Returns the entry order and
+        the critical lane's cost (instructions)."""
+        L = ENT_LANES >> tl
+
+        def cost(t):
+            return 10 + 14 * tl + 18 * ((len(t[1]) + (1 << tl) - 1) >> tl) + (50 if t[2] & ENT_RCP else 0)
+
+        lanes: list[list] = [[] for _ in range(min(L, max(len(lvl), 1)))]
+        load = [0] * len(lanes)
+        todo = sorted(lvl, key=lambda t: -cost(t))
+        for p0 in range(0, len(todo), len(lanes)):
+            batch = todo[p0:p0 + len(lanes)]
+            for ent, w in zip(batch, sorted(range(len(lanes)), key=lambda k: load[k])):
+                lanes[w].append(ent)
+                load[w] += cost(ent)
+        order = sorted(range(len(lanes)), key=lambda k: (-len(lanes[k]), -load[k]))
+        lanes = [lanes[k] for k in order]
+        ordered = []
+        for ps in range(max((len(x) for x in lanes), default=0)):
+            ordered.extend(x[ps] for x in lanes if len(x) > ps)
+        return ordered, max(load, default=0)
+
+    for lvl in levels + blevels:
+        best = min(range(4), key=lambda tl: (assign(lvl, tl)[1], tl))
+        team.append(best)
+        ordered, _ = assign(lvl, best)
+        for (e, prods, flags, r) in ordered:
+            if len(prods) > 255:
+                return None
+            ent_e.append(e)
+            ent_q0.append(len(pl) if prods else r)
+            ent_cf.append(len(prods) | flags)
+            for (l, p, u) in prods:
+                pl.append(l); pp.append(p); pu.append(u)
+        lvl_ptr.append(len(ent_e))
+    if max(n_slots, len(pl), len(ent_e)) >= 65536:
+        return None
+    return EntrySched(ent_e=as_i32(ent_e), ent_q0=as_i32(ent_q0), ent_cf=as_i32(ent_cf),
+                      prod_l=as_i32(pl), prod_p=as_i32(pp), prod_u=as_i32(pu),
+                      lvl_ptr=as_i32(lvl_ptr), team_log=as_i32(team), n_elim=n_elim, n_bwd=n_bwd,
+                      n_slots=n_slots, y0=y0)
+
+
+def numeric_entries(sym: Symbolic, E: EntrySched, wvals: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """NumPy emulation of `rbs_ent_levels` for one member (same summation order)."""
+    S = np.zeros(E.n_slots)
+    for e in range(sym.n_lu):
+        S[e] = wvals[sym.ldu_wsrc[e]] if sym.ldu_wsrc[e] >= 0 else 0.0
+    S[E.y0:E.y0 + sym.n] = b[sym.perm]
+    for lv in range(E.n_elim + E.n_bwd):
+        ts = 1 << int(E.team_log[lv])
+        new = {}
+        for k in range(int(E.lvl_ptr[lv]), int(E.lvl_ptr[lv + 1])):
+            e, q0, cf = int(E.ent_e[k]), int(E.ent_q0[k]), int(E.ent_cf[k])
+            cnt = cf & 0xFF
+            part = []
+            for t in range(ts):
+                acc = 0.0
+                for q in range(q0 + t, q0 + cnt, ts) if cnt else ():
+                    acc += (S[E.prod_l[q]] * S[E.prod_p[q]]) * S[E.prod_u[q]]
+                part.append(acc)
+            step = 1
+            while step < ts:  # butterfly: lane t adds lane t ^ step
+                part = [part[t] + part[t ^ step] for t in range(ts)]
+                step <<= 1
+            old = S[e]
+            if cf & ENT_SCALE:
+                old = old * S[E.prod_p[q0] if cnt else q0]
+            v = old - part[0]
+            new[e] = 1.0 / v if cf & ENT_RCP else v
+        for e, v in new.items():  # a level only reads earlier levels
+            S[e] = v
+    out = np.empty(sym.n)
+    out[sym.perm] = S[E.y0:E.y0 + sym.n]
+    return out

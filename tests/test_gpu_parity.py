@@ -249,10 +249,11 @@ def test_member_independence_and_determinism():
     assert np.array_equal(S_sub, S_all[:, pick])
 
 
-@pytest.mark.parametrize("lin_mode,n_groups", [(0, 1), (1, 1), (2, 1), (2, 3)])
+@pytest.mark.parametrize("lin_mode,n_groups", [(0, 1), (1, 1), (2, 1), (2, 3), (3, 1), (3, 3), (-1, 0)])
 def test_linear_solver_tiers_agree(lin_mode, n_groups):
-    """The three execution tiers of the Newton linear solve (level-per-launch, factors in L2,
-    factors in shared memory with the LDU schedule) and any member grouping give the same
+    """The execution tiers of the Newton linear solve (level-per-launch, factors in L2, factors
+    in shared memory with the LDU schedule, record schedule with the forward substitution fused
+    into the factorisation) and any member grouping give the same
     trajectories up to the rounding of their different elimination arithmetic."""
     from ribasim_b200.testmodels import hws_like_model
     case = make_case(hws_like_model(n_basins=60, n_days=2), 40, seed=13, t=0.0)

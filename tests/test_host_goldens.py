@@ -11,8 +11,8 @@ import pytest
 
 from ribasim_b200.flatten import flatten
 from ribasim_b200.network import build_params
-from ribasim_b200.symbolic import (analyse, numeric_factor, numeric_factor_ldu, numeric_solve,
-                                   numeric_solve_ldu)
+from ribasim_b200.symbolic import (analyse, build_entries, numeric_entries, numeric_factor,
+                                   numeric_factor_ldu, numeric_solve, numeric_solve_ldu)
 from ribasim_b200.tables import ModelTables
 from ribasim_b200.testmodels import MODELS
 
@@ -195,6 +195,11 @@ def test_symbolic_lu_solves(name, kw):
     xd = numeric_solve_ldu(sym, lud, b)
     assert np.allclose(W @ xd, b, rtol=1e-10, atol=1e-10)
     assert len(sym.ldu_level_ptr) - 1 == sym.n_rounds
+    # entry schedule of the tile kernels (emulation with the kernel's summation order)
+    ent = build_entries(sym)
+    xe = numeric_entries(sym, ent, wv, b)
+    assert np.allclose(W @ xe, b, rtol=1e-10, atol=1e-10)
+    assert ent.lvl_ptr[-1] == ent.ent_e.size and len(ent.team_log) == ent.n_elim + ent.n_bwd
 
 
 def test_symbolic_lu_chain_is_logarithmic():
