@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--smem-threads", type=int, default=1024)
     ap.add_argument("--lin-mode", type=int, default=-1)
     ap.add_argument("--groups", type=int, default=0, help="member groups on own streams (0 = auto)")
+    ap.add_argument("--e2e-window", type=int, default=24,
+                    help="outer steps per rbs_advance_window call of the end-to-end leg (1 = one call per step)")
     ap.add_argument("--strong", action="store_true", help="keep --members as the job total")
     ap.add_argument("--cpu-members", type=int, default=0, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -302,22 +304,52 @@ def main():
     t = 0.0
     step = 0
 
+    W = max(1, min(args.e2e_window, 24))
+    stage_w: dict[int, dict] = {}  # day -> pinned [W][entity][member] slices (one per outer step)
+    results = [pinned((W, nb, nm)) for _ in range(2)]
+    e2e_count = {"h2d": 0, "d2h": 0, "calls": 0}
+
+    def fill_day_window(day):
+        """Per-step forcing slices of one day for the forced-window calls (host side, untimed:
+        the ensemble's input producer)."""
+        if day in stage_w:
+            return
+        fill_day(day)
+        stage_w[day] = {}
+        for k in keys:
+            buf = pinned((W,) + tuple(stage[day][k].shape))
+            buf[:] = stage[day][k]
+            stage_w[day][k] = buf
+
+    def stage_window(step0, w):
+        """Slices of outer steps step0 .. step0 + w - 1 (a window may span a daily change: one
+        chunk per day)."""
+        first = 0
+        while first < w:
+            day = (step0 + first) // 24
+            cnt = min(w - first, 24 - (step0 + first) % 24)
+            for key in keys:
+                src = stage_w[day][key]
+                h.stage_forcing_window(key, src.data_ptr(), src.shape[1], cnt, first_step=first)
+                e2e_count["h2d"] += cnt * src.shape[1] * nm * 8
+            first += cnt
+
     def run_steps(k, e2e=False):
         """Device-resident path: windows of outer steps up to the next daily forcing change in one
-        rbs_advance call.  e2e path: one call per step with host forcing in / host storages out."""
+        rbs_advance call.  e2e path: forced windows of W outer steps through the C ABI with HOST
+        buffers - every outer step's forcing slice is uploaded from pinned memory and every outer
+        step's storages are downloaded inside the timed region; the upload of window k+1 and the
+        download of window k-1 overlap with the computation of window k."""
         nonlocal t, step
         done = 0
         while done < k:
             if e2e:
-                # step k computes while the forcing of step k+1 is uploaded from pinned memory
-                # and the storages of step k-1 are downloaded; every step's inputs and results
-                # cross PCIe inside the timed region
-                nxt = stage[(step + 1) // 24]
-                for key in keys:
-                    h.set_member_ptr_async(key, nxt[key].data_ptr(), nxt[key].shape[0])
-                h.step(t, DT, want_status=False)
-                h.get_member_ptr_async("storage", result.data_ptr(), nb)
-                w = 1
+                w = min(W, k - done)
+                left = k - done - w
+                stage_window(step + w, min(W, left) if left > 0 else W)  # live when this window returns
+                h.advance_window(t, DT, w, results[e2e_count["calls"] % 2].data_ptr(), want_status=False)
+                e2e_count["d2h"] += w * nb * nm * 8
+                e2e_count["calls"] += 1
             else:
                 w = min(k - done, 24 - step % 24)
                 h.advance(t, DT, w, want_status=False)
@@ -346,6 +378,8 @@ def main():
         barrier()
         ev0.record(stream)
         run_steps(k, e2e)
+        if e2e:
+            h.synchronize()  # the download of the last window's results belongs to the timed region
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -367,15 +401,17 @@ def main():
     # the forcing of the days covered is generated beforehand, the copies are timed
     for d in [d for d in stage if d < step // 24]:
         del stage[d]
-    for d in range(step // 24, (step + args.steps + 1) // 24 + 1):
-        fill_day(d)
-    upload(step // 24)
-    run_steps(1, e2e=True)
+    for d in range(step // 24, (step + args.steps + 3 * W) // 24 + 1):
+        fill_day_window(d)
+    stage_window(step, W)
+    h.commit_forcing_window()
+    run_steps(W, e2e=True)  # primes the pipeline: the first timed window's slices are in flight
+    e2e_count.update(h2d=0, d2h=0)
     ms_e2e = timed(args.steps, e2e=True)
     h.synchronize()
     e2e_value = total_members * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(int(v.numel()) * 8 for v in next(iter(stage.values())).values())
-    d2h = int(result.numel()) * 8
+    h2d = e2e_count["h2d"] // args.steps
+    d2h = e2e_count["d2h"] // args.steps
 
     # per-kernel durations (CUDA events on the library's stream) over the same number of steps
     # (one member group = one stream, so that kernels do not overlap and every event pair brackets
@@ -405,7 +441,10 @@ def main():
             "data": "synthetic", "config": workload_config(args, flat, sym, nm, world),
             "simulated_days_per_s": value * DT / 86400.0,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "steps_per_call": W,
+                    "how": "rbs_stage_forcing_window (pinned host forcing slices of every outer step) + "
+                           "rbs_advance_window (pinned host storages of every outer step out)"},
             "gpu_launches": l1 - l0,
             "clocks": clocks,
             "newton_iters_per_member_step": (s1["newton_iters"] - s0["newton_iters"]) / member_steps,
@@ -418,7 +457,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = args.cpu_members or 32 * cores
+            sample = args.cpu_members or min(nm, 256 * cores)
             cpu_steps = min(args.steps, 24)
             val, el, st = cpu_arm(p, flat, sample, cpu_steps, args.spinup + args.warmup,
                                   args.full_newton, cores)

@@ -138,6 +138,30 @@ int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_
  * result is identical to n_steps calls of rbs_step_implicit_euler.  status bits are OR-ed over
  * the window. */
 int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member);
+/* Forced window: n_steps outer steps whose forcing differs per step, with the per-step results
+ * streamed back.  This is the batched form of the reference's main loop, where the forcing of the
+ * whole horizon is known up front (`update_basin!` at the forcing tstops, core/src/callback.jl:
+ * 846-866, and the `saveat` storage output, core/src/callback.jl:125-182): every member walks
+ * through the window at its own pace reading the forcing slice of the outer step it is in, so
+ * members that need many sub-steps do not stall the ensemble at every step boundary.
+ * rbs_stage_forcing_window uploads, asynchronously from PINNED host memory, the slices
+ * [n_steps][n_entity][n_members] of outer steps first_step .. first_step + n_steps - 1 of the
+ * window (a window may be staged in several chunks) of one forcing array ("precipitation", "surface_runoff",
+ * "potential_evaporation", "drainage", "infiltration", "fb_rate") into a shadow buffer; the
+ * staged slices become live when the next rbs_advance_window returns (so: stage window k+1, then
+ * run window k, and the upload overlaps with the computation) or at once with
+ * rbs_commit_forcing_window (before the first window).  A live set of slices serves one
+ * rbs_advance_window; arrays without live slices keep their current value for the whole window.
+ * rbs_advance_window runs the
+ * window and, when storage_out_pinned is not NULL, starts the background download of the basin
+ * storages at the end of every outer step, [n_steps][n_basin][n_members]; the buffer is valid
+ * after rbs_synchronize (or after the next but one rbs_advance_window returns).  Results are
+ * identical to rbs_set_member_f64 + rbs_step_implicit_euler per step. */
+int rbs_stage_forcing_window(rbs_handle* h, const char* key, const double* pinned_host,
+                             int64_t n_entity, int32_t first_step, int32_t n_steps);
+int rbs_commit_forcing_window(rbs_handle* h);
+int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
+                       double* storage_out_pinned, int32_t* status_per_member);
 /* Solver options: abstol, reltol (core/src/config.jl:187-188), max Newton iterations. */
 int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter);
 /* Stepper options.  full_newton: 0 = J and W evaluated once per attempt at (uprev, t + h) like

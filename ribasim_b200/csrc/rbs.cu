@@ -65,6 +65,17 @@ struct rbs_handle {
     cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
     std::map<std::string, void*> shadow_in, shadow_out;
     std::vector<std::string> staged;
+    // forced windows (rbs_stage_forcing_window / rbs_advance_window): per forcing array a live and
+    // a shadow buffer [steps][entity][B]; two result buffers so that the download of one window
+    // overlaps with the computation of the next
+    double *fw_live[6] = {}, *fw_shadow[6] = {};
+    size_t fw_bytes[6] = {};
+    int fw_staged_steps[6] = {}, fw_live_steps[6] = {};
+    double* fw_res[2] = {nullptr, nullptr};
+    size_t fw_res_bytes = 0;
+    int fw_res_cur = 0;
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_win = nullptr, ev_d2h[2] = {nullptr, nullptr};
     // member groups: independent state machines on their own streams, so the latency-bound
     // kernels of one group overlap with the kernels of the others
     struct Group {
@@ -218,7 +229,7 @@ void bind_net(rbs_handle* h) {
 #define M_I(name) n.name = (int*)h->member[#name].p
     M_I(nstat); M_I(status); M_I(active_count);
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
-    M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep);
+    M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep); M_I(mroll);
     M_I(dc_truth); M_I(dc_state); M_I(cnt_dc);
 #undef M_I
 #undef S_D
@@ -420,6 +431,12 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess)
         return bail("rbs_create: copy stream creation failed");
+    if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_win, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_d2h[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_d2h[1], cudaEventDisableTiming) != cudaSuccess)
+        return bail("rbs_create: window stream creation failed");
     if (cudaMallocHost(&h->h_active, 2 * sizeof(int)) != cudaSuccess) return bail("rbs_create: pinned alloc failed");
     if (make_groups(h, geti(b, "n_groups", 0))) return bail("rbs_create: group setup failed");
     for (auto& kv : b->i) { h->hi[kv.first] = kv.second; if (upload(h, kv.first, kv.second, true)) return bail("upload"); }
@@ -494,7 +511,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
     for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mneg2", "mclamp", "mlast",
-                          "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep", "cnt_dc"})
+                          "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep", "mroll", "cnt_dc"})
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
     if (alloc_member(h, "dc_truth", n.n_dc_cond, true) || alloc_member(h, "dc_state", n.n_dc, true))
         return bail("member alloc");
@@ -755,6 +772,11 @@ void rbs_destroy(rbs_handle* h) {
     free_groups(h);
     for (auto& kv : h->shadow_in) if (kv.second) cudaFree(kv.second);
     for (auto& kv : h->shadow_out) if (kv.second) cudaFree(kv.second);
+    for (int k = 0; k < 6; k++) { if (h->fw_live[k]) cudaFree(h->fw_live[k]); if (h->fw_shadow[k]) cudaFree(h->fw_shadow[k]); }
+    for (int k = 0; k < 2; k++) { if (h->fw_res[k]) cudaFree(h->fw_res[k]); if (h->ev_d2h[k]) cudaEventDestroy(h->ev_d2h[k]); }
+    if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
+    if (h->ev_win) cudaEventDestroy(h->ev_win);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -982,6 +1004,7 @@ int rbs_synchronize(rbs_handle* h) {
     cudaSetDevice(h->device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     return check_async(h, "rbs_synchronize");
 }
 
@@ -1215,9 +1238,7 @@ int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_pe
     return check_async(h, "rbs_time_linear");
 }
 
-int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
-    if (!h) return fail("rbs_advance: null handle");
-    if (!(dt > 0) || n_steps < 1) return fail("rbs_advance: dt must be positive and n_steps >= 1");
+static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
     cudaSetDevice(h->device);
     Net& n = h->net;
     long long B = n.B;
@@ -1276,6 +1297,135 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
         for (int m = 0; m < n.B; m++) if (status_per_member[m] & 1) h->n_failed++;
     }
     return check_async(h, "rbs_advance");
+}
+
+int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
+    if (!h) return fail("rbs_advance: null handle");
+    if (!(dt > 0) || n_steps < 1) return fail("rbs_advance: dt must be positive and n_steps >= 1");
+    return advance_impl(h, t, dt, n_steps, status_per_member);
+}
+
+static const char* const FW_KEYS[6] = {"precipitation", "surface_runoff", "potential_evaporation",
+                                       "drainage", "infiltration", "fb_rate"};
+
+int rbs_stage_forcing_window(rbs_handle* h, const char* key, const double* pinned_host,
+                             int64_t n_entity, int32_t first_step, int32_t n_steps) {
+    if (!h || !key || !pinned_host) return fail("rbs_stage_forcing_window: null argument");
+    if (n_steps < 1 || first_step < 0) return fail("rbs_stage_forcing_window: invalid step range");
+    cudaSetDevice(h->device);
+    int k = -1;
+    for (int i = 0; i < 6; i++) if (!strcmp(key, FW_KEYS[i])) k = i;
+    if (k < 0) return fail(std::string("rbs_stage_forcing_window: not a forcing array: ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    size_t slice = (size_t)n_entity * h->B * sizeof(double);
+    size_t need = slice * (size_t)(first_step + n_steps);
+    if (need > h->fw_bytes[k]) {
+        // grow both buffers of this array, keeping what they hold (slices staged so far, slices
+        // committed for the next window)
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+        size_t cap = std::max(need, slice * 8);
+        for (double** buf : {&h->fw_live[k], &h->fw_shadow[k]}) {
+            double* nb_ = nullptr;
+            CUDA_TRY(cudaMalloc(&nb_, cap));
+            if (*buf) {
+                CUDA_TRY(cudaMemcpy(nb_, *buf, h->fw_bytes[k], cudaMemcpyDeviceToDevice));
+                cudaFree(*buf);
+            }
+            *buf = nb_;
+        }
+        h->fw_bytes[k] = cap;
+    }
+    // the previous window's tail (copy of its last slice into the current arrays) reads the buffer
+    // that is the shadow now
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_win, 0));
+    CUDA_TRY(cudaMemcpyAsync((char*)h->fw_shadow[k] + slice * first_step, pinned_host, slice * n_steps,
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_h2d, h->copy_stream));
+    h->fw_staged_steps[k] = std::max(h->fw_staged_steps[k], first_step + n_steps);
+    return 0;
+}
+
+// staged slices -> live (the shadow buffers take the next upload)
+static int commit_window(rbs_handle* h) {
+    bool any = false;
+    for (int k = 0; k < 6; k++) {
+        if (h->fw_staged_steps[k] == 0) continue;
+        std::swap(h->fw_live[k], h->fw_shadow[k]);
+        h->fw_live_steps[k] = h->fw_staged_steps[k];
+        h->fw_staged_steps[k] = 0;
+        any = true;
+    }
+    if (any) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d, 0));
+    return 0;
+}
+
+int rbs_commit_forcing_window(rbs_handle* h) {
+    if (!h) return fail("rbs_commit_forcing_window: null handle");
+    cudaSetDevice(h->device);
+    return commit_window(h);
+}
+
+int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
+                       double* storage_out_pinned, int32_t* status_per_member) {
+    if (!h) return fail("rbs_advance_window: null handle");
+    if (!(dt > 0) || n_steps < 1) return fail("rbs_advance_window: dt must be positive and n_steps >= 1");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    const double** wp[6] = {&n.w_precipitation, &n.w_surface_runoff, &n.w_potential_evaporation,
+                            &n.w_drainage, &n.w_infiltration, &n.w_fb_rate};
+    for (int k = 0; k < 6; k++) {
+        *wp[k] = nullptr;
+        if (h->fw_live_steps[k] == 0) continue;
+        if (h->fw_live_steps[k] < n_steps)
+            return fail(std::string("rbs_advance_window: fewer steps staged than advanced: ") + FW_KEYS[k]);
+        *wp[k] = h->fw_live[k];
+    }
+    n.fw_sb = (long long)n.n_basin * n.B;
+    n.fw_sf = (long long)n.n_fb * n.B;
+    n.w_storage = nullptr;
+    int cur = h->fw_res_cur;
+    size_t res_bytes = (size_t)n_steps * n.n_basin * n.B * sizeof(double);
+    if (storage_out_pinned && n.n_basin > 0) {
+        if (res_bytes > h->fw_res_bytes) {
+            CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
+            for (int k = 0; k < 2; k++) {
+                if (h->fw_res[k]) cudaFree(h->fw_res[k]);
+                h->fw_res[k] = nullptr;
+                CUDA_TRY(cudaMalloc(&h->fw_res[k], res_bytes));
+            }
+            h->fw_res_bytes = res_bytes;
+        }
+        // the download of the window before last used this buffer
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h[cur], 0));
+        n.w_storage = h->fw_res[cur];
+    }
+    n.fw_on = 1;
+    int rc = advance_impl(h, t, dt, n_steps, status_per_member);
+    n.fw_on = 0;
+    if (rc) return rc;
+    // the last slice stays in force (and readable through rbs_get_member_f64) after the window
+    for (int k = 0; k < 6; k++) {
+        if (!*wp[k]) continue;
+        int64_t ne = h->member_entities[FW_KEYS[k]];
+        size_t slice = (size_t)ne * n.B * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(h->member[FW_KEYS[k]].p, (const char*)h->fw_live[k] + slice * (n_steps - 1), slice,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+        *wp[k] = nullptr;
+        h->fw_live_steps[k] = 0;  // a window of slices serves one rbs_advance_window
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_win, h->stream));
+    if (n.w_storage) {
+        CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_win, 0));
+        CUDA_TRY(cudaMemcpyAsync(storage_out_pinned, h->fw_res[cur], res_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+        CUDA_TRY(cudaEventRecord(h->ev_d2h[cur], h->d2h_stream));
+        h->fw_res_cur = cur ^ 1;
+        n.w_storage = nullptr;
+    }
+    // slices staged while this window was running serve the next window
+    if (commit_window(h)) return 1;
+    return check_async(h, "rbs_advance_window");
 }
 
 int rbs_step_implicit_euler(rbs_handle* h, double t, double dt, int32_t* status_per_member) {

@@ -107,7 +107,21 @@ struct Net {
     int *cnt_iters, *cnt_sub, *cnt_rej;
     int* mstep;  // outer steps completed in the current window
     double *mh, *mhnom, *melapsed, *mhlast, *zlast;
+    // forced window (rbs_advance_window): forcing slices [step][entity][member] per outer step of
+    // the window (nullptr = the current array applies to every step) and per-step storage snapshots
+    int fw_on;
+    long long fw_sb, fw_sf;  // elements per step: n_basin*B, n_fb*B
+    const double *w_precipitation, *w_surface_runoff, *w_potential_evaporation, *w_drainage,
+        *w_infiltration, *w_fb_rate;
+    double* w_storage;
+    int* mroll;  // set by k_step_decide: the decision completed an outer step
 };
+
+// Forcing array that applies to outer step `idx` of the window.
+__device__ __forceinline__ const double* rbs_fw(const Net& n, const double* cur, const double* win,
+                                                long long stride, int idx) {
+    return (n.fw_on && win) ? win + stride * idx : cur;
+}
 
 // Member predicate of the step path: a kernel launched with `mphase != nullptr` only works on
 // members whose phase equals `want`; with `mjac != nullptr` only on members whose Jacobian
@@ -266,7 +280,9 @@ __global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pre
         n.darea[o] = e.darea;
     }
     if (write_du) {
-        double E = n.potential_evaporation[o], I = n.infiltration[o];
+        const int ws = n.fw_on ? n.mstep[m] : 0;
+        double E = rbs_fw(n, n.potential_evaporation, n.w_potential_evaporation, n.fw_sb, ws)[o];
+        double I = rbs_fw(n, n.infiltration, n.w_infiltration, n.fw_sb, ws)[o];
         n.du[(long long)(n.off_evap + b) * n.B + m] = e.area * phi * E;
         n.du[(long long)(n.off_infil + b) * n.B + m] = phi * I;
         if (JAC) {
@@ -464,11 +480,13 @@ __global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred) {
         // FlowBoundary inflows enter with their instantaneous rate (graph.jl:346-366)
         // inflow order: neighbour list order is (connector states..., boundaries) — the
         // boundary rates are added after the connector flows (rounding-level difference only)
+        const int ws = n.fw_on ? n.mstep[m] : 0;
+        const double* fbr = rbs_fw(n, n.fb_rate, n.w_fb_rate, n.fw_sf, ws);
         for (int k = n.bfb_ptr[L]; k < n.bfb_ptr[L + 1]; k++)
-            dS += n.fb_rate[(long long)n.bfb_idx[k] * n.B + m];
-        dS += n.fixed_area[L] * n.precipitation[lo];
-        dS += n.surface_runoff[lo];
-        dS += n.drainage[lo];
+            dS += fbr[(long long)n.bfb_idx[k] * n.B + m];
+        dS += n.fixed_area[L] * rbs_fw(n, n.precipitation, n.w_precipitation, n.fw_sb, ws)[lo];
+        dS += rbs_fw(n, n.surface_runoff, n.w_surface_runoff, n.fw_sb, ws)[lo];
+        dS += rbs_fw(n, n.drainage, n.w_drainage, n.fw_sb, ws)[lo];
         dS -= n.du[(long long)(n.off_evap + L) * n.B + m];
         dS -= n.du[(long long)(n.off_infil + L) * n.B + m];
         N = 0.0 - dS / area;  // dtarget = 0 for a ConstantInterpolation target (solve.jl:298-300)
@@ -1251,7 +1269,8 @@ __device__ __forceinline__ bool rbs_flow_bounds(const Net& n, int s, int m,
     if (s < n.off_integral) {
         int b = s - n.off_infil;
         double fmin_ = rbs_min_low_storage_factor(n, KIND_BASIN, b, m);
-        double infil = n.infiltration[(long long)b * n.B + m];
+        double infil = rbs_fw(n, n.infiltration, n.w_infiltration, n.fw_sb,
+                              n.fw_on ? n.mstep[m] : 0)[(long long)b * n.B + m];
         lo = fmin_ * infil; hi = infil;
         return true;
     }
@@ -1395,20 +1414,29 @@ __global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out
 // Exact cumulative forcing at the end of the member's current attempt (solve.jl:137-150, 86-99);
 // on ACCEPT first advances the cumulatives by the accepted length (callback.jl:125-182).
 __device__ __forceinline__ void rbs_exact_update(const Net& n, int b, int m, bool accept, double h_acc,
-                                                 bool next, double h_next) {
+                                                 bool next, double h_next, int ws_acc, int ws_next) {
+    // ws_acc / ws_next: outer step (of a forced window) the accepted attempt belonged to / the
+    // next attempt belongs to
     long long o = (long long)b * n.B + m;
-    double P = n.fixed_area[b] * n.precipitation[o], R = n.surface_runoff[o], D = n.drainage[o];
     double cp = n.cum_precipitation[o], cr = n.cum_surface_runoff[o], cd = n.cum_drainage[o];
     if (accept) {
+        double P = n.fixed_area[b] * rbs_fw(n, n.precipitation, n.w_precipitation, n.fw_sb, ws_acc)[o];
+        double R = rbs_fw(n, n.surface_runoff, n.w_surface_runoff, n.fw_sb, ws_acc)[o];
+        double D = rbs_fw(n, n.drainage, n.w_drainage, n.fw_sb, ws_acc)[o];
         cp += P * h_acc; cr += h_acc * R; cd += h_acc * D;
         n.cum_precipitation[o] = cp; n.cum_surface_runoff[o] = cr; n.cum_drainage[o] = cd;
     }
+    double P = n.fixed_area[b] * rbs_fw(n, n.precipitation, n.w_precipitation, n.fw_sb, ws_next)[o];
+    double R = rbs_fw(n, n.surface_runoff, n.w_surface_runoff, n.fw_sb, ws_next)[o];
+    double D = rbs_fw(n, n.drainage, n.w_drainage, n.fw_sb, ws_next)[o];
     double ex = ((cp + P * h_next) + (cr + h_next * R)) + (cd + h_next * D);
+    const double* fr_acc = rbs_fw(n, n.fb_rate, n.w_fb_rate, n.fw_sf, ws_acc);
+    const double* fr_next = rbs_fw(n, n.fb_rate, n.w_fb_rate, n.fw_sf, ws_next);
     for (int k = n.bfb_ptr[b]; k < n.bfb_ptr[b + 1]; k++) {
         long long f = (long long)n.bfb_idx[k] * n.B + m;
-        double fc = n.fb_cum[f], fr = n.fb_rate[f];
-        if (accept) { fc += fr * h_acc; n.fb_cum[f] = fc; }
-        ex += fc + fr * h_next;
+        double fc = n.fb_cum[f];
+        if (accept) { fc += fr_acc[f] * h_acc; n.fb_cum[f] = fc; }
+        ex += fc + fr_next[f] * h_next;
     }
     if (next) n.exact[o] = ex;
 }
@@ -1427,7 +1455,7 @@ __global__ void k_step_begin(Net n, double dt, int predictor) {
     }
     long long bt = tid - total;
     if (bt >= 0 && bt < (long long)n.n_basin * n.B)
-        rbs_exact_update(n, (int)(bt / n.B), m, false, 0.0, true, h);
+        rbs_exact_update(n, (int)(bt / n.B), m, false, 0.0, true, h, 0, 0);
     long long mt = bt - (long long)n.n_basin * n.B;
     if (mt >= 0 && mt < n.B) {
         n.mhnom[m] = hnom;
@@ -1496,6 +1524,7 @@ __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, 
         n.cnt_rej[m] += 1;
         n.maction[m] = ACTION_REJECT;
     }
+    n.mroll[m] = elapsed >= dt;
     if (elapsed >= dt) {
         // outer step finished: the member goes straight on to its next outer step of the
         // window (members never wait for each other), or is done
@@ -1547,7 +1576,12 @@ __global__ void k_step_apply(Net n, int predictor) {
         if (next) n.z[o] = (predictor && hl > 0.0) ? zl * (h_next / hl) : 0.0;
         return;
     }
-    rbs_exact_update(n, ent - n.n_state, m, action == ACTION_ACCEPT, hl, next, h_next);
+    const int ws = n.mstep[m], roll = n.mroll[m];
+    const int b = ent - n.n_state;
+    // the forcing of a finished window's last step keeps applying until the caller changes it
+    rbs_exact_update(n, b, m, action == ACTION_ACCEPT, hl, next, h_next, ws - roll, next ? ws : ws - roll);
+    if (n.fw_on && n.w_storage && roll)  // storages at the end of outer step ws - 1
+        n.w_storage[n.fw_sb * (ws - 1) + (long long)b * n.B + m] = n.storage[(long long)b * n.B + m];
 }
 
 // ---- DiscreteControl (apply_discrete_control!, core/src/callback.jl:608-661) ----------------------

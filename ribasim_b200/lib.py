@@ -83,6 +83,9 @@ def load() -> ctypes.CDLL:
         "rbs_get_member_f64": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_set_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_get_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
+        "rbs_stage_forcing_window": (ctypes.c_int, [vp, cp, dp, i64, i32, i32]),
+        "rbs_advance_window": (ctypes.c_int, [vp, f64, f64, i32, dp, ip]),
+        "rbs_commit_forcing_window": (ctypes.c_int, [vp]),
         "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
         "rbs_get_member_i32": (ctypes.c_int, [vp, cp, ip, i64]),
         "rbs_apply_discrete_control": (ctypes.c_int, [vp]),
@@ -118,7 +121,7 @@ EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64", "rbs_set_member_f64_async",
-    "rbs_get_member_f64_async",
+    "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
     "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
@@ -297,6 +300,27 @@ class Handle:
         """Background download into pinned memory; valid after synchronize()."""
         _check(self.L.rbs_get_member_f64_async(
             self.h, key.encode(), ctypes.cast(pinned_ptr, ctypes.POINTER(ctypes.c_double)), n_entity))
+
+    def stage_forcing_window(self, key: str, pinned_ptr: int, n_entity: int, n_steps: int,
+                             first_step: int = 0) -> None:
+        """Upload the forcing slices [n_steps][n_entity][B] of outer steps first_step.. of the next
+        forced window (pinned host memory, asynchronous)."""
+        _check(self.L.rbs_stage_forcing_window(
+            self.h, key.encode(), ctypes.cast(pinned_ptr, ctypes.POINTER(ctypes.c_double)), n_entity,
+            int(first_step), int(n_steps)))
+
+    def commit_forcing_window(self) -> None:
+        """Make the staged slices live now (before the first window)."""
+        _check(self.L.rbs_commit_forcing_window(self.h))
+
+    def advance_window(self, t: float, dt: float, n_steps: int, storage_out_ptr: int | None = None,
+                       want_status: bool = True) -> np.ndarray | None:
+        """Forced window: staged per-step forcing in, per-step storages out (pinned, background)."""
+        st = np.zeros(self.B, dtype=np.int32) if want_status else None
+        out = ctypes.cast(storage_out_ptr, ctypes.POINTER(ctypes.c_double)) if storage_out_ptr else None
+        _check(self.L.rbs_advance_window(self.h, float(t), float(dt), int(n_steps), out,
+                                         _ip(st) if want_status else None))
+        return st
 
     def copy_member_to_device(self, key: str, device_ptr: int, n_entity: int) -> None:
         _check(self.L.rbs_copy_member_to_device(self.h, key.encode(), ctypes.c_void_p(device_ptr),

@@ -402,6 +402,74 @@ def test_advance_window_equals_single_steps():
     assert out[1][3]["passes"] <= out[0][3]["passes"]
 
 
+def test_forced_window_equals_per_step_forcing():
+    """rbs_stage_forcing_window + rbs_advance_window (forcing that changes every outer step, staged
+    from pinned memory; members cross the step boundaries at their own pace) = rbs_set_member_f64 +
+    rbs_step_implicit_euler per step, bitwise; the streamed-back storages are the storages at the
+    end of every outer step.  Two windows back to back exercise the buffer swap."""
+    import torch
+    from ribasim_b200.testmodels import hws_like_model
+    B, W, dt = 40, 5, 1800.0
+    case = make_case(hws_like_model(n_basins=60, n_days=2), B, seed=23, t=0.0)
+    flat = case["flat"]
+    n, nb, nfb = flat["n_state"], flat["n_basin"], flat["n_fb"]
+    rng = np.random.default_rng(5)
+    keys = {"precipitation": nb, "potential_evaporation": nb, "drainage": nb, "fb_rate": nfb}
+    base = {k: (case["fb_rate"] if k == "fb_rate" else case["forcing"][k]) for k in keys}
+    # forcing of the 2 W outer steps: member- and step-dependent factors
+    series = {k: np.stack([base[k] * rng.lognormal(0.0, 0.4, size=base[k].shape) for _ in range(2 * W)])
+              for k in keys}
+
+    def prepare():
+        h = gpu_handle_for(case)
+        h.set_stepper(full_newton=True)
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        return h
+
+    h = prepare()
+    try:
+        S_ref, st_ref = [], np.zeros(B, dtype=np.int32)
+        for s in range(2 * W):
+            for k in keys:
+                h.set_member(k, series[k][s])
+            st_ref |= h.step(s * dt, dt)
+            S_ref.append(h.get_member("storage", nb))
+        u_ref, stats_ref = h.get_member("u", n), h.stats()
+    finally:
+        h.close()
+    h = prepare()
+    try:
+        pinned = {k: [torch.from_numpy(np.ascontiguousarray(series[k][w * W:(w + 1) * W])).pin_memory()
+                      for w in range(2)] for k in keys}
+        out = [torch.zeros((W, nb, B), dtype=torch.float64).pin_memory() for _ in range(2)]
+        st = np.zeros(B, dtype=np.int32)
+        for k in keys:
+            h.stage_forcing_window(k, pinned[k][0].data_ptr(), keys[k], W)
+        h.commit_forcing_window()
+        for w in range(2):
+            if w == 0:  # uploaded (in two chunks) while window 0 runs, live when it returns
+                for k in keys:
+                    sl = keys[k] * B * 8
+                    h.stage_forcing_window(k, pinned[k][1].data_ptr(), keys[k], 2)
+                    h.stage_forcing_window(k, pinned[k][1].data_ptr() + 2 * sl, keys[k], W - 2, first_step=2)
+            st |= h.advance_window(w * W * dt, dt, W, out[w].data_ptr())
+        h.synchronize()
+        u, stats = h.get_member("u", n), h.stats()
+        last = {k: h.get_member(k, keys[k]) for k in keys}
+    finally:
+        h.close()
+    assert np.array_equal(u, u_ref)
+    assert np.array_equal(st, st_ref)
+    for k in ("substeps", "newton_iters", "rejects"):
+        assert stats[k] == stats_ref[k]
+    assert stats["passes"] <= stats_ref["passes"]
+    for s in range(2 * W):
+        assert np.array_equal(out[s // W][s % W].numpy(), S_ref[s]), s
+    for k in keys:  # the last slice stays in force
+        assert np.array_equal(last[k], series[k][2 * W - 1])
+
+
 @pytest.mark.parametrize("n_basins,B", [(200, 512), (500, 4096)])
 def test_water_balance_closes_at_full_size(n_basins, B):
     """Size-independent property up to the full bench size (BASELINE config 4: 500 basins x 4096
