@@ -154,14 +154,18 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
  * rbs_advance_window; arrays without live slices keep their current value for the whole window.
  * rbs_advance_window runs the
  * window and, when storage_out_pinned is not NULL, starts the background download of the basin
- * storages at the end of every outer step, [n_steps][n_basin][n_members]; the buffer is valid
- * after rbs_synchronize (or after the next but one rbs_advance_window returns).  Results are
- * identical to rbs_set_member_f64 + rbs_step_implicit_euler per step. */
+ * storages at the end of every outer step, [n_steps][n_basin][n_members]; with flow_out_pinned
+ * likewise the mean flow over every outer step of every state (increment of the cumulative
+ * state / dt: what `save_flow` stores per saveat interval, core/src/callback.jl:390-456),
+ * [n_steps][n_state][n_members].  The buffers are valid after rbs_synchronize (or after the next
+ * but one rbs_advance_window returns).  Results are identical to rbs_set_member_f64 +
+ * rbs_step_implicit_euler per step. */
 int rbs_stage_forcing_window(rbs_handle* h, const char* key, const double* pinned_host,
                              int64_t n_entity, int32_t first_step, int32_t n_steps);
 int rbs_commit_forcing_window(rbs_handle* h);
 int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
-                       double* storage_out_pinned, int32_t* status_per_member);
+                       double* storage_out_pinned, double* flow_out_pinned,
+                       int32_t* status_per_member);
 /* Solver options: abstol, reltol (core/src/config.jl:187-188), max Newton iterations. */
 int rbs_set_solver(rbs_handle* h, double abstol, double reltol, int32_t max_iter);
 /* Stepper options.  full_newton: 0 = J and W evaluated once per attempt at (uprev, t + h) like

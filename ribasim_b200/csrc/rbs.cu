@@ -73,6 +73,8 @@ struct rbs_handle {
     int fw_staged_steps[6] = {}, fw_live_steps[6] = {};
     double* fw_res[2] = {nullptr, nullptr};
     size_t fw_res_bytes = 0;
+    double* fw_flow[2] = {nullptr, nullptr};
+    size_t fw_flow_bytes = 0;
     int fw_res_cur = 0;
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_win = nullptr, ev_d2h[2] = {nullptr, nullptr};
@@ -507,7 +509,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         {"level_prev", n.n_basin}, {"fb_rate", n.n_fb}, {"fb_cum", n.n_fb}, {"frp", n.n_pump},
         {"fro", n.n_outlet}, {"jv", n.nnz_j}, {"wv", n.nnz_w}, {"lu", n.n_lu},
         {"norm_part", h->n_part}, {"ndz", 1}, {"ndz_prev", 1}, {"eta", 1},
-        {"zlast", n.n_state}, {"mh", 1}, {"mhnom", 1}, {"melapsed", 1}, {"mhlast", 1},
+        {"zlast", n.n_state}, {"ustep", n.n_state}, {"mh", 1}, {"mhnom", 1}, {"melapsed", 1}, {"mhlast", 1},
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
     for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mneg2", "mclamp", "mlast",
@@ -773,7 +775,11 @@ void rbs_destroy(rbs_handle* h) {
     for (auto& kv : h->shadow_in) if (kv.second) cudaFree(kv.second);
     for (auto& kv : h->shadow_out) if (kv.second) cudaFree(kv.second);
     for (int k = 0; k < 6; k++) { if (h->fw_live[k]) cudaFree(h->fw_live[k]); if (h->fw_shadow[k]) cudaFree(h->fw_shadow[k]); }
-    for (int k = 0; k < 2; k++) { if (h->fw_res[k]) cudaFree(h->fw_res[k]); if (h->ev_d2h[k]) cudaEventDestroy(h->ev_d2h[k]); }
+    for (int k = 0; k < 2; k++) {
+        if (h->fw_res[k]) cudaFree(h->fw_res[k]);
+        if (h->fw_flow[k]) cudaFree(h->fw_flow[k]);
+        if (h->ev_d2h[k]) cudaEventDestroy(h->ev_d2h[k]);
+    }
     if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
     if (h->ev_win) cudaEventDestroy(h->ev_win);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
@@ -1368,7 +1374,8 @@ int rbs_commit_forcing_window(rbs_handle* h) {
 }
 
 int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
-                       double* storage_out_pinned, int32_t* status_per_member) {
+                       double* storage_out_pinned, double* flow_out_pinned,
+                       int32_t* status_per_member) {
     if (!h) return fail("rbs_advance_window: null handle");
     if (!(dt > 0) || n_steps < 1) return fail("rbs_advance_window: dt must be positive and n_steps >= 1");
     cudaSetDevice(h->device);
@@ -1397,10 +1404,26 @@ int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
             }
             h->fw_res_bytes = res_bytes;
         }
-        // the download of the window before last used this buffer
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h[cur], 0));
         n.w_storage = h->fw_res[cur];
     }
+    n.w_flow = nullptr;
+    n.fw_dt = dt;
+    size_t flow_bytes = (size_t)n_steps * n.n_state * n.B * sizeof(double);
+    if (flow_out_pinned) {
+        if (flow_bytes > h->fw_flow_bytes) {
+            CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
+            for (int k = 0; k < 2; k++) {
+                if (h->fw_flow[k]) cudaFree(h->fw_flow[k]);
+                h->fw_flow[k] = nullptr;
+                CUDA_TRY(cudaMalloc(&h->fw_flow[k], flow_bytes));
+            }
+            h->fw_flow_bytes = flow_bytes;
+        }
+        n.w_flow = h->fw_flow[cur];
+        n.ustep = mp(h, "ustep");
+    }
+    // the downloads of the window before last used these buffers
+    if (n.w_storage || n.w_flow) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h[cur], 0));
     n.fw_on = 1;
     int rc = advance_impl(h, t, dt, n_steps, status_per_member);
     n.fw_on = 0;
@@ -1416,12 +1439,16 @@ int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
         h->fw_live_steps[k] = 0;  // a window of slices serves one rbs_advance_window
     }
     CUDA_TRY(cudaEventRecord(h->ev_win, h->stream));
-    if (n.w_storage) {
+    if (n.w_storage || n.w_flow) {
         CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_win, 0));
-        CUDA_TRY(cudaMemcpyAsync(storage_out_pinned, h->fw_res[cur], res_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (n.w_storage)
+            CUDA_TRY(cudaMemcpyAsync(storage_out_pinned, h->fw_res[cur], res_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (n.w_flow)
+            CUDA_TRY(cudaMemcpyAsync(flow_out_pinned, h->fw_flow[cur], flow_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
         CUDA_TRY(cudaEventRecord(h->ev_d2h[cur], h->d2h_stream));
         h->fw_res_cur = cur ^ 1;
         n.w_storage = nullptr;
+        n.w_flow = nullptr;
     }
     // slices staged while this window was running serve the next window
     if (commit_window(h)) return 1;

@@ -114,6 +114,8 @@ struct Net {
     const double *w_precipitation, *w_surface_runoff, *w_potential_evaporation, *w_drainage,
         *w_infiltration, *w_fb_rate;
     double* w_storage;
+    double *w_flow, *ustep;  // mean flows per outer step [step][state][member]; u at its start
+    double fw_dt;            // length of an outer step of the window
     int* mroll;  // set by k_step_decide: the decision completed an outer step
 };
 
@@ -1450,7 +1452,9 @@ __global__ void k_step_begin(Net n, double dt, int predictor) {
     double h = hnom;  // elapsed = 0: the remainder is dt
     if (tid < total) {
         double hl = n.mhlast[m];
-        n.uprev[tid] = n.u[tid];
+        const double u0 = n.u[tid];
+        n.uprev[tid] = u0;
+        if (n.fw_on && n.w_flow) n.ustep[tid] = u0;
         n.z[tid] = (predictor && hl > 0.0) ? n.zlast[tid] * (h / hl) : 0.0;
     }
     long long bt = tid - total;
@@ -1569,6 +1573,12 @@ __global__ void k_step_apply(Net n, int predictor) {
             zl = un - n.uprev[o];
             n.zlast[o] = zl;
             n.uprev[o] = un;
+            if (n.fw_on && n.w_flow && n.mroll[m]) {
+                // mean flow over the finished outer step = increment of the cumulative state
+                // (save_flow, core/src/callback.jl:390-456)
+                n.w_flow[(long long)n.n_state * n.B * (n.mstep[m] - 1) + o] = (un - n.ustep[o]) / n.fw_dt;
+                n.ustep[o] = un;
+            }
         } else {
             n.u[o] = n.uprev[o];
             zl = n.zlast[o];

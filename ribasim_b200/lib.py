@@ -84,7 +84,7 @@ def load() -> ctypes.CDLL:
         "rbs_set_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_get_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_stage_forcing_window": (ctypes.c_int, [vp, cp, dp, i64, i32, i32]),
-        "rbs_advance_window": (ctypes.c_int, [vp, f64, f64, i32, dp, ip]),
+        "rbs_advance_window": (ctypes.c_int, [vp, f64, f64, i32, dp, dp, ip]),
         "rbs_commit_forcing_window": (ctypes.c_int, [vp]),
         "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
         "rbs_get_member_i32": (ctypes.c_int, [vp, cp, ip, i64]),
@@ -314,11 +314,14 @@ class Handle:
         _check(self.L.rbs_commit_forcing_window(self.h))
 
     def advance_window(self, t: float, dt: float, n_steps: int, storage_out_ptr: int | None = None,
-                       want_status: bool = True) -> np.ndarray | None:
-        """Forced window: staged per-step forcing in, per-step storages out (pinned, background)."""
+                       want_status: bool = True, flow_out_ptr: int | None = None) -> np.ndarray | None:
+        """Forced window: staged per-step forcing in; per-step storages and mean flows out
+        (pinned host buffers, filled in the background)."""
         st = np.zeros(self.B, dtype=np.int32) if want_status else None
-        out = ctypes.cast(storage_out_ptr, ctypes.POINTER(ctypes.c_double)) if storage_out_ptr else None
-        _check(self.L.rbs_advance_window(self.h, float(t), float(dt), int(n_steps), out,
+        dpt = ctypes.POINTER(ctypes.c_double)
+        out = ctypes.cast(storage_out_ptr, dpt) if storage_out_ptr else None
+        fout = ctypes.cast(flow_out_ptr, dpt) if flow_out_ptr else None
+        _check(self.L.rbs_advance_window(self.h, float(t), float(dt), int(n_steps), out, fout,
                                          _ip(st) if want_status else None))
         return st
 

@@ -429,12 +429,13 @@ def test_forced_window_equals_per_step_forcing():
 
     h = prepare()
     try:
-        S_ref, st_ref = [], np.zeros(B, dtype=np.int32)
+        S_ref, U_ref, st_ref = [], [h.get_member("u", n)], np.zeros(B, dtype=np.int32)
         for s in range(2 * W):
             for k in keys:
                 h.set_member(k, series[k][s])
             st_ref |= h.step(s * dt, dt)
             S_ref.append(h.get_member("storage", nb))
+            U_ref.append(h.get_member("u", n))
         u_ref, stats_ref = h.get_member("u", n), h.stats()
     finally:
         h.close()
@@ -443,6 +444,7 @@ def test_forced_window_equals_per_step_forcing():
         pinned = {k: [torch.from_numpy(np.ascontiguousarray(series[k][w * W:(w + 1) * W])).pin_memory()
                       for w in range(2)] for k in keys}
         out = [torch.zeros((W, nb, B), dtype=torch.float64).pin_memory() for _ in range(2)]
+        flow = [torch.zeros((W, n, B), dtype=torch.float64).pin_memory() for _ in range(2)]
         st = np.zeros(B, dtype=np.int32)
         for k in keys:
             h.stage_forcing_window(k, pinned[k][0].data_ptr(), keys[k], W)
@@ -453,7 +455,7 @@ def test_forced_window_equals_per_step_forcing():
                     sl = keys[k] * B * 8
                     h.stage_forcing_window(k, pinned[k][1].data_ptr(), keys[k], 2)
                     h.stage_forcing_window(k, pinned[k][1].data_ptr() + 2 * sl, keys[k], W - 2, first_step=2)
-            st |= h.advance_window(w * W * dt, dt, W, out[w].data_ptr())
+            st |= h.advance_window(w * W * dt, dt, W, out[w].data_ptr(), flow_out_ptr=flow[w].data_ptr())
         h.synchronize()
         u, stats = h.get_member("u", n), h.stats()
         last = {k: h.get_member(k, keys[k]) for k in keys}
@@ -466,6 +468,8 @@ def test_forced_window_equals_per_step_forcing():
     assert stats["passes"] <= stats_ref["passes"]
     for s in range(2 * W):
         assert np.array_equal(out[s // W][s % W].numpy(), S_ref[s]), s
+        # mean flow of every state over the outer step = increment of the cumulative state / dt
+        assert np.array_equal(flow[s // W][s % W].numpy(), (U_ref[s + 1] - U_ref[s]) / dt), s
     for k in keys:  # the last slice stays in force
         assert np.array_equal(last[k], series[k][2 * W - 1])
 
