@@ -487,7 +487,7 @@ def main():
 def ncu_traffic(group: str):
     """dram read+write bytes per launch of the group's main kernel from the committed
     `ncu --set full` capture (profiles/r1_*.txt; full 4096-member launch), or None."""
-    main = {"linear_solve": "k_newton_linear_smem", "rhs_jacobian": "k_links",
+    main = {"linear_solve": "k_newton_linear_ent", "rhs_jacobian": "k_links",
             "newton_update": "k_newton_update", "limiter_accept": "k_step_apply"}.get(group)
     f = ROOT / "profiles" / f"r1_{main}.txt"
     if main is None or not f.exists():
