@@ -317,34 +317,18 @@ def main():
     step = 0
 
     W = max(1, min(args.e2e_window, 24))
-    stage_w: dict[int, dict] = {}  # day -> pinned [W][entity][member] slices (one per outer step)
     results = [pinned((W, nb, nm)) for _ in range(2)]
     e2e_count = {"h2d": 0, "d2h": 0, "calls": 0}
 
-    def fill_day_window(day):
-        """Per-step forcing slices of one day for the forced-window calls (host side, untimed:
-        the ensemble's input producer)."""
-        if day in stage_w:
-            return
-        fill_day(day)
-        stage_w[day] = {}
-        for k in keys:
-            buf = pinned((W,) + tuple(stage[day][k].shape))
-            buf[:] = stage[day][k]
-            stage_w[day][k] = buf
-
     def stage_window(step0, w):
-        """Slices of outer steps step0 .. step0 + w - 1 (a window may span a daily change: one
-        chunk per day)."""
-        first = 0
-        while first < w:
-            day = (step0 + first) // 24
-            cnt = min(w - first, 24 - (step0 + first) % 24)
+        """Forcing slices of outer steps step0 .. step0 + w - 1, one upload per outer step from the
+        pinned arrays of its day (a window may span a daily change)."""
+        for s in range(w):
+            day = (step0 + s) // 24
             for key in keys:
-                src = stage_w[day][key]
-                h.stage_forcing_window(key, src.data_ptr(), src.shape[1], cnt, first_step=first)
-                e2e_count["h2d"] += cnt * src.shape[1] * nm * 8
-            first += cnt
+                src = stage[day][key]
+                h.stage_forcing_window(key, src.data_ptr(), src.shape[0], 1, first_step=s)
+                e2e_count["h2d"] += src.shape[0] * nm * 8
 
     def run_steps(k, e2e=False):
         """Device-resident path: windows of outer steps up to the next daily forcing change in one
@@ -414,7 +398,7 @@ def main():
     for d in [d for d in stage if d < step // 24]:
         del stage[d]
     for d in range(step // 24, (step + args.steps + 3 * W) // 24 + 1):
-        fill_day_window(d)
+        fill_day(d)
     stage_window(step, W)
     h.commit_forcing_window()
     run_steps(W, e2e=True)  # primes the pipeline: the first timed window's slices are in flight
