@@ -171,9 +171,13 @@ def test_patterns_are_consistent(name):
 
 
 @pytest.mark.parametrize("name,kw", [("basic", {}), ("backwater", {}), ("pid_control", {}),
-                                     ("outlet_continuous_control", {}), ("user_demand", {})])
+                                     ("outlet_continuous_control", {}), ("user_demand", {}),
+                                     ("hws_like", dict(n_basins=150, n_days=1)),
+                                     ("random_tree", dict(n_basins=400, n_hours=2))])
 def test_symbolic_lu_solves(name, kw):
-    p = build_params(MODELS[name](**kw))
+    from ribasim_b200.testmodels import hws_like_model, random_tree_model
+    make = dict(MODELS, hws_like=hws_like_model, random_tree=random_tree_model)[name]
+    p = build_params(make(**kw))
     flat = flatten(p)
     nr = flat["n_reduced"]
     sym = analyse(nr, flat["wrow_ptr"], flat["wcol"])
@@ -200,6 +204,19 @@ def test_symbolic_lu_solves(name, kw):
     xe = numeric_entries(sym, ent, wv, b)
     assert np.allclose(W @ xe, b, rtol=1e-10, atol=1e-10)
     assert ent.lvl_ptr[-1] == ent.ent_e.size and len(ent.team_log) == ent.n_elim + ent.n_bwd
+    # race freedom of a level on the device: a slot is written by one entry only and no entry
+    # reads a slot that the level writes (levels are separated by block barriers)
+    for lv in range(ent.n_elim + ent.n_bwd):
+        written, read = [], set()
+        for k in range(ent.lvl_ptr[lv], ent.lvl_ptr[lv + 1]):
+            written.append(int(ent.ent_e[k]))
+            cnt, q0 = int(ent.ent_cf[k]) & 0xFF, int(ent.ent_q0[k])
+            for q in range(q0, q0 + cnt):
+                read.update((int(ent.prod_l[q]), int(ent.prod_p[q]), int(ent.prod_u[q])))
+            if int(ent.ent_cf[k]) & 0x200 and cnt == 0:
+                read.add(q0)  # the reciprocal pivot of a row without U entries
+        assert len(written) == len(set(written)), lv
+        assert not (read & set(written)), lv
 
 
 def test_symbolic_lu_chain_is_logarithmic():
