@@ -73,6 +73,32 @@ def full_reports():
             f.write(f"# dram traffic (read+write): {rd + wr:.3f} {d['dram__bytes_read.sum'][0]}\n")
 
 
+def summary_table():
+    """Achieved DRAM bandwidth per kernel (ncu dram bytes / duration of one full launch) against
+    the box-measured copy peak and the nominal 8 TB/s (BASELINE.json: 'RHS HBM GB/s')."""
+    import json
+    import re
+    peaks = ROOT / "MEASURED_PEAKS.json"
+    peak = float(json.loads(peaks.read_text())["hbm_gbs"]) if peaks.exists() else 6542.1
+    rows = []
+    for f in sorted((ROOT / "profiles").glob(f"{tag}_k_*.txt")):
+        txt = f.read_text()
+        name = re.search(r"one launch of (?:void )?([^(]+)", txt).group(1).strip()
+        us = float(re.search(r"gpu__time_duration.sum\s+([\d.,]+)\s+us", txt).group(1).replace(",", ""))
+        m = re.search(r"# dram traffic \(read\+write\): ([\d.]+) (\w+)", txt)
+        mb = float(m.group(1)) * {"Mbyte": 1.0, "Gbyte": 1e3, "Kbyte": 1e-3}[m.group(2)]
+        gbs = mb * 1e6 / (us * 1e-6) / 1e9
+        rows.append((name, us, mb, gbs))
+    with open(ROOT / "profiles" / f"summary_{tag}.md", "w") as out:
+        out.write(f"# ncu --set full, one full launch each (4096 members, 500 basins), round {tag}\n\n"
+                  f"Peak: {peak:.0f} GB/s measured copy bandwidth (MEASURED_PEAKS.json); 8000 GB/s nominal.\n\n"
+                  "| kernel | duration (us) | DRAM read+write (MB) | GB/s | % of measured peak | % of 8 TB/s |\n"
+                  "|---|---|---|---|---|---|\n")
+        for name, us, mb, gbs in rows:
+            out.write(f"| `{name}` | {us:.1f} | {mb:.1f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {100 * gbs / 8000:.0f} |\n")
+
+
 launch_list()
 full_reports()
+summary_table()
 print("written:", sorted(p.name for p in (ROOT / "profiles").glob(f"*{tag}*")))
