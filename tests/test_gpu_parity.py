@@ -474,6 +474,40 @@ def test_forced_window_equals_per_step_forcing():
         assert np.array_equal(last[k], series[k][2 * W - 1])
 
 
+def test_forced_window_argument_errors():
+    """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
+    slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
+    import torch
+    from ribasim_b200 import lib
+    case = make_case("basic", 4, seed=3, t=0.0)
+    flat = case["flat"]
+    nb = flat["n_basin"]
+    ref = gpu_handle_for(case)
+    h = gpu_handle_for(case)
+    try:
+        for x in (ref, h):
+            x.refresh(0.0)
+            x.set_member("level_prev", x.get_member("level", nb))
+        buf = torch.zeros((3, nb, 4), dtype=torch.float64).pin_memory()
+        buf[:] = torch.from_numpy(case["forcing"]["precipitation"])
+        with pytest.raises(lib.RbsError, match="not a forcing array"):
+            h.stage_forcing_window("level", buf.data_ptr(), nb, 3)
+        with pytest.raises(lib.RbsError, match="size mismatch"):
+            h.stage_forcing_window("precipitation", buf.data_ptr(), nb + 1, 3)
+        h.stage_forcing_window("precipitation", buf.data_ptr(), nb, 3)
+        h.commit_forcing_window()
+        with pytest.raises(lib.RbsError, match="fewer steps staged"):
+            h.advance_window(0.0, 3600.0, 4)
+        st = h.advance_window(0.0, 3600.0, 3)      # the staged slices equal the current forcing
+        st2 = h.advance_window(3 * 3600.0, 3600.0, 2)  # nothing staged: constant forcing
+        st_ref = ref.advance(0.0, 3600.0, 5)
+        assert np.array_equal(st | st2, st_ref)
+        assert np.array_equal(h.get_member("u", flat["n_state"]), ref.get_member("u", flat["n_state"]))
+    finally:
+        h.close()
+        ref.close()
+
+
 @pytest.mark.parametrize("n_basins,B", [(200, 512), (500, 4096)])
 def test_water_balance_closes_at_full_size(n_basins, B):
     """Size-independent property up to the full bench size (BASELINE config 4: 500 basins x 4096
