@@ -543,3 +543,56 @@ def test_water_balance_closes_at_full_size(n_basins, B):
         assert np.max(np.abs(S - S_expect) / scale) < 1e-11
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("n_basins,B", [(200, 512), (500, 4096)])
+def test_forced_window_outputs_close_the_water_balance(n_basins, B):
+    """Size-independent property of the streamed window outputs up to the full bench size: for
+    every basin, member and outer step the storage increment equals dt x (the mean flows of the
+    incident states with their signs - evaporation - infiltration + the step's own forcing slice),
+    i.e. storages, mean flows and forcing slices belong to the same outer step."""
+    import torch
+    from ribasim_b200.testmodels import hws_like_model
+    W, dt = 4, 3600.0
+    case = make_case(hws_like_model(n_basins=n_basins, n_days=2), B, seed=31, t=0.0)
+    flat, p = case["flat"], case["p"]
+    nb, n, nfb = flat["n_basin"], flat["n_state"], flat["n_fb"]
+    rng = np.random.default_rng(9)
+    keys = {"precipitation": nb, "drainage": nb, "fb_rate": nfb}
+    base = {k: (case["fb_rate"] if k == "fb_rate" else case["forcing"][k]) for k in keys}
+    fac = rng.lognormal(0.0, 0.3, size=(W, 1, 1))  # one factor per outer step keeps memory small
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(base[k][None] * fac)).pin_memory() for k in keys}
+    out = torch.zeros((W, nb, B), dtype=torch.float64).pin_memory()
+    flow = torch.zeros((W, n, B), dtype=torch.float64).pin_memory()
+    h = gpu_handle_for(case)
+    try:
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        S0 = h.get_member("storage", nb)
+        for k in keys:
+            h.stage_forcing_window(k, pinned[k].data_ptr(), keys[k], W)
+        h.commit_forcing_window()
+        st = h.advance_window(0.0, dt, W, out.data_ptr(), flow_out_ptr=flow.data_ptr())
+        h.synchronize()
+        assert not np.any(st), "forced accepts / negative storage"
+    finally:
+        h.close()
+    S = np.concatenate([S0[None], out.numpy()])
+    F = flow.numpy()
+    area = np.array([a[-1] for a in p.basin.areas])[:, None]
+    inc_ptr, inc_state, inc_sign = flat["inc_ptr"], flat["inc_state"], flat["inc_sign"]
+    worst = 0.0
+    for k in range(W):
+        net = np.zeros((nb, B))
+        for b in range(nb):
+            for q in range(inc_ptr[b], inc_ptr[b + 1]):
+                net[b] += inc_sign[q] * F[k, inc_state[q]]
+            for q in range(flat["bfb_ptr"][b], flat["bfb_ptr"][b + 1]):
+                net[b] += pinned["fb_rate"][k, flat["bfb_idx"][q]].numpy()
+        net -= F[k, flat["off_evap"]:flat["off_evap"] + nb] + F[k, flat["off_infil"]:flat["off_infil"] + nb]
+        net += pinned["precipitation"][k].numpy() * area + case["forcing"]["surface_runoff"] \
+            + pinned["drainage"][k].numpy()
+        dS = S[k + 1] - S[k]
+        scale = np.maximum(np.abs(S[k + 1]), 1.0)
+        worst = max(worst, float(np.max(np.abs(dS - dt * net) / scale)))
+    assert worst < 1e-10, worst
