@@ -716,21 +716,36 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             es.n_elim = geti(b, "ent_n_elim"); es.n_bwd = geti(b, "ent_n_bwd");
             es.n_slots = n.n_lu + n.n_reduced; es.y0 = n.n_lu;
             es.dbg = getenv("RBS_ENT_DBG") ? atoi(getenv("RBS_ENT_DBG")) : 0;
-            std::vector<uint16_t> hb;
-            auto put16 = [&](const std::vector<int32_t>& v) {
-                int off = (int)hb.size();
-                for (int32_t x : v) hb.push_back((uint16_t)x);
-                return off;
-            };
-            put16(geta("ent_e"));
-            es.off_q0 = put16(geta("ent_q0")); es.off_cf = put16(geta("ent_cf"));
-            es.off_pl = put16(geta("ent_prod_l")); es.off_pp = put16(geta("ent_prod_p"));
-            es.off_pu = put16(geta("ent_prod_u")); es.off_lvl = put16(geta("ent_lvl_ptr"));
-            es.off_team = put16(geta("ent_team_log")); es.off_perm = put16(geta("perm"));
-            while (hb.size() % 8) hb.push_back(0);
-            es.total = (int)hb.size();
-            bool ok = n.n_lu + n.n_reduced < 65536 && geta("ent_prod_l").size() < 65536 &&
-                      (int)geta("ent_lvl_ptr").size() == es.n_elim + es.n_bwd + 1;
+            // device form: 64-bit level / entry / product words, then perm (uint16)
+            auto &ee = geta("ent_e"), &eq = geta("ent_q0"), &ec = geta("ent_cf");
+            auto &pl = geta("ent_prod_l"), &pp = geta("ent_prod_p"), &pu = geta("ent_prod_u");
+            auto &lp = geta("ent_lvl_ptr"), &tm_ = geta("ent_team_log"), &pm = geta("perm");
+            bool ok = n.n_lu + n.n_reduced < 65536 && pl.size() < 65536 && ee.size() < 65536 &&
+                      (int)lp.size() == es.n_elim + es.n_bwd + 1 && tm_.size() + 1 == lp.size() &&
+                      ee.size() == eq.size() && ee.size() == ec.size() && pl.size() == pp.size() &&
+                      pl.size() == pu.size();
+            std::vector<unsigned long long> hb;
+            size_t o_lvl = 0, o_ent = 0, o_prod = 0, o_perm = 0;
+            if (ok) {
+                for (size_t k = 0; k + 1 < lp.size(); k++)
+                    hb.push_back((unsigned long long)(uint16_t)lp[k] | ((unsigned long long)(uint16_t)lp[k + 1] << 16) |
+                                 ((unsigned long long)(uint16_t)tm_[k] << 32));
+                o_ent = hb.size();
+                for (size_t k = 0; k < ee.size(); k++)
+                    hb.push_back((unsigned long long)(uint16_t)ee[k] | ((unsigned long long)(uint16_t)eq[k] << 16) |
+                                 ((unsigned long long)(uint16_t)ec[k] << 32));
+                o_prod = hb.size();
+                for (size_t k = 0; k < pl.size(); k++)
+                    hb.push_back((unsigned long long)(uint16_t)pl[k] | ((unsigned long long)(uint16_t)pp[k] << 16) |
+                                 ((unsigned long long)(uint16_t)pu[k] << 32));
+                o_perm = hb.size();
+                for (size_t k = 0; k < pm.size(); k += 4) {
+                    unsigned long long w = 0;
+                    for (size_t q = 0; q < 4 && k + q < pm.size(); q++) w |= (unsigned long long)(uint16_t)pm[k + q] << (16 * q);
+                    hb.push_back(w);
+                }
+                hb.push_back(0);
+            }
             // member tile: small tiles let several blocks share an SM (the level loop is latency
             // bound); the largest of 2 / 4 / 8 members that still leaves room for 4 blocks per SM,
             // else whatever fits
@@ -741,11 +756,16 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                     if (((size_t)es.n_slots * cand * sizeof(double) + 1024) * 4 <= (size_t)228 * 1024) et = cand;
                 if (et == 0) et = 2;
             }
-            size_t sb = (size_t)es.n_slots * et * sizeof(double);
+            es.n_words = (int)o_perm;
+            es.smem_sched = getenv("RBS_ENT_SMEM_SCHED") ? atoi(getenv("RBS_ENT_SMEM_SCHED")) : 0;
+            size_t sb = (size_t)es.n_slots * et * sizeof(double) + (es.smem_sched ? (size_t)es.n_words * 8 : 0);
             if (ok && sb + 256 <= (size_t)dev_smem) {
-                if (cudaMalloc(&h->d_ent_blob, hb.size() * 2) != cudaSuccess) return bail("schedule alloc");
-                cudaMemcpyAsync(h->d_ent_blob, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice, h->stream);
+                if (cudaMalloc(&h->d_ent_blob, hb.size() * 8) != cudaSuccess) return bail("schedule alloc");
+                cudaMemcpyAsync(h->d_ent_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream);
                 cudaStreamSynchronize(h->stream);
+                const unsigned long long* d = (const unsigned long long*)h->d_ent_blob;
+                es.lvl = d + o_lvl; es.ent = d + o_ent; es.prod = d + o_prod;
+                es.perm = (const uint16_t*)(d + o_perm);
                 cudaError_t e3 =
                     et == 2 ? cudaFuncSetAttribute(k_newton_linear_ent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
                     : et == 4 ? cudaFuncSetAttribute(k_newton_linear_ent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
@@ -1117,12 +1137,11 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * n.NA, n, sp<int>(h, "dsrc_ptr"),
                sp<int>(h, "dsrc_code"));
         int et = h->ent_tile, blocks = (n.NA + et - 1) / et, nt = RBS_ENT_LANES * et / 2;
-        const uint16_t* ixd = (const uint16_t*)h->d_ent_blob;
         int wl = h->full_newton ? 0 : 1;
         prof_begin(h, "k_newton_linear_ent");
-        if (et == 2) k_newton_linear_ent<2><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, ixd, wl, c);
-        else if (et == 4) k_newton_linear_ent<4><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, ixd, wl, c);
-        else k_newton_linear_ent<8><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, ixd, wl, c);
+        if (et == 2) k_newton_linear_ent<2><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, wl, c);
+        else if (et == 4) k_newton_linear_ent<4><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, wl, c);
+        else k_newton_linear_ent<8><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, wl, c);
         prof_end(h);
         h->launches++;
     } else if (h->lin_smem) {

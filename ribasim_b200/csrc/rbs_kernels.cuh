@@ -1081,10 +1081,17 @@ k_newton_linear_smem(Net n, LduSched sc, const IT* __restrict__ blob, int write_
 #define RBS_ENT_RCP 0x100
 #define RBS_ENT_SCALE 0x200
 #define RBS_ENT_LANES 256
+// The schedule as the device reads it: one 64-bit word per level, entry and product, so that a
+// lane fetches its work with one load each (the level loop is bound by instruction count and
+// dependent-load latency, not by bytes).
+//   level word   : e0 | e1 << 16 | team_log << 32
+//   entry word   : target slot | q0 << 16 | (count | RCP | SCALE) << 32
+//   product word : l | p << 16 | u << 32
 struct EntSched {
-    // offsets (uint16 elements) into the schedule blob; ent_e starts at 0
-    int off_q0, off_cf, off_pl, off_pp, off_pu, off_lvl, off_team, off_perm;
-    int total;                // uint16 elements, multiple of 8
+    const unsigned long long *lvl, *ent, *prod;   // lvl, ent, prod are contiguous (lvl first)
+    const uint16_t* perm;
+    int n_words;              // 64-bit words of lvl + ent + prod
+    int smem_sched;           // copy the schedule into shared memory (after the slots)
     int n_elim, n_bwd, n_slots, y0;
     int dbg;
 };
@@ -1099,57 +1106,71 @@ __device__ __forceinline__ void rbs_cp_async_wait_all() {
 
 // facmask: bit 0 / 1 set = first / second member of this thread's pair refreshes its factors
 template <int TILE>
-__device__ __forceinline__ void rbs_ent_levels(double* S, const uint16_t* __restrict__ ix, const EntSched& es,
-                                               int lv0, int lv1, unsigned facmask) {
+__device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, int lv0, int lv1,
+                                               unsigned facmask) {
     constexpr int TPL = TILE / 2;            // threads per entry lane
     constexpr int EL = RBS_ENT_LANES;
     const int lane_e = threadIdx.x / TPL;
+    const int warp_lane0 = (int)(threadIdx.x >> 5) * (32 / TPL);
     const double* Sc = S + (threadIdx.x % TPL) * 2;  // this thread's member pair
-    const uint16_t *ent_e = ix, *ent_q0 = ix + es.off_q0, *ent_cf = ix + es.off_cf;
-    const uint16_t *pl = ix + es.off_pl, *pp = ix + es.off_pp, *pu = ix + es.off_pu;
-    const uint16_t *lvl = ix + es.off_lvl, *team = ix + es.off_team;
+    const unsigned long long* ent = es.ent;
+    const unsigned long long* prod = es.prod;
     for (int lv = lv0; lv < lv1; lv++) {
-        const int e0 = lvl[lv], e1 = lvl[lv + 1], tl = team[lv];
-        const int ts = 1 << tl, t = lane_e & (ts - 1), stride = EL >> tl;
+        const unsigned long long lw = es.lvl[lv];
+        const int e0 = (int)(lw & 0xFFFFu), e1 = (int)((lw >> 16) & 0xFFFFu), tl = (int)(lw >> 32);
         // warps whose lanes get no entry in the first pass have none in the later ones either:
         // they go straight to the barrier
-        if ((int)(threadIdx.x >> 5) * (32 / TPL) < min((e1 - e0) << tl, EL))
-        for (int base = e0; base < e1; base += stride) {  // warp-uniform trip count
-            const int k = base + (lane_e >> tl);
-            const bool valid = k < e1;
-            double a0 = 0.0, a1 = 0.0;
-            int e = 0, q0 = 0, cf = 0;
-            if (valid) {
-                e = ent_e[k]; q0 = ent_q0[k]; cf = ent_cf[k];
-                const int q1 = q0 + (cf & 0xFF);
+        if (warp_lane0 < min((e1 - e0) << tl, EL)) {
+            const int ts = 1 << tl, t = lane_e & (ts - 1), stride = EL >> tl;
+            for (int base = e0; base < e1; base += stride) {  // warp-uniform trip count
+                const int k = base + (lane_e >> tl);
+                const bool valid = k < e1;
+                double a0 = 0.0, a1 = 0.0;
+                unsigned e = 0, q0 = 0, cf = 0;
+                if (valid) {
+                    const unsigned long long ew = ent[k];
+                    e = (unsigned)ew & 0xFFFFu; q0 = ((unsigned)ew) >> 16; cf = (unsigned)(ew >> 32);
+                    const unsigned q1 = q0 + (cf & 0xFFu);
 #pragma unroll 2
-                for (int q = q0 + t; q < q1; q += ts) {
-                    double2 l = *(const double2*)(Sc + (int)pl[q] * TILE);
-                    double2 p = *(const double2*)(Sc + (int)pp[q] * TILE);
-                    double2 u = *(const double2*)(Sc + (int)pu[q] * TILE);
-                    a0 += (l.x * p.x) * u.x;
-                    a1 += (l.y * p.y) * u.y;
+                    for (unsigned q = q0 + t; q < q1; q += ts) {
+                        const unsigned long long pw = prod[q];
+                        const double2 l = *(const double2*)(Sc + ((unsigned)pw & 0xFFFFu) * TILE);
+                        const double2 p = *(const double2*)(Sc + (((unsigned)pw) >> 16) * TILE);
+                        const double2 u = *(const double2*)(Sc + ((unsigned)(pw >> 32) & 0xFFFFu) * TILE);
+                        a0 += (l.x * p.x) * u.x;
+                        a1 += (l.y * p.y) * u.y;
+                    }
                 }
-            }
-            for (int sft = 0; sft < tl; sft++) {  // uniform; teams are aligned groups of lanes
-                a0 += __shfl_xor_sync(0xffffffffu, a0, TPL << sft);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, TPL << sft);
-            }
-            if (valid && t == 0) {
-                double2* T = (double2*)(const_cast<double*>(Sc) + e * TILE);
-                const double2 o = *T;
-                double2 v = o;
-                if (cf & RBS_ENT_SCALE) {
-                    const double2 r = *(const double2*)(Sc + (int)((cf & 0xFF) ? pp[q0] : q0) * TILE);
-                    v.x *= r.x; v.y *= r.y;
+                if (tl) {  // uniform; teams are aligned groups of lanes
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, TPL);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, TPL);
+                    if (tl > 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, TPL * 2);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, TPL * 2);
+                        if (tl > 2) {
+                            a0 += __shfl_xor_sync(0xffffffffu, a0, TPL * 4);
+                            a1 += __shfl_xor_sync(0xffffffffu, a1, TPL * 4);
+                        }
+                    }
                 }
-                v.x -= a0; v.y -= a1;
-                if (cf & RBS_ENT_RCP) { v.x = 1.0 / v.x; v.y = 1.0 / v.y; }
-                if (e < es.y0 && facmask != 3u) {
-                    if (!(facmask & 1u)) v.x = o.x;
-                    if (!(facmask & 2u)) v.y = o.y;
+                if (valid && t == 0) {
+                    double2* T = (double2*)(const_cast<double*>(Sc) + e * TILE);
+                    const double2 o = *T;
+                    double2 v = o;
+                    if (cf & RBS_ENT_SCALE) {
+                        // the reciprocal pivot: p of the first product, or q0 itself without products
+                        const unsigned r = (cf & 0xFFu) ? (((unsigned)prod[q0]) >> 16) : q0;
+                        const double2 rv = *(const double2*)(Sc + r * TILE);
+                        v.x *= rv.x; v.y *= rv.y;
+                    }
+                    v.x -= a0; v.y -= a1;
+                    if (cf & RBS_ENT_RCP) { v.x = 1.0 / v.x; v.y = 1.0 / v.y; }
+                    if ((int)e < es.y0 && facmask != 3u) {
+                        if (!(facmask & 1u)) v.x = o.x;
+                        if (!(facmask & 2u)) v.y = o.y;
+                    }
+                    *T = v;
                 }
-                *T = v;
             }
         }
         __syncthreads();
@@ -1164,12 +1185,11 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const uint16_t* __rest
 // side in `br` (k_assemble_linear).
 template <int TILE>
 __global__ void __launch_bounds__(RBS_ENT_LANES * TILE / 2)
-k_newton_linear_ent(Net n, EntSched es, const uint16_t* __restrict__ ix, int write_lu,
-                    double* __restrict__ x) {
+k_newton_linear_ent(Net n, EntSched es, int write_lu, double* __restrict__ x) {
     constexpr int NT = RBS_ENT_LANES * TILE / 2;
     extern __shared__ double smem[];
     double* S = smem;                                    // [n_slots][TILE]
-    const uint16_t* perm = ix + es.off_perm;
+    const uint16_t* __restrict__ perm = es.perm;
     __shared__ int mem_s[TILE], fac_s[TILE];
     int m0 = blockIdx.x * TILE;
     int tm = min(TILE, n.NA - m0);
@@ -1181,6 +1201,13 @@ k_newton_linear_ent(Net n, EntSched es, const uint16_t* __restrict__ ix, int wri
         if (mm >= 0 && n.mphase[mm] != PHASE_NEWTON) mm = -1;
         mem_s[jj] = mm;
         fac_s[jj] = mm >= 0 && n.mjac[mm] != 0;
+    }
+    if (es.smem_sched) {
+        unsigned long long* sw = (unsigned long long*)(S + (size_t)es.n_slots * TILE);
+        for (int w = threadIdx.x; w < es.n_words; w += NT) sw[w] = es.lvl[w];
+        es.ent = sw + (es.ent - es.lvl);
+        es.prod = sw + (es.prod - es.lvl);
+        es.lvl = sw;
     }
     __syncthreads();
     LIN_CLK(1);
@@ -1200,11 +1227,11 @@ k_newton_linear_ent(Net n, EntSched es, const uint16_t* __restrict__ ix, int wri
     LIN_CLK(2);
     const int c2 = (threadIdx.x % (TILE / 2)) * 2;
     const unsigned facmask = (fac_s[c2] ? 1u : 0u) | (fac_s[c2 + 1] ? 2u : 0u);
-    rbs_ent_levels<TILE>(S, ix, es, 0, es.n_elim, facmask);
+    rbs_ent_levels<TILE>(S, es, 0, es.n_elim, facmask);
     LIN_CLK(3);
     LIN_CLK(4);
     LIN_CLK(5);
-    rbs_ent_levels<TILE>(S, ix, es, es.n_elim, es.n_elim + es.n_bwd, facmask);
+    rbs_ent_levels<TILE>(S, es, es.n_elim, es.n_elim + es.n_bwd, facmask);
     LIN_CLK(6);
     if (m >= 0) {
         for (int i = slot; i < n.n_reduced; i += n_slot)
