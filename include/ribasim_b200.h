@@ -203,6 +203,12 @@ int rbs_profile_report(rbs_handle* h, char* buf, int32_t len);
  * back launches on the handle's stream.  Leaves the stepping state machine reset. */
 int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_per_launch);
 
+/* Page-locked host memory for the asynchronous and forced-window entry points (a host language
+ * without its own pinned allocator, e.g. Julia via unsafe_wrap, takes its staging buffers from
+ * here).  NULL on failure (rbs_last_error tells why). */
+void* rbs_host_alloc(int64_t bytes);
+void rbs_host_free(void* p);
+
 /* Raw device pointer of a per-member array (for zero-copy interop, e.g. NCCL gathers or
  * torch tensors wrapping library memory); NULL if unknown. */
 void* rbs_device_ptr(rbs_handle* h, const char* key);

@@ -1025,6 +1025,15 @@ void* rbs_device_ptr(rbs_handle* h, const char* key) {
     return it == h->member.end() ? nullptr : it->second.p;
 }
 void* rbs_stream(rbs_handle* h) { return h ? (void*)h->stream : nullptr; }
+void* rbs_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0) { fail("rbs_host_alloc: size must be positive"); return nullptr; }
+    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fail(std::string("rbs_host_alloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void rbs_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int rbs_synchronize(rbs_handle* h) {
     if (!h) return fail("rbs_synchronize: null handle");
     cudaSetDevice(h->device);

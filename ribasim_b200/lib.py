@@ -86,6 +86,8 @@ def load() -> ctypes.CDLL:
         "rbs_stage_forcing_window": (ctypes.c_int, [vp, cp, dp, i64, i32, i32]),
         "rbs_advance_window": (ctypes.c_int, [vp, f64, f64, i32, dp, dp, ip]),
         "rbs_commit_forcing_window": (ctypes.c_int, [vp]),
+        "rbs_host_alloc": (vp, [i64]),
+        "rbs_host_free": (None, [vp]),
         "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
         "rbs_get_member_i32": (ctypes.c_int, [vp, cp, ip, i64]),
         "rbs_apply_discrete_control": (ctypes.c_int, [vp]),
@@ -121,7 +123,7 @@ EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64", "rbs_set_member_f64_async",
-    "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window",
+    "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window", "rbs_host_alloc", "rbs_host_free",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
     "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
@@ -163,6 +165,34 @@ PARAM_F64 = [
     "pid_derivative", "cc_sv_const", "dc_thr_hi", "dc_thr_lo", "dc_sv_const",
 ]
 PARAM_I32 = ["trc_table_idx"]
+
+
+class PinnedArray:
+    """A float64 numpy array over page-locked host memory from `rbs_host_alloc` (staging buffer of
+    the asynchronous / forced-window calls for hosts without torch)."""
+
+    def __init__(self, shape):
+        L = load()
+        self.shape = tuple(int(x) for x in shape)
+        n = int(np.prod(self.shape))
+        self._L = L
+        self.ptr = L.rbs_host_alloc(max(n, 1) * 8)
+        if not self.ptr:
+            raise RbsError(last_error())
+        buf = (ctypes.c_double * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(self.shape)
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._L.rbs_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Handle:

@@ -477,7 +477,6 @@ def test_forced_window_equals_per_step_forcing():
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
-    import torch
     from ribasim_b200 import lib
     case = make_case("basic", 4, seed=3, t=0.0)
     flat = case["flat"]
@@ -488,13 +487,13 @@ def test_forced_window_argument_errors():
         for x in (ref, h):
             x.refresh(0.0)
             x.set_member("level_prev", x.get_member("level", nb))
-        buf = torch.zeros((3, nb, 4), dtype=torch.float64).pin_memory()
-        buf[:] = torch.from_numpy(case["forcing"]["precipitation"])
+        buf = lib.PinnedArray((3, nb, 4))  # page-locked memory from the library (rbs_host_alloc)
+        buf.array[:] = case["forcing"]["precipitation"]
         with pytest.raises(lib.RbsError, match="not a forcing array"):
-            h.stage_forcing_window("level", buf.data_ptr(), nb, 3)
+            h.stage_forcing_window("level", buf.ptr, nb, 3)
         with pytest.raises(lib.RbsError, match="size mismatch"):
-            h.stage_forcing_window("precipitation", buf.data_ptr(), nb + 1, 3)
-        h.stage_forcing_window("precipitation", buf.data_ptr(), nb, 3)
+            h.stage_forcing_window("precipitation", buf.ptr, nb + 1, 3)
+        h.stage_forcing_window("precipitation", buf.ptr, nb, 3)
         h.commit_forcing_window()
         with pytest.raises(lib.RbsError, match="fewer steps staged"):
             h.advance_window(0.0, 3600.0, 4)
@@ -503,6 +502,8 @@ def test_forced_window_argument_errors():
         st_ref = ref.advance(0.0, 3600.0, 5)
         assert np.array_equal(st | st2, st_ref)
         assert np.array_equal(h.get_member("u", flat["n_state"]), ref.get_member("u", flat["n_state"]))
+        h.synchronize()
+        buf.close()
     finally:
         h.close()
         ref.close()
