@@ -1143,8 +1143,8 @@ int rbs_refresh(rbs_handle* h, double t) {
 static void launch_linear(rbs_handle* h, double* c, Pred nw) {
     Net& n = h->net;
     if (h->lin_ent) {
-        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * n.NA, n, sp<int>(h, "dsrc_ptr"),
-               sp<int>(h, "dsrc_code"));
+        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
+               sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
         int et = h->ent_tile, blocks = (n.NA + et - 1) / et, nt = RBS_ENT_LANES * et / 2;
         int wl = h->full_newton ? 0 : 1;
         prof_begin(h, "k_newton_linear_ent");
@@ -1154,8 +1154,8 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
         prof_end(h);
         h->launches++;
     } else if (h->lin_smem) {
-        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * n.NA, n, sp<int>(h, "dsrc_ptr"),
-               sp<int>(h, "dsrc_code"));
+        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
+               sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
         int blocks = (n.NA + 7) / 8;
         prof_begin(h, "k_newton_linear_smem");
         if (h->lin_smem16)

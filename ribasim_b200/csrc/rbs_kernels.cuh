@@ -871,27 +871,62 @@ struct LduSched {          // offsets (in index elements) into the packed schedu
 // factor slot (W = A J - I/h scattered into the LU pattern; ordered signed sums, code < 0 is the
 // "- 1/h" of a diagonal entry) for members that refresh their Jacobian, and the reduced
 // right-hand side b_r = A*((h du - z)/h) for every member in the Newton phase.
+// RBS_MPT members per thread (positions j, j + 32, ... of a tile of 32 * RBS_MPT members of the
+// launch domain): the index loads of an item are shared by all of them and every load instruction
+// is still a coalesced 256 B request.  The kernel is bound by instruction issue, not by bytes.
+#define RBS_MPT 2
 __global__ void k_assemble_linear(Net n, const int* __restrict__ dsrc_ptr,
                                   const int* __restrict__ dsrc_code) {
+    const int n_tiles = (n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT);
     long long tid = RBS_TID;
-    int e = (int)(tid / n.NA);
+    const int lane = (int)(tid & 31);
+    long long wid = tid >> 5;                 // (item, tile)
+    int e = (int)(wid / n_tiles);
     if (e >= n.n_lu + n.n_reduced) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)e * n.NA));
-    if (n.mphase[m] != PHASE_NEWTON) return;
+    int tile = (int)(wid - (long long)e * n_tiles);
+    int m[RBS_MPT];
+    int any = -1;
+#pragma unroll
+    for (int q = 0; q < RBS_MPT; q++) {
+        int j = tile * 32 * RBS_MPT + q * 32 + lane;
+        int mm = j < n.NA ? RBS_MEMBER(n, j) : -1;
+        if (mm >= 0 && n.mphase[mm] != PHASE_NEWTON) mm = -1;
+        if (mm >= 0 && e < n.n_lu && n.mjac[mm] == 0) mm = -1;
+        m[q] = mm;
+        if (mm >= 0) any = mm;
+    }
+    if (any < 0) return;
     if (e < n.n_lu) {
-        if (n.mjac[m] == 0) return;
-        double invh = 1.0 / n.mh[m];
-        double v = 0.0;
+        int a[RBS_MPT];
+        double invh[RBS_MPT], v[RBS_MPT];
+#pragma unroll
+        for (int q = 0; q < RBS_MPT; q++) {
+            a[q] = m[q] >= 0 ? m[q] : any;  // a valid address for idle positions
+            invh[q] = 1.0 / n.mh[a[q]];
+            v[q] = 0.0;
+        }
         for (int k = dsrc_ptr[e]; k < dsrc_ptr[e + 1]; k++) {
             int code = dsrc_code[k];
-            if (code < 0) { v = v - invh; continue; }
-            double jvv = n.jv[(long long)(code >> 1) * n.B + m];
-            v = (code & 1) ? v - jvv : v + jvv;
+            if (code < 0) {
+#pragma unroll
+                for (int q = 0; q < RBS_MPT; q++) v[q] = v[q] - invh[q];
+                continue;
+            }
+            const double* row = n.jv + (long long)(code >> 1) * n.B;
+            double x[RBS_MPT];
+#pragma unroll
+            for (int q = 0; q < RBS_MPT; q++) x[q] = row[a[q]];
+#pragma unroll
+            for (int q = 0; q < RBS_MPT; q++) v[q] = (code & 1) ? v[q] - x[q] : v[q] + x[q];
         }
-        n.lu[(long long)e * n.B + m] = v;
+#pragma unroll
+        for (int q = 0; q < RBS_MPT; q++)
+            if (m[q] >= 0) n.lu[(long long)e * n.B + m[q]] = v[q];
     } else {
         int r = e - n.n_lu;
-        n.br[(long long)r * n.B + m] = rbs_solve_rhs<true>(n, nullptr, r, m);
+#pragma unroll
+        for (int q = 0; q < RBS_MPT; q++)
+            if (m[q] >= 0) n.br[(long long)r * n.B + m[q]] = rbs_solve_rhs<true>(n, nullptr, r, m[q]);
     }
 }
 
