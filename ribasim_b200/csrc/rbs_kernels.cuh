@@ -871,62 +871,43 @@ struct LduSched {          // offsets (in index elements) into the packed schedu
 // factor slot (W = A J - I/h scattered into the LU pattern; ordered signed sums, code < 0 is the
 // "- 1/h" of a diagonal entry) for members that refresh their Jacobian, and the reduced
 // right-hand side b_r = A*((h du - z)/h) for every member in the Newton phase.
-// RBS_MPT members per thread (positions j, j + 32, ... of a tile of 32 * RBS_MPT members of the
-// launch domain): the index loads of an item are shared by all of them and every load instruction
-// is still a coalesced 256 B request.  The kernel is bound by instruction issue, not by bytes.
+// Two members per thread (positions j and j + 32 of a 64-member tile of the launch domain): the
+// index loads of an item are shared by both, every load instruction is still a coalesced 256 B
+// request.  The kernel is bound by instruction issue, not by bytes.
 #define RBS_MPT 2
 __global__ void k_assemble_linear(Net n, const int* __restrict__ dsrc_ptr,
                                   const int* __restrict__ dsrc_code) {
-    const int n_tiles = (n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT);
+    const int n_tiles = (n.NA + 63) >> 6;
     long long tid = RBS_TID;
     const int lane = (int)(tid & 31);
     long long wid = tid >> 5;                 // (item, tile)
     int e = (int)(wid / n_tiles);
     if (e >= n.n_lu + n.n_reduced) return;
     int tile = (int)(wid - (long long)e * n_tiles);
-    int m[RBS_MPT];
-    int any = -1;
-#pragma unroll
-    for (int q = 0; q < RBS_MPT; q++) {
-        int j = tile * 32 * RBS_MPT + q * 32 + lane;
-        int mm = j < n.NA ? RBS_MEMBER(n, j) : -1;
-        if (mm >= 0 && n.mphase[mm] != PHASE_NEWTON) mm = -1;
-        if (mm >= 0 && e < n.n_lu && n.mjac[mm] == 0) mm = -1;
-        m[q] = mm;
-        if (mm >= 0) any = mm;
-    }
-    if (any < 0) return;
+    int j0 = tile * 64 + lane, j1 = j0 + 32;
+    int m0 = j0 < n.NA ? RBS_MEMBER(n, j0) : -1, m1 = j1 < n.NA ? RBS_MEMBER(n, j1) : -1;
+    if (m0 >= 0 && n.mphase[m0] != PHASE_NEWTON) m0 = -1;
+    if (m1 >= 0 && n.mphase[m1] != PHASE_NEWTON) m1 = -1;
     if (e < n.n_lu) {
-        int a[RBS_MPT];
-        double invh[RBS_MPT], v[RBS_MPT];
-#pragma unroll
-        for (int q = 0; q < RBS_MPT; q++) {
-            a[q] = m[q] >= 0 ? m[q] : any;  // a valid address for idle positions
-            invh[q] = 1.0 / n.mh[a[q]];
-            v[q] = 0.0;
-        }
+        if (m0 >= 0 && n.mjac[m0] == 0) m0 = -1;
+        if (m1 >= 0 && n.mjac[m1] == 0) m1 = -1;
+        if (m0 < 0 && m1 < 0) return;
+        const int a0 = m0 >= 0 ? m0 : m1, a1 = m1 >= 0 ? m1 : m0;  // valid addresses for both
+        const double invh0 = 1.0 / n.mh[a0], invh1 = 1.0 / n.mh[a1];
+        double v0 = 0.0, v1 = 0.0;
         for (int k = dsrc_ptr[e]; k < dsrc_ptr[e + 1]; k++) {
             int code = dsrc_code[k];
-            if (code < 0) {
-#pragma unroll
-                for (int q = 0; q < RBS_MPT; q++) v[q] = v[q] - invh[q];
-                continue;
-            }
+            if (code < 0) { v0 = v0 - invh0; v1 = v1 - invh1; continue; }
             const double* row = n.jv + (long long)(code >> 1) * n.B;
-            double x[RBS_MPT];
-#pragma unroll
-            for (int q = 0; q < RBS_MPT; q++) x[q] = row[a[q]];
-#pragma unroll
-            for (int q = 0; q < RBS_MPT; q++) v[q] = (code & 1) ? v[q] - x[q] : v[q] + x[q];
+            double x0 = row[a0], x1 = row[a1];
+            if (code & 1) { v0 = v0 - x0; v1 = v1 - x1; } else { v0 = v0 + x0; v1 = v1 + x1; }
         }
-#pragma unroll
-        for (int q = 0; q < RBS_MPT; q++)
-            if (m[q] >= 0) n.lu[(long long)e * n.B + m[q]] = v[q];
+        if (m0 >= 0) n.lu[(long long)e * n.B + m0] = v0;
+        if (m1 >= 0) n.lu[(long long)e * n.B + m1] = v1;
     } else {
         int r = e - n.n_lu;
-#pragma unroll
-        for (int q = 0; q < RBS_MPT; q++)
-            if (m[q] >= 0) n.br[(long long)r * n.B + m[q]] = rbs_solve_rhs<true>(n, nullptr, r, m[q]);
+        if (m0 >= 0) n.br[(long long)r * n.B + m0] = rbs_solve_rhs<true>(n, nullptr, r, m0);
+        if (m1 >= 0) n.br[(long long)r * n.B + m1] = rbs_solve_rhs<true>(n, nullptr, r, m1);
     }
 }
 
