@@ -1212,7 +1212,7 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
     double* c = mp(h, "cvec");
     launch_linear(h, c, nw);
     {
-        dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 31) / 32, h->n_part);
+        dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 63) / 64, h->n_part);
         LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
     }
     n.NA = n.B;

@@ -1343,39 +1343,51 @@ __global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __rest
 // dz = gamma*h * (J_i c - b),  b = (h k - z)/(gamma h);  z <- z - dz;
 // atmp = dz / (abstol + max(|uprev|, |uprev + z_old|) * reltol); partial sums of atmp^2.
 #define RBS_DZ_ROWS 8
+// Two members per thread (positions j and j + 32 of a 64-member tile): the row pointers and
+// column indices of J_intermediate are loaded once for both.
 __global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
                                 int rows_per_block) {
-    int j = blockIdx.x * 32 + threadIdx.x;
-    int m = j < n.NA ? RBS_MEMBER(n, j) : 0;
-    int r0 = blockIdx.y * rows_per_block;
-    double acc = 0.0;
-    bool live = j < n.NA && n.mphase[m] == PHASE_NEWTON;
-    if (live) {
-        double dt = n.mh[m], inv_dt = 1.0 / dt;
-        int r1 = min(r0 + rows_per_block, n.n_state);
+    const int j0 = blockIdx.x * 64 + threadIdx.x, j1 = j0 + 32;
+    int m0 = j0 < n.NA ? RBS_MEMBER(n, j0) : -1, m1 = j1 < n.NA ? RBS_MEMBER(n, j1) : -1;
+    if (m0 >= 0 && n.mphase[m0] != PHASE_NEWTON) m0 = -1;
+    if (m1 >= 0 && n.mphase[m1] != PHASE_NEWTON) m1 = -1;
+    const int r0 = blockIdx.y * rows_per_block;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (m0 >= 0 || m1 >= 0) {
+        const int a0 = m0 >= 0 ? m0 : m1, a1 = m1 >= 0 ? m1 : m0;  // valid addresses for both
+        const double dt0 = n.mh[a0], dt1 = n.mh[a1], inv0 = 1.0 / dt0, inv1 = 1.0 / dt1;
+        const int r1 = min(r0 + rows_per_block, n.n_state);
         for (int r = r0 + threadIdx.y; r < r1; r += RBS_DZ_ROWS) {
-            long long o = (long long)r * n.B + m;
-            double jc = 0.0;
-            for (int e = n.jrow_ptr[r]; e < n.jrow_ptr[r + 1]; e++)
-                jc += n.jv[(long long)e * n.B + m] * c[(long long)n.jcol[e] * n.B + m];
-            double zo = n.z[o];
-            double b = (dt * n.du[o] - zo) * inv_dt;
-            double dz = (jc - b) * dt;
-            double up = n.uprev[o];
-            double ustep = up + zo;
-            double sc = abstol + fmax(fabs(up), fabs(ustep)) * reltol;
-            double a = dz / sc;
-            acc += a * a;
-            n.z[o] = zo - dz;
+            const long long o0 = (long long)r * n.B + a0, o1 = (long long)r * n.B + a1;
+            double jc0 = 0.0, jc1 = 0.0;
+            for (int e = n.jrow_ptr[r]; e < n.jrow_ptr[r + 1]; e++) {
+                const double* jrow = n.jv + (long long)e * n.B;
+                const double* crow = c + (long long)n.jcol[e] * n.B;
+                jc0 += jrow[a0] * crow[a0];
+                jc1 += jrow[a1] * crow[a1];
+            }
+            const double zo0 = n.z[o0], zo1 = n.z[o1];
+            const double b0 = (dt0 * n.du[o0] - zo0) * inv0, b1 = (dt1 * n.du[o1] - zo1) * inv1;
+            const double dz0 = (jc0 - b0) * dt0, dz1 = (jc1 - b1) * dt1;
+            const double up0 = n.uprev[o0], up1 = n.uprev[o1];
+            const double s0 = abstol + fmax(fabs(up0), fabs(up0 + zo0)) * reltol;
+            const double s1 = abstol + fmax(fabs(up1), fabs(up1 + zo1)) * reltol;
+            const double q0 = dz0 / s0, q1 = dz1 / s1;
+            if (m0 >= 0) { acc0 += q0 * q0; n.z[o0] = zo0 - dz0; }
+            if (m1 >= 0) { acc1 += q1 * q1; n.z[o1] = zo1 - dz1; }
         }
     }
-    __shared__ double sh[RBS_DZ_ROWS][33];
-    sh[threadIdx.y][threadIdx.x] = acc;
+    __shared__ double sh[2][RBS_DZ_ROWS][33];
+    sh[0][threadIdx.y][threadIdx.x] = acc0;
+    sh[1][threadIdx.y][threadIdx.x] = acc1;
     __syncthreads();
-    if (threadIdx.y == 0 && j < n.NA) {
-        double s = 0.0;
-        for (int y = 0; y < RBS_DZ_ROWS; y++) s += sh[y][threadIdx.x];
-        n.norm_part[(long long)blockIdx.y * n.B + m] = s;
+    if (threadIdx.y < 2) {
+        const int mm = threadIdx.y == 0 ? m0 : m1;
+        if (mm >= 0) {
+            double s = 0.0;
+            for (int y = 0; y < RBS_DZ_ROWS; y++) s += sh[threadIdx.y][y][threadIdx.x];
+            n.norm_part[(long long)blockIdx.y * n.B + mm] = s;
+        }
     }
 }
 
