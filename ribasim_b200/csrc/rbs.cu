@@ -183,7 +183,7 @@ void bind_net(rbs_handle* h) {
     S_D(storage0); S_D(low_storage_threshold); S_D(fixed_area);
     S_I(prof_ptr); S_D(prof_level); S_D(prof_dSdh); S_D(prof_dSdh_slope); S_D(prof_cumS);
     S_D(prof_area); S_D(prof_area_slope);
-    S_I(inc_ptr); S_I(inc_state); S_D(inc_sign); S_I(bfb_ptr); S_I(bfb_idx);
+    S_I(inc_ptr); S_I(inc_state); S_D(inc_sign); S_I(bfb_ptr); S_I(bfb_idx); S_I(basin_obs);
     S_I(conn_type); S_I(conn_idx); S_I(src_kind); S_I(src_idx); S_I(dst_kind); S_I(dst_idx);
     S_D(lr_resistance); S_D(lr_max_flow_rate);
     S_D(mn_length); S_D(mn_manning_n); S_D(mn_profile_width); S_D(mn_profile_slope);
@@ -492,6 +492,17 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     if (h->shared.find("cc_sv_const") == h->shared.end()) {
         size_t nsv = h->hi.count("cc_sv_kind") ? h->hi["cc_sv_kind"].size() : 0;
         if (upload(h, "cc_sv_const", std::vector<double>(nsv, 0.0), false)) return bail("param alloc");
+    }
+    {
+        // basins whose storage / area a controller reads while the RHS is evaluated
+        std::vector<int32_t> obs((size_t)std::max(n.n_basin, 1), 0);
+        auto mark = [&](const char* key) { auto it = h->hi.find(key); if (it != h->hi.end()) for (int32_t b_ : it->second) if (b_ >= 0 && b_ < n.n_basin) obs[b_] = 1; };
+        mark("pid_listen_basin");
+        auto ik = h->hi.find("cc_sv_kind"), ii = h->hi.find("cc_sv_idx");
+        if (ik != h->hi.end() && ii != h->hi.end())
+            for (size_t k = 0; k < ik->second.size() && k < ii->second.size(); k++)
+                if (ik->second[k] <= 1 && ii->second[k] >= 0 && ii->second[k] < n.n_basin) obs[ii->second[k]] = 1;
+        if (upload(h, "basin_obs", obs, true)) return bail("param alloc");
     }
     // per-member arrays
     h->rows_per_block = 64;

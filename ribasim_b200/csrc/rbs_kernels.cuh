@@ -39,6 +39,7 @@ struct Net {
     const int *inc_ptr, *inc_state;
     const double* inc_sign;
     const int *bfb_ptr, *bfb_idx;
+    const int* basin_obs;  // 1 = storage / area of this basin are read by a controller during the RHS
     // connectors (shared)
     const int *conn_type, *conn_idx, *src_kind, *src_idx, *dst_kind, *dst_idx;
     const double *lr_resistance, *lr_max_flow_rate;
@@ -271,15 +272,21 @@ __global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pre
     RbsBasinEval e = rbs_basin_eval(S, np, n.prof_level + p0, n.prof_dSdh + p0,
                                     n.prof_dSdh_slope + p0, n.prof_cumS + p0, n.prof_area + p0,
                                     n.prof_area_slope + p0);
-    n.storage[o] = S;
+    // Newton iterates of the step path (SRC 1 with the Jacobian): the links only read level, factor
+    // and their partials; storage / area are written for the basins a controller observes.  The
+    // finalize half and the seam calls write everything.
+    const bool lean = JAC && SRC == 1 && !n.basin_obs[b];
     n.factor[o] = phi;
     n.level[o] = e.level;
-    n.area[o] = e.area;
+    if (!lean) {
+        n.storage[o] = S;
+        n.area[o] = e.area;
+    }
     if (flag_negative && S < 0.0) atomicOr(flag_negative == 2 ? &n.mneg2[m] : &n.mneg[m], 1);  // integer flag only
     if (JAC) {
         n.dlevel[o] = e.dlevel;
         n.dfactor[o] = dphi;
-        n.darea[o] = e.darea;
+        if (!lean) n.darea[o] = e.darea;
     }
     if (write_du) {
         const int ws = n.fw_on ? n.mstep[m] : 0;
