@@ -14,6 +14,7 @@ Only plain `sqlite3` is used (GeoPackage geometry columns are not needed by the 
 
 from __future__ import annotations
 
+import math
 import sqlite3
 import tomllib
 from dataclasses import dataclass, field
@@ -200,6 +201,165 @@ def parse_time(x: Any) -> datetime:
     return datetime.strptime(s, TIME_FMT)
 
 
+def snake_case(name: str) -> str:
+    """CamelCase -> snake_case (core/src/config.jl:134-138)."""
+    import re
+    return re.sub(r"(?<!^)(?=[A-Z])", "_", name).lower()
+
+
+NC_DIM_NAMES = ("time", "node_id", "link_id", "subgrid_id", "substance", "demand_priority")
+_CF_UNIT_SECONDS = dict(seconds=1.0, second=1.0, s=1.0, minutes=60.0, minute=60.0, hours=3600.0,
+                        hour=3600.0, days=86400.0, day=86400.0, milliseconds=1e-3)
+
+
+def _nc_attr(var, name: str) -> str | None:
+    v = getattr(var, name, None)
+    if v is None:
+        return None
+    return v.decode() if isinstance(v, bytes) else str(v)
+
+
+def load_netcdf(path: str | Path, table_name: str) -> list[dict[str, Any]]:
+    """A table stored as dense arrays in a NetCDF file -> rows (`load_netcdf`,
+    core/src/read.jl:1889-1984; coordinate detection `:1986-2050`).
+
+    Every table has a node_id dimension (`cf_role = "timeseries_id"` or name `node_id`, integers
+    or the NetCDF3 char matrix Delft-FEWS writes), some a time (`axis = "T"`, `standard_name =
+    "time"` or name `time`) and a priority dimension (`realization`).  Data variables are stored
+    with dimensions (time, [priority,] node) in file order; rows whose data variables are all
+    missing are dropped.  Read with scipy's classic-format reader (NetCDF4/HDF5 files need
+    netCDF4, which is not a dependency)."""
+    import numpy as np
+    from scipy.io import netcdf_file
+
+    cols, _ = SCHEMA[table_name]
+    data_names = [c for c in cols if c not in NC_DIM_NAMES]
+    with netcdf_file(str(path), "r", mmap=False) as ds:
+        def find(pred):
+            for name, var in ds.variables.items():
+                if pred(name, var):
+                    return name, var
+            return None, None
+
+        _, id_var = find(lambda n, v: _nc_attr(v, "cf_role") == "timeseries_id" or n == "node_id")
+        if id_var is None:
+            raise ValueError(f"{path}: no node_id coordinate (cf_role = timeseries_id)")
+        ids = np.array(id_var[:])
+        if ids.dtype.kind == "S" and ids.ndim == 2:  # (n_id, n_char) char matrix, NUL padded
+            node_id = np.array([int(b"".join(row).split(b"\0")[0].decode().strip()) for row in ids],
+                               dtype=np.int64)
+        else:
+            node_id = ids.astype(np.int64).reshape(-1)
+        _, t_var = find(lambda n, v: _nc_attr(v, "axis") == "T"
+                        or _nc_attr(v, "standard_name") == "time" or n == "time")
+        _, p_var = find(lambda n, v: _nc_attr(v, "standard_name") == "realization"
+                        or n == "realization")
+        n_id = len(node_id)
+        times = None
+        if t_var is not None:
+            units = _nc_attr(t_var, "units") or ""
+            unit, _, since = units.partition(" since ")
+            if unit.strip() not in _CF_UNIT_SECONDS or not since:
+                raise ValueError(f"{path}: unsupported time units `{units}`")
+            t0 = parse_time(since.strip().replace("Z", "").split("+")[0].strip())
+            from datetime import timedelta
+            times = [t0 + timedelta(seconds=float(x) * _CF_UNIT_SECONDS[unit.strip()])
+                     for x in np.array(t_var[:]).reshape(-1)]
+        prio = None if p_var is None else np.array(p_var[:]).astype(np.int64).reshape(-1)
+        n_t = 1 if times is None else len(times)
+        n_p = 1 if prio is None else len(prio)
+        n = n_id * n_p * n_t
+        columns: dict[str, Any] = {}
+        for name in data_names:
+            if name not in ds.variables:
+                continue
+            var = ds.variables[name]
+            arr = np.array(var[:], dtype=np.float64)
+            for att in ("_FillValue", "missing_value"):
+                fv = getattr(var, att, None)
+                if fv is not None:
+                    arr = np.where(arr == np.float64(np.array(fv).reshape(-1)[0]), np.nan, arr)
+            if table_name == "UserDemand / time":
+                # demand (time, priority, node), return_factor (time, node), min_level (node)
+                if arr.ndim == 1:
+                    arr = np.broadcast_to(arr[None, None, :], (n_t, n_p, n_id))
+                elif arr.ndim == 2:
+                    arr = np.broadcast_to(arr[:, None, :], (n_t, n_p, n_id))
+            flat = np.ascontiguousarray(arr).reshape(-1)
+            if flat.size != n:
+                raise ValueError(f"Inconsistent lengths in NetCDF file {path} for variable {name}")
+            columns[name] = flat
+    rows: list[dict[str, Any]] = []
+    for k in range(n):  # node fastest, then priority, then time
+        i, rest = k % n_id, k // n_id
+        pk, tk = rest % n_p, rest // n_p
+        vals = {c: float(v[k]) for c, v in columns.items()}
+        if vals and all(math.isnan(x) for x in vals.values()):
+            continue
+        row: dict[str, Any] = {c: None for c in cols}
+        row["node_id"] = int(node_id[i])
+        if times is not None and "time" in cols:
+            row["time"] = times[tk]
+        if prio is not None and "demand_priority" in cols:
+            row["demand_priority"] = int(prio[pk])
+        for c, x in vals.items():
+            if math.isnan(x):
+                row[c] = None
+            elif cols[c] == "i":
+                row[c] = int(x)
+            elif cols[c] == "b":
+                row[c] = bool(x)
+            else:
+                row[c] = x
+        rows.append(row)
+    return rows
+
+
+def write_netcdf(path: str | Path, table_name: str, rows: list[dict[str, Any]],
+                 starttime: datetime, char_ids: bool = False) -> None:
+    """Write a time table as the dense (time, node) NetCDF the core reads (classic format);
+    `char_ids` stores the ids as the Delft-FEWS char matrix."""
+    import numpy as np
+    from scipy.io import netcdf_file
+
+    cols, _ = SCHEMA[table_name]
+    data_names = [c for c in cols if c not in NC_DIM_NAMES and cols[c] in ("f", "i")]
+    ids = sorted({int(r["node_id"]) for r in rows})
+    times = sorted({parse_time(r["time"]) for r in rows}) if "time" in cols else []
+    with netcdf_file(str(path), "w") as ds:
+        ds.createDimension("stations", len(ids))
+        if char_ids:
+            ds.createDimension("char_leng_id", 16)
+            v = ds.createVariable("station_id", "c", ("stations", "char_leng_id"))
+            v.cf_role = "timeseries_id"
+            for i, x in enumerate(ids):
+                txt = str(x).encode().ljust(16, b"\0")
+                v[i] = np.frombuffer(txt, dtype="S1")
+        else:
+            v = ds.createVariable("node_id", "i", ("stations",))
+            v.cf_role = "timeseries_id"
+            v[:] = np.array(ids, dtype=np.int32)
+        dims = ("stations",)
+        if times:
+            ds.createDimension("time", len(times))
+            tv = ds.createVariable("time", "d", ("time",))
+            tv.units = "seconds since " + starttime.strftime(TIME_FMT)
+            tv.axis = "T"
+            tv[:] = np.array([(t - starttime).total_seconds() for t in times])
+            dims = ("time", "stations")
+        ii = {x: k for k, x in enumerate(ids)}
+        ti = {t: k for k, t in enumerate(times)}
+        for name in data_names:
+            arr = np.full((len(times) or 1, len(ids)), np.nan)
+            for r in rows:
+                if r.get(name) is not None:
+                    arr[ti[parse_time(r["time"])] if times else 0, ii[int(r["node_id"])]] = float(r[name])
+            var = ds.createVariable(name, "d", dims)
+            var._FillValue = np.float64(-999.0)
+            arr = np.where(np.isnan(arr), -999.0, arr)
+            var[:] = arr if times else arr[0]
+
+
 def _sort_key(cols: tuple[str, ...]):
     # `missing` sorts after every value in the reference (Julia `isless`).
     def key(row: dict[str, Any]):
@@ -230,6 +390,7 @@ class ModelTables:
     node: list[dict[str, Any]] = field(default_factory=list)
     link: list[dict[str, Any]] = field(default_factory=list)
     tables: dict[str, list[dict[str, Any]]] = field(default_factory=dict)
+    external_tables: dict[str, str] = field(default_factory=dict)  # table -> NetCDF path in input_dir
 
     # ------------------------------------------------------------------ builder
     def add_node(self, node_type: str, node_id: int, *, subnetwork_id: int | None = None,
@@ -330,6 +491,15 @@ class ModelTables:
                         lines.append(f'{k} = "{v}"')
                     else:
                         lines.append(f"{k} = {v!r}")
+        by_section: dict[str, list[str]] = {}
+        for name, rel in self.external_tables.items():
+            node_type, kind = name.split(" / ")
+            by_section.setdefault(snake_case(node_type), []).append(f'{kind} = "{rel}"')
+            write_netcdf(directory / self.input_dir / rel, name, self.table(name), self.starttime)
+        for section, entries in by_section.items():
+            lines.append("")
+            lines.append(f"[{section}]")
+            lines.extend(entries)
         toml_path.write_text("\n".join(lines) + "\n")
 
         db_path = directory / self.input_dir / "database.gpkg"
@@ -357,6 +527,8 @@ class ModelTables:
             )
             sqltype = dict(f="REAL", i="INTEGER", s="TEXT", t="TEXT", b="INTEGER")
             for name in self.tables:
+                if name in self.external_tables:
+                    continue
                 cols, _ = SCHEMA[name]
                 decl = ", ".join(f'"{c}" {sqltype[k]}' for c, k in cols.items())
                 con.execute(f'CREATE TABLE "{name}" ({decl})')
@@ -435,4 +607,16 @@ class ModelTables:
                     m.tables[name] = rows
         finally:
             con.close()
+        # tables stored outside the database: `[basin] time = "basin_time.nc"` (load_data,
+        # core/src/read.jl:2057-2098; only NetCDF is supported there too)
+        for name in SCHEMA:
+            node_type, kind = name.split(" / ")
+            path = cfg.get(snake_case(node_type), {}).get(kind) if isinstance(cfg.get(snake_case(node_type)), dict) else None
+            if path is None:
+                continue
+            table_path = toml_path.parent / m.input_dir / path
+            if table_path.suffix.lower() != ".nc":
+                raise ValueError(f"Unsupported file format: {table_path}. Only '.nc' is supported.")
+            m.tables[name] = load_netcdf(table_path, name)
+            m.external_tables[name] = str(path)
         return m

@@ -242,6 +242,49 @@ def test_tables_roundtrip(tmp_path):
         assert np.array_equal(v, f2.arrays[k], equal_nan=True), k
 
 
+@pytest.mark.parametrize("char_ids", [False, True])
+def test_netcdf_forcing_table_equals_database_table(tmp_path, char_ids):
+    """`Basin / time` stored as a dense (time, node) NetCDF file named in the TOML (`[basin] time =
+    "basin_time.nc"`, core/src/read.jl:1889-2098) compiles to the same network and forcing series
+    as the same rows in the GeoPackage; ids as integers or as the Delft-FEWS char matrix."""
+    from ribasim_b200.tables import load_netcdf, write_netcdf
+    m = MODELS["basic_transient"]()
+    ref = build_params(m)
+    m.external_tables["Basin / time"] = "basin_time.nc"
+    toml = m.write(tmp_path / "nc")
+    if char_ids:
+        write_netcdf(tmp_path / "nc" / m.input_dir / "basin_time.nc", "Basin / time",
+                     m.table("Basin / time"), m.starttime, char_ids=True)
+    assert "basin_time.nc" in toml.read_text()
+    m2 = ModelTables.read(toml)
+    assert m2.external_tables == {"Basin / time": "basin_time.nc"}
+    rows = load_netcdf(tmp_path / "nc" / m.input_dir / "basin_time.nc", "Basin / time")
+    assert len(rows) == len(m.table("Basin / time")) == 4 * 367
+    assert rows[0]["node_id"] == 1 and rows[1]["node_id"] == 3  # node fastest, then time
+    p2 = build_params(m2)
+    f1, f2 = flatten(ref), flatten(p2)
+    assert f1.ints == f2.ints
+    for k, v in f1.arrays.items():
+        assert np.array_equal(v, f2.arrays[k], equal_nan=True), k
+    for name in ("precipitation", "potential_evaporation", "drainage", "infiltration"):
+        for a, b in zip(ref.basin.forcing[name], p2.basin.forcing[name]):
+            assert np.array_equal(a.t, b.t) and np.array_equal(a.u, b.u, equal_nan=True)
+    assert ref.tstops == p2.tstops
+
+
+def test_netcdf_drops_all_missing_rows(tmp_path):
+    """Rows of the dense grid whose data variables are all missing do not exist in the table."""
+    from datetime import datetime
+    from ribasim_b200.tables import load_netcdf, write_netcdf
+    t0 = datetime(2020, 1, 1)
+    rows = [dict(node_id=7, time="2020-01-01 00:00:00", flow_rate=1.0),
+            dict(node_id=9, time="2020-01-02 00:00:00", flow_rate=2.5)]
+    write_netcdf(tmp_path / "fb.nc", "FlowBoundary / time", rows, t0)
+    got = load_netcdf(tmp_path / "fb.nc", "FlowBoundary / time")
+    assert [(r["node_id"], r["time"], r["flow_rate"]) for r in got] == \
+        [(7, datetime(2020, 1, 1), 1.0), (9, datetime(2020, 1, 2), 2.5)]
+
+
 def test_pump_discrete_control_compiles():
     p = build_params(MODELS["pump_discrete_control"]())
     flat = flatten(p)
