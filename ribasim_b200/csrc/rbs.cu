@@ -726,7 +726,6 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             EntSched& es = h->esched;
             es.n_elim = geti(b, "ent_n_elim"); es.n_bwd = geti(b, "ent_n_bwd");
             es.n_slots = n.n_lu + n.n_reduced; es.y0 = n.n_lu;
-            es.dbg = getenv("RBS_ENT_DBG") ? atoi(getenv("RBS_ENT_DBG")) : 0;
             // device form: 64-bit level / entry / product words, then perm (uint16)
             auto &ee = geta("ent_e"), &eq = geta("ent_q0"), &ec = geta("ent_cf");
             auto &pl = geta("ent_prod_l"), &pp = geta("ent_prod_p"), &pu = geta("ent_prod_u");

@@ -1116,7 +1116,6 @@ struct EntSched {
     int n_words;              // 64-bit words of lvl + ent + prod
     int smem_sched;           // copy the schedule into shared memory (after the slots)
     int n_elim, n_bwd, n_slots, y0;
-    int dbg;
 };
 
 __device__ __forceinline__ void rbs_cp_async8(void* smem_dst, const void* gmem_src) {
