@@ -157,8 +157,9 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
  * storages at the end of every outer step, [n_steps][n_basin][n_members]; with flow_out_pinned
  * likewise the mean flow over every outer step of every state (increment of the cumulative
  * state / dt: what `save_flow` stores per saveat interval, core/src/callback.jl:390-456),
- * [n_steps][n_state][n_members].  The buffers are valid after rbs_synchronize (or after the next
- * but one rbs_advance_window returns).  Results are identical to rbs_set_member_f64 +
+ * [n_steps][n_state][n_members].  The slices of an outer step go out as soon as every member has
+ * completed it, while the stragglers of the window are still computing; the buffers are valid
+ * after rbs_synchronize (or after the next but one rbs_advance_window returns).  Results are identical to rbs_set_member_f64 +
  * rbs_step_implicit_euler per step. */
 int rbs_stage_forcing_window(rbs_handle* h, const char* key, const double* pinned_host,
                              int64_t n_entity, int32_t first_step, int32_t n_steps);

@@ -75,6 +75,14 @@ struct rbs_handle {
     size_t fw_res_bytes = 0;
     double* fw_flow[2] = {nullptr, nullptr};
     size_t fw_flow_bytes = 0;
+    // progressive download of a running window's results: slices of outer steps that every member
+    // has completed go out while the stragglers are still computing
+    struct WinOut {
+        bool on = false;
+        double *host_s = nullptr, *dev_s = nullptr, *host_f = nullptr, *dev_f = nullptr;
+        size_t slice_s = 0, slice_f = 0;
+        int streamed = 0;
+    } wout;
     int fw_res_cur = 0;
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_win = nullptr, ev_d2h[2] = {nullptr, nullptr};
@@ -85,8 +93,8 @@ struct rbs_handle {
         cudaEvent_t ev = nullptr;
         int lo = 0, hi = 0;
         int *d_alist = nullptr, *d_llist = nullptr, *d_counts = nullptr;
-        int* h_counts = nullptr;  // pinned {n_active, n_limit}
-        int n_active = 0, n_limit = 0;
+        int* h_counts = nullptr;  // pinned {n_active, n_limit, outer steps completed by all members}
+        int n_active = 0, n_limit = 0, min_step = 0;
         bool pending = false, done = false;
     };
     std::vector<Group> groups;
@@ -367,8 +375,8 @@ int make_groups(rbs_handle* h, int ng) {
         size_t nb_ = sizeof(int) * std::max(G.hi - G.lo, 1);
         CUDA_TRY(cudaMalloc(&G.d_alist, nb_));
         CUDA_TRY(cudaMalloc(&G.d_llist, nb_));
-        CUDA_TRY(cudaMalloc(&G.d_counts, 2 * sizeof(int)));
-        CUDA_TRY(cudaMallocHost(&G.h_counts, 2 * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&G.d_counts, 4 * sizeof(int)));
+        CUDA_TRY(cudaMallocHost(&G.h_counts, 4 * sizeof(int)));
     }
     return 0;
 }
@@ -1300,6 +1308,7 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
         G.n_limit = 0;
         G.pending = false;
         G.done = G.n_active == 0;
+        G.min_step = G.done ? n_steps : 0;
     }
     h->cur = h->stream;
     // safety net only: every attempt either advances the member or halves its sub-step
@@ -1318,11 +1327,28 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
                 G.pending = false;
                 G.n_active = G.h_counts[0];
                 G.n_limit = G.h_counts[1];
+                G.min_step = G.h_counts[2];
+                if (h->wout.on) {
+                    // every kernel that wrote the slices of steps < ready has been observed complete
+                    int ready = n_steps;
+                    for (auto& G2 : h->groups) ready = std::min(ready, G2.min_step);
+                    if (ready > h->wout.streamed) {
+                        auto& w = h->wout;
+                        int k0 = w.streamed, cnt = ready - k0;
+                        if (w.dev_s)
+                            CUDA_TRY(cudaMemcpyAsync((char*)w.host_s + w.slice_s * k0, (char*)w.dev_s + w.slice_s * k0,
+                                                     w.slice_s * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+                        if (w.dev_f)
+                            CUDA_TRY(cudaMemcpyAsync((char*)w.host_f + w.slice_f * k0, (char*)w.dev_f + w.slice_f * k0,
+                                                     w.slice_f * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+                        w.streamed = ready;
+                    }
+                }
                 if (G.n_active == 0) { G.done = true; n_done++; progressed = true; continue; }
             }
             if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
             launch_pass(h, G, dt, h_min, n_steps);
-            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
             CUDA_TRY(cudaEventRecord(G.ev, G.stream));
             G.pending = true;
             progressed = true;
@@ -1463,8 +1489,15 @@ int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
     // the downloads of the window before last used these buffers
     if (n.w_storage || n.w_flow) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h[cur], 0));
     n.fw_on = 1;
+    h->wout.on = n.w_storage || n.w_flow;
+    h->wout.host_s = storage_out_pinned; h->wout.dev_s = n.w_storage;
+    h->wout.host_f = flow_out_pinned; h->wout.dev_f = n.w_flow;
+    h->wout.slice_s = (size_t)n.n_basin * n.B * sizeof(double);
+    h->wout.slice_f = (size_t)n.n_state * n.B * sizeof(double);
+    h->wout.streamed = 0;
     int rc = advance_impl(h, t, dt, n_steps, status_per_member);
     n.fw_on = 0;
+    h->wout.on = false;
     if (rc) return rc;
     // the last slice stays in force (and readable through rbs_get_member_f64) after the window
     for (int k = 0; k < 6; k++) {
@@ -1478,11 +1511,15 @@ int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
     }
     CUDA_TRY(cudaEventRecord(h->ev_win, h->stream));
     if (n.w_storage || n.w_flow) {
+        // what the progressive download has not taken yet
         CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_win, 0));
-        if (n.w_storage)
-            CUDA_TRY(cudaMemcpyAsync(storage_out_pinned, h->fw_res[cur], res_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
-        if (n.w_flow)
-            CUDA_TRY(cudaMemcpyAsync(flow_out_pinned, h->fw_flow[cur], flow_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+        const int k0 = h->wout.streamed, cnt = n_steps - k0;
+        if (n.w_storage && cnt > 0)
+            CUDA_TRY(cudaMemcpyAsync((char*)storage_out_pinned + h->wout.slice_s * k0, (char*)h->fw_res[cur] + h->wout.slice_s * k0,
+                                     h->wout.slice_s * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (n.w_flow && cnt > 0)
+            CUDA_TRY(cudaMemcpyAsync((char*)flow_out_pinned + h->wout.slice_f * k0, (char*)h->fw_flow[cur] + h->wout.slice_f * k0,
+                                     h->wout.slice_f * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
         CUDA_TRY(cudaEventRecord(h->ev_d2h[cur], h->d2h_stream));
         h->fw_res_cur = cur ^ 1;
         n.w_storage = nullptr;

@@ -1471,6 +1471,18 @@ __global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out
         if (ph == PHASE_LIMIT) llist_out[pl++] = m;
     }
     if (t == T - 1) { counts[0] = sa[t]; counts[1] = sl[t]; }
+    // counts[2]: outer steps of the window that every member of the group has completed (the
+    // host streams the result slices of finished steps back while the window is still running)
+    __syncthreads();
+    int mn = 0x7fffffff;
+    for (int m = lo; m < hi; m++) mn = min(mn, n.mstep[m]);
+    sa[t] = mn;
+    __syncthreads();
+    for (int off = T >> 1; off > 0; off >>= 1) {
+        if (t < off) sa[t] = min(sa[t], sa[t + off]);
+        __syncthreads();
+    }
+    if (t == 0) counts[2] = sa[0];
 }
 
 // ---- sub-stepping state machine -------------------------------------------------------------------
