@@ -236,7 +236,7 @@ template <int SRC> __device__ __forceinline__ double rbs_state_in(const Net& n, 
     return SRC == 1 ? n.uprev[o] + n.z[o] : n.u[o];
 }
 template <bool JAC, int SRC>
-__global__ void k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
+__global__ void __launch_bounds__(256, 6) k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
                         int flag_negative) {
     // flag_negative: 0 none; 1 = proposed state (sets mneg); 2 = clamped state (only members the
     // limiter changed, sets mneg2)
