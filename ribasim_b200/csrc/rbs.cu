@@ -236,6 +236,8 @@ void bind_net(rbs_handle* h) {
     M_D(exact); M_D(fb_rate); M_D(fb_cum); M_D(frp); M_D(fro); M_D(jv); M_D(wv); M_D(lu);
     M_D(norm_part); M_D(ndz); M_D(ndz_prev); M_D(eta); M_D(storage_prev); M_D(level_prev);
     M_D(mh); M_D(mhnom); M_D(melapsed); M_D(mhlast); M_D(zlast);
+    n.pm_mn_manning_n = mp(h, "pm_mn_manning_n"); n.pm_lr_resistance = mp(h, "pm_lr_resistance");
+    n.pm_pump_flow_rate = mp(h, "pm_pump_flow_rate"); n.pm_outlet_flow_rate = mp(h, "pm_outlet_flow_rate");
 #define M_I(name) n.name = (int*)h->member[#name].p
     M_I(nstat); M_I(status); M_I(active_count);
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
@@ -855,6 +857,33 @@ int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64
     if (n > 0) CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+int rbs_set_member_param_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity) {
+    if (!h || !key) return fail("rbs_set_member_param_f64: null argument");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    struct PK { const char* key; int count; };
+    const PK keys[] = {{"mn_manning_n", n.n_manning}, {"lr_resistance", n.n_lr},
+                       {"pump_flow_rate", n.n_pump}, {"outlet_flow_rate", n.n_outlet}};
+    const PK* pk = nullptr;
+    for (auto& k : keys) if (!strcmp(key, k.key)) pk = &k;
+    if (!pk) return fail(std::string("rbs_set_member_param_f64: no per-member override for ") + key);
+    std::string mk = std::string("pm_") + key;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!host) {  // back to the shared value
+        auto it = h->member.find(mk);
+        if (it != h->member.end()) { cudaFree(it->second.p); h->member.erase(it); h->member_entities.erase(mk); }
+        bind_net(h);
+        return 0;
+    }
+    if (n_entity != pk->count) return fail(std::string("parameter size mismatch: ") + key);
+    if (n_entity == 0) return 0;
+    if (h->member.find(mk) == h->member.end() && alloc_member(h, mk, n_entity)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(h->member[mk].p, host, (size_t)n_entity * h->B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    bind_net(h);
+    return check_async(h, "rbs_set_member_param_f64");
 }
 
 int rbs_set_member_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity, int32_t broadcast) {

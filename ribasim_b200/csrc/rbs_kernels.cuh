@@ -40,6 +40,9 @@ struct Net {
     const double* inc_sign;
     const int *bfb_ptr, *bfb_idx;
     const int* basin_obs;  // 1 = storage / area of this basin are read by a controller during the RHS
+    // parameter ensembles: per-member overrides [entity][member] of shared link parameters
+    // (nullptr = every member uses the shared value); set with rbs_set_member_param_f64
+    const double *pm_mn_manning_n, *pm_lr_resistance, *pm_pump_flow_rate, *pm_outlet_flow_rate;
     // connectors (shared)
     const int *conn_type, *conn_idx, *src_kind, *src_idx, *dst_kind, *dst_idx;
     const double *lr_resistance, *lr_max_flow_rate;
@@ -159,6 +162,9 @@ __device__ __forceinline__ int rbs_dc_row(const Net& n, const int* __restrict__ 
     return st < 0 ? -1 : cs_ptr[k] + st;
 }
 #define RBS_P(row, cs_arr, shared_arr, k) ((row) >= 0 ? (cs_arr)[(row)] : (shared_arr)[(k)])
+// the same with a per-member override of the shared value (parameter ensembles)
+#define RBS_PM(n, row, cs_arr, shared_arr, pm_arr, k, m) \
+    ((row) >= 0 ? (cs_arr)[(row)] : ((pm_arr) ? (pm_arr)[(long long)(k) * (n).B + (m)] : (shared_arr)[(k)]))
 
 template <bool JAC>
 __device__ __forceinline__ RbsEnd rbs_fetch_end(const Net& n, int kind, int idx, int m) {
@@ -368,8 +374,8 @@ __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* _
         int row = outlet ? rbs_dc_row(n, n.outlet_dc, n.outlet_cs_ptr, k, m)
                          : rbs_dc_row(n, n.pump_dc, n.pump_cs_ptr, k, m);
         double fr = controlled ? (outlet ? n.fro : n.frp)[(long long)k * n.B + m]
-                               : (outlet ? RBS_P(row, n.outlet_cs_flow_rate, n.outlet_flow_rate, k)
-                                         : RBS_P(row, n.pump_cs_flow_rate, n.pump_flow_rate, k));
+                               : (outlet ? RBS_PM(n, row, n.outlet_cs_flow_rate, n.outlet_flow_rate, n.pm_outlet_flow_rate, k, m)
+                                         : RBS_PM(n, row, n.pump_cs_flow_rate, n.pump_flow_rate, n.pm_pump_flow_rate, k, m));
         q = rbs_pump_outlet_flow(
             fr, a.h, b.h, a.f, a.dh, b.dh, a.df,
             outlet ? RBS_P(row, n.outlet_cs_min_flow_rate, n.outlet_min_flow_rate, k)
@@ -388,11 +394,12 @@ __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* _
         if (ct == CT_LR) {
             int row = rbs_dc_row(n, n.lr_dc, n.lr_cs_ptr, k, m);
             q = rbs_lr_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df,
-                            RBS_P(row, n.lr_cs_resistance, n.lr_resistance, k),
+                            RBS_PM(n, row, n.lr_cs_resistance, n.lr_resistance, n.pm_lr_resistance, k, m),
                             RBS_P(row, n.lr_cs_max_flow_rate, n.lr_max_flow_rate, k), dq_a, dq_b);
         } else if (ct == CT_MANNING) {
             q = rbs_manning_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df, n.mn_length[k],
-                                 n.mn_manning_n[k], n.mn_profile_width[k], n.mn_profile_slope[k],
+                                 n.pm_mn_manning_n ? n.pm_mn_manning_n[(long long)k * n.B + m] : n.mn_manning_n[k],
+                                 n.mn_profile_width[k], n.mn_profile_slope[k],
                                  n.mn_upstream_bottom[k], n.mn_downstream_bottom[k], dq_a, dq_b, JAC);
         } else {  // CT_TRC
             int row = rbs_dc_row(n, n.trc_dc, n.trc_cs_ptr, k, m);

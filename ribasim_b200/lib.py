@@ -79,6 +79,7 @@ def load() -> ctypes.CDLL:
         "rbs_kernel_launches": (i64, [vp]),
         "rbs_set_param_f64": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_set_param_i32": (ctypes.c_int, [vp, cp, ip, i64]),
+        "rbs_set_member_param_f64": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_set_member_f64": (ctypes.c_int, [vp, cp, dp, i64, i32]),
         "rbs_get_member_f64": (ctypes.c_int, [vp, cp, dp, i64]),
         "rbs_set_member_f64_async": (ctypes.c_int, [vp, cp, dp, i64]),
@@ -122,7 +123,7 @@ def load() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
-    "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_f64", "rbs_get_member_f64", "rbs_set_member_f64_async",
+    "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_param_f64", "rbs_set_member_f64", "rbs_get_member_f64", "rbs_set_member_f64_async",
     "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window", "rbs_host_alloc", "rbs_host_free",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
@@ -296,6 +297,14 @@ class Handle:
         for k in PARAM_I32:
             if k in tp:
                 self.set_param(k, np.asarray(tp[k], dtype=np.int32))
+
+    def set_member_param(self, key: str, arr) -> None:
+        """Per-member override `[n_entity][B]` of a shared link parameter (None drops it)."""
+        if arr is None:
+            _check(self.L.rbs_set_member_param_f64(self.h, key.encode(), None, 0))
+            return
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64))
+        _check(self.L.rbs_set_member_param_f64(self.h, key.encode(), _dp(a.reshape(-1)), a.size // self.B))
 
     def set_member(self, key: str, arr, broadcast: bool = False) -> None:
         a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64))

@@ -474,6 +474,89 @@ def test_forced_window_equals_per_step_forcing():
         assert np.array_equal(last[k], series[k][2 * W - 1])
 
 
+def test_parameter_ensemble_per_member_overrides():
+    """Parameter ensembles (north star (4)): per-member Manning n, LinearResistance resistance and
+    Pump / Outlet flow rates.  RHS and Jacobian of every member match an oracle instance built with
+    that member's parameters to 1e-12; a few implicit-Euler steps match it within the solver
+    tolerance; a member whose override equals the shared value is bitwise the shared-value run."""
+    from oracle.oracle import _dp, advance_opts
+    from ribasim_b200.testmodels import hws_like_model
+    B = 5
+    case = make_case(hws_like_model(n_basins=60, n_days=2), B, seed=41, t=0.0)
+    flat, tp = case["flat"], case["tp"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    rng = np.random.default_rng(12)
+
+    def spread(base):
+        f = rng.lognormal(0.0, 0.3, size=(len(base), B))
+        f[:, 0] = 1.0  # member 0 keeps the shared value
+        return np.ascontiguousarray(np.asarray(base, dtype=float)[:, None] * f)
+
+    over = {"mn_manning_n": spread(flat["mn_manning_n"]), "lr_resistance": spread(flat["lr_resistance"]),
+            "pump_flow_rate": spread(tp["pump_flow_rate"]), "outlet_flow_rate": spread(tp["outlet_flow_rate"])}
+    assert all(v.shape[0] > 0 for v in over.values())
+
+    def oracle_member(m):
+        om = oracle_for_member(case, m)
+        for k, v in over.items():
+            om.set_f64(k, v[:, m])
+        return om
+
+    h = gpu_handle_for(case)
+    ref = gpu_handle_for(case)
+    try:
+        with pytest.raises(Exception, match="no per-member override"):
+            h.set_member_param("mn_length", over["mn_manning_n"])
+        for k, v in over.items():
+            h.set_member_param(k, v)
+        du, _ = h.rhs(case["ur"], 0.0, with_cache=True)
+        jv, _ = h.jac(case["ur"], 0.0, gamma=3600.0)
+        for m in range(B):
+            om = oracle_member(m)
+            du_o = om.rhs(case["ur"][:, m], 0.0)
+            scale = np.maximum(np.abs(du_o), 1e-12 * np.abs(du_o).max())
+            assert np.max(np.abs(du[:, m] - du_o) / scale) <= 1e-12, m
+            Jo = om.jac_dense(case["ur"][:, m], 0.0)
+            Jg = csr_to_dense(flat, jv[:, m])
+            rs = np.maximum(np.abs(Jo).max(axis=1, keepdims=True), 1e-300)
+            assert np.max(np.abs(Jg - Jo) / rs) <= 1e-12, m
+        # the overrides change the answer ...
+        du_ref, _ = ref.rhs(case["ur"], 0.0, with_cache=True)
+        assert np.array_equal(du[:, 0], du_ref[:, 0]) and not np.array_equal(du[:, 1:], du_ref[:, 1:])
+        # dropping the overrides restores the shared parameters
+        for k in over:
+            h.set_member_param(k, None)
+        du2, _ = h.rhs(case["ur"], 0.0, with_cache=True)
+        assert np.array_equal(du2, du_ref)
+        for k, v in over.items():
+            h.set_member_param(k, v)
+        # ... and a few steps follow the per-member oracle
+        for x in (h, ref):
+            x.refresh(0.0)
+            x.set_member("level_prev", x.get_member("level", nb))
+        dt = 3600.0
+        st = h.advance(0.0, dt, 3)
+        ref.advance(0.0, dt, 3)
+        assert not np.any(st & 1)
+        ug = h.get_member("u", n)
+        assert np.array_equal(ug[:, 0], ref.get_member("u", n)[:, 0])
+        opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1, 1, 2)
+        for m in (1, B - 1):
+            om = oracle_member(m)
+            _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
+            om.L.orc_set_level_prev(om.h, _dp(np.ascontiguousarray(c0["level"])))
+            om.set_f64("fb_rate_step", case["fb_rate"][:, m])
+            u = np.zeros(n)
+            eta, htry = 1.0, dt
+            for k in range(3):
+                _, _, htry, eta = om.advance(u, k * dt, dt, opts, htry, eta)
+            scale = 1e-5 + np.abs(u) * 1e-5
+            assert np.max(np.abs(ug[:, m] - u) / scale) <= 1e-2, m
+    finally:
+        h.close()
+        ref.close()
+
+
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
