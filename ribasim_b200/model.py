@@ -118,6 +118,12 @@ class Model:
         self.h.set_member(name, values)
         self._member_forcing = True
 
+    def set_member_param(self, name: str, values: np.ndarray | None) -> None:
+        """Parameter ensemble: per-member values `[n_nodes][n_members]` of a shared link parameter
+        (`mn_manning_n`, `lr_resistance`, `pump_flow_rate`, `outlet_flow_rate`); None restores the
+        shared value of the model tables."""
+        self.h.set_member_param(name, values)
+
     def set_flow_boundary_rate(self, values: np.ndarray | None) -> None:
         """Per-member FlowBoundary rates `[n_fb][n_members]` for the coming steps."""
         self._fb_rate_members = None if values is None else np.ascontiguousarray(values)
