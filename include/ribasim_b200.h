@@ -66,9 +66,10 @@ int64_t rbs_kernel_launches(const rbs_handle* h);
 int rbs_set_param_f64(rbs_handle* h, const char* key, const double* host, int64_t n);
 int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64_t n);
 /* Parameter ensembles: a per-member override `[n_entity][n_members]` of a shared link parameter
- * ("mn_manning_n", "lr_resistance", "pump_flow_rate", "outlet_flow_rate": the fields of
- * ManningResistance / LinearResistance / Pump / Outlet, core/src/parameter.jl:513-772, that one
- * perturbs in a calibration or uncertainty ensemble).  A node under DiscreteControl keeps reading
+ * ("mn_manning_n", "lr_resistance", "pump_flow_rate", "outlet_flow_rate", "lb_level": the fields
+ * of ManningResistance / LinearResistance / Pump / Outlet / LevelBoundary,
+ * core/src/parameter.jl:513-772, that one perturbs in a calibration, uncertainty or boundary-
+ * scenario ensemble).  A node under DiscreteControl keeps reading
  * its control-state table.  host = NULL drops the override (all members use the shared value
  * again).  A member whose override equals the shared value gets bitwise the shared-value result. */
 int rbs_set_member_param_f64(rbs_handle* h, const char* key, const double* host, int64_t n_entity);

@@ -238,6 +238,7 @@ void bind_net(rbs_handle* h) {
     M_D(mh); M_D(mhnom); M_D(melapsed); M_D(mhlast); M_D(zlast);
     n.pm_mn_manning_n = mp(h, "pm_mn_manning_n"); n.pm_lr_resistance = mp(h, "pm_lr_resistance");
     n.pm_pump_flow_rate = mp(h, "pm_pump_flow_rate"); n.pm_outlet_flow_rate = mp(h, "pm_outlet_flow_rate");
+    n.pm_lb_level = mp(h, "pm_lb_level");
 #define M_I(name) n.name = (int*)h->member[#name].p
     M_I(nstat); M_I(status); M_I(active_count);
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
@@ -865,7 +866,8 @@ int rbs_set_member_param_f64(rbs_handle* h, const char* key, const double* host,
     Net& n = h->net;
     struct PK { const char* key; int count; };
     const PK keys[] = {{"mn_manning_n", n.n_manning}, {"lr_resistance", n.n_lr},
-                       {"pump_flow_rate", n.n_pump}, {"outlet_flow_rate", n.n_outlet}};
+                       {"pump_flow_rate", n.n_pump}, {"outlet_flow_rate", n.n_outlet},
+                       {"lb_level", n.n_lb}};
     const PK* pk = nullptr;
     for (auto& k : keys) if (!strcmp(key, k.key)) pk = &k;
     if (!pk) return fail(std::string("rbs_set_member_param_f64: no per-member override for ") + key);

@@ -42,7 +42,8 @@ struct Net {
     const int* basin_obs;  // 1 = storage / area of this basin are read by a controller during the RHS
     // parameter ensembles: per-member overrides [entity][member] of shared link parameters
     // (nullptr = every member uses the shared value); set with rbs_set_member_param_f64
-    const double *pm_mn_manning_n, *pm_lr_resistance, *pm_pump_flow_rate, *pm_outlet_flow_rate;
+    const double *pm_mn_manning_n, *pm_lr_resistance, *pm_pump_flow_rate, *pm_outlet_flow_rate,
+        *pm_lb_level;
     // connectors (shared)
     const int *conn_type, *conn_idx, *src_kind, *src_idx, *dst_kind, *dst_idx;
     const double *lr_resistance, *lr_max_flow_rate;
@@ -176,7 +177,8 @@ __device__ __forceinline__ RbsEnd rbs_fetch_end(const Net& n, int kind, int idx,
         e.dh = JAC ? n.dlevel[o] : 0.0;
         e.df = JAC ? n.dfactor[o] : 0.0;
     } else if (kind == KIND_LEVEL_BOUNDARY) {
-        e.h = n.lb_level[idx]; e.f = 1.0; e.dh = 0.0; e.df = 0.0;
+        e.h = n.pm_lb_level ? n.pm_lb_level[(long long)idx * n.B + m] : n.lb_level[idx];
+        e.f = 1.0; e.dh = 0.0; e.df = 0.0;
     } else {  // Terminal: bottomless pit (core/src/util.jl:184-187)
         e.h = -RBS_INF; e.f = 1.0; e.dh = 0.0; e.df = 0.0;
     }

@@ -120,7 +120,7 @@ class Model:
 
     def set_member_param(self, name: str, values: np.ndarray | None) -> None:
         """Parameter ensemble: per-member values `[n_nodes][n_members]` of a shared link parameter
-        (`mn_manning_n`, `lr_resistance`, `pump_flow_rate`, `outlet_flow_rate`); None restores the
+        (`mn_manning_n`, `lr_resistance`, `pump_flow_rate`, `outlet_flow_rate`, `lb_level`); None restores the
         shared value of the model tables."""
         self.h.set_member_param(name, values)
 

@@ -476,7 +476,7 @@ def test_forced_window_equals_per_step_forcing():
 
 def test_parameter_ensemble_per_member_overrides():
     """Parameter ensembles (north star (4)): per-member Manning n, LinearResistance resistance and
-    Pump / Outlet flow rates.  RHS and Jacobian of every member match an oracle instance built with
+    Pump / Outlet flow rates, LevelBoundary levels.  RHS and Jacobian of every member match an oracle instance built with
     that member's parameters to 1e-12; a few implicit-Euler steps match it within the solver
     tolerance; a member whose override equals the shared value is bitwise the shared-value run."""
     from oracle.oracle import _dp, advance_opts
@@ -493,7 +493,9 @@ def test_parameter_ensemble_per_member_overrides():
         return np.ascontiguousarray(np.asarray(base, dtype=float)[:, None] * f)
 
     over = {"mn_manning_n": spread(flat["mn_manning_n"]), "lr_resistance": spread(flat["lr_resistance"]),
-            "pump_flow_rate": spread(tp["pump_flow_rate"]), "outlet_flow_rate": spread(tp["outlet_flow_rate"])}
+            "pump_flow_rate": spread(tp["pump_flow_rate"]), "outlet_flow_rate": spread(tp["outlet_flow_rate"]),
+            "lb_level": np.ascontiguousarray(np.asarray(tp["lb_level"])[:, None] + np.concatenate(
+                [np.zeros((len(tp["lb_level"]), 1)), rng.normal(0.0, 0.2, size=(len(tp["lb_level"]), B - 1))], axis=1))}
     assert all(v.shape[0] > 0 for v in over.values())
 
     def oracle_member(m):
