@@ -559,6 +559,55 @@ def test_parameter_ensemble_per_member_overrides():
         ref.close()
 
 
+def test_async_member_staging_matches_synchronous_calls():
+    """rbs_set_member_f64_async / rbs_get_member_f64_async (pinned buffers, copy stream): values
+    staged before step k apply from step k + 1 on, the background download returns the array as
+    it was when requested; trajectories are bitwise those of the synchronous calls."""
+    from ribasim_b200 import lib
+    B = 12
+    case = make_case("basic", B, seed=19, t=0.0)
+    flat = case["flat"]
+    nb, n = flat["n_basin"], flat["n_state"]
+    rng = np.random.default_rng(2)
+    series = [case["forcing"]["precipitation"] * rng.lognormal(0.0, 0.5, size=(nb, B)) for _ in range(5)]
+    dt = 3600.0
+
+    def prepare():
+        h = gpu_handle_for(case)
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        h.set_member("precipitation", series[0])
+        return h
+
+    ref = prepare()
+    try:
+        S_ref = []
+        for k in range(4):
+            ref.step(k * dt, dt)
+            S_ref.append(ref.get_member("storage", nb))
+            ref.set_member("precipitation", series[k + 1])
+        u_ref = ref.get_member("u", n)
+    finally:
+        ref.close()
+    h = prepare()
+    try:
+        stage = [lib.PinnedArray((nb, B)) for _ in range(2)]
+        out = [lib.PinnedArray((nb, B)) for _ in range(4)]
+        for k in range(4):
+            stage[k % 2].array[:] = series[k + 1]
+            h.set_member_ptr_async("precipitation", stage[k % 2].ptr, nb)  # live after step k
+            h.step(k * dt, dt)
+            h.get_member_ptr_async("storage", out[k].ptr, nb)
+        h.synchronize()
+        for k in range(4):
+            assert np.array_equal(out[k].array, S_ref[k]), k
+        assert np.array_equal(h.get_member("u", n), u_ref)
+        for a in stage + out:
+            a.close()
+    finally:
+        h.close()
+
+
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
