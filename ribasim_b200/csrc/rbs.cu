@@ -134,6 +134,7 @@ struct rbs_handle {
     size_t smem_bytes = 0;
     int *d_lsrc_ptr = nullptr, *d_lsrc_code = nullptr;
     std::vector<int> list_phase[3];
+    bool pid_fused = false;  // k_pid also formulates its controlled pump / outlet
     int* d_list_phase[3] = {nullptr, nullptr, nullptr};
     int n_part = 1, rows_per_block = 64;
     bool factor_valid = false;
@@ -292,9 +293,10 @@ template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pr
                   (int)h->list_phase[1].size(), pred);
     }
     if (n.n_pid > 0) {
-        LAUNCH_AS(h, JAC ? "k_pid<jac>" : "k_pid<rhs>", k_pid<JAC>, (long long)n.n_pid * B, n, n.ur, pred);
-        LAUNCH_AS(h, JAC ? "k_links_pid<jac>" : "k_links_pid<rhs>", k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
-                  (int)h->list_phase[2].size(), pred);
+        LAUNCH_AS(h, JAC ? "k_pid<jac>" : "k_pid<rhs>", k_pid<JAC>, (long long)n.n_pid * B, n, n.ur, pred, h->pid_fused ? 1 : 0);
+        if (!h->pid_fused)
+            LAUNCH_AS(h, JAC ? "k_links_pid<jac>" : "k_links_pid<rhs>", k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
+                      (int)h->list_phase[2].size(), pred);
     }
 }
 // W = A J - I/gamma and its LU.  FROM_J: assembled on the fly (step path, per-member gamma = h).
@@ -565,6 +567,34 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     auto& oct = h->hi["outlet_control_type"];
     for (int k = 0; k < n.n_pump; k++) if (pct[k] != CONTROL_NONE) h->list_phase[pct[k]].push_back(n.off_pump + k);
     for (int k = 0; k < n.n_outlet; k++) if (oct[k] != CONTROL_NONE) h->list_phase[oct[k]].push_back(n.off_outlet + k);
+    {
+        // The controlled link can be formulated by the controller's own thread when no PidControl
+        // reads the flow of a PID-controlled node (then nothing depends on the order between the
+        // controllers and the controlled links) and every target has exactly one controller.
+        std::vector<char> is_target((size_t)std::max(n.n_state, 1), 0);
+        for (int s_ : h->list_phase[CONTROL_PID]) is_target[s_] = 1;
+        bool ok = (int)h->list_phase[CONTROL_PID].size() == n.n_pid;
+        auto it_t = h->hi.find("pid_term_state"), it_s = h->hi.find("pid_target_state");
+        auto it_p = h->hi.find("pid_term_ptr");
+        if (it_s == h->hi.end() || (int)it_s->second.size() < n.n_pid) ok = false;
+        // a controller may read the (still zero) flow of its own target: it does so before it
+        // formulates it; the flow of another controller's target must not be read
+        if (ok && it_t != h->hi.end() && it_p != h->hi.end() && (int)it_p->second.size() > n.n_pid)
+            for (int i = 0; i < n.n_pid; i++)
+                for (int k = it_p->second[i]; k < it_p->second[i + 1]; k++) {
+                    int s_ = it_t->second[k];
+                    if (s_ >= 0 && s_ < n.n_state && is_target[s_] && s_ != it_s->second[i]) ok = false;
+                }
+        else if (n.n_pid > 0) ok = false;
+        else {
+            std::vector<char> seen((size_t)std::max(n.n_state, 1), 0);
+            for (int i = 0; i < n.n_pid; i++) {
+                int s_ = it_s->second[i];
+                if (s_ < 0 || s_ >= n.n_state || !is_target[s_] || seen[s_]) ok = false; else seen[s_] = 1;
+            }
+        }
+        h->pid_fused = ok && n.n_pid > 0;
+    }
     for (int ph = 1; ph <= 2; ph++) {
         std::string key = std::string("list_phase") + char('0' + ph);
         if (upload(h, key, std::vector<int32_t>(h->list_phase[ph].begin(), h->list_phase[ph].end()), true)) return bail("list upload");

@@ -328,15 +328,9 @@ __device__ __forceinline__ double rbs_ud_link(const Net& n, int k, int m, double
 // ---- connector flows (formulate_flows!, solve.jl:811-834) ---------------------------------------
 // PHASE 0: every connector state whose flow does not depend on a controller;
 // PHASE 1/2: the pumps/outlets listed in `list` (controlled by ContinuousControl / PidControl).
+// flow (and its partials) of connector state s for member m
 template <bool JAC>
-__global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
-    long long tid = RBS_TID;
-    int li = (int)(tid / n.NA);
-    int count = phase == 0 ? n.n_conn : n_list;
-    if (li >= count) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)li * n.NA));
-    if (rbs_skip<JAC>(pred, m)) return;
-    int s = phase == 0 ? li : list[li];
+__device__ __forceinline__ void rbs_link_item(const Net& n, int s, int m, int phase) {
     int ct = n.conn_type[s], k = n.conn_idx[s];
     long long so = (long long)s * n.B + m;
     double q = 0.0, dq_a = 0.0, dq_b = 0.0;
@@ -429,6 +423,17 @@ __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* _
     }
 }
 
+template <bool JAC>
+__global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
+    long long tid = RBS_TID;
+    int li = (int)(tid / n.NA);
+    int count = phase == 0 ? n.n_conn : n_list;
+    if (li >= count) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)li * n.NA));
+    if (rbs_skip<JAC>(pred, m)) return;
+    rbs_link_item<JAC>(n, phase == 0 ? li : list[li], m, phase);
+}
+
 // ---- ContinuousControl (solve.jl:101-113, callback.jl:757-763) ----------------------------------
 template <bool JAC>
 __global__ void k_continuous_control(Net n, Pred pred) {
@@ -467,8 +472,11 @@ __global__ void k_continuous_control(Net n, Pred pred) {
 }
 
 // ---- PidControl (solve.jl:229-346) ---------------------------------------------------------------
+// fuse_link: also formulate the flow of the controlled pump / outlet in the same thread (allowed
+// when no controller reads the flow of a PID-controlled node, so that the launch order between
+// the controllers and the controlled links does not matter: checked on the host)
 template <bool JAC>
-__global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred) {
+__global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred, int fuse_link) {
     long long tid = RBS_TID;
     int i = (int)(tid / n.NA);
     if (i >= n.n_pid) return;
@@ -540,6 +548,7 @@ __global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred) {
         }
         n.jv[(long long)n.pid_jpos_listen[i] * n.B + m] += d_listen;
     }
+    if (fuse_link) rbs_link_item<JAC>(n, n.pid_target_state[i], m, CONTROL_PID);
 }
 
 // ---- W_inner = A*J_i - I/gamma (calc_J_inner! + jacobian2W!, differentiation.jl:153-271) --------
