@@ -244,15 +244,10 @@ template <int SRC> __device__ __forceinline__ double rbs_state_in(const Net& n, 
     return SRC == 1 ? n.uprev[o] + n.z[o] : n.u[o];
 }
 template <bool JAC, int SRC>
-__global__ void __launch_bounds__(256, 6) k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
-                        int flag_negative) {
+__device__ __forceinline__ void rbs_basin_item(const Net& n, const double* ur, bool write_du,
+                                               int flag_negative, int b, int m) {
     // flag_negative: 0 none; 1 = proposed state (sets mneg); 2 = clamped state (only members the
     // limiter changed, sets mneg2)
-    long long tid = RBS_TID;
-    int b = (int)(tid / n.NA);
-    if (b >= n.n_reduced) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)b * n.NA));
-    if (rbs_skip<JAC>(pred, m)) return;
     if (flag_negative == 2 && n.mclamp[m] == 0) return;
     long long o = (long long)b * n.B + m;
     if (b >= n.n_basin) {
@@ -307,6 +302,17 @@ __global__ void __launch_bounds__(256, 6) k_basin(Net n, const double* __restric
             n.jv[(long long)n.jrow_ptr[n.off_infil + b] * n.B + m] = dphi * I;
         }
     }
+}
+
+template <bool JAC, int SRC>
+__global__ void __launch_bounds__(256, 6) k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
+                        int flag_negative) {
+    long long tid = RBS_TID;
+    int b = (int)(tid / n.NA);
+    if (b >= n.n_reduced) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)b * n.NA));
+    if (rbs_skip<JAC>(pred, m)) return;
+    rbs_basin_item<JAC, SRC>(n, ur, write_du, flag_negative, b, m);
 }
 
 // ---- one user-demand inflow link (solve.jl:385-397) ---------------------------------------------
@@ -436,12 +442,7 @@ __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* _
 
 // ---- ContinuousControl (solve.jl:101-113, callback.jl:757-763) ----------------------------------
 template <bool JAC>
-__global__ void k_continuous_control(Net n, Pred pred) {
-    long long tid = RBS_TID;
-    int i = (int)(tid / n.NA);
-    if (i >= n.n_cc) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
-    if (rbs_skip<JAC>(pred, m)) return;
+__device__ __forceinline__ void rbs_cc_item(const Net& n, int i, int m) {
     double value = 0.0;
     for (int j = n.cc_sv_ptr[i]; j < n.cc_sv_ptr[i + 1]; j++) {
         int kind = n.cc_sv_kind[j], idx = n.cc_sv_idx[j];
@@ -471,17 +472,22 @@ __global__ void k_continuous_control(Net n, Pred pred) {
     }
 }
 
+template <bool JAC>
+__global__ void k_continuous_control(Net n, Pred pred) {
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.NA);
+    if (i >= n.n_cc) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
+    if (rbs_skip<JAC>(pred, m)) return;
+    rbs_cc_item<JAC>(n, i, m);
+}
+
 // ---- PidControl (solve.jl:229-346) ---------------------------------------------------------------
 // fuse_link: also formulate the flow of the controlled pump / outlet in the same thread (allowed
 // when no controller reads the flow of a PID-controlled node, so that the launch order between
 // the controllers and the controlled links does not matter: checked on the host)
 template <bool JAC>
-__global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred, int fuse_link) {
-    long long tid = RBS_TID;
-    int i = (int)(tid / n.NA);
-    if (i >= n.n_pid) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
-    if (rbs_skip<JAC>(pred, m)) return;
+__device__ __forceinline__ void rbs_pid_item(const Net& n, const double* ur, int fuse_link, int i, int m) {
     int L = n.pid_listen_basin[i];
     long long lo = (long long)L * n.B + m;
     double err = n.pid_target[i] - n.level[lo];
@@ -549,6 +555,15 @@ __global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred, int fuse_
         n.jv[(long long)n.pid_jpos_listen[i] * n.B + m] += d_listen;
     }
     if (fuse_link) rbs_link_item<JAC>(n, n.pid_target_state[i], m, CONTROL_PID);
+}
+template <bool JAC>
+__global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred, int fuse_link) {
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.NA);
+    if (i >= n.n_pid) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
+    if (rbs_skip<JAC>(pred, m)) return;
+    rbs_pid_item<JAC>(n, ur, fuse_link, i, m);
 }
 
 // ---- W_inner = A*J_i - I/gamma (calc_J_inner! + jacobian2W!, differentiation.jl:153-271) --------
@@ -896,6 +911,27 @@ struct LduSched {          // offsets (in index elements) into the packed schedu
 // factor slot (W = A J - I/h scattered into the LU pattern; ordered signed sums, code < 0 is the
 // "- 1/h" of a diagonal entry) for members that refresh their Jacobian, and the reduced
 // right-hand side b_r = A*((h du - z)/h) for every member in the Newton phase.
+// one item (factor slot or reduced right-hand-side row) of one member: the arithmetic of
+// k_assemble_linear, used by the cooperative window kernel
+__device__ __forceinline__ void rbs_assemble_item(const Net& n, const int* __restrict__ dsrc_ptr,
+                                                  const int* __restrict__ dsrc_code, int e, int m) {
+    if (e < n.n_lu) {
+        if (n.mjac[m] == 0) return;
+        const double invh = 1.0 / n.mh[m];
+        double v = 0.0;
+        for (int k = dsrc_ptr[e]; k < dsrc_ptr[e + 1]; k++) {
+            int code = dsrc_code[k];
+            if (code < 0) { v = v - invh; continue; }
+            double x = n.jv[(long long)(code >> 1) * n.B + m];
+            v = (code & 1) ? v - x : v + x;
+        }
+        n.lu[(long long)e * n.B + m] = v;
+    } else {
+        int r = e - n.n_lu;
+        n.br[(long long)r * n.B + m] = rbs_solve_rhs<true>(n, nullptr, r, m);
+    }
+}
+
 // Two members per thread (positions j and j + 32 of a 64-member tile of the launch domain): the
 // index loads of an item are shared by both, every load instruction is still a coalesced 256 B
 // request.  The kernel is bound by instruction issue, not by bytes.
@@ -1223,15 +1259,14 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, in
 // Newton linear solve of one member tile per block on the entry schedule; input as for
 // k_newton_linear_smem: the initial slot values / stored factors in `lu`, the reduced right-hand
 // side in `br` (k_assemble_linear).
+// the solve of the member tile [m0, m0 + TILE) of the launch domain by one block (block barriers
+// inside; `S` = the block's dynamic shared memory)
 template <int TILE>
-__global__ void __launch_bounds__(RBS_ENT_LANES * TILE / 2)
-k_newton_linear_ent(Net n, EntSched es, int write_lu, double* __restrict__ x) {
+__device__ __forceinline__ void rbs_lin_tile(const Net& n, EntSched es, double* S, int m0, int write_lu,
+                                             double* x) {
     constexpr int NT = RBS_ENT_LANES * TILE / 2;
-    extern __shared__ double smem[];
-    double* S = smem;                                    // [n_slots][TILE]
     const uint16_t* __restrict__ perm = es.perm;
     __shared__ int mem_s[TILE], fac_s[TILE];
-    int m0 = blockIdx.x * TILE;
     int tm = min(TILE, n.NA - m0);
     if (tm <= 0) return;
     LIN_CLK(0);
@@ -1280,6 +1315,12 @@ k_newton_linear_ent(Net n, EntSched es, int write_lu, double* __restrict__ x) {
             for (int e = slot; e < n.n_lu; e += n_slot) n.lu[(long long)e * B + m] = S[e * TILE + j];
     }
     LIN_CLK(7);
+}
+template <int TILE>
+__global__ void __launch_bounds__(RBS_ENT_LANES * TILE / 2)
+k_newton_linear_ent(Net n, EntSched es, int write_lu, double* __restrict__ x) {
+    extern __shared__ double smem[];
+    rbs_lin_tile<TILE>(n, es, smem, blockIdx.x * TILE, write_lu, x);
 }
 
 // ---- limit_flow! (solve.jl:840-984); needs storage/level at the proposed u ------------------------
@@ -1369,19 +1410,22 @@ __global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __rest
 #define RBS_DZ_ROWS 8
 // Two members per thread (positions j and j + 32 of a 64-member tile): the row pointers and
 // column indices of J_intermediate are loaded once for both.
-__global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
-                                int rows_per_block) {
-    const int j0 = blockIdx.x * 64 + threadIdx.x, j1 = j0 + 32;
+// one (64-member tile, row block) unit; tx in [0, 32), ty in [0, RBS_DZ_ROWS); all threads of the
+// block take part (block barrier inside)
+__device__ __forceinline__ void rbs_update_unit(const Net& n, const double* c, double abstol,
+                                                double reltol, int rows_per_block, int tile64, int part,
+                                                int tx, int ty, double (*sh)[RBS_DZ_ROWS][33]) {
+    const int j0 = tile64 * 64 + tx, j1 = j0 + 32;
     int m0 = j0 < n.NA ? RBS_MEMBER(n, j0) : -1, m1 = j1 < n.NA ? RBS_MEMBER(n, j1) : -1;
     if (m0 >= 0 && n.mphase[m0] != PHASE_NEWTON) m0 = -1;
     if (m1 >= 0 && n.mphase[m1] != PHASE_NEWTON) m1 = -1;
-    const int r0 = blockIdx.y * rows_per_block;
+    const int r0 = part * rows_per_block;
     double acc0 = 0.0, acc1 = 0.0;
     if (m0 >= 0 || m1 >= 0) {
         const int a0 = m0 >= 0 ? m0 : m1, a1 = m1 >= 0 ? m1 : m0;  // valid addresses for both
         const double dt0 = n.mh[a0], dt1 = n.mh[a1], inv0 = 1.0 / dt0, inv1 = 1.0 / dt1;
         const int r1 = min(r0 + rows_per_block, n.n_state);
-        for (int r = r0 + threadIdx.y; r < r1; r += RBS_DZ_ROWS) {
+        for (int r = r0 + ty; r < r1; r += RBS_DZ_ROWS) {
             const long long o0 = (long long)r * n.B + a0, o1 = (long long)r * n.B + a1;
             double jc0 = 0.0, jc1 = 0.0;
             for (int e = n.jrow_ptr[r]; e < n.jrow_ptr[r + 1]; e++) {
@@ -1401,18 +1445,22 @@ __global__ void k_newton_update(Net n, const double* __restrict__ c, double abst
             if (m1 >= 0) { acc1 += q1 * q1; n.z[o1] = zo1 - dz1; }
         }
     }
-    __shared__ double sh[2][RBS_DZ_ROWS][33];
-    sh[0][threadIdx.y][threadIdx.x] = acc0;
-    sh[1][threadIdx.y][threadIdx.x] = acc1;
+    sh[0][ty][tx] = acc0;
+    sh[1][ty][tx] = acc1;
     __syncthreads();
-    if (threadIdx.y < 2) {
-        const int mm = threadIdx.y == 0 ? m0 : m1;
+    if (ty < 2) {
+        const int mm = ty == 0 ? m0 : m1;
         if (mm >= 0) {
             double s = 0.0;
-            for (int y = 0; y < RBS_DZ_ROWS; y++) s += sh[threadIdx.y][y][threadIdx.x];
-            n.norm_part[(long long)blockIdx.y * n.B + mm] = s;
+            for (int y = 0; y < RBS_DZ_ROWS; y++) s += sh[ty][y][tx];
+            n.norm_part[(long long)part * n.B + mm] = s;
         }
     }
+}
+__global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
+                                int rows_per_block) {
+    __shared__ double sh[2][RBS_DZ_ROWS][33];
+    rbs_update_unit(n, c, abstol, reltol, rows_per_block, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, sh);
 }
 
 // per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve);
@@ -1572,12 +1620,8 @@ __global__ void k_step_begin(Net n, double dt, int predictor) {
 }
 
 // PHASE_LIMIT members: u <- clamp(uprev + z) (limit_flow! on the proposed state)
-__global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
-                             const double* __restrict__ alloc_total) {
-    long long tid = RBS_TID;
-    int s = (int)(tid / n.NA);
-    if (s >= n.n_state) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)s * n.NA));
+__device__ __forceinline__ void rbs_step_limit_item(const Net& n, const int* __restrict__ from_ts,
+                                                    const double* __restrict__ alloc_total, int s, int m) {
     if (n.mphase[m] != PHASE_LIMIT) return;
     long long o = (long long)s * n.B + m;
     double up = n.uprev[o];
@@ -1591,12 +1635,18 @@ __global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
     n.u[o] = v;
 }
 
+__global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
+                             const double* __restrict__ alloc_total) {
+    long long tid = RBS_TID;
+    int s = (int)(tid / n.NA);
+    if (s >= n.n_state) return;
+    int m = RBS_MEMBER(n, (int)(tid - (long long)s * n.NA));
+    rbs_step_limit_item(n, from_ts, alloc_total, s, m);
+}
+
 // PHASE_LIMIT members: accept or reject the attempt, choose the next attempt
-__global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters,
-                              int n_steps, int shrink_log2) {
-    int j = (int)RBS_TID;
-    if (j >= n.NA) return;
-    int m = RBS_MEMBER(n, j);
+__device__ __forceinline__ void rbs_step_decide_item(const Net& n, double dt, double h_min, int max_halvings,
+                                                     int grow_iters, int n_steps, int shrink_log2, int m) {
     if (n.mphase[m] != PHASE_LIMIT) { n.maction[m] = ACTION_NONE; return; }
     bool conv = n.mconv[m] != 0, last = n.mlast[m] != 0;
     bool neg = (n.mclamp[m] ? n.mneg2[m] : n.mneg[m]) != 0;
@@ -1646,12 +1696,15 @@ __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, 
     n.ndz_prev[m] = 0.0;
 }
 
+__global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters,
+                              int n_steps, int shrink_log2) {
+    int j = (int)RBS_TID;
+    if (j >= n.NA) return;
+    rbs_step_decide_item(n, dt, h_min, max_halvings, grow_iters, n_steps, shrink_log2, RBS_MEMBER(n, j));
+}
+
 // apply the decision to the states and the exact-forcing bookkeeping
-__global__ void k_step_apply(Net n, int predictor) {
-    long long tid = RBS_TID;
-    int ent = (int)(tid / n.NA);
-    if (ent >= n.n_state + n.n_basin) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)ent * n.NA));
+__device__ __forceinline__ void rbs_step_apply_item(const Net& n, int predictor, int ent, int m) {
     int action = n.maction[m];
     if (action == ACTION_NONE) return;
     bool next = n.mphase[m] == PHASE_NEWTON;
@@ -1685,17 +1738,20 @@ __global__ void k_step_apply(Net n, int predictor) {
         n.w_storage[n.fw_sb * (ws - 1) + (long long)b * n.B + m] = n.storage[(long long)b * n.B + m];
 }
 
+__global__ void k_step_apply(Net n, int predictor) {
+    long long tid = RBS_TID;
+    int ent = (int)(tid / n.NA);
+    if (ent >= n.n_state + n.n_basin) return;
+    rbs_step_apply_item(n, predictor, ent, RBS_MEMBER(n, (int)(tid - (long long)ent * n.NA)));
+}
+
 // ---- DiscreteControl (apply_discrete_control!, core/src/callback.jl:608-661) ----------------------
 // One thread per (DiscreteControl node, member), after an accepted (sub-)step of that member:
 // compound variables -> hysteresis conditions -> truth state -> control state.  Flows are the
 // mean flows of the accepted step (u - uprev)/h, which is what get_du holds after an implicit
 // Euler step; with `initial` (t = 0) the RHS du of the initial state is used and the control
 // state is set even without a truth-state change.
-__global__ void k_discrete_control(Net n, int initial) {
-    long long tid = RBS_TID;
-    int i = (int)(tid / n.NA);
-    if (i >= n.n_dc) return;
-    int m = RBS_MEMBER(n, (int)(tid - (long long)i * n.NA));
+__device__ __forceinline__ void rbs_discrete_control_item(const Net& n, int initial, int i, int m) {
     if (!initial && n.maction[m] != ACTION_ACCEPT) return;
     double inv_h = (!initial && n.mhlast[m] > 0.0) ? 1.0 / n.mhlast[m] : 0.0;
     int c0 = n.dc_cond_ptr[i], c1 = n.dc_cond_ptr[i + 1];
@@ -1725,6 +1781,13 @@ __global__ void k_discrete_control(Net n, int initial) {
         if (snew < 0) atomicOr(&n.status[m], 4);  // no control state specified for this truth state
         else if (snew != n.dc_state[so]) { n.dc_state[so] = snew; atomicAdd(&n.cnt_dc[m], 1); }
     }
+}
+
+__global__ void k_discrete_control(Net n, int initial) {
+    long long tid = RBS_TID;
+    int i = (int)(tid / n.NA);
+    if (i >= n.n_dc) return;
+    rbs_discrete_control_item(n, initial, i, RBS_MEMBER(n, (int)(tid - (long long)i * n.NA)));
 }
 
 __global__ void k_fill(double* p, long long nelem, double v) {
