@@ -15,6 +15,7 @@
 
 #include "../../include/ribasim_b200.h"
 #include "rbs_kernels.cuh"
+#include "rbs_coop.cuh"
 
 namespace {
 
@@ -135,6 +136,11 @@ struct rbs_handle {
     int *d_lsrc_ptr = nullptr, *d_lsrc_code = nullptr;
     std::vector<int> list_phase[3];
     bool pid_fused = false;  // k_pid also formulates its controlled pump / outlet
+    // cooperative window kernel (rbs_coop.cuh): used when the ensemble is small
+    int coop_members = 0;    // use it for ensembles of at most this many members (0 = never)
+    int coop_blocks = 0;     // co-resident grid size (0 = unavailable)
+    int* d_coop_counters = nullptr;
+    int* h_coop_counters = nullptr;  // pinned
     int* d_list_phase[3] = {nullptr, nullptr, nullptr};
     int n_part = 1, rows_per_block = 64;
     bool factor_valid = false;
@@ -826,6 +832,24 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             }
         }
         if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; h->lin_ent = false; }
+        // ---- cooperative window kernel: needs the entry schedule with 2-member tiles in shared
+        // memory and a grid that is co-resident
+        if (h->lin_ent) {
+            size_t sb2 = (size_t)h->esched.n_slots * 2 * sizeof(double);
+            int coop_ok = 0, per_sm = 0, n_sm = 0;
+            cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, device);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            if (coop_ok && sb2 + 8192 <= (size_t)dev_smem &&
+                cudaFuncSetAttribute(k_window_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb2) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_window_coop, RBS_COOP_THREADS, sb2) == cudaSuccess &&
+                per_sm > 0) {
+                h->coop_blocks = per_sm * n_sm;
+                if (cudaMalloc(&h->d_coop_counters, 4 * sizeof(int)) != cudaSuccess ||
+                    cudaMallocHost(&h->h_coop_counters, 4 * sizeof(int)) != cudaSuccess) return bail("coop alloc");
+                int cm = geti(b, "coop_members", -1);
+                h->coop_members = cm >= 0 ? cm : 32;  // measured: pays below a few dozen members
+            } else cudaGetLastError();
+        }
     }
     bind_net(h);
     n.cc_tab_offset = geti(b, "cc_tab_offset");
@@ -860,6 +884,8 @@ void rbs_destroy(rbs_handle* h) {
     if (h->d_blob) cudaFree(h->d_blob);
     if (h->d_blob2) cudaFree(h->d_blob2);
     if (h->d_ent_blob) cudaFree(h->d_ent_blob);
+    if (h->d_coop_counters) cudaFree(h->d_coop_counters);
+    if (h->h_coop_counters) cudaFreeHost(h->h_coop_counters);
     if (h->d_alist) cudaFree(h->d_alist);
     if (h->d_llist) cudaFree(h->d_llist);
     if (h->d_counts) cudaFree(h->d_counts);
@@ -1351,6 +1377,47 @@ int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_pe
     return check_async(h, "rbs_time_linear");
 }
 
+// the window as one cooperative kernel (small ensembles, full Newton)
+static int advance_coop(rbs_handle* h, double dt, double h_min, int32_t n_steps) {
+    Net& n = h->net;
+    n.NA = n.B;
+    n.alist = nullptr;
+    CoopArgs a{};
+    a.from_ts = sp<int>(h, "ud_demand_from_timeseries");
+    a.alloc_total = sp<double>(h, "ud_alloc_total");
+    a.dsrc_ptr = sp<int>(h, "dsrc_ptr");
+    a.dsrc_code = sp<int>(h, "dsrc_code");
+    a.list_cc = h->d_list_phase[1]; a.n_list_cc = (int)h->list_phase[1].size();
+    a.list_pid = h->d_list_phase[2]; a.n_list_pid = (int)h->list_phase[2].size();
+    a.pid_fused = h->pid_fused ? 1 : 0;
+    a.c = mp(h, "cvec");
+    a.dt = dt; a.h_min = h_min; a.abstol = h->abstol; a.reltol = h->reltol;
+    a.max_halvings = h->max_halvings; a.grow_iters = h->grow_iters; a.n_steps = n_steps;
+    a.shrink_log2 = h->shrink_log2; a.predictor = h->predictor; a.early_exit = h->early_exit;
+    a.max_iter = h->max_iter; a.n_part = h->n_part; a.rows_per_block = h->rows_per_block;
+    a.max_passes = std::min<long long>(h->max_passes, 4000) * (long long)n_steps;  // safety net
+    a.counters = h->d_coop_counters;
+    CUDA_TRY(cudaMemsetAsync(h->d_coop_counters, 0, 4 * sizeof(int), h->stream));
+    EntSched es = h->esched;
+    es.smem_sched = 0;
+    size_t sb2 = (size_t)es.n_slots * 2 * sizeof(double);
+    // no more blocks than there is work in the widest phase
+    long long widest = (long long)std::max(n.n_state + n.n_basin, n.n_lu + n.n_reduced) * n.B;
+    int blocks = (int)std::max<long long>(1, std::min<long long>(h->coop_blocks, (widest + RBS_COOP_THREADS - 1) / RBS_COOP_THREADS));
+    void* args[] = {&n, &es, &a};
+    prof_begin(h, "k_window_coop");
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_window_coop, dim3(blocks), dim3(RBS_COOP_THREADS), args, sb2, h->stream));
+    prof_end(h);
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(h->h_coop_counters, h->d_coop_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const int np_ = h->h_coop_counters[3];
+    if (np_ >= a.max_passes && h->h_coop_counters[(np_ + 2) % 3] != 0)
+        return fail("rbs_advance: pass limit exceeded");
+    h->n_passes += np_;
+    return 0;
+}
+
 static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
     cudaSetDevice(h->device);
     Net& n = h->net;
@@ -1358,6 +1425,18 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
     double h_min = std::ldexp(dt, -h->max_halvings);
     h->cur = h->stream;
     LAUNCH(h, k_step_begin, (long long)(n.n_state + n.n_basin + 1) * B, n, dt, h->predictor);
+    if (h->coop_blocks > 0 && h->full_newton && n.B <= h->coop_members && !h->profiling) {
+        if (advance_coop(h, dt, h_min, n_steps)) return 1;
+        h->tprev = t + dt * n_steps;
+        h->n_steps += n_steps;
+        if (commit_staged(h)) return 1;
+        if (status_per_member) {
+            CUDA_TRY(cudaMemcpyAsync(status_per_member, n.status, (size_t)n.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            for (int m = 0; m < n.B; m++) if (status_per_member[m] & 1) h->n_failed++;
+        }
+        return check_async(h, "rbs_advance");
+    }
     // fork: every group starts from the common begin on its own stream
     cudaEvent_t ev_begin = h->groups[0].ev;
     CUDA_TRY(cudaEventRecord(ev_begin, h->stream));

@@ -201,7 +201,8 @@ class Handle:
 
     def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
                  device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
-                 smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0):
+                 smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0,
+                 coop_members: int = -1):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -264,6 +265,9 @@ class Handle:
             set_i("smem_threads", [smem_threads])
             set_i("lin_mode", [lin_mode])
             set_i("n_groups", [n_groups])
+            # ensembles of at most this many members run a window as one cooperative kernel
+            # (-1 = the library's default)
+            set_i("coop_members", [int(os.environ.get("RBS_COOP_MEMBERS", str(coop_members)))])
             self.h = self.L.rbs_create(b, self.B, int(device))
         finally:
             self.L.rbs_builder_destroy(b)

@@ -608,6 +608,44 @@ def test_async_member_staging_matches_synchronous_calls():
         h.close()
 
 
+@pytest.mark.parametrize("name", ["basic", "backwater", "user_demand", "pid_control",
+                                  "outlet_continuous_control", "pump_discrete_control", "hws_like"])
+def test_cooperative_window_kernel_equals_stream_path(name):
+    """Small ensembles run a window as one cooperative kernel (rbs_coop.cuh: grid barriers between
+    the phases, predicates instead of work lists).  Same device functions, same summation orders:
+    states, storages, status flags and the iteration / sub-step / reject counters are bitwise those
+    of the stream path (one launch per phase, compacted member lists)."""
+    from ribasim_b200.testmodels import hws_like_model
+    B = 37
+    case = make_case(hws_like_model(n_basins=60, n_days=2) if name == "hws_like" else name, B, seed=29, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    for coop in (0, 4096):
+        h = gpu_handle_for(case, coop_members=coop)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if flat["n_dc"] > 0:
+                h.apply_discrete_control()
+                h.refresh(0.0)
+            l0 = h.kernel_launches()
+            st = h.advance(0.0, 3600.0, 5)
+            st |= h.step(5 * 3600.0, 1800.0)
+            launches = h.kernel_launches() - l0
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats(), launches,
+                        h.get_member_i32("dc_state", flat["n_dc"]) if flat["n_dc"] else None))
+        finally:
+            h.close()
+    (u0, S0, st0, stats0, l_stream, dc0), (u1, S1, st1, stats1, l_coop, dc1) = out
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert stats0[k] == stats1[k], k
+    if dc0 is not None:
+        assert np.array_equal(dc0, dc1)
+    assert l_coop <= 4 < l_stream  # k_step_begin + the cooperative kernel per call
+
+
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
