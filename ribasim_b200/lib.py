@@ -35,7 +35,7 @@ class RbsError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile librbs.so for sm_100a in-tree (so that it travels with the repo snapshot)."""
-    srcs = [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_math.cuh",
+    srcs = [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_coop.cuh", CSRC / "rbs_math.cuh",
             PKG_DIR.parent / "include" / "ribasim_b200.h"]
     if not force and LIB_PATH.exists() and all(
             LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
