@@ -769,3 +769,36 @@ def test_forced_window_outputs_close_the_water_balance(n_basins, B):
         scale = np.maximum(np.abs(S[k + 1]), 1.0)
         worst = max(worst, float(np.max(np.abs(dS - dt * net) / scale)))
     assert worst < 1e-10, worst
+
+
+def test_full_size_ensemble_members_match_oracle():
+    """BASELINE config 4 at full size (500 basins x 4096 members, four member groups): sampled
+    members of the ensemble follow the oracle's restatement of the same stepping algorithm within
+    a small fraction of the solver tolerance."""
+    from oracle.oracle import _dp, advance_opts
+    from ribasim_b200.testmodels import hws_like_model
+    B = 4096
+    case = make_case(hws_like_model(n_basins=500, n_days=2), B, seed=77, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    h = gpu_handle_for(case)
+    try:
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        st = h.advance(0.0, 3600.0, 3)
+        ug = h.get_member("u", n)
+    finally:
+        h.close()
+    assert not np.any(st & 1)
+    opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1, 1, 2)
+    for m in (0, 1023, 1024, 2777, B - 1):  # first / last of a group, interior, last member
+        om = oracle_for_member(case, m)
+        _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
+        om.L.orc_set_level_prev(om.h, _dp(np.ascontiguousarray(c0["level"])))
+        om.set_f64("fb_rate_step", case["fb_rate"][:, m])
+        u = np.zeros(n)
+        eta, htry = 1.0, 3600.0
+        for k in range(3):
+            _, _, htry, eta = om.advance(u, k * 3600.0, 3600.0, opts, htry, eta)
+        scale = 1e-5 + np.abs(u) * 1e-5
+        assert np.max(np.abs(ug[:, m] - u) / scale) <= 1e-2, m
