@@ -62,3 +62,45 @@ def test_backwater_single_instance_against_standard_step_method():
         assert model.status_counts == dict(newton_failed=0, negative_storage=0)
     finally:
         model.finalize()
+
+
+def test_reference_analytic_solutions_on_gpu():
+    # core/test/equations_test.jl: TabulatedRatingCurve (:49-70), PID control (:115-154) and
+    # MiscellaneousNodes (:156-181) against their closed-form solutions, device path
+    from ribasim_b200.model import Model
+    from ribasim_b200.network import build_params
+    from ribasim_b200.testmodels import MODELS
+    from tests.test_oracle_golden import _pid_equation_storage, _rating_curve_storage
+
+    p = build_params(MODELS["rating_curve"]())
+    model = Model(p, n_members=2, dt=3600.0)
+    try:
+        area, S0 = p.basin.areas[0][1], float(p.basin.storage0[0])
+        for days in (1, 10, 100, 366):
+            model.update_until(days * 86400.0)
+            assert model.storage()[0, 1] == pytest.approx(_rating_curve_storage(days * 86400.0, S0, area), rel=0.01)
+    finally:
+        model.finalize()
+
+    p = build_params(MODELS["pid_control_equation"]())
+    model = Model(p, n_members=1, dt=1.0)
+    try:
+        for t_end in (60.0, 300.0):
+            model.update_until(t_end)
+            assert model.storage()[0, 0] == pytest.approx(_pid_equation_storage(p, t_end), rel=0.01)
+    finally:
+        model.finalize()
+
+    p = build_params(MODELS["misc_nodes"]())
+    model = Model(p, n_members=3, dt=86400.0)
+    try:
+        S0 = p.basin.storage0.copy()
+        for days in (1, 30, 366):
+            model.update_until(days * 86400.0)
+            t = days * 86400.0
+            S = model.storage()
+            assert S[0, 2] == pytest.approx(S0[0] + t * (1.5e-4 - 1e-4), rel=1e-9)
+            assert S[1, 2] == pytest.approx(S0[1] + t * 1e-4, rel=1e-9)
+    finally:
+        model.finalize()
+

@@ -185,6 +185,58 @@ def test_linear_resistance_analytic():
         assert S[0] == pytest.approx(expect, rel=1e-4)
 
 
+def _rating_curve_storage(t, S0, area):
+    # core/test/equations_test.jl:46-70: w' = -alpha/A w^2
+    storage_min, alpha = 50.005, 24 * 60 * 60
+    return storage_min + 1.0 / (t / (alpha * area ** 2) + 1.0 / (S0 - storage_min))
+
+
+def test_tabulated_rating_curve_analytic():
+    # core/test/equations_test.jl:49-70 (rtol 0.01 on the whole trajectory; here several end times)
+    p = build_params(MODELS["rating_curve"]())
+    area = p.basin.areas[0][1]
+    S0 = float(p.basin.storage0[0])
+    for days in (1, 10, 100, 366):
+        u, S, lv, st = run_oracle(p, 3600.0, t_end=days * 86400.0)
+        assert S[0] == pytest.approx(_rating_curve_storage(days * 86400.0, S0, area), rel=0.01)
+
+
+def _pid_equation_storage(p, t):
+    # core/test/equations_test.jl:115-154
+    pid = p.nodes["pid_control"]
+    SP, K_p, K_i, K_d = (pid[k][0](0.0) for k in ("target", "proportional", "integral", "derivative"))
+    storage_min, level_min = 50.005, p.basin.levels[0][1]
+    S0, area = float(p.basin.storage0[0]), p.basin.areas[0][1]
+    level0 = level_min + (S0 - storage_min) / area
+    a, b, g = 1 - K_d / area, -K_p / area, -K_i / area
+    d = -K_i * (SP - level_min + storage_min / area)
+    l1 = (-b + np.sqrt(b * b - 4 * a * g)) / (2 * a)
+    l2 = (-b - np.sqrt(b * b - 4 * a * g)) / (2 * a)
+    c1, c2 = S0 - d / g, -K_p * (SP - level0) / (1 - K_d / area)
+    k1, k2 = (l2 * c1 - c2) / (l2 - l1), (-l1 * c1 + c2) / (l2 - l1)
+    return k1 * np.exp(l1 * t) + k2 * np.exp(l2 * t) + d / g
+
+
+def test_pid_control_equation_analytic():
+    # core/test/equations_test.jl:115-154: second-order linear ODE of the controlled basin
+    p = build_params(MODELS["pid_control_equation"]())
+    for t_end in (60.0, 300.0):
+        u, S, lv, st = run_oracle(p, 1.0, t_end=t_end)
+        assert S[0] == pytest.approx(_pid_equation_storage(p, t_end), rel=0.01)
+
+
+def test_misc_nodes_linear_storages():
+    # core/test/equations_test.jl:156-181: storage1 = S1(0) + t (q_boundary - q_pump), storage2 = S2(0) + t q_pump
+    p = build_params(MODELS["misc_nodes"]())
+    q_boundary, q_pump = 1.5e-4, 1e-4
+    S0 = p.basin.storage0.copy()
+    for days in (1, 30, 366):
+        t = days * 86400.0
+        u, S, lv, st = run_oracle(p, 86400.0, t_end=t)
+        assert S[0] == pytest.approx(S0[0] + t * (q_boundary - q_pump), rel=1e-9)
+        assert S[1] == pytest.approx(S0[1] + t * q_pump, rel=1e-9)
+
+
 @pytest.mark.parametrize("name", ["basic", "backwater", "pid_control", "outlet_continuous_control",
                                   "user_demand", "misc_nodes"])
 def test_dual_jacobian_matches_finite_differences(name):
