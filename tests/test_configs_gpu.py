@@ -104,3 +104,17 @@ def test_reference_analytic_solutions_on_gpu():
     finally:
         model.finalize()
 
+
+def test_user_demand_withdrawal_levels_on_gpu():
+    # core/test/run_models_test.jl:388-412
+    model = _model("user_demand", n_members=2)
+    try:
+        assert model.storage()[0, 0] == pytest.approx(1000.0)
+        model.update_until(150 * 86400.0)
+        assert model.storage()[0, 1] == pytest.approx(900.0, abs=5.0)
+        model.update_until(200 * 86400.0)
+        assert model.storage()[0, 1] == pytest.approx(500.0, abs=2.0)
+        assert model.status_counts["newton_failed"] == 0
+    finally:
+        model.finalize()
+

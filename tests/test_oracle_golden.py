@@ -225,6 +225,16 @@ def test_pid_control_equation_analytic():
         assert S[0] == pytest.approx(_pid_equation_storage(p, t_end), rel=0.01)
 
 
+def test_user_demand_withdrawal_levels():
+    # core/test/run_models_test.jl:388-412: the constant UserDemand withdraws down to its minimum
+    # level 0.9 m (900 m3), the dynamic one to 0.5 m (500 m3)
+    p = build_params(MODELS["user_demand"]())
+    assert p.basin.storage0[0] == pytest.approx(1000.0)
+    for days, expect, atol in ((150, 900.0, 5.0), (200, 500.0, 2.0)):
+        u, S, lv, st = run_oracle(p, 3600.0, t_end=days * 86400.0, full_newton=1, max_halvings=20, predictor=1)
+        assert st["failed"] == 0 and S[0] == pytest.approx(expect, abs=atol)
+
+
 def test_misc_nodes_linear_storages():
     # core/test/equations_test.jl:156-181: storage1 = S1(0) + t (q_boundary - q_pump), storage2 = S2(0) + t q_pump
     p = build_params(MODELS["misc_nodes"]())
