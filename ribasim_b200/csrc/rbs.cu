@@ -15,7 +15,7 @@
 
 #include "../../include/ribasim_b200.h"
 #include "rbs_kernels.cuh"
-#include "rbs_coop.cuh"
+#include "rbs_tile.cuh"
 
 namespace {
 
@@ -139,6 +139,8 @@ struct rbs_handle {
     // cooperative window kernel (rbs_coop.cuh): used when the ensemble is small
     int coop_members = 0;    // use it for ensembles of at most this many members (0 = never)
     int coop_blocks = 0;     // co-resident grid size (0 = unavailable)
+    int tile_window = 0;     // members per block of the tile window kernel (0 = stream path)
+    size_t tile_smem = 0;
     int* d_coop_counters = nullptr;
     int* h_coop_counters = nullptr;  // pinned
     int* d_list_phase[3] = {nullptr, nullptr, nullptr};
@@ -849,6 +851,22 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 int cm = geti(b, "coop_members", -1);
                 h->coop_members = cm >= 0 ? cm : 32;  // measured: pays below a few dozen members
             } else cudaGetLastError();
+            // tile window kernel: a block per member tile runs the whole window (rbs_tile.cuh)
+            int tw = geti(b, "tile_window", -1);
+            if (tw < 0) tw = 0;
+            if (tw == 2 || tw == 4) {
+                size_t words = std::max<size_t>((size_t)h->esched.n_slots, (size_t)h->n_part * RBS_DZ_ROWS);
+                size_t sbt = words * tw * sizeof(double);
+                cudaError_t e4 = sbt + 1024 > (size_t)dev_smem ? cudaErrorInvalidValue
+                    : tw == 2 ? cudaFuncSetAttribute(k_window_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt)
+                              : cudaFuncSetAttribute(k_window_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt);
+                if (e4 == cudaSuccess) {
+                    h->tile_window = tw; h->tile_smem = sbt;
+                    if (!h->d_coop_counters &&
+                        (cudaMalloc(&h->d_coop_counters, 4 * sizeof(int)) != cudaSuccess ||
+                         cudaMallocHost(&h->h_coop_counters, 4 * sizeof(int)) != cudaSuccess)) return bail("tile alloc");
+                } else cudaGetLastError();
+            }
         }
     }
     bind_net(h);
@@ -1418,6 +1436,43 @@ static int advance_coop(rbs_handle* h, double dt, double h_min, int32_t n_steps)
     return 0;
 }
 
+// the window as one kernel with a block per member tile (full Newton)
+static int advance_tile(rbs_handle* h, double dt, double h_min, int32_t n_steps) {
+    Net& n = h->net;
+    n.NA = n.B;
+    n.alist = nullptr;
+    CoopArgs a{};
+    a.from_ts = sp<int>(h, "ud_demand_from_timeseries");
+    a.alloc_total = sp<double>(h, "ud_alloc_total");
+    a.dsrc_ptr = sp<int>(h, "dsrc_ptr");
+    a.dsrc_code = sp<int>(h, "dsrc_code");
+    a.list_cc = h->d_list_phase[1]; a.n_list_cc = (int)h->list_phase[1].size();
+    a.list_pid = h->d_list_phase[2]; a.n_list_pid = (int)h->list_phase[2].size();
+    a.pid_fused = h->pid_fused ? 1 : 0;
+    a.c = mp(h, "cvec");
+    a.dt = dt; a.h_min = h_min; a.abstol = h->abstol; a.reltol = h->reltol;
+    a.max_halvings = h->max_halvings; a.grow_iters = h->grow_iters; a.n_steps = n_steps;
+    a.shrink_log2 = h->shrink_log2; a.predictor = h->predictor; a.early_exit = h->early_exit;
+    a.max_iter = h->max_iter; a.n_part = h->n_part; a.rows_per_block = h->rows_per_block;
+    a.max_passes = std::min<long long>(h->max_passes, 4000) * (long long)n_steps;  // safety net
+    a.counters = h->d_coop_counters;
+    CUDA_TRY(cudaMemsetAsync(h->d_coop_counters, 0, 4 * sizeof(int), h->stream));
+    EntSched es = h->esched;
+    es.smem_sched = 0;
+    const int tw = h->tile_window, blocks = (n.B + tw - 1) / tw, threads = RBS_ENT_LANES * tw / 2;
+    prof_begin(h, "k_window_tile");
+    if (tw == 2) k_window_tile<2><<<blocks, threads, h->tile_smem, h->stream>>>(n, es, a);
+    else k_window_tile<4><<<blocks, threads, h->tile_smem, h->stream>>>(n, es, a);
+    prof_end(h);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(h->h_coop_counters, h->d_coop_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->h_coop_counters[0] != 0) return fail("rbs_advance: pass limit exceeded");
+    h->n_passes += h->h_coop_counters[3];
+    return 0;
+}
+
 static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
     cudaSetDevice(h->device);
     Net& n = h->net;
@@ -1425,8 +1480,9 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
     double h_min = std::ldexp(dt, -h->max_halvings);
     h->cur = h->stream;
     LAUNCH(h, k_step_begin, (long long)(n.n_state + n.n_basin + 1) * B, n, dt, h->predictor);
-    if (h->coop_blocks > 0 && h->full_newton && n.B <= h->coop_members && !h->profiling) {
-        if (advance_coop(h, dt, h_min, n_steps)) return 1;
+    const bool use_coop = h->coop_blocks > 0 && n.B <= h->coop_members;
+    if ((use_coop || h->tile_window > 0) && h->full_newton && !h->profiling) {
+        if (use_coop ? advance_coop(h, dt, h_min, n_steps) : advance_tile(h, dt, h_min, n_steps)) return 1;
         h->tprev = t + dt * n_steps;
         h->n_steps += n_steps;
         if (commit_staged(h)) return 1;

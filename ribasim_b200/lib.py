@@ -35,7 +35,7 @@ class RbsError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile librbs.so for sm_100a in-tree (so that it travels with the repo snapshot)."""
-    srcs = [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_coop.cuh", CSRC / "rbs_math.cuh",
+    srcs = [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_coop.cuh", CSRC / "rbs_tile.cuh", CSRC / "rbs_math.cuh",
             PKG_DIR.parent / "include" / "ribasim_b200.h"]
     if not force and LIB_PATH.exists() and all(
             LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
@@ -202,7 +202,7 @@ class Handle:
     def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
                  device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
                  smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0,
-                 coop_members: int = -1):
+                 coop_members: int = -1, tile_window: int = -1):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -268,6 +268,9 @@ class Handle:
             # ensembles of at most this many members run a window as one cooperative kernel
             # (-1 = the library's default)
             set_i("coop_members", [int(os.environ.get("RBS_COOP_MEMBERS", str(coop_members)))])
+            # > 0: a block per tile of that many members (2 or 4) runs a whole window
+            # (rbs_tile.cuh); 0 = the stream path; -1 = the library's default
+            set_i("tile_window", [int(os.environ.get("RBS_TILE_WINDOW", str(tile_window)))])
             self.h = self.L.rbs_create(b, self.B, int(device))
         finally:
             self.L.rbs_builder_destroy(b)

@@ -11,6 +11,14 @@ from ribasim_b200.network import build_params
 from ribasim_b200.testmodels import MODELS
 from ribasim_b200.timecache import eval_time_params, flow_boundary_increment
 
+def golden(key: str) -> dict:
+    """Known answers of the reference's tests (tests/golden/reference_goldens.json)."""
+    import json
+    from pathlib import Path
+
+    return json.loads((Path(__file__).parent / "golden" / "reference_goldens.json").read_text())[key]
+
+
 FORCING = ("precipitation", "surface_runoff", "potential_evaporation", "drainage", "infiltration")
 
 

@@ -646,6 +646,45 @@ def test_cooperative_window_kernel_equals_stream_path(name):
     assert l_coop <= 4 < l_stream  # k_step_begin + the cooperative kernel per call
 
 
+@pytest.mark.parametrize("tile", [2, 4])
+@pytest.mark.parametrize("name", ["basic", "backwater", "user_demand", "pid_control",
+                                  "outlet_continuous_control", "pump_discrete_control", "hws_like"])
+def test_tile_window_kernel_equals_stream_path(name, tile):
+    """A block per member tile runs the whole window (rbs_tile.cuh: block barriers between the
+    phases, intermediates stay in L1 / L2).  Same device functions, same summation orders: states,
+    storages, status flags and the iteration / sub-step / reject counters are bitwise those of the
+    stream path, also for a member count that does not fill the last tile."""
+    from ribasim_b200.testmodels import hws_like_model
+    B = 37
+    case = make_case(hws_like_model(n_basins=60, n_days=2) if name == "hws_like" else name, B, seed=31, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    for tw in (0, tile):
+        h = gpu_handle_for(case, coop_members=0, tile_window=tw)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if flat["n_dc"] > 0:
+                h.apply_discrete_control()
+                h.refresh(0.0)
+            l0 = h.kernel_launches()
+            st = h.advance(0.0, 3600.0, 5)
+            st |= h.step(5 * 3600.0, 1800.0)
+            launches = h.kernel_launches() - l0
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats(), launches,
+                        h.get_member_i32("dc_state", flat["n_dc"]) if flat["n_dc"] else None))
+        finally:
+            h.close()
+    (u0, S0, st0, stats0, l_stream, dc0), (u1, S1, st1, stats1, l_tile, dc1) = out
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert stats0[k] == stats1[k], k
+    if dc0 is not None:
+        assert np.array_equal(dc0, dc1)
+    assert l_tile <= 4 < l_stream  # k_step_begin + the tile kernel per call
+
+
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
