@@ -184,6 +184,14 @@ class Model:
         a, b = eval_time_params(self.p, t_a), eval_time_params(self.p, t_b)
         return all(np.array_equal(a[k], b[k], equal_nan=True) for k in a)
 
+    def _fb_rate_constant(self) -> bool:
+        """False when FlowBoundary rates are interpolated linearly: every step then gets its own
+        exact mean rate (`formulate_flow_boundary!` integrates per step, solve.jl:86-99) instead
+        of sharing one rate over a window."""
+        if self.flat.ints["n_fb"] == 0 or self._fb_rate_members is not None:
+            return True
+        return all(s.kind == "constant" for s in self.p.nodes["flow_boundary"]["flow_rate"])
+
     def update_until(self, time: float, want_status: bool = True) -> None:
         """BMI.update_until (core/src/bmi.jl:41-52).  Whole `dt` steps that end before the next
         tstop run as one `rbs_advance` window; the step that lands on a tstop (or on `time`)
@@ -196,7 +204,8 @@ class Model:
             n_full = int(math.floor((t_stop - self.t) / self.dt + 1e-9))
             if n_full >= 1 and self.t + n_full * self.dt >= t_stop - 1e-9 * self.dt:
                 n_full -= 1  # the step that ends on the stop is taken separately
-            if n_full >= 2 and self._params_constant(self.t + self.dt, self.t + n_full * self.dt):
+            if n_full >= 2 and self._fb_rate_constant() and \
+                    self._params_constant(self.t + self.dt, self.t + n_full * self.dt):
                 t0 = self.t
                 self._push_time_params(t0 + self.dt)
                 self._push_fb_rate(t0, t0 + n_full * self.dt)
@@ -207,8 +216,30 @@ class Model:
             else:
                 self._step_to(self._next_time(time), want_status)
 
-    def run(self) -> None:
-        self.update_until(self.t_end)
+    def run(self, saveat: float | None = None, results_dir: str | Path | None = None,
+            check_water_balance: bool = True):
+        """`Ribasim.run` for the ensemble (core/src/main.jl, model.jl:285-297).  With `saveat`
+        (seconds; default the TOML's `solver.saveat`) or `results_dir` the run records the
+        reference's per-period outputs (`results.Results`: storages, levels, mean flows and the
+        water balance per Basin, callback.jl:390-558) and, given a directory, writes basin.nc,
+        flow.nc and basin_state.nc (write.jl:6-67); returns the recorder."""
+        if saveat is None and results_dir is None:
+            self.update_until(self.t_end)
+            return None
+        from .results import Results
+
+        step = float(saveat if saveat is not None else self.tables.solver_option("saveat"))
+        if not step > 0:  # saveat = 0: every solver step
+            step = self.dt
+        res = Results(self, check_water_balance)
+        t0, k = self.t, 0
+        while self.t < self.t_end:
+            k += 1
+            self.update_until(min(t0 + k * step, self.t_end))
+            res.save()
+        if results_dir is not None:
+            res.write(results_dir)
+        return res
 
     # ------------------------------------------------------------------ results
     def storage(self) -> np.ndarray:

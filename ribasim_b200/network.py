@@ -86,6 +86,7 @@ class Graph:
         self.out: dict[int, set[int]] = {}
         self.inn: dict[int, set[int]] = {}
         self.edge: dict[tuple[NodeID, NodeID], LinkMeta] = {}
+        self.flow_link_pairs: list[tuple[int, int]] = []  # (external id, internal id), graph.jl:205-208
 
     def add_vertex(self, label: NodeID) -> None:
         code = len(self.code_of) + 1
@@ -260,19 +261,30 @@ def create_graph(m: ModelTables) -> tuple[Graph, list[NodeID], list[LinkMeta], l
 
     # simplify_graph!: remove junctions (graph.jl:140-211)
     internal = [e for e in external if e.link[0].type != "Junction" and e.link[1].type != "Junction"]
+    # flow_link_map: (external link id, internal link id) pairs; an external link carries the sum
+    # of the internal links routed over it (graph.jl:155-208)
+    pairs = [(e.id, e.id) for e in internal]
+    link_mapping: dict[int, list[int]] = {}
     new_id = max_link_id + 1
     junctions = sorted((n for n in node_ids_all if n.type == "Junction"), key=lambda n: n.value)
     for j in junctions:
         for a in g.inneighbors(j):
             for b in g.outneighbors(j):
+                lid = g.edge[(a, j)].id
+                ext_ids = list(link_mapping.get(lid, [lid]))
+                lid = g.edge[(j, b)].id
+                ext_ids += link_mapping.get(lid, [lid])
                 meta = LinkMeta(new_id, "flow", (a, b))
                 if a.type != "Junction" and b.type != "Junction":
+                    pairs += [(x, new_id) for x in ext_ids]
                     internal.append(meta)
+                link_mapping[new_id] = ext_ids
                 new_id += 1
                 if g.has_edge(a, b):
                     raise ValueError(f"Duplicate link: Junction links form cycle: {a} -> {b}")
                 g.add_edge(a, b, meta)
         g.rem_vertex(j)
+    g.flow_link_pairs = pairs
     return g, node_ids_all, internal, external
 
 

@@ -80,6 +80,25 @@ def basic_transient_model() -> ModelTables:
     return m
 
 
+def flow_boundary_time_model() -> ModelTables:
+    """One Basin fed by a constant and a time-varying (linearly interpolated) FlowBoundary
+    (python/ribasim_testmodels/ribasim_testmodels/time.py:12-56)."""
+    m = _model(interpolation=dict(flow_boundary="linear"))
+    m.add_node("FlowBoundary", 3, static=dict(flow_rate=1.0))
+    n_times = 100
+    t0, t1 = datetime(2020, 3, 1), datetime(2020, 10, 1)
+    span = (t1 - t0).total_seconds()
+    times = [t0 + timedelta(seconds=round(span * k / (n_times - 1))) for k in range(n_times)]
+    flow_rate = 1 + np.sin(np.pi * np.linspace(0, 0.5, n_times)) ** 2
+    m.add_node("FlowBoundary", 1, time=dict(time=[t.strftime(TIME_FMT) for t in times],
+                                            flow_rate=[float(q) for q in flow_rate]))
+    m.add_node("Basin", 2, profile=dict(area=[0.01, 1000.0], level=[0.0, 1.0]),
+               state=dict(level=0.04471158417652035))
+    m.add_link(1, 2)
+    m.add_link(3, 2)
+    return m
+
+
 def backwater_model(n_basins: int = 50) -> ModelTables:
     """FlowBoundary -> n x (Basin, ManningResistance) -> huge Basin (backwater.py:16-84).
 
@@ -596,4 +615,5 @@ MODELS = dict(
     outlet_continuous_control=outlet_continuous_control_model,
     user_demand=user_demand_model,
     pump_discrete_control=pump_discrete_control_model,
+    flow_boundary_time=flow_boundary_time_model,
 )

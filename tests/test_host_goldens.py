@@ -298,6 +298,7 @@ def test_junction_elimination_link_counts():
     assert all(v.type != "Junction" for v in p.graph.code_of)
     p = build_params(MODELS["junction_chained"]())
     assert len(p.internal_flow_links) == 4 and len(p.external_flow_links) == 6
+    assert len(p.graph.flow_link_pairs) == 8  # nnz(flow_link_map), run_models_test.jl:699-701
     assert all(v.type != "Junction" for v in p.graph.code_of)
     # both LinearResistance nodes flow out of Basin #1 through the eliminated junction chain
     lr = p.nodes["linear_resistance"]

@@ -1,0 +1,136 @@
+"""The reference's result tables and files from a device run (ribasim_b200/results.py after
+core/src/callback.jl:390-558 `save_flow` / `check_water_balance_error!` and core/src/write.jl)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(name, dt=3600.0, **kw):
+    from ribasim_b200.model import Model
+    from ribasim_b200.network import build_params
+    from ribasim_b200.testmodels import MODELS
+
+    return Model(build_params(MODELS[name]()), dt=dt, **kw)
+
+
+def test_basic_results_close_the_water_balance(tmp_path):
+    """core/test/run_models_test.jl:224-276 (basic model results): one row per Basin and saved
+    period, storages / levels at the start of the period, mean rates over it; the balance error
+    of every Basin and period is within the reference's tolerances (it raises otherwise)."""
+    from scipy.io import netcdf_file
+
+    B = 3
+    model = _model("basic", n_members=B)
+    try:
+        rng = np.random.default_rng(0)
+        model.set_forcing("precipitation",
+                          model.p.basin.vertical_flux["precipitation"][:, None] * rng.uniform(0.5, 2.0, (4, B)))
+        S0 = model.storage()
+        res = model.run(saveat=86400.0, results_dir=tmp_path)
+        bd, fd = res.basin_data(), res.flow_data()
+        n_t = 366
+        assert bd["time"].shape == (n_t,) and bd["time"][1] == 86400.0
+        assert bd["storage"].shape == (n_t, 4, B) and np.array_equal(bd["storage"][0], S0)
+        # the storages of the next period's start are storage + storage_rate * saveat
+        assert np.allclose(bd["storage"][1:], bd["storage"][:-1] + 86400.0 * bd["storage_rate"][:-1],
+                           rtol=1e-12, atol=1e-9)
+        # water balance of every basin, period and member (run_models_test.jl:259-271)
+        assert np.all(np.abs(bd["balance_error"]) < 1e-3 * np.maximum(1.0, np.abs(bd["storage_rate"])))
+        assert np.all(bd["inflow_rate"] >= 0) and np.all(bd["outflow_rate"] >= 0)
+        assert np.all(bd["precipitation"] > 0) and np.all(bd["evaporation"] >= 0)
+        # members differ through their precipitation only
+        assert not np.array_equal(bd["precipitation"][..., 0], bd["precipitation"][..., 1])
+        # flow table: the reference's external links (17 flow links in the basic model)
+        assert fd["flow_rate"].shape == (n_t, len(model.p.external_flow_links), B)
+        assert list(fd["link_id"]) == [l.id for l in model.p.external_flow_links]
+        # a Basin's horizontal balance can be rebuilt from the link flows
+        k = 100
+        for b, nid in enumerate(bd["node_id"]):
+            q_in = fd["flow_rate"][k][fd["to_node_id"] == nid].sum(axis=0)
+            q_out = fd["flow_rate"][k][fd["from_node_id"] == nid].sum(axis=0)
+            net = bd["inflow_rate"][k, b] - bd["outflow_rate"][k, b]
+            assert np.allclose(q_in - q_out, net, rtol=1e-9, atol=1e-12)
+        # files: names, dimensions and variables of write.jl
+        with netcdf_file(str(tmp_path / "basin.nc"), "r", mmap=False) as ds:
+            assert ds.variables["storage"].dimensions == ("realization", "time", "node_id")
+            assert ds.variables["storage"].shape == (B, n_t, 4)
+            assert np.array_equal(ds.variables["node_id"][:], bd["node_id"])
+            assert np.array_equal(ds.variables["level"][:][1], bd["level"][..., 1])
+            assert ds.variables["level"].units == b"m"
+            for name in ("inflow_rate", "outflow_rate", "storage_rate", "precipitation", "surface_runoff",
+                         "evaporation", "drainage", "infiltration", "balance_error", "relative_error"):
+                assert name in ds.variables
+        with netcdf_file(str(tmp_path / "flow.nc"), "r", mmap=False) as ds:
+            assert ds.variables["flow_rate"].dimensions == ("realization", "time", "link_id")
+            assert np.array_equal(ds.variables["from_node_id"][:], fd["from_node_id"])
+        with netcdf_file(str(tmp_path / "basin_state.nc"), "r", mmap=False) as ds:
+            assert np.array_equal(ds.variables["level"][:], model.level().T)
+    finally:
+        model.finalize()
+
+
+def test_junction_flows_are_summed_over_external_links():
+    """core/test/run_models_test.jl:665-704: with Junctions the external links carry the sum of
+    the internal links routed over them; flow is conserved across every Junction."""
+    model = _model("junction_combined", n_members=1)
+    try:
+        res = model.run(saveat=5 * 86400.0)
+        fd = res.flow_data()
+        q = fd["flow_rate"][-1, :, 0]
+        junctions = [n.value for n in model.p.node_ids_all if n.type == "Junction"]
+        assert junctions
+        for j in junctions:
+            assert q[fd["to_node_id"] == j].sum() == pytest.approx(q[fd["from_node_id"] == j].sum(), rel=1e-12)
+        assert np.any(q != 0.0)
+    finally:
+        model.finalize()
+
+
+def test_water_balance_error_is_raised():
+    from ribasim_b200.results import Results, WaterBalanceError
+
+    model = _model("basic", n_members=1)
+    try:
+        res = Results(model)
+        model.update_until(86400.0)
+        res._prev["storage"] = res._prev["storage"] + 1.0e4  # a storage the flows cannot explain
+        with pytest.raises(WaterBalanceError, match="Too large water balance error"):
+            res.save()
+    finally:
+        model.finalize()
+
+
+def test_mean_flow_for_every_saveat():
+    """core/test/run_models_test.jl:525-591 (`mean_flow`): the link from the constant FlowBoundary
+    carries a mean flow of exactly 1 for every choice of saveat; one row per (started) period.  The
+    linearly interpolated boundary is integrated exactly (solve.jl:86-99)."""
+    dt = 24 * 24 * 60.0  # the solver step of the reference test
+    t_end = 3.16224e7  # 366 days
+    for saveat, n_rows in ((86400.0, 366), (float(round(10000 * np.pi)), int(np.ceil(t_end / round(10000 * np.pi)))),
+                           (float("inf"), 1)):
+        model = _model("flow_boundary_time", dt=dt, n_members=1)
+        try:
+            assert model.t_end == t_end
+            res = model.run(saveat=saveat)
+            fd = res.flow_data()
+            flow = fd["flow_rate"][:, (fd["from_node_id"] == 3) & (fd["to_node_id"] == 2), 0].ravel()
+            assert len(flow) == n_rows and len(res.times) == n_rows + 1
+            assert np.allclose(flow, 1.0, rtol=1e-12, atol=0.0)
+            # the time-varying boundary: mean over the period of the piecewise-linear series
+            series = model.p.nodes["flow_boundary"]["flow_rate"][0]
+            q1 = fd["flow_rate"][:, (fd["from_node_id"] == 1) & (fd["to_node_id"] == 2), 0].ravel()
+            ts = np.array(res.times)
+            grid = np.unique(np.concatenate([ts, np.asarray(series.t, dtype=float)]))
+            grid = grid[(grid >= 0) & (grid <= t_end)]
+            vals = np.array([series(float(x)) for x in grid])
+            cum = np.concatenate([[0.0], np.cumsum(0.5 * (vals[1:] + vals[:-1]) * np.diff(grid))])
+            exact = np.diff(np.interp(ts, grid, cum)) / np.diff(ts)
+            assert np.allclose(q1, exact, rtol=1e-9)
+            bd = res.basin_data()
+            assert np.all(np.abs(bd["balance_error"]) < 1e-6)
+        finally:
+            model.finalize()
