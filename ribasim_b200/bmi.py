@@ -40,7 +40,7 @@ class RibasimBmi:
             "basin.cumulative_infiltration": np.zeros(nb),
             "basin.cumulative_drainage": np.zeros(nb),
             "basin.cumulative_surface_runoff": np.zeros(nb),
-            "basin.subgrid_level": np.zeros(0),
+            "basin.subgrid_level": np.full(len(m.subgrid), np.nan),
             "user_demand.cumulative_inflow": np.zeros(nu),
             "user_demand.demand": m.p.nodes["user_demand"]["demand"].reshape(-1),
         }
@@ -88,6 +88,11 @@ class RibasimBmi:
             return
         m.update_until(time)
         self._refresh_outputs()
+
+    def update_subgrid_level(self) -> None:
+        """libribasim `update_subgrid_level` (build/libribasim.jl:98-101, core/src/bmi.jl:54-57)."""
+        m = self._require()
+        self._values["basin.subgrid_level"][:] = m.subgrid_level()[:, 0]
 
     # -- variables (core/src/bmi.jl:59-89; libribasim get_var_type/rank/shape: :115-160)
     def get_value_ptr(self, name: str) -> np.ndarray:

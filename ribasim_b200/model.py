@@ -89,6 +89,9 @@ class Model:
             self.h.apply_discrete_control()
             self.h.refresh(0.0)
         self.status_counts = dict(newton_failed=0, negative_storage=0)
+        from .subgrid import Subgrid
+
+        self.subgrid = Subgrid(self.tables, [n.value for n in self.p.basin.node_id])
 
     # ------------------------------------------------------------------ forcing / parameters
     def _push_time_params(self, t: float) -> None:
@@ -250,6 +253,11 @@ class Model:
 
     def u(self) -> np.ndarray:
         return self.h.get_member("u", self.flat.ints["n_state"])
+
+    def subgrid_level(self) -> np.ndarray:
+        """`update_subgrid_level!` (core/src/callback.jl:788-813): `[n_subgrid][n_members]` from
+        the current Basin levels and the h(h) relations in force at the current time."""
+        return self.subgrid.levels(self.level(), self.t)
 
     def control_state(self) -> np.ndarray:
         """Control state index per DiscreteControl node and member (-1 = none); the names are

@@ -18,7 +18,8 @@ import numpy as np
 
 from .flatten import KIND_BASIN
 
-RESULTS_FILENAME = dict(basin_state="basin_state.nc", basin="basin.nc", flow="flow.nc")
+RESULTS_FILENAME = dict(basin_state="basin_state.nc", basin="basin.nc", flow="flow.nc",
+                        subgrid_level="subgrid_level.nc")
 
 CF_GLOBAL = {"Conventions": "CF-1.12", "references": "https://ribasim.org"}
 _RATE = "m3 s-1"
@@ -44,6 +45,9 @@ CF = {
     "evaporation": dict(units=_RATE, standard_name="water_evaporation_flux", long_name="evaporation rate"),
     "drainage": dict(units=_RATE, long_name="drainage rate"),
     "infiltration": dict(units=_RATE, long_name="infiltration rate"),
+    "subgrid_id": dict(cf_role="timeseries_id", long_name="subgrid element identifier"),
+    "subgrid_level": dict(units="m", standard_name="water_surface_height_above_reference_datum",
+                          long_name="subgrid water level above reference datum"),
     "balance_error": dict(units=_RATE, long_name="water balance error"),
     "relative_error": dict(units="1", long_name="relative water balance error"),
 }
@@ -122,6 +126,8 @@ class Results:
         self.times = [float(model.t)]
         self.periods: list[dict[str, np.ndarray]] = []
         self._prev = self._snapshot()
+        # save_subgrid_level: at the start and at every saveat (callback.jl:60-64, 816-822)
+        self.subgrid_levels = [model.subgrid.levels(self._prev["level"], self.times[0])]
 
     # ------------------------------------------------------------------ bookkeeping
     def _snapshot(self) -> dict[str, np.ndarray]:
@@ -170,6 +176,7 @@ class Results:
         self.periods.append(rec)
         self.times.append(t)
         self._prev = new
+        self.subgrid_levels.append(self.m.subgrid.levels(new["level"], t))
         if self.check:
             bad = (np.abs(rec["balance_error"]) > self.abstol) & (np.abs(rec["relative_error"]) > self.reltol)
             if bad.any():
@@ -209,6 +216,12 @@ class Results:
             rate[k] = self._map @ internal
         return dict(time=np.array(self.times[:-1]), link_id=self.link_id, from_node_id=self.from_node_id,
                     to_node_id=self.to_node_id, flow_rate=rate)
+
+    def subgrid_level_data(self) -> dict[str, np.ndarray]:
+        """`subgrid_level_data(model; table=false)` (write.jl:797-817): every save time including
+        the start; `[n_times][n_subgrid][n_members]`."""
+        return dict(time=np.array(self.times), subgrid_id=self.m.subgrid.subgrid_id,
+                    subgrid_level=np.stack(self.subgrid_levels))
 
     def basin_state_data(self) -> dict[str, np.ndarray]:
         return dict(node_id=self.node_id, level=self.m.level())
@@ -268,4 +281,10 @@ class Results:
                     fd["time"], dict(flow_rate=fd["flow_rate"]))
         self._write(paths["basin_state"], "basin_state", "node_id", dict(node_id=self.node_id), None,
                     dict(level=self.basin_state_data()["level"]))
+        if len(self.m.subgrid):
+            sd = self.subgrid_level_data()
+            self._write(paths["subgrid_level"], "subgrid_level", "subgrid_id", dict(subgrid_id=sd["subgrid_id"]),
+                        sd["time"], dict(subgrid_level=sd["subgrid_level"]))
+        else:
+            del paths["subgrid_level"]
         return paths

@@ -69,6 +69,14 @@ SCHEMA: dict[str, tuple[dict[str, str], tuple[str, ...]]] = {
         ("node_id", "level"),
     ),
     "Basin / state": (dict(node_id="i", level="f"), ("node_id",)),
+    "Basin / subgrid": (
+        dict(subgrid_id="i", node_id="i", basin_level="f", subgrid_level="f"),
+        ("subgrid_id", "basin_level"),
+    ),
+    "Basin / subgrid_time": (
+        dict(subgrid_id="i", node_id="i", time="t", basin_level="f", subgrid_level="f"),
+        ("subgrid_id", "time", "basin_level"),
+    ),
     "Pump / static": (
         dict(node_id="i", flow_rate="f", min_flow_rate="f", max_flow_rate="f",
              min_upstream_level="f", max_downstream_level="f", control_state="s",

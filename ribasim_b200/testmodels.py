@@ -99,6 +99,26 @@ def flow_boundary_time_model() -> ModelTables:
     return m
 
 
+def two_basin_model() -> ModelTables:
+    """Two unconnected Basins with subgrid h(h) relations, one of them time dependent
+    (python/ribasim_testmodels/ribasim_testmodels/two_basin.py:10-79)."""
+    m = _model()
+    m.add_node("FlowBoundary", 1, static=dict(flow_rate=1e-2))
+    shared = dict(profile=dict(area=[400.0, 400.0], level=[0.0, 1.0]), state=dict(level=0.01))
+    m.add_node("Basin", 2, **shared,
+               subgrid=dict(subgrid_id=1, basin_level=[0.0, 1.0], subgrid_level=[0.0, 1.0]))
+    m.add_node("Basin", 3, **shared,
+               subgrid_time=dict(subgrid_id=2,
+                                 time=["2020-01-01 00:00:00", "2020-01-01 00:00:00",
+                                       "2020-02-01 00:00:00", "2020-02-01 00:00:00"],
+                                 basin_level=[0.0, 1.0, 0.0, 1.0], subgrid_level=[0.0, 1.0, 1.0, 2.0]))
+    m.add_node("TabulatedRatingCurve", 4, static=dict(level=[0.0, 1.0], flow_rate=[0.0, 0.01]))
+    m.add_node("Terminal", 5)
+    for a, b in [(1, 2), (3, 4), (4, 5)]:
+        m.add_link(a, b)
+    return m
+
+
 def backwater_model(n_basins: int = 50) -> ModelTables:
     """FlowBoundary -> n x (Basin, ManningResistance) -> huge Basin (backwater.py:16-84).
 
@@ -616,4 +636,5 @@ MODELS = dict(
     user_demand=user_demand_model,
     pump_discrete_control=pump_discrete_control_model,
     flow_boundary_time=flow_boundary_time_model,
+    two_basin=two_basin_model,
 )

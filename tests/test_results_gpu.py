@@ -134,3 +134,41 @@ def test_mean_flow_for_every_saveat():
             assert np.all(np.abs(bd["balance_error"]) < 1e-6)
         finally:
             model.finalize()
+
+
+def test_two_basin_subgrid_levels(tmp_path):
+    """core/test/run_models_test.jl:638-663 (`two_basin`): daily subgrid levels including the start,
+    0.01 m at t0; the time-dependent h(h) relation of subgrid 2 rises by a metre after a month;
+    apart from that shift the relations are 1:1."""
+    from ribasim_b200.bmi import RibasimBmi
+    from ribasim_b200.testmodels import MODELS
+
+    model = _model("two_basin", n_members=2)
+    try:
+        res = model.run(saveat=86400.0, results_dir=tmp_path)
+        sd = res.subgrid_level_data()
+        ntime = 367
+        assert sd["subgrid_level"].shape == (ntime, 2, 2) and list(sd["subgrid_id"]) == [1, 2]
+        assert sd["time"][0] == 0.0 and sd["time"][-1] == model.t_end
+        assert np.all(sd["subgrid_level"][0] == 0.01)
+        i_change = 31  # 2020-02-01
+        assert sd["subgrid_level"][i_change, 1, 0] - sd["subgrid_level"][i_change - 1, 1, 0] == \
+            pytest.approx(1.0, rel=3.4e-4)  # `≈ 1.0f0`: the Basin level itself moves a little in a day
+        basin_level = model.level()
+        basin_level[1] += 1
+        assert np.allclose(basin_level, sd["subgrid_level"][-1], rtol=1e-14)
+        assert np.allclose(basin_level, model.subgrid_level(), rtol=1e-14)
+        assert (tmp_path / "subgrid_level.nc").exists()
+    finally:
+        model.finalize()
+    # BMI: update_subgrid_level fills basin.subgrid_level (core/test/bmi_test.jl:52-90, build/libribasim.jl:98-101)
+    toml = MODELS["two_basin"]().write(tmp_path / "model")
+    b = RibasimBmi()
+    b.initialize(toml)
+    try:
+        assert b.get_value_ptr("basin.subgrid_level").shape == (2,)
+        b.update_until(86400.0)
+        b.update_subgrid_level()
+        assert np.allclose(b.get_value_ptr("basin.subgrid_level"), b.get_value_ptr("basin.level"), rtol=1e-14)
+    finally:
+        b.finalize()
