@@ -288,8 +288,8 @@ struct Model {
     std::vector<double> storage_prev, level_prev;
 
     // bound views of the named arrays (rebound by bind() after every set/clone)
-#define RBS_D_FIELDS(X) X(dc_sv_weight) X(dc_thr_hi) X(dc_thr_lo) X(dc_sv_const) X(pump_cs_flow_rate) X(pump_cs_min_flow_rate) X(pump_cs_max_flow_rate) X(pump_cs_min_upstream_level) X(pump_cs_max_downstream_level) X(outlet_cs_flow_rate) X(outlet_cs_min_flow_rate) X(outlet_cs_max_flow_rate) X(outlet_cs_min_upstream_level) X(outlet_cs_max_downstream_level) X(lr_cs_resistance) X(lr_cs_max_flow_rate) X(cc_sv_const) X(cc_sv_weight) X(cumulative_drainage) X(cumulative_precipitation) X(cumulative_surface_runoff) X(drainage) X(fb_cumulative_flow) X(fb_incr) X(fb_rate_now) X(fb_rate_step) X(fixed_area) X(infiltration) X(lb_level) X(low_storage_threshold) X(lr_max_flow_rate) X(lr_resistance) X(mn_downstream_bottom) X(mn_length) X(mn_manning_n) X(mn_profile_slope) X(mn_profile_width) X(mn_upstream_bottom) X(pid_derivative) X(pid_integral) X(pid_proportional) X(pid_target) X(potential_evaporation) X(precipitation) X(prof_area) X(prof_cumS) X(prof_dSdh) X(prof_level) X(storage0) X(surface_runoff) X(tab_t) X(tab_u) X(trc_max_downstream_level) X(ud_allocated) X(ud_demand) X(ud_demand_static) X(ud_link_alloc) X(ud_min_level) X(ud_return_factor) X(pump_flow_rate) X(pump_min_flow_rate) X(pump_max_flow_rate) X(pump_min_upstream_level) X(pump_max_downstream_level) X(pump_flow_demand) X(outlet_flow_rate) X(outlet_min_flow_rate) X(outlet_max_flow_rate) X(outlet_min_upstream_level) X(outlet_max_downstream_level) X(outlet_flow_demand)
-#define RBS_I_FIELDS(X) X(dc_cond_ptr) X(dc_csv_ptr) X(dc_sv_kind) X(dc_sv_idx) X(dc_logic_ptr) X(dc_logic) X(pump_dc) X(pump_cs_ptr) X(outlet_dc) X(outlet_cs_ptr) X(lr_dc) X(lr_cs_ptr) X(trc_dc) X(trc_cs_ptr) X(trc_cs_table) X(bin_idx) X(bin_ptr) X(bin_type) X(bout_idx) X(bout_ptr) X(bout_type) X(cc_sv_idx) X(cc_sv_kind) X(cc_sv_ptr) X(cc_table_idx) X(cc_target_idx) X(cc_target_is_outlet) X(fb_dst_idx) X(fb_dst_type) X(lr_dst_idx) X(lr_dst_type) X(lr_src_idx) X(lr_src_type) X(mn_dst_idx) X(mn_dst_type) X(mn_src_idx) X(mn_src_type) X(pid_listen_basin) X(pid_target_idx) X(pid_target_is_outlet) X(prof_ptr) X(tab_left_linear) X(tab_ptr) X(tab_right_linear) X(trc_dst_idx) X(trc_dst_type) X(trc_src_idx) X(trc_src_type) X(trc_table_idx) X(ud_demand_from_timeseries) X(ud_dst_idx) X(ud_dst_type) X(ud_has_priority) X(ud_link_ptr) X(ud_link_src_idx) X(ud_link_src_type) X(pump_control_type) X(pump_src_type) X(pump_src_idx) X(pump_dst_type) X(pump_dst_idx) X(outlet_control_type) X(outlet_src_type) X(outlet_src_idx) X(outlet_dst_type) X(outlet_dst_idx)
+#define RBS_D_FIELDS(X) X(dc_sv_weight) X(dc_thr_hi) X(dc_thr_lo) X(dc_sv_const) X(pump_cs_flow_rate) X(pump_cs_min_flow_rate) X(pump_cs_max_flow_rate) X(pump_cs_min_upstream_level) X(pump_cs_max_downstream_level) X(outlet_cs_flow_rate) X(outlet_cs_min_flow_rate) X(outlet_cs_max_flow_rate) X(outlet_cs_min_upstream_level) X(outlet_cs_max_downstream_level) X(lr_cs_resistance) X(lr_cs_max_flow_rate) X(mn_cs_length) X(mn_cs_manning_n) X(mn_cs_profile_width) X(mn_cs_profile_slope) X(pid_cs_target) X(pid_cs_proportional) X(pid_cs_integral) X(pid_cs_derivative) X(cc_sv_const) X(cc_sv_weight) X(cumulative_drainage) X(cumulative_precipitation) X(cumulative_surface_runoff) X(drainage) X(fb_cumulative_flow) X(fb_incr) X(fb_rate_now) X(fb_rate_step) X(fixed_area) X(infiltration) X(lb_level) X(low_storage_threshold) X(lr_max_flow_rate) X(lr_resistance) X(mn_downstream_bottom) X(mn_length) X(mn_manning_n) X(mn_profile_slope) X(mn_profile_width) X(mn_upstream_bottom) X(pid_derivative) X(pid_integral) X(pid_proportional) X(pid_target) X(potential_evaporation) X(precipitation) X(prof_area) X(prof_cumS) X(prof_dSdh) X(prof_level) X(storage0) X(surface_runoff) X(tab_t) X(tab_u) X(trc_max_downstream_level) X(ud_allocated) X(ud_demand) X(ud_demand_static) X(ud_link_alloc) X(ud_min_level) X(ud_return_factor) X(pump_flow_rate) X(pump_min_flow_rate) X(pump_max_flow_rate) X(pump_min_upstream_level) X(pump_max_downstream_level) X(pump_flow_demand) X(outlet_flow_rate) X(outlet_min_flow_rate) X(outlet_max_flow_rate) X(outlet_min_upstream_level) X(outlet_max_downstream_level) X(outlet_flow_demand)
+#define RBS_I_FIELDS(X) X(dc_cond_ptr) X(dc_csv_ptr) X(dc_sv_kind) X(dc_sv_idx) X(dc_logic_ptr) X(dc_logic) X(pump_dc) X(pump_cs_ptr) X(outlet_dc) X(outlet_cs_ptr) X(lr_dc) X(lr_cs_ptr) X(mn_dc) X(mn_cs_ptr) X(pid_dc) X(pid_cs_ptr) X(trc_dc) X(trc_cs_ptr) X(trc_cs_table) X(bin_idx) X(bin_ptr) X(bin_type) X(bout_idx) X(bout_ptr) X(bout_type) X(cc_sv_idx) X(cc_sv_kind) X(cc_sv_ptr) X(cc_table_idx) X(cc_target_idx) X(cc_target_is_outlet) X(fb_dst_idx) X(fb_dst_type) X(lr_dst_idx) X(lr_dst_type) X(lr_src_idx) X(lr_src_type) X(mn_dst_idx) X(mn_dst_type) X(mn_src_idx) X(mn_src_type) X(pid_listen_basin) X(pid_target_idx) X(pid_target_is_outlet) X(prof_ptr) X(tab_left_linear) X(tab_ptr) X(tab_right_linear) X(trc_dst_idx) X(trc_dst_type) X(trc_src_idx) X(trc_src_type) X(trc_table_idx) X(ud_demand_from_timeseries) X(ud_dst_idx) X(ud_dst_type) X(ud_has_priority) X(ud_link_ptr) X(ud_link_src_idx) X(ud_link_src_type) X(pump_control_type) X(pump_src_type) X(pump_src_idx) X(pump_dst_type) X(pump_dst_idx) X(outlet_control_type) X(outlet_src_type) X(outlet_src_idx) X(outlet_dst_type) X(outlet_dst_idx)
 #define X(name) double* name = nullptr;
     RBS_D_FIELDS(X)
 #undef X
@@ -967,6 +967,24 @@ void dc_write_params(Model& m) {
         int row = m.lr_cs_ptr[k] + m.dc_state[d];
         m.lr_resistance[k] = m.lr_cs_resistance[row];
         m.lr_max_flow_rate[k] = m.lr_cs_max_flow_rate[row];
+    }
+    for (int k = 0; k < m.n_manning; k++) {
+        int d = m.mn_dc ? m.mn_dc[k] : -1;
+        if (d < 0 || m.dc_state[d] < 0) continue;
+        int row = m.mn_cs_ptr[k] + m.dc_state[d];
+        m.mn_length[k] = m.mn_cs_length[row];
+        m.mn_manning_n[k] = m.mn_cs_manning_n[row];
+        m.mn_profile_width[k] = m.mn_cs_profile_width[row];
+        m.mn_profile_slope[k] = m.mn_cs_profile_slope[row];
+    }
+    for (int k = 0; k < m.n_pid; k++) {
+        int d = m.pid_dc ? m.pid_dc[k] : -1;
+        if (d < 0 || m.dc_state[d] < 0) continue;
+        int row = m.pid_cs_ptr[k] + m.dc_state[d];
+        m.pid_target[k] = m.pid_cs_target[row];
+        m.pid_proportional[k] = m.pid_cs_proportional[row];
+        m.pid_integral[k] = m.pid_cs_integral[row];
+        m.pid_derivative[k] = m.pid_cs_derivative[row];
     }
     for (int k = 0; k < m.n_trc; k++) {
         int d = m.trc_dc ? m.trc_dc[k] : -1;

@@ -233,6 +233,9 @@ void bind_net(rbs_handle* h) {
     S_D(outlet_cs_flow_rate); S_D(outlet_cs_min_flow_rate); S_D(outlet_cs_max_flow_rate);
     S_D(outlet_cs_min_upstream_level); S_D(outlet_cs_max_downstream_level);
     S_D(lr_cs_resistance); S_D(lr_cs_max_flow_rate);
+    S_I(mn_dc); S_I(mn_cs_ptr); S_I(pid_dc); S_I(pid_cs_ptr);
+    S_D(mn_cs_length); S_D(mn_cs_manning_n); S_D(mn_cs_profile_width); S_D(mn_cs_profile_slope);
+    S_D(pid_cs_target); S_D(pid_cs_proportional); S_D(pid_cs_integral); S_D(pid_cs_derivative);
     S_I(jrow_ptr); S_I(jcol); S_I(jpos_src); S_I(jpos_dst); S_I(ud_out_jpos);
     S_I(wsrc_ptr); S_I(wsrc_pos); S_I(wdiag_flag); S_D(wsrc_sign);
     S_I(lu_wsrc); S_I(lu_pivot); S_I(lu_prod_ptr); S_I(lu_prod_l); S_I(lu_prod_u); S_I(lu_diag);

@@ -106,6 +106,9 @@ struct Net {
     const double *outlet_cs_flow_rate, *outlet_cs_min_flow_rate, *outlet_cs_max_flow_rate,
         *outlet_cs_min_upstream_level, *outlet_cs_max_downstream_level;
     const double *lr_cs_resistance, *lr_cs_max_flow_rate;
+    const int *mn_dc, *mn_cs_ptr, *pid_dc, *pid_cs_ptr;
+    const double *mn_cs_length, *mn_cs_manning_n, *mn_cs_profile_width, *mn_cs_profile_slope;
+    const double *pid_cs_target, *pid_cs_proportional, *pid_cs_integral, *pid_cs_derivative;
     int *dc_truth, *dc_state, *cnt_dc;
     // per-member sub-stepping state machine (rbs_step.cuh)
     int *mphase, *mjac, *miter, *mconv, *mneg, *mneg2, *mclamp, *mlast, *maction;
@@ -399,9 +402,12 @@ __device__ __forceinline__ void rbs_link_item(const Net& n, int s, int m, int ph
                             RBS_PM(n, row, n.lr_cs_resistance, n.lr_resistance, n.pm_lr_resistance, k, m),
                             RBS_P(row, n.lr_cs_max_flow_rate, n.lr_max_flow_rate, k), dq_a, dq_b);
         } else if (ct == CT_MANNING) {
-            q = rbs_manning_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df, n.mn_length[k],
-                                 n.pm_mn_manning_n ? n.pm_mn_manning_n[(long long)k * n.B + m] : n.mn_manning_n[k],
-                                 n.mn_profile_width[k], n.mn_profile_slope[k],
+            int row = rbs_dc_row(n, n.mn_dc, n.mn_cs_ptr, k, m);
+            q = rbs_manning_flow(a.h, b.h, a.f, b.f, a.dh, b.dh, a.df, b.df,
+                                 RBS_P(row, n.mn_cs_length, n.mn_length, k),
+                                 RBS_PM(n, row, n.mn_cs_manning_n, n.mn_manning_n, n.pm_mn_manning_n, k, m),
+                                 RBS_P(row, n.mn_cs_profile_width, n.mn_profile_width, k),
+                                 RBS_P(row, n.mn_cs_profile_slope, n.mn_profile_slope, k),
                                  n.mn_upstream_bottom[k], n.mn_downstream_bottom[k], dq_a, dq_b, JAC);
         } else {  // CT_TRC
             int row = rbs_dc_row(n, n.trc_dc, n.trc_cs_ptr, k, m);
@@ -490,9 +496,14 @@ template <bool JAC>
 __device__ __forceinline__ void rbs_pid_item(const Net& n, const double* ur, int fuse_link, int i, int m) {
     int L = n.pid_listen_basin[i];
     long long lo = (long long)L * n.B + m;
-    double err = n.pid_target[i] - n.level[lo];
+    // a DiscreteControl state replaces the (time-dependent) parameters by its constants
+    // (PidControl control_mapping, read.jl:328-427)
+    const int crow = rbs_dc_row(n, n.pid_dc, n.pid_cs_ptr, i, m);
+    double err = RBS_P(crow, n.pid_cs_target, n.pid_target, i) - n.level[lo];
     n.du[(long long)(n.off_integral + i) * n.B + m] = err;
-    double K_p = n.pid_proportional[i], K_i = n.pid_integral[i], K_d = n.pid_derivative[i];
+    double K_p = RBS_P(crow, n.pid_cs_proportional, n.pid_proportional, i),
+           K_i = RBS_P(crow, n.pid_cs_integral, n.pid_integral, i),
+           K_d = RBS_P(crow, n.pid_cs_derivative, n.pid_derivative, i);
     double integral = ur[(long long)(n.n_basin + i) * n.B + m];
     double area = 1.0, D = 1.0;
     if (K_d != 0.0) {

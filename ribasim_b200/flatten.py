@@ -338,15 +338,24 @@ def _flatten_discrete_control(p: Params, f: Flat) -> None:
                            dict(resistance=lr["resistance"], max_flow_rate=lr["max_flow_rate"]))
     A["lr_dc"], A["lr_cs_ptr"] = ctrl, ptr
     A["lr_cs_resistance"], A["lr_cs_max_flow_rate"] = vals["resistance"], vals["max_flow_rate"]
+    mn = n["manning_resistance"]
+    mn_fields = ["length", "manning_n", "profile_width", "profile_slope"]
+    ctrl, ptr, vals = rows("manning_resistance", mn_fields, {fl: mn[fl] for fl in mn_fields})
+    A["mn_dc"], A["mn_cs_ptr"] = ctrl, ptr
+    for fl in mn_fields:
+        A[f"mn_cs_{fl}"] = vals[fl]
+    pid = n["pid_control"]
+    pid_fields = ["target", "proportional", "integral", "derivative"]
+    ctrl, ptr, vals = rows("pid_control", pid_fields,
+                           {fl: np.array([float(s(0.0)) for s in pid[fl]]) for fl in pid_fields})
+    A["pid_dc"], A["pid_cs_ptr"] = ctrl, ptr
+    for fl in pid_fields:
+        A[f"pid_cs_{fl}"] = vals[fl]
     trc = n["tabulated_rating_curve"]
     base_tab = np.array([float(s(0.0)) for s in trc["current_interpolation_index"]])
     ctrl, ptr, vals = rows("tabulated_rating_curve", ["table"], dict(table=base_tab))
     A["trc_dc"], A["trc_cs_ptr"] = ctrl, ptr
     A["trc_cs_table"] = as_i32(vals["table"] - 1)  # 0-based table index
-    for key in ("manning_resistance", "pid_control"):
-        for nid in n[key]["node_id"]:
-            if nid.value in dc_of:
-                raise NotImplementedError(f"DiscreteControl of {nid} is not supported yet")
 
 
 def _node_state(p: Params, nid: NodeID, inflow: bool) -> int | None:

@@ -336,6 +336,49 @@ def pump_discrete_control_model() -> ModelTables:
     return m
 
 
+def discrete_control_of_pid_control_model() -> ModelTables:
+    """A DiscreteControl node listening to a (transient) LevelBoundary sets the target level of a
+    PidControl node (python/ribasim_testmodels/ribasim_testmodels/pid_control.py:66-152)."""
+    m = _model(end=datetime(2020, 12, 1))
+    m.add_node("LevelBoundary", 1, time=dict(
+        time=["2020-01-01 00:00:00", "2020-07-01 00:00:00", "2021-01-01 00:00:00"], level=[7.0, 3.0, 3.0]))
+    m.add_node("Outlet", 2, static=dict(flow_rate=0.0))
+    m.add_node("Basin", 3, state=dict(level=6.0), profile=dict(area=[1000.0, 1000.0], level=[0.0, 1.0]))
+    m.add_node("TabulatedRatingCurve", 4, static=dict(level=[0.0, 1.0], flow_rate=[0.0, 10 / 86400]))
+    m.add_node("Terminal", 5)
+    m.add_node("PidControl", 6, static=dict(
+        listen_node_id=3, control_state=["target_high", "target_low"], target=[5.0, 3.0],
+        proportional=1e-2, integral=1e-8, derivative=-1e-1))
+    m.add_node("DiscreteControl", 7,
+               variable=dict(listen_node_id=1, variable="level", compound_variable_id=1),
+               condition=dict(threshold_high=5.0, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["target_high", "target_low"]))
+    for a, b in [(1, 2), (2, 3), (3, 4), (4, 5), (6, 2), (7, 6)]:
+        m.add_link(a, b)
+    return m
+
+
+def manning_discrete_control_model() -> ModelTables:
+    """Two Basins joined by a ManningResistance whose roughness and width a DiscreteControl node
+    switches on the upstream level (ManningResistance control_state rows, read.jl:328-427)."""
+    m = _model(end=datetime(2020, 3, 1))
+    m.add_node("FlowBoundary", 1, static=dict(flow_rate=3e-3))
+    m.add_node("Basin", 2, state=dict(level=0.3), profile=dict(area=[100.0, 100.0], level=[0.0, 1.0]))
+    m.add_node("ManningResistance", 3, static=dict(
+        length=[100.0, 80.0], manning_n=[0.08, 0.02], profile_width=[1.0, 2.0], profile_slope=[1.0, 0.5],
+        control_state=["rough", "smooth"]))
+    m.add_node("Basin", 4, state=dict(level=0.1), profile=dict(area=[100.0, 100.0], level=[0.0, 1.0]))
+    m.add_node("TabulatedRatingCurve", 5, static=dict(level=[0.0, 1.0], flow_rate=[0.0, 5e-3]))
+    m.add_node("Terminal", 6)
+    m.add_node("DiscreteControl", 7,
+               variable=dict(listen_node_id=2, variable="level", compound_variable_id=1),
+               condition=dict(threshold_high=0.6, threshold_low=0.4, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["smooth", "rough"]))
+    for a, b in [(1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (7, 3)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -637,4 +680,6 @@ MODELS = dict(
     pump_discrete_control=pump_discrete_control_model,
     flow_boundary_time=flow_boundary_time_model,
     two_basin=two_basin_model,
+    discrete_control_of_pid_control=discrete_control_of_pid_control_model,
+    manning_discrete_control=manning_discrete_control_model,
 )

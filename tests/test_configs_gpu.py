@@ -140,3 +140,20 @@ def test_pid_control_tracks_the_target_on_gpu():
         assert model.status_counts["newton_failed"] == 0
     finally:
         model.finalize()
+
+
+def test_discrete_control_sets_the_pid_target_on_gpu():
+    # core/test/control_test.jl:166-199: the level follows target_high until the LevelBoundary
+    # falls through the threshold (day 91), then target_low until the end of the run
+    g = golden("discrete_control_of_pid_control")
+    model = _model("discrete_control_of_pid_control", n_members=2)
+    try:
+        model.update_until(g["t_jump_days"] * 86400.0)
+        assert np.all(np.abs(model.level()[0] - g["target_high"]) < g["atol"])
+        model.run()
+        assert np.all(np.abs(model.level()[0] - g["target_low"]) < g["atol"])
+        assert model.status_counts["newton_failed"] == 0
+        names = model.flat.dc_state_names[0]
+        assert [names[k] for k in model.control_state()[0]] == ["target_low", "target_low"]
+    finally:
+        model.finalize()

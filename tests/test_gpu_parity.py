@@ -19,7 +19,8 @@ RTOL_ENTRY = 1e-12
 MODELS_RHS = ["basic", "basic_transient", "backwater", "trivial", "bucket", "linear_resistance",
               "rating_curve", "rating_curve_between_basins", "manning_resistance", "misc_nodes",
               "user_demand", "pid_control", "pid_control_equation", "outlet_continuous_control",
-              "pump_discrete_control", "junction_combined", "junction_chained",
+              "pump_discrete_control", "discrete_control_of_pid_control", "manning_discrete_control",
+              "junction_combined", "junction_chained",
               "tabulated_rating_curve"]
 
 
@@ -367,6 +368,55 @@ def test_discrete_control_per_member():
             assert changes[m] == om.discrete_control_state()[2]
         assert len(set(changes.tolist())) > 1 or len({tuple(c) for c in dcs.T}) > 1, \
             "members were meant to diverge"
+    finally:
+        h.close()
+
+
+def test_manning_discrete_control_per_member():
+    """ManningResistance control states (length, roughness, profile) switched per member on the
+    device: members with different boundary inflow cross the threshold at different times;
+    control states and trajectories match the oracle member by member."""
+    from oracle.oracle import _dp, advance_opts
+    B = 5
+    case = make_case("manning_discrete_control", B, seed=23, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    case["fb_rate"][0, :] = np.linspace(1.5e-3, 6e-3, B)
+    h = gpu_handle_for(case)
+    opts = advance_opts(1e-5, 1e-5, 10, 1, 4, 20, 1, 1, 2)
+    try:
+        h.refresh(0.0)
+        h.set_member("level_prev", h.get_member("level", nb))
+        h.apply_discrete_control()
+        h.refresh(0.0)
+        dt, n_win, win = 3600.0, 6, 8
+        oms, us, etas, htry = [], [], [1.0] * B, [dt] * B
+        for m in range(B):
+            om = oracle_for_member(case, m)
+            _, c0 = om.rhs(np.zeros(flat["n_reduced"]), 0.0, with_cache=True)
+            om.L.orc_set_level_prev(om.h, _dp(np.ascontiguousarray(c0["level"])))
+            om.set_f64("fb_rate_step", case["fb_rate"][:, m])
+            om.apply_discrete_control(np.zeros(flat["n_reduced"]), 0.0)
+            oms.append(om)
+            us.append(np.zeros(n))
+        t = 0.0
+        seen = set()
+        for k in range(n_win):
+            st = h.advance(t, dt, win)
+            assert not np.any(st)
+            for m, om in enumerate(oms):
+                for j in range(win):
+                    _, _, htry[m], etas[m] = om.advance(us[m], t + j * dt, dt, opts, htry[m], etas[m])
+            t += win * dt
+            dcs = h.get_member_i32("dc_state", flat["n_dc"])
+            for m, om in enumerate(oms):
+                assert np.array_equal(dcs[:, m], om.discrete_control_state()[0]), (k, m)
+            seen |= {tuple(c) for c in dcs.T}
+        ug = h.get_member("u", n)
+        for m in range(B):
+            scale = 1e-5 + np.abs(us[m]) * 1e-5
+            assert np.max(np.abs(ug[:, m] - us[m]) / scale) <= 1e-2
+        assert len(seen) > 1, "both control states were meant to occur"
     finally:
         h.close()
 

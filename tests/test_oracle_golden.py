@@ -241,6 +241,20 @@ def test_pid_control_tracks_the_target():
         assert st["failed"] == 0 and abs(lv[0] - target(t)) < tol
 
 
+def test_discrete_control_sets_the_pid_target():
+    # core/test/control_test.jl:166-199
+    g = golden("discrete_control_of_pid_control")
+    p = build_params(MODELS["discrete_control_of_pid_control"]())
+    flat = flatten(p)
+    u, S, lv, st = run_oracle(p, 3600.0, t_end=g["t_jump_days"] * 86400.0, full_newton=1, max_halvings=20,
+                              predictor=1)
+    assert st["failed"] == 0 and abs(lv[0] - g["target_high"]) < g["atol"]
+    u, S, lv, st = run_oracle(p, 3600.0, full_newton=1, max_halvings=20, predictor=1)
+    assert st["failed"] == 0 and abs(lv[0] - g["target_low"]) < g["atol"]
+    rec = st["oracle"].discrete_control_record()
+    assert [flat.dc_state_names[i][s_] for i, _, s_ in rec] == ["target_high", "target_low"]
+
+
 def test_user_demand_withdrawal_levels():
     # core/test/run_models_test.jl:388-412: the constant UserDemand withdraws down to its minimum
     # level 0.9 m (900 m3), the dynamic one to 0.5 m (500 m3)
