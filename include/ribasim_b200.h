@@ -94,7 +94,10 @@ int rbs_get_member_f64_async(rbs_handle* h, const char* key, double* pinned_host
 int rbs_copy_member_to_device(rbs_handle* h, const char* key, void* dst_device, int64_t n_entity);
 /* Integer per-member arrays: "status", "dc_state" (control state index per DiscreteControl
  * node, -1 = none yet), "dc_truth" (per condition), counters "cnt_iters", "cnt_sub", "cnt_rej",
- * "cnt_dc" (control state changes). */
+ * "cnt_dc" (control state changes).  The DiscreteControl record of the reference
+ * (`discrete_control.record`, core/src/callback.jl:698-716) is kept per member for the first 64
+ * changes: entry r < cnt_dc[m] is ("dc_rec_t" f64 [64][n_members] model time, "dc_rec_ns" i32 =
+ * DiscreteControl index | control state index << 16, "dc_rec_bits" i32 = truth state bits). */
 int rbs_get_member_i32(rbs_handle* h, const char* key, int32_t* host, int64_t n_entity);
 /* DiscreteControl at the initial time (`apply_discrete_control!` with t == 0,
  * core/src/callback.jl:608-661): evaluates every condition on the caches of the last

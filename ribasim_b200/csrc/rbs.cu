@@ -17,6 +17,8 @@
 #include "rbs_kernels.cuh"
 #include "rbs_tile.cuh"
 
+#define RBS_DC_REC_CAP 64  // DiscreteControl changes recorded per member
+
 namespace {
 
 thread_local std::string g_err;
@@ -256,6 +258,10 @@ void bind_net(rbs_handle* h) {
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
     M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep); M_I(mroll);
     M_I(dc_truth); M_I(dc_state); M_I(cnt_dc);
+    n.dc_rec_cap = n.n_dc > 0 ? RBS_DC_REC_CAP : 0;
+    n.dc_rec_t = n.n_dc > 0 ? mp(h, "dc_rec_t") : nullptr;
+    n.dc_rec_ns = n.n_dc > 0 ? (int*)h->member["dc_rec_ns"].p : nullptr;
+    n.dc_rec_bits = n.n_dc > 0 ? (int*)h->member["dc_rec_bits"].p : nullptr;
 #undef M_I
 #undef S_D
 #undef S_I
@@ -551,6 +557,9 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                           "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep", "mroll", "cnt_dc"})
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
     if (alloc_member(h, "dc_truth", n.n_dc_cond, true) || alloc_member(h, "dc_state", n.n_dc, true))
+        return bail("member alloc");
+    if (n.n_dc > 0 && (alloc_member(h, "dc_rec_t", RBS_DC_REC_CAP) || alloc_member(h, "dc_rec_ns", RBS_DC_REC_CAP, true) ||
+                       alloc_member(h, "dc_rec_bits", RBS_DC_REC_CAP, true)))
         return bail("member alloc");
     // no control state set yet
     cudaMemsetAsync(h->member["dc_state"].p, 0xFF, h->member["dc_state"].bytes, h->stream);
@@ -1064,6 +1073,7 @@ int rbs_apply_discrete_control(rbs_handle* h) {
     if (!h) return fail("rbs_apply_discrete_control: null handle");
     cudaSetDevice(h->device);
     Net& n = h->net;
+    n.win_t0 = h->tprev;
     if (n.n_dc > 0) LAUNCH(h, k_discrete_control, (long long)n.n_dc * n.B, n, 1);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return check_async(h, "rbs_apply_discrete_control");
@@ -1482,6 +1492,7 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
     long long B = n.B;
     double h_min = std::ldexp(dt, -h->max_halvings);
     h->cur = h->stream;
+    n.win_t0 = t; n.win_dt = dt;
     LAUNCH(h, k_step_begin, (long long)(n.n_state + n.n_basin + 1) * B, n, dt, h->predictor);
     const bool use_coop = h->coop_blocks > 0 && n.B <= h->coop_members;
     if ((use_coop || h->tile_window > 0) && h->full_newton && !h->profiling) {

@@ -124,6 +124,12 @@ struct Net {
     double* w_storage;
     double *w_flow, *ustep;  // mean flows per outer step [step][state][member]; u at its start
     double fw_dt;            // length of an outer step of the window
+    // DiscreteControl record per member (callback.jl:698-716 `discrete_control.record`): entry r <
+    // cnt_dc[m] = (time, node | state << 16, truth bits), the first dc_rec_cap changes are kept
+    double win_t0, win_dt;   // start time and outer step of the running window
+    int dc_rec_cap;
+    double* dc_rec_t;
+    int *dc_rec_ns, *dc_rec_bits;
     int* mroll;  // set by k_step_decide: the decision completed an outer step
 };
 
@@ -1790,7 +1796,18 @@ __device__ __forceinline__ void rbs_discrete_control_item(const Net& n, int init
         int snew = n.dc_logic[n.dc_logic_ptr[i] + bits];
         long long so = (long long)i * n.B + m;
         if (snew < 0) atomicOr(&n.status[m], 4);  // no control state specified for this truth state
-        else if (snew != n.dc_state[so]) { n.dc_state[so] = snew; atomicAdd(&n.cnt_dc[m], 1); }
+        else if (snew != n.dc_state[so]) {
+            n.dc_state[so] = snew;
+            const int r = atomicAdd(&n.cnt_dc[m], 1);
+            if (n.dc_rec_t && r < n.dc_rec_cap) {
+                const long long ro = (long long)r * n.B + m;
+                const double t_rel = initial ? 0.0
+                    : (n.mroll[m] ? n.mstep[m] * n.win_dt : n.mstep[m] * n.win_dt + n.melapsed[m]);
+                n.dc_rec_t[ro] = n.win_t0 + t_rel;
+                n.dc_rec_ns[ro] = i | (snew << 16);
+                n.dc_rec_bits[ro] = bits;
+            }
+        }
     }
 }
 

@@ -264,6 +264,31 @@ class Model:
         `flat.dc_state_names[i]`."""
         return self.h.get_member_i32("dc_state", self.flat.ints["n_dc"])
 
+    DC_RECORD_CAP = 64  # RBS_DC_REC_CAP of the library
+
+    def control_record(self, member: int = 0) -> list[tuple[float, int, str, str]]:
+        """`discrete_control.record` of one member (core/src/callback.jl:698-716):
+        `(time, control_node_id, truth_state, control_state)` per control state change, the
+        initial states at t = 0 included, in time order (ties in node order)."""
+        n_dc = self.flat.ints["n_dc"]
+        if n_dc == 0:
+            return []
+        cap = self.DC_RECORD_CAP
+        cnt = int(self.h.get_member_i32("cnt_dc", 1)[0, member])
+        if cnt > cap:
+            raise RuntimeError(f"member {member} changed control state {cnt} times; only the first {cap} are recorded")
+        t = self.h.get_member("dc_rec_t", cap)[:cnt, member]
+        ns = self.h.get_member_i32("dc_rec_ns", cap)[:cnt, member]
+        bits = self.h.get_member_i32("dc_rec_bits", cap)[:cnt, member]
+        ids = [x.value for x in self.p.nodes["discrete_control"]["node_id"]]
+        n_cond = np.diff(self.flat.arrays["dc_cond_ptr"])
+        rec = []
+        for k in sorted(range(cnt), key=lambda k: (t[k], int(ns[k]) & 0xFFFF)):
+            i, st = int(ns[k]) & 0xFFFF, int(ns[k]) >> 16
+            truth = "".join("T" if (int(bits[k]) >> j) & 1 else "F" for j in range(int(n_cond[i])))
+            rec.append((float(t[k]), ids[i], truth, self.flat.dc_state_names[i][st]))
+        return rec
+
     def flow(self) -> np.ndarray:
         return self.h.get_member("du", self.flat.ints["n_state"])
 

@@ -19,7 +19,7 @@ import numpy as np
 from .flatten import KIND_BASIN
 
 RESULTS_FILENAME = dict(basin_state="basin_state.nc", basin="basin.nc", flow="flow.nc",
-                        subgrid_level="subgrid_level.nc")
+                        subgrid_level="subgrid_level.nc", control="control.nc")
 
 CF_GLOBAL = {"Conventions": "CF-1.12", "references": "https://ribasim.org"}
 _RATE = "m3 s-1"
@@ -223,6 +223,40 @@ class Results:
         return dict(time=np.array(self.times), subgrid_id=self.m.subgrid.subgrid_id,
                     subgrid_level=np.stack(self.subgrid_levels))
 
+    def discrete_control_data(self) -> dict[str, np.ndarray]:
+        """`discrete_control_data` (write.jl:565-572) as a table over all members: one row per
+        control state change; `realization` tells the member."""
+        rows = [(m, *rec) for m in range(self.m.B) for rec in self.m.control_record(m)]
+        return dict(realization=np.array([x[0] for x in rows], dtype=np.int32),
+                    time=np.array([x[1] for x in rows], dtype=float),
+                    control_node_id=np.array([x[2] for x in rows], dtype=np.int32),
+                    truth_state=[x[3] for x in rows], control_state=[x[4] for x in rows])
+
+    def _write_control(self, path: Path) -> None:
+        from scipy.io import netcdf_file
+
+        d = self.discrete_control_data()
+        n = len(d["time"])
+        with netcdf_file(str(path), "w") as ds:
+            for k, v in CF_GLOBAL.items():
+                setattr(ds, k, v)
+            ds.title = "Ribasim results: control"
+            ds.createDimension("time", n)
+            tv = ds.createVariable("time", "d", ("time",))
+            tv.units = "seconds since " + self.m.tables.starttime.strftime("%Y-%m-%d %H:%M:%S")
+            for k, v in CF["time"].items():
+                setattr(tv, k, v)
+            tv[:] = d["time"]
+            for name in ("control_node_id", "realization"):
+                v = ds.createVariable(name, "i", ("time",))
+                v[:] = d[name]
+            for name in ("truth_state", "control_state"):
+                width = max([len(x) for x in d[name]] + [1])
+                ds.createDimension(f"{name}_strlen", width)
+                v = ds.createVariable(name, "c", ("time", f"{name}_strlen"))
+                for k, x in enumerate(d[name]):
+                    v[k] = np.frombuffer(x.encode().ljust(width, b"\0"), dtype="S1")
+
     def basin_state_data(self) -> dict[str, np.ndarray]:
         return dict(node_id=self.node_id, level=self.m.level())
 
@@ -287,4 +321,8 @@ class Results:
                         sd["time"], dict(subgrid_level=sd["subgrid_level"]))
         else:
             del paths["subgrid_level"]
+        if self.m.flat.ints["n_dc"] > 0:
+            self._write_control(paths["control"])
+        else:
+            del paths["control"]
         return paths

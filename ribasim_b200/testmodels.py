@@ -379,6 +379,45 @@ def manning_discrete_control_model() -> ModelTables:
     return m
 
 
+def flow_condition_model() -> ModelTables:
+    """DiscreteControl on the flow rate of a FlowBoundary, 60 days ahead
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:128-191)."""
+    m = _model(interpolation=dict(flow_boundary="linear"))
+    m.add_node("FlowBoundary", 1, time=dict(time=["2020-01-01 00:00:00", "2022-01-01 00:00:00"],
+                                            flow_rate=[0.0, 40 / 86400]))
+    m.add_node("Basin", 2, profile=dict(level=[0.0, 1.0], area=[100.0, 100.0]), state=dict(level=2.5))
+    m.add_node("Pump", 3, static=dict(flow_rate=[0.0, 1e-3], control_state=["off", "on"]))
+    m.add_node("Terminal", 4)
+    m.add_node("DiscreteControl", 5,
+               variable=dict(listen_node_id=1, variable="flow_rate", look_ahead=60 * 86400.0,
+                             compound_variable_id=1),
+               condition=dict(threshold_high=20 / 86400, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["off", "on"]))
+    for a, b in [(1, 2), (2, 3), (3, 4), (5, 3)]:
+        m.add_link(a, b)
+    return m
+
+
+def level_boundary_condition_model() -> ModelTables:
+    """DiscreteControl on the level of a transient LevelBoundary, 60 days ahead
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:194-264)."""
+    m = _model()
+    m.add_node("LevelBoundary", 1, time=dict(
+        time=["2020-01-01 00:00:00", "2020-06-01 00:00:00", "2022-01-01 00:00:00"], level=[5.0, 7.0, 10.0]))
+    m.add_node("LinearResistance", 2, static=dict(resistance=5e3))
+    m.add_node("Basin", 3, profile=dict(level=[0.0, 1.0], area=[100.0, 100.0]), state=dict(level=2.5))
+    m.add_node("Outlet", 4, static=dict(flow_rate=[0.5 / 3600, 0.0], control_state=["on", "off"]))
+    m.add_node("Terminal", 5)
+    m.add_node("DiscreteControl", 6,
+               variable=dict(listen_node_id=1, variable="level", look_ahead=60 * 86400.0,
+                             compound_variable_id=1),
+               condition=dict(threshold_high=6.0, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["on", "off"]))
+    for a, b in [(1, 2), (2, 3), (3, 4), (4, 5), (6, 4)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -682,4 +721,6 @@ MODELS = dict(
     two_basin=two_basin_model,
     discrete_control_of_pid_control=discrete_control_of_pid_control_model,
     manning_discrete_control=manning_discrete_control_model,
+    flow_condition=flow_condition_model,
+    level_boundary_condition=level_boundary_condition_model,
 )

@@ -144,7 +144,7 @@ def test_pid_control_tracks_the_target_on_gpu():
 
 def test_discrete_control_sets_the_pid_target_on_gpu():
     # core/test/control_test.jl:166-199: the level follows target_high until the LevelBoundary
-    # falls through the threshold (day 91), then target_low until the end of the run
+    # falls through the threshold (2020-07-01), then target_low until the end of the run
     g = golden("discrete_control_of_pid_control")
     model = _model("discrete_control_of_pid_control", n_members=2)
     try:
@@ -155,5 +155,64 @@ def test_discrete_control_sets_the_pid_target_on_gpu():
         assert model.status_counts["newton_failed"] == 0
         names = model.flat.dc_state_names[0]
         assert [names[k] for k in model.control_state()[0]] == ["target_low", "target_low"]
+    finally:
+        model.finalize()
+
+
+def test_discrete_control_record_on_gpu(tmp_path):
+    """`discrete_control.record` kept per member on the device.
+    core/test/control_test.jl:33-64 (pump_discrete_control: the sequence of control state changes,
+    the levels at the control times, no flow at the end), :66-84 (flow condition with look-ahead),
+    :86-107 (transient level boundary condition with look-ahead)."""
+    from scipy.io import netcdf_file
+
+    g = golden("pump_discrete_control_record")
+    model = _model("pump_discrete_control", n_members=2)
+    try:
+        levels = {}
+        res = model.run(saveat=86400.0, results_dir=tmp_path)
+        rec = model.control_record(0)
+        assert rec == model.control_record(1)
+        assert [r[1] for r in rec] == g["control_node_id"]
+        assert [r[3] for r in rec] == g["control_state"]
+        assert [r[2] for r in rec] == g["truth_state"]
+        assert rec[0][0] == 0.0 and rec[1][0] == 0.0 and all(a[0] <= b[0] for a, b in zip(rec, rec[1:]))
+        level = res.basin_data()["level"][..., 0]  # [period][basin], start of period
+        t = np.array(res.times[:-1])
+        # control_test.jl:50-58: Basin 1 has dropped to its threshold (0.8) at the third change,
+        # Basin 3 has risen to its threshold (0.4) at the fourth
+        assert level[np.searchsorted(t, rec[2][0]), 0] <= 0.8
+        assert level[np.searchsorted(t, rec[3][0]), 1] >= 0.4
+        du = model.flow()[:, 0]
+        f = model.flat.ints
+        assert abs(du[f["off_lr"]]) < 1e-10 and abs(du[f["off_pump"]]) < 1e-10
+        with netcdf_file(str(tmp_path / "control.nc"), "r", mmap=False) as ds:
+            assert ds.variables["time"].shape == (2 * len(rec),)
+            names = [b"".join(row).rstrip(b"\0").decode() for row in ds.variables["control_state"][:]]
+            assert names[: len(rec)] == g["control_state"]
+    finally:
+        model.finalize()
+
+    model = _model("flow_condition", n_members=1)
+    try:
+        model.run()
+        rec = model.control_record(0)
+        assert [r[3] for r in rec] == ["on", "off"]
+        t_control, ahead = rec[1][0], 60 * 86400.0
+        flow = model.p.nodes["flow_boundary"]["flow_rate"][0]
+        threshold = 20 / 86400
+        assert abs(flow(t_control) - threshold) > 0.005 * threshold
+        assert flow(t_control + ahead) == pytest.approx(threshold, rel=0.005)
+    finally:
+        model.finalize()
+
+    model = _model("level_boundary_condition", n_members=1)
+    try:
+        model.run()
+        rec = model.control_record(0)
+        assert [r[3] for r in rec] == ["off", "on"]
+        t_control, ahead = rec[1][0], 60 * 86400.0
+        level = model.p.nodes["level_boundary"]["level"][0]
+        assert level(t_control) < 6.0 <= level(t_control + ahead)
     finally:
         model.finalize()
