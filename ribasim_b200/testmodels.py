@@ -418,6 +418,94 @@ def level_boundary_condition_model() -> ModelTables:
     return m
 
 
+def tabulated_rating_curve_control_model() -> ModelTables:
+    """DiscreteControl raises the crest of a rating curve above a threshold level
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:268-338)."""
+    m = _model()
+    m.add_node("Basin", 1, static=dict(precipitation=0.002 / 86400),
+               state=dict(level=0.04471158417652035), profile=dict(area=[0.01, 1000.0], level=[0.0, 1.0]))
+    m.add_node("TabulatedRatingCurve", 2, static=dict(
+        level=[0.0, 1.2, 0.0, 1.0], flow_rate=[0.0, 1 / 86400, 0.0, 1 / 86400],
+        control_state=["low", "low", "high", "high"]))
+    m.add_node("Terminal", 3)
+    m.add_node("DiscreteControl", 4,
+               variable=dict(listen_node_id=1, variable="level", compound_variable_id=1),
+               condition=dict(threshold_high=0.5, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["low", "high"]))
+    for a, b in [(1, 2), (2, 3), (4, 2)]:
+        m.add_link(a, b)
+    return m
+
+
+def compound_variable_condition_model() -> ModelTables:
+    """A condition on the weighted sum of two FlowBoundary rates
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:341-397)."""
+    m = _model(interpolation=dict(flow_boundary="linear"))
+    m.add_node("Basin", 1, profile=dict(area=[1000.0, 1000.0], level=[0.0, 1.0]), state=dict(level=1.0))
+    m.add_node("FlowBoundary", 2, static=dict(flow_rate=0.0))
+    m.add_node("FlowBoundary", 3, time=dict(time=["2020-01-01 00:00:00", "2021-01-01 00:00:00"],
+                                            flow_rate=[0.0, 2.0]))
+    m.add_node("Pump", 4, static=dict(control_state=["Off", "On"], flow_rate=[0.0, 1.0]))
+    m.add_node("Terminal", 5)
+    m.add_node("DiscreteControl", 6,
+               variable=dict(listen_node_id=[2, 3], variable="flow_rate", weight=0.5, compound_variable_id=1),
+               condition=dict(threshold_high=0.5, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["On", "Off"]))
+    for a, b in [(2, 1), (3, 1), (1, 4), (4, 5), (6, 4)]:
+        m.add_link(a, b)
+    return m
+
+
+def connector_node_flow_condition_model() -> ModelTables:
+    """A condition on the flow through a LinearResistance that the control node itself closes
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:540-590)."""
+    m = _model()
+    m.add_node("Basin", 1, profile=dict(area=[1000.0, 1000.0], level=[0.0, 1.0]), state=dict(level=20.0))
+    m.add_node("LinearResistance", 2, static=dict(control_state=["On", "Off"], resistance=[1e4, float("inf")]))
+    m.add_node("Basin", 3, profile=dict(area=[1000.0, 1000.0], level=[0.0, 1.0]), state=dict(level=10.0))
+    m.add_node("DiscreteControl", 4,
+               variable=dict(listen_node_id=2, variable="flow_rate", compound_variable_id=1),
+               condition=dict(threshold_high=1e-4, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["On", "Off"]))
+    for a, b in [(1, 2), (2, 3), (4, 2)]:
+        m.add_link(a, b)
+    return m
+
+
+def storage_condition_model() -> ModelTables:
+    """A Pump switched on the storage of a Basin
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:495-537)."""
+    m = _model()
+    m.add_node("FlowBoundary", 1, static=dict(flow_rate=1e-3))
+    m.add_node("Basin", 2, profile=dict(area=[1000.0, 1000.0], level=[0.0, 10.0]), state=dict(level=5.0))
+    m.add_node("Pump", 3, static=dict(control_state=["off", "on"], flow_rate=[0.0, 1e-3]))
+    m.add_node("Terminal", 4)
+    m.add_node("DiscreteControl", 5,
+               variable=dict(compound_variable_id=1, listen_node_id=2, variable="storage"),
+               condition=dict(compound_variable_id=1, condition_id=1, threshold_high=7500.0),
+               logic=dict(truth_state=["F", "T"], control_state=["off", "on"]))
+    for a, b in [(1, 2), (2, 3), (3, 4), (5, 3)]:
+        m.add_link(a, b)
+    return m
+
+
+def transient_condition_model() -> ModelTables:
+    """A threshold that changes in time (cyclic)
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:755-798)."""
+    m = _model(end=datetime(2020, 3, 1))
+    m.add_node("LevelBoundary", 1, static=dict(level=2.0))
+    m.add_node("Pump", 2, static=dict(control_state=["A", "B"], flow_rate=[1.0, 2.0]))
+    m.add_node("Basin", 3, state=dict(level=2.0), profile=dict(level=[0.0, 1.0], area=[100.0, 100.0]))
+    m.add_node("DiscreteControl", 4, cyclic_time=True,
+               variable=dict(listen_node_id=1, variable="level", compound_variable_id=1),
+               condition=dict(compound_variable_id=1, condition_id=1, threshold_high=[1.0, 3.0, 1.0],
+                              time=["2020-01-01 00:00:00", "2020-02-01 00:00:00", "2020-03-01 00:00:00"]),
+               logic=dict(truth_state=["F", "T"], control_state=["A", "B"]))
+    for a, b in [(1, 2), (2, 3), (4, 2)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -723,4 +811,9 @@ MODELS = dict(
     manning_discrete_control=manning_discrete_control_model,
     flow_condition=flow_condition_model,
     level_boundary_condition=level_boundary_condition_model,
+    tabulated_rating_curve_control=tabulated_rating_curve_control_model,
+    compound_variable_condition=compound_variable_condition_model,
+    connector_node_flow_condition=connector_node_flow_condition_model,
+    storage_condition=storage_condition_model,
+    transient_condition=transient_condition_model,
 )

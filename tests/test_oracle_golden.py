@@ -255,6 +255,22 @@ def test_discrete_control_sets_the_pid_target():
     assert [flat.dc_state_names[i][s_] for i, _, s_ in rec] == ["target_high", "target_low"]
 
 
+@pytest.mark.parametrize("name", ["tabulated_rating_curve_control", "compound_variable_condition",
+                                  "connector_node_flow_condition", "transient_condition", "storage_condition"])
+def test_reference_control_sequences(name):
+    # core/test/control_test.jl:133-164, 201-261, 311-332, 374-383: truth and control states of the record
+    g = golden("control_records")[name]
+    p = build_params(MODELS[name]())
+    flat = flatten(p)
+    u, S, lv, st = run_oracle(p, 3600.0, full_newton=1, max_halvings=20, predictor=1)
+    assert st["failed"] == 0
+    rec = st["oracle"].discrete_control_record()
+    assert [flat.dc_state_names[i][s_] for i, _, s_ in rec] == g["control_state"]
+    assert ["T" if b & 1 else "F" for _, b, _ in rec] == g["truth_state"]
+    if "storage_below" in g:
+        assert S[0] < g["storage_below"]
+
+
 def test_user_demand_withdrawal_levels():
     # core/test/run_models_test.jl:388-412: the constant UserDemand withdraws down to its minimum
     # level 0.9 m (900 m3), the dynamic one to 0.5 m (500 m3)
