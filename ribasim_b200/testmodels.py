@@ -506,6 +506,34 @@ def transient_condition_model() -> ModelTables:
     return m
 
 
+def outlet_model() -> ModelTables:
+    """An Outlet between a transient LevelBoundary and a Basin that meets its constraints
+    (python/ribasim_testmodels/ribasim_testmodels/basic.py:364-407)."""
+    m = _model()
+    m.add_node("Basin", 3, profile=dict(area=[1000.0, 1000.0], level=[0.0, 10.0]), state=dict(level=0.0))
+    m.add_node("LevelBoundary", 1, time=dict(
+        time=["2020-01-01 00:00:00", "2020-06-01 00:00:00", "2021-01-01 00:00:00"], level=[1.0, 3.0, 3.0]))
+    m.add_node("Outlet", 2, static=dict(flow_rate=1e-3, min_upstream_level=2.0))
+    m.add_link(1, 2)
+    m.add_link(2, 3)
+    return m
+
+
+def flow_boundary_interpolation_model() -> ModelTables:
+    """A cyclic FlowBoundary with block interpolation
+    (python/ribasim_testmodels/ribasim_testmodels/basic.py:590-627)."""
+    m = _model(end=datetime(2020, 1, 9), interpolation=dict(flow_boundary="block", block_transition_period=0.0))
+    m.add_node("FlowBoundary", 1, cyclic_time=True, time=dict(
+        time=["2020-01-01 00:00:00", "2020-01-02 00:00:00", "2020-01-03 00:00:00", "2020-01-04 00:00:00"],
+        flow_rate=[1e-3, 2.5e-3, 0.0, 1e-3]))
+    m.add_node("Basin", 2, state=dict(level=1.0), profile=dict(level=[0.0, 3.0], area=[1000.0, 1000.0]))
+    m.add_node("TabulatedRatingCurve", 3, static=dict(level=[0.0, 2.0], flow_rate=[0.0, 1e-3]))
+    m.add_node("Terminal", 4)
+    for a, b in [(1, 2), (2, 3), (3, 4)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -816,4 +844,6 @@ MODELS = dict(
     connector_node_flow_condition=connector_node_flow_condition_model,
     storage_condition=storage_condition_model,
     transient_condition=transient_condition_model,
+    outlet=outlet_model,
+    flow_boundary_interpolation=flow_boundary_interpolation_model,
 )

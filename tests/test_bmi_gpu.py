@@ -99,3 +99,31 @@ def test_windowed_update_matches_stepwise(basic_toml):
     finally:
         a.finalize()
         b.finalize()
+
+
+def test_stroboscopic_forcing(tmp_path):
+    """core/test/run_models_test.jl:593-636: drainage and infiltration written through the BMI
+    pointers on alternating days are integrated exactly into the cumulative arrays."""
+    b = _bmi(MODELS["bucket"]().write(tmp_path))
+    try:
+        drn, drn_sum = b.get_value_ptr("basin.drainage"), b.get_value_ptr("basin.cumulative_drainage")
+        inf, inf_sum = b.get_value_ptr("basin.infiltration"), b.get_value_ptr("basin.cumulative_infiltration")
+        nday, dt = 300, 86400.0
+        inf_out, drn_out = np.full(nday, np.nan), np.full(nday, np.nan)
+        for day in range(nday):
+            if day % 2 == 0:
+                drn[:] = 25.0 / dt
+                inf[:] = 0.0
+            else:
+                drn[:] = 0.0
+                inf[:] = 25.0 / dt
+            b.update_until(day * dt)
+            inf_out[day], drn_out[day] = inf_sum[0], drn_sum[0]
+        d_drn, d_inf = np.diff(drn_out), np.diff(inf_out)
+        # the forcing set before `update_until(day)` acts on the day that ends at `day`
+        assert np.all(d_drn[0::2] == 0.0)
+        assert np.allclose(d_drn[1::2], 25.0, rtol=0, atol=1e-10)
+        assert np.allclose(d_inf[0::2], 25.0, rtol=0, atol=1e-10)
+        assert np.all(d_inf[1::2] == 0.0)
+    finally:
+        b.finalize()

@@ -172,3 +172,38 @@ def test_two_basin_subgrid_levels(tmp_path):
         assert np.allclose(b.get_value_ptr("basin.subgrid_level"), b.get_value_ptr("basin.level"), rtol=1e-14)
     finally:
         b.finalize()
+
+
+def test_outlet_constraints():
+    """core/test/run_models_test.jl:356-386: no Outlet flow while the upstream level is below the
+    minimum upstream level; afterwards the Basin converges to the LevelBoundary level."""
+    model = _model("outlet", n_members=1)
+    try:
+        res = model.run(saveat=86400.0)
+        fd, bd = res.flow_data(), res.basin_data()
+        level = model.p.nodes["level_boundary"]["level"][0]
+        min_up = 2.0
+        t_min = level.t[1] * (min_up - level.u[0]) / (level.u[1] - level.u[0])
+        q = fd["flow_rate"][:, (fd["from_node_id"] == 2) & (fd["to_node_id"] == 3), 0].ravel()
+        t_end_of_period = np.array(res.times[1:])
+        assert np.all(q[t_end_of_period <= t_min] == 0.0)
+        assert q.max() == pytest.approx(1e-3, rel=1e-6)
+        assert model.level()[0, 0] == pytest.approx(level.u[2], abs=5e-2)
+        assert model.status_counts["newton_failed"] == 0
+    finally:
+        model.finalize()
+
+
+def test_flow_boundary_block_interpolation():
+    """core/test/run_models_test.jl:729-761: with block interpolation the daily mean flows out of
+    the (cyclic) FlowBoundary are the table's values, period after period."""
+    model = _model("flow_boundary_interpolation", n_members=1)
+    try:
+        res = model.run(saveat=86400.0)
+        fd = res.flow_data()
+        q = fd["flow_rate"][:, fd["from_node_id"] == 1, 0].ravel()
+        table = [1e-3, 2.5e-3, 0.0, 1e-3]
+        assert np.allclose(q[0:4], table, rtol=1e-12, atol=1e-18)
+        assert np.allclose(q[3:7], table, rtol=1e-12, atol=1e-18)
+    finally:
+        model.finalize()
