@@ -207,3 +207,24 @@ def test_flow_boundary_block_interpolation():
         assert np.allclose(q[3:7], table, rtol=1e-12, atol=1e-18)
     finally:
         model.finalize()
+
+
+def test_outlet_continuous_control_flow_split():
+    """core/test/control_test.jl:263-288: two continuously controlled Outlets split the inflow
+    through the LinearResistance 60 / 40 (mean flows per link from flow_data)."""
+    model = _model("outlet_continuous_control", n_members=1)
+    try:
+        fd = model.run(saveat=86400.0).flow_data()
+
+        def link_flow(a, b):
+            return fd["flow_rate"][:, (fd["from_node_id"] == a) & (fd["to_node_id"] == b), 0].ravel()
+
+        inflow = link_flow(2, 3)
+        assert inflow.size == 366 and np.any(inflow > 0) and np.any(inflow < 0)
+        scale = np.abs(inflow).max()
+        for (a, b), frac in (((3, 4), 0.6), ((4, 6), 0.6), ((3, 5), 0.4), ((5, 7), 0.4)):
+            # `≈` with rtol on the whole vector: norm-wise
+            diff = link_flow(a, b) - np.maximum(frac * inflow, 0.0)
+            assert np.linalg.norm(diff) <= 1e-3 * np.linalg.norm(np.maximum(frac * inflow, 0.0)) + 1e-12 * scale
+    finally:
+        model.finalize()
