@@ -276,7 +276,10 @@ class Model:
         cap = self.DC_RECORD_CAP
         cnt = int(self.h.get_member_i32("cnt_dc", 1)[0, member])
         if cnt > cap:
-            raise RuntimeError(f"member {member} changed control state {cnt} times; only the first {cap} are recorded")
+            import warnings
+
+            warnings.warn(f"member {member} changed control state {cnt} times; only the first {cap} are recorded")
+            cnt = cap
         t = self.h.get_member("dc_rec_t", cap)[:cnt, member]
         ns = self.h.get_member_i32("dc_rec_ns", cap)[:cnt, member]
         bits = self.h.get_member_i32("dc_rec_bits", cap)[:cnt, member]
