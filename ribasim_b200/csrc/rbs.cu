@@ -129,6 +129,10 @@ struct rbs_handle {
     bool sched16 = false;
     // entry schedule (factorisation with fused forward substitution), see symbolic.build_entries
     EntSched esched{};
+    EntSched esched_c{};         // compact slots (full-Newton path): more tiles per SM
+    void* d_entc_blob = nullptr;
+    size_t entc_smem_bytes = 0;
+    bool lin_entc = false;
     void* d_ent_blob = nullptr;
     bool lin_ent = false;
     int ent_tile = 2;
@@ -434,6 +438,29 @@ int rbs_builder_set_f64(rbs_builder* b, const char* key, const double* data, int
     if (!b || !key || (n > 0 && !data)) return fail("rbs_builder_set_f64: null argument");
     b->d[key].assign(data, data + n);
     return 0;
+}
+
+// Shared-memory carve-out of the entry-schedule solve.  What is not carved out is L1, and the
+// schedule words (47 KB for the 500-basin network) are read through L1 by every tile: measured on
+// the bench workload (profiles/compact_slots.sh), three resident tiles with the rest as L1 beat
+// four to six tiles with a small L1, alone and next to the other member groups' kernels.  The
+// preference is therefore three tiles' worth, for the slot layout the current stepper mode uses.
+static void apply_carveout(rbs_handle* h) {
+    if (!h->lin_ent) return;
+    const bool cmp = h->lin_entc && h->full_newton;
+    const size_t tile = (cmp ? h->entc_smem_bytes : h->ent_smem_bytes) + 1040;
+    // the carve-out sizes of sm_100 (KB); the preference is given in percent of the largest
+    int kb = 228;
+    for (int cand : {8, 16, 32, 64, 100, 132, 164, 196, 228})
+        if ((size_t)cand * 1024 >= 3 * tile) { kb = cand; break; }
+    int pct = (kb * 100 + 227) / 228;
+    if (getenv("RBS_ENT_CARVEOUT")) pct = atoi(getenv("RBS_ENT_CARVEOUT"));
+    if (pct < 0) return;  // RBS_ENT_CARVEOUT=-1: the driver's default
+    if (pct > 100) pct = 100;
+    if (h->ent_tile == 2) cudaFuncSetAttribute(k_newton_linear_ent<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    else if (h->ent_tile == 4) cudaFuncSetAttribute(k_newton_linear_ent<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    else cudaFuncSetAttribute(k_newton_linear_ent<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaGetLastError();
 }
 
 rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) {
@@ -845,7 +872,63 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 else cudaGetLastError();
             }
         }
-        if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; h->lin_ent = false; }
+        // ---- the same schedule with compacted slots for the full-Newton path
+        if (h->lin_ent && b->i.count("entc_e") && !(getenv("RBS_ENT_COMPACT") && atoi(getenv("RBS_ENT_COMPACT")) == 0)) {
+            EntSched es = h->esched;
+            es.n_slots = geti(b, "entc_n_slots"); es.y0 = geti(b, "entc_y0");
+            auto &ee = geta("entc_e"), &eq = geta("entc_q0"), &ec = geta("entc_cf");
+            auto &pl = geta("entc_prod_l"), &pp = geta("entc_prod_p"), &pu = geta("entc_prod_u");
+            auto &lp = geta("entc_lvl_ptr"), &tm_ = geta("entc_team_log"), &pm = geta("perm");
+            auto &le = geta("entc_load_e"), &ls = geta("entc_load_s");
+            bool ok = es.n_slots > 0 && es.n_slots <= h->esched.n_slots && es.y0 + n.n_reduced == es.n_slots &&
+                      pl.size() < 65536 && ee.size() < 65536 &&
+                      (int)lp.size() == es.n_elim + es.n_bwd + 1 && tm_.size() + 1 == lp.size() &&
+                      ee.size() == eq.size() && ee.size() == ec.size() && pl.size() == pp.size() &&
+                      pl.size() == pu.size() && le.size() == ls.size() && !le.empty();
+            if (ok) {
+                std::vector<unsigned long long> hb;
+                for (size_t k = 0; k + 1 < lp.size(); k++)
+                    hb.push_back((unsigned long long)(uint16_t)lp[k] | ((unsigned long long)(uint16_t)lp[k + 1] << 16) |
+                                 ((unsigned long long)(uint16_t)tm_[k] << 32));
+                size_t o_ent = hb.size();
+                for (size_t k = 0; k < ee.size(); k++)
+                    hb.push_back((unsigned long long)(uint16_t)ee[k] | ((unsigned long long)(uint16_t)eq[k] << 16) |
+                                 ((unsigned long long)(uint16_t)ec[k] << 32));
+                size_t o_prod = hb.size();
+                for (size_t k = 0; k < pl.size(); k++)
+                    hb.push_back((unsigned long long)(uint16_t)pl[k] | ((unsigned long long)(uint16_t)pp[k] << 16) |
+                                 ((unsigned long long)(uint16_t)pu[k] << 32));
+                size_t o_perm = hb.size();
+                for (size_t k = 0; k < pm.size(); k += 4) {
+                    unsigned long long w = 0;
+                    for (size_t q = 0; q < 4 && k + q < pm.size(); q++) w |= (unsigned long long)(uint16_t)pm[k + q] << (16 * q);
+                    hb.push_back(w);
+                }
+                hb.push_back(0);
+                size_t o_load = hb.size();
+                for (size_t k = 0; k < le.size(); k += 2) {
+                    unsigned long long w = 0;
+                    for (size_t q = 0; q < 2 && k + q < le.size(); q++)
+                        w |= (unsigned long long)((unsigned)(uint16_t)le[k + q] | ((unsigned)(uint16_t)ls[k + q] << 16)) << (32 * q);
+                    hb.push_back(w);
+                }
+                es.n_words = (int)o_perm;
+                es.smem_sched = 0;
+                es.n_load = (int)le.size();
+                if (cudaMalloc(&h->d_entc_blob, hb.size() * 8) != cudaSuccess) return bail("schedule alloc");
+                cudaMemcpyAsync(h->d_entc_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream);
+                cudaStreamSynchronize(h->stream);
+                const unsigned long long* d = (const unsigned long long*)h->d_entc_blob;
+                es.lvl = d; es.ent = d + o_ent; es.prod = d + o_prod;
+                es.perm = (const uint16_t*)(d + o_perm);
+                es.load = (const unsigned*)(d + o_load);
+                h->esched_c = es;
+                h->entc_smem_bytes = (size_t)es.n_slots * h->ent_tile * sizeof(double);
+                h->lin_entc = true;
+            }
+        }
+        if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; h->lin_ent = false; h->lin_entc = false; }
+        apply_carveout(h);
         // ---- cooperative window kernel: needs the entry schedule with 2-member tiles in shared
         // memory and a grid that is co-resident
         if (h->lin_ent) {
@@ -914,6 +997,7 @@ void rbs_destroy(rbs_handle* h) {
     if (h->d_blob) cudaFree(h->d_blob);
     if (h->d_blob2) cudaFree(h->d_blob2);
     if (h->d_ent_blob) cudaFree(h->d_ent_blob);
+    if (h->d_entc_blob) cudaFree(h->d_entc_blob);
     if (h->d_coop_counters) cudaFree(h->d_coop_counters);
     if (h->h_coop_counters) cudaFreeHost(h->h_coop_counters);
     if (h->d_alist) cudaFree(h->d_alist);
@@ -1095,6 +1179,8 @@ int rbs_set_stepper(rbs_handle* h, int32_t full_newton, int32_t predictor, int32
     if (max_halvings < 0 || max_halvings > 60 || grow_iters < 0 || shrink_log2 < 1 || shrink_log2 > 8)
         return fail("rbs_set_stepper: invalid option");
     h->full_newton = full_newton != 0; h->predictor = predictor != 0;
+    cudaSetDevice(h->device);
+    apply_carveout(h);
     h->max_halvings = max_halvings; h->grow_iters = grow_iters;
     h->early_exit = early_exit != 0; h->shrink_log2 = shrink_log2;
     return 0;
@@ -1283,10 +1369,15 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
                sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
         int et = h->ent_tile, blocks = (n.NA + et - 1) / et, nt = RBS_ENT_LANES * et / 2;
         int wl = h->full_newton ? 0 : 1;
+        // every iteration of the full-Newton path refactors and nobody reads the factors later:
+        // the compact slots serve it (more tiles per SM); the frozen path keeps all factors
+        const bool cmp = h->lin_entc && h->full_newton;
+        const EntSched& es = cmp ? h->esched_c : h->esched;
+        const size_t sb = cmp ? h->entc_smem_bytes : h->ent_smem_bytes;
         prof_begin(h, "k_newton_linear_ent");
-        if (et == 2) k_newton_linear_ent<2><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, wl, c);
-        else if (et == 4) k_newton_linear_ent<4><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, wl, c);
-        else k_newton_linear_ent<8><<<blocks, nt, h->ent_smem_bytes, h->cur>>>(n, h->esched, wl, c);
+        if (et == 2) k_newton_linear_ent<2><<<blocks, nt, sb, h->cur>>>(n, es, wl, c);
+        else if (et == 4) k_newton_linear_ent<4><<<blocks, nt, sb, h->cur>>>(n, es, wl, c);
+        else k_newton_linear_ent<8><<<blocks, nt, sb, h->cur>>>(n, es, wl, c);
         prof_end(h);
         h->launches++;
     } else if (h->lin_smem) {
@@ -1429,7 +1520,7 @@ static int advance_coop(rbs_handle* h, double dt, double h_min, int32_t n_steps)
     a.max_passes = std::min<long long>(h->max_passes, 4000) * (long long)n_steps;  // safety net
     a.counters = h->d_coop_counters;
     CUDA_TRY(cudaMemsetAsync(h->d_coop_counters, 0, 4 * sizeof(int), h->stream));
-    EntSched es = h->esched;
+    EntSched es = h->lin_entc ? h->esched_c : h->esched;
     es.smem_sched = 0;
     size_t sb2 = (size_t)es.n_slots * 2 * sizeof(double);
     // no more blocks than there is work in the widest phase
@@ -1470,12 +1561,13 @@ static int advance_tile(rbs_handle* h, double dt, double h_min, int32_t n_steps)
     a.max_passes = std::min<long long>(h->max_passes, 4000) * (long long)n_steps;  // safety net
     a.counters = h->d_coop_counters;
     CUDA_TRY(cudaMemsetAsync(h->d_coop_counters, 0, 4 * sizeof(int), h->stream));
-    EntSched es = h->esched;
+    EntSched es = h->lin_entc ? h->esched_c : h->esched;
     es.smem_sched = 0;
     const int tw = h->tile_window, blocks = (n.B + tw - 1) / tw, threads = RBS_ENT_LANES * tw / 2;
+    const size_t sbt = std::max<size_t>((size_t)es.n_slots, (size_t)h->n_part * RBS_DZ_ROWS) * tw * sizeof(double);
     prof_begin(h, "k_window_tile");
-    if (tw == 2) k_window_tile<2><<<blocks, threads, h->tile_smem, h->stream>>>(n, es, a);
-    else k_window_tile<4><<<blocks, threads, h->tile_smem, h->stream>>>(n, es, a);
+    if (tw == 2) k_window_tile<2><<<blocks, threads, sbt, h->stream>>>(n, es, a);
+    else k_window_tile<4><<<blocks, threads, sbt, h->stream>>>(n, es, a);
     prof_end(h);
     CUDA_TRY(cudaGetLastError());
     h->launches++;

@@ -1174,6 +1174,7 @@ k_newton_linear_smem(Net n, LduSched sc, const IT* __restrict__ blob, int write_
 // Members that reuse stored factors (`fac` bit clear) only update the right-hand-side column.
 #define RBS_ENT_RCP 0x100
 #define RBS_ENT_SCALE 0x200
+#define RBS_ENT_FRESH 0x400
 #define RBS_ENT_LANES 256
 // The schedule as the device reads it: one 64-bit word per level, entry and product, so that a
 // lane fetches its work with one load each (the level loop is bound by instruction count and
@@ -1187,6 +1188,12 @@ struct EntSched {
     int n_words;              // 64-bit words of lvl + ent + prod
     int smem_sched;           // copy the schedule into shared memory (after the slots)
     int n_elim, n_bwd, n_slots, y0;
+    // compact form (symbolic.py `_compact_slots`): fill-ins take over the slots of dead entries, so
+    // the tile needs peak-live instead of all slots.  `load[k]` = LU entry | slot << 16 of the
+    // entries that start from the assembled values; a FRESH entry ignores what its slot held.
+    // The factors are gone afterwards: full-Newton path only.  n_load = 0: LU entry e in slot e.
+    const unsigned* load;
+    int n_load;
 };
 
 __device__ __forceinline__ void rbs_cp_async8(void* smem_dst, const void* gmem_src) {
@@ -1248,7 +1255,8 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, in
                 }
                 if (valid && t == 0) {
                     double2* T = (double2*)(const_cast<double*>(Sc) + e * TILE);
-                    const double2 o = *T;
+                    double2 o = *T;
+                    if (cf & RBS_ENT_FRESH) { o.x = 0.0; o.y = 0.0; }
                     double2 v = o;
                     if (cf & RBS_ENT_SCALE) {
                         // the reciprocal pivot: p of the first product, or q0 itself without products
@@ -1309,7 +1317,14 @@ __device__ __forceinline__ void rbs_lin_tile(const Net& n, EntSched es, double* 
     const long long B = n.B;
     if (m >= 0) {
         const double* lug = n.lu + m;
-        for (int e = slot; e < n.n_lu; e += n_slot) rbs_cp_async8(S + e * TILE + j, lug + (long long)e * B);
+        if (es.n_load == 0) {
+            for (int e = slot; e < n.n_lu; e += n_slot) rbs_cp_async8(S + e * TILE + j, lug + (long long)e * B);
+        } else {
+            for (int k = slot; k < es.n_load; k += n_slot) {
+                const unsigned w = es.load[k];
+                rbs_cp_async8(S + (w >> 16) * TILE + j, lug + (long long)(w & 0xFFFFu) * B);
+            }
+        }
         const double* br = n.br + m;
         for (int i = slot; i < n.n_reduced; i += n_slot)
             rbs_cp_async8(S + (es.y0 + i) * TILE + j, br + (long long)(int)perm[i] * B);
@@ -1328,7 +1343,7 @@ __device__ __forceinline__ void rbs_lin_tile(const Net& n, EntSched es, double* 
     if (m >= 0) {
         for (int i = slot; i < n.n_reduced; i += n_slot)
             x[(long long)(int)perm[i] * B + m] = S[(es.y0 + i) * TILE + j];
-        if (write_lu && fac_s[j])
+        if (write_lu && fac_s[j] && es.n_load == 0)
             for (int e = slot; e < n.n_lu; e += n_slot) n.lu[(long long)e * B + m] = S[e * TILE + j];
     }
     LIN_CLK(7);

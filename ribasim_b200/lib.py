@@ -259,6 +259,22 @@ class Handle:
                 set_i("ent_n_elim", [ent.n_elim])
                 set_i("ent_n_bwd", [ent.n_bwd])
                 set_i("ent_tile", [int(os.environ.get("RBS_ENT_TILE", "0"))])
+                # the same schedule on compacted slots (fill-ins take over dead slots) for the
+                # full-Newton path: fewer slots per tile, more tiles per SM
+                entc = build_entries(sym, compact=True)
+                if entc is not None and entc.n_slots < ent.n_slots:
+                    set_i("entc_e", entc.ent_e)
+                    set_i("entc_q0", entc.ent_q0)
+                    set_i("entc_cf", entc.ent_cf)
+                    set_i("entc_prod_l", entc.prod_l)
+                    set_i("entc_prod_p", entc.prod_p)
+                    set_i("entc_prod_u", entc.prod_u)
+                    set_i("entc_lvl_ptr", entc.lvl_ptr)
+                    set_i("entc_team_log", entc.team_log)
+                    set_i("entc_load_e", entc.load_e)
+                    set_i("entc_load_s", entc.load_s)
+                    set_i("entc_n_slots", [entc.n_slots])
+                    set_i("entc_y0", [entc.y0])
             set_i("lu_mode", [lu_mode])
             set_i("lu_tile", [lu_tile])
             set_i("smem_tile", [smem_tile])

@@ -392,6 +392,7 @@ def numeric_solve_ldu(sym: Symbolic, lu: np.ndarray, b: np.ndarray) -> np.ndarra
 #   backward level      : x_i = y_i r_i - sum_j (slot(i,j) r_i) x_j
 ENT_RCP = 1 << 8
 ENT_SCALE = 1 << 9
+ENT_FRESH = 1 << 10  # first write of a fill-in that took over a dead slot: the old content is not read
 ENT_LANES = 256  # entry lanes per block (1024 threads, four per entry: two members each)
 
 
@@ -409,15 +410,72 @@ class EntrySched:
     n_bwd: int
     n_slots: int
     y0: int
+    # compact form (slots of dead entries taken over by later fill-ins): the original entries of W
+    # to load, `load_e[k]` = LU entry, `load_s[k]` = its slot; None = every LU entry e in slot e
+    load_e: np.ndarray | None = None
+    load_s: np.ndarray | None = None
 
     def smem_bytes(self, tile: int = 8) -> int:
         idx = 2 * (self.ent_e.size * 3 + self.prod_l.size * 3 + self.lvl_ptr.size + self.team_log.size)
         return self.n_slots * tile * 8 + idx + 64
 
 
-def build_entries(sym: Symbolic) -> EntrySched | None:
+def _compact_slots(sym: Symbolic, all_levels: list[list], n_ids: int):
+    """Slot assignment by liveness: an LU entry's slot is free again after the last level that
+    reads or writes it (the multipliers of a column die with their elimination round), and a
+    fill-in is only born in the level of its first update.  Every level ends with a block barrier,
+    so a fill-in may take over any slot whose last use lies in an earlier level.  Greedy in birth
+    order is optimal for intervals: the slot count is the peak number of live entries.
+    Returns (slot of every id, number of LU slots, ids whose first write is FRESH)."""
+    n, n_lu = sym.n, sym.n_lu
+    first_w = np.full(n_ids, 1 << 30, dtype=np.int64)
+    last_use = np.full(n_ids, -1, dtype=np.int64)
+    for lv, lvl in enumerate(all_levels):
+        for (e, prods, flags, r) in lvl:
+            first_w[e] = min(first_w[e], lv)
+            last_use[e] = max(last_use[e], lv)
+            for trip in prods:
+                for s_ in trip:
+                    last_use[s_] = max(last_use[s_], lv)
+            if flags & ENT_SCALE:
+                rr = prods[0][1] if prods else r
+                last_use[rr] = max(last_use[rr], lv)
+    # loaded from the assembled values: the entries of W, and fill-ins of the symbolic pattern
+    # that no product ever updates (they stay zero and may still be read)
+    orig = (np.asarray(sym.ldu_wsrc)[:n_lu] >= 0) | (first_w[:n_lu] >= (1 << 30))
+    slot_of = np.full(n_ids, -1, dtype=np.int64)
+    nxt = 0
+    pool: list[tuple[int, int]] = []  # (last use, slot) of the ids placed so far
+    for e in range(n_lu):
+        if orig[e]:
+            slot_of[e] = nxt
+            pool.append((int(last_use[e]), nxt))
+            nxt += 1
+    import heapq
+
+    heapq.heapify(pool)
+    fresh = set()
+    fills = [e for e in range(n_lu) if not orig[e]]
+    for e in sorted(fills, key=lambda e: (first_w[e], e)):
+        b = int(first_w[e])
+        if pool and pool[0][0] < b:
+            _, sl = heapq.heappop(pool)
+        else:
+            sl = nxt
+            nxt += 1
+        slot_of[e] = sl
+        fresh.add(e)
+        heapq.heappush(pool, (int(last_use[e]), sl))
+    for i in range(n):
+        slot_of[n_lu + i] = nxt + i
+    return slot_of, nxt, fresh, [e for e in range(n_lu) if orig[e]]
+
+
+def build_entries(sym: Symbolic, compact: bool = False) -> EntrySched | None:
     """Entry schedule of the LDU elimination (+ fused forward substitution) and the backward
-    substitution.  None when an index does not fit 16 bits."""
+    substitution.  None when an index does not fit 16 bits.  `compact`: fill-ins take over the
+    slots of dead entries (`_compact_slots`); the factors are then not available afterwards, so
+    this form serves the full-Newton path only (every iteration refactors)."""
     n, n_lu = sym.n, sym.n_lu
     y0 = n_lu
     n_slots = n_lu + n
@@ -453,6 +511,25 @@ def build_entries(sym: Symbolic) -> EntrySched | None:
             r_i = int(diag[i])
             prods = [(int(sym.ldu_bwd_u[q]), r_i, y0 + int(sym.ldu_bwd_k[q])) for q in range(q0, q1)]
             blevels[lv].append((y0 + i, prods, ENT_SCALE, r_i))
+    load_e = load_s = None
+    if compact:
+        slot_of, y0, fresh, loaded = _compact_slots(sym, levels + blevels, n_lu + n)
+        n_slots = y0 + n
+        seen: set[int] = set()
+
+        def remap(lvl):
+            out = []
+            for (e, prods, flags, r) in lvl:
+                if e in fresh and e not in seen:
+                    seen.add(e)
+                    flags |= ENT_FRESH
+                out.append((int(slot_of[e]), [tuple(int(slot_of[x]) for x in t) for t in prods], flags,
+                            int(slot_of[r]) if flags & ENT_SCALE else r))
+            return out
+
+        levels = [remap(l) for l in levels]
+        blevels = [remap(l) for l in blevels]
+        load_e, load_s = as_i32(loaded), as_i32([slot_of[e] for e in loaded])
     ent_e, ent_q0, ent_cf, pl, pp, pu, lvl_ptr, team = [], [], [], [], [], [], [0], []
     def assign(lvl, tl):
         """Lane k of the block takes entries k, k + L, k + 2L, ... of the level (L lanes, or teams
@@ -497,14 +574,19 @@ def build_entries(sym: Symbolic) -> EntrySched | None:
     return EntrySched(ent_e=as_i32(ent_e), ent_q0=as_i32(ent_q0), ent_cf=as_i32(ent_cf),
                       prod_l=as_i32(pl), prod_p=as_i32(pp), prod_u=as_i32(pu),
                       lvl_ptr=as_i32(lvl_ptr), team_log=as_i32(team), n_elim=n_elim, n_bwd=n_bwd,
-                      n_slots=n_slots, y0=y0)
+                      n_slots=n_slots, y0=y0, load_e=load_e, load_s=load_s)
 
 
 def numeric_entries(sym: Symbolic, E: EntrySched, wvals: np.ndarray, b: np.ndarray) -> np.ndarray:
     """NumPy emulation of `rbs_ent_levels` for one member (same summation order)."""
     S = np.zeros(E.n_slots)
-    for e in range(sym.n_lu):
-        S[e] = wvals[sym.ldu_wsrc[e]] if sym.ldu_wsrc[e] >= 0 else 0.0
+    if E.load_e is None:
+        for e in range(sym.n_lu):
+            S[e] = wvals[sym.ldu_wsrc[e]] if sym.ldu_wsrc[e] >= 0 else 0.0
+    else:
+        S[:] = np.nan  # what a slot held before is never read
+        for e, sl in zip(E.load_e, E.load_s):
+            S[sl] = wvals[sym.ldu_wsrc[e]] if sym.ldu_wsrc[e] >= 0 else 0.0
     S[E.y0:E.y0 + sym.n] = b[sym.perm]
     for lv in range(E.n_elim + E.n_bwd):
         ts = 1 << int(E.team_log[lv])
@@ -522,7 +604,7 @@ def numeric_entries(sym: Symbolic, E: EntrySched, wvals: np.ndarray, b: np.ndarr
             while step < ts:  # butterfly: lane t adds lane t ^ step
                 part = [part[t] + part[t ^ step] for t in range(ts)]
                 step <<= 1
-            old = S[e]
+            old = 0.0 if cf & ENT_FRESH else S[e]
             if cf & ENT_SCALE:
                 old = old * S[E.prod_p[q0] if cnt else q0]
             v = old - part[0]

@@ -735,6 +735,36 @@ def test_tile_window_kernel_equals_stream_path(name, tile):
     assert l_tile <= 4 < l_stream  # k_step_begin + the tile kernel per call
 
 
+@pytest.mark.parametrize("name", ["basic", "backwater", "pid_control", "pump_discrete_control", "hws_like"])
+def test_compact_solve_slots_equal_plain(name, monkeypatch):
+    """The full-Newton path solves on compacted shared-memory slots (fill-ins take over the slots
+    of dead multipliers, symbolic._compact_slots): the same arithmetic in other places, so the
+    trajectories are bitwise those of the plain slot layout (`RBS_ENT_COMPACT=0`)."""
+    from ribasim_b200.testmodels import hws_like_model
+    B = 21
+    case = make_case(hws_like_model(n_basins=120, n_days=2) if name == "hws_like" else name, B, seed=37, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    for compact in ("0", "1"):
+        monkeypatch.setenv("RBS_ENT_COMPACT", compact)
+        h = gpu_handle_for(case, coop_members=0)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if flat["n_dc"] > 0:
+                h.apply_discrete_control()
+                h.refresh(0.0)
+            st = h.advance(0.0, 3600.0, 6)
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats()))
+        finally:
+            h.close()
+    (u0, S0, st0, s0), (u1, S1, st1, s1) = out
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert s0[k] == s1[k], k
+
+
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""

@@ -206,17 +206,25 @@ def test_symbolic_lu_solves(name, kw):
     assert ent.lvl_ptr[-1] == ent.ent_e.size and len(ent.team_log) == ent.n_elim + ent.n_bwd
     # race freedom of a level on the device: a slot is written by one entry only and no entry
     # reads a slot that the level writes (levels are separated by block barriers)
-    for lv in range(ent.n_elim + ent.n_bwd):
-        written, read = [], set()
-        for k in range(ent.lvl_ptr[lv], ent.lvl_ptr[lv + 1]):
-            written.append(int(ent.ent_e[k]))
-            cnt, q0 = int(ent.ent_cf[k]) & 0xFF, int(ent.ent_q0[k])
-            for q in range(q0, q0 + cnt):
-                read.update((int(ent.prod_l[q]), int(ent.prod_p[q]), int(ent.prod_u[q])))
-            if int(ent.ent_cf[k]) & 0x200 and cnt == 0:
-                read.add(q0)  # the reciprocal pivot of a row without U entries
-        assert len(written) == len(set(written)), lv
-        assert not (read & set(written)), lv
+    # the compact form (fill-ins take over the slots of dead entries, full-Newton path): fewer
+    # slots, the same bits — the emulation starts from NaN in every slot that is not loaded, so a
+    # read of stale content would show
+    entc = build_entries(sym, compact=True)
+    assert entc.n_slots <= ent.n_slots and entc.y0 + nr == entc.n_slots
+    assert np.array_equal(numeric_entries(sym, entc, wv, b), xe)
+    assert len(set(entc.load_s.tolist())) == entc.load_s.size
+    for ent in (ent, entc):
+        for lv in range(ent.n_elim + ent.n_bwd):
+            written, read = [], set()
+            for k in range(ent.lvl_ptr[lv], ent.lvl_ptr[lv + 1]):
+                written.append(int(ent.ent_e[k]))
+                cnt, q0 = int(ent.ent_cf[k]) & 0xFF, int(ent.ent_q0[k])
+                for q in range(q0, q0 + cnt):
+                    read.update((int(ent.prod_l[q]), int(ent.prod_p[q]), int(ent.prod_u[q])))
+                if int(ent.ent_cf[k]) & 0x200 and cnt == 0:
+                    read.add(q0)  # the reciprocal pivot of a row without U entries
+            assert len(written) == len(set(written)), lv
+            assert not (read & set(written)), lv
 
 
 def test_symbolic_lu_chain_is_logarithmic():
