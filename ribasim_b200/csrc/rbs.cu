@@ -856,7 +856,8 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             }
             es.n_words = (int)o_perm;
             es.smem_sched = getenv("RBS_ENT_SMEM_SCHED") ? atoi(getenv("RBS_ENT_SMEM_SCHED")) : 0;
-            size_t sb = (size_t)es.n_slots * et * sizeof(double) + (es.smem_sched ? (size_t)es.n_words * 8 : 0);
+            size_t sb = (size_t)es.n_slots * et * sizeof(double) +
+                        (es.smem_sched == 2 ? o_prod * 8 : es.smem_sched ? (size_t)es.n_words * 8 : 0);
             if (ok && sb + 256 <= (size_t)dev_smem) {
                 if (cudaMalloc(&h->d_ent_blob, hb.size() * 8) != cudaSuccess) return bail("schedule alloc");
                 cudaMemcpyAsync(h->d_ent_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream);
@@ -913,7 +914,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                     hb.push_back(w);
                 }
                 es.n_words = (int)o_perm;
-                es.smem_sched = 0;
+                es.smem_sched = getenv("RBS_ENT_SMEM_SCHED") ? atoi(getenv("RBS_ENT_SMEM_SCHED")) : 0;
                 es.n_load = (int)le.size();
                 if (cudaMalloc(&h->d_entc_blob, hb.size() * 8) != cudaSuccess) return bail("schedule alloc");
                 cudaMemcpyAsync(h->d_entc_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream);
@@ -923,7 +924,16 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 es.perm = (const uint16_t*)(d + o_perm);
                 es.load = (const unsigned*)(d + o_load);
                 h->esched_c = es;
-                h->entc_smem_bytes = (size_t)es.n_slots * h->ent_tile * sizeof(double);
+                h->entc_smem_bytes = (size_t)es.n_slots * h->ent_tile * sizeof(double) +
+                                     (es.smem_sched == 2 ? o_prod * 8 : es.smem_sched ? (size_t)es.n_words * 8 : 0);
+                if (h->entc_smem_bytes > h->ent_smem_bytes) {
+                    // the opt-in size of the kernel was set for the plain form
+                    cudaError_t e5 = h->ent_tile == 2 ? cudaFuncSetAttribute(k_newton_linear_ent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->entc_smem_bytes)
+                        : h->ent_tile == 4 ? cudaFuncSetAttribute(k_newton_linear_ent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->entc_smem_bytes)
+                                           : cudaFuncSetAttribute(k_newton_linear_ent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->entc_smem_bytes);
+                    if (e5 != cudaSuccess) { cudaGetLastError(); es.smem_sched = 0; h->esched_c = es;
+                        h->entc_smem_bytes = (size_t)es.n_slots * h->ent_tile * sizeof(double); }
+                }
                 h->lin_entc = true;
             }
         }

@@ -1303,10 +1303,13 @@ __device__ __forceinline__ void rbs_lin_tile(const Net& n, EntSched es, double* 
         fac_s[jj] = mm >= 0 && n.mjac[mm] != 0;
     }
     if (es.smem_sched) {
+        // 1: the whole schedule behind the slots; 2: level and entry words only (a lane's entry
+        // word heads its dependent chain in every level; the product words stay behind L1)
         unsigned long long* sw = (unsigned long long*)(S + (size_t)es.n_slots * TILE);
-        for (int w = threadIdx.x; w < es.n_words; w += NT) sw[w] = es.lvl[w];
+        const int n_copy = es.smem_sched == 2 ? (int)(es.prod - es.lvl) : es.n_words;
+        for (int w = threadIdx.x; w < n_copy; w += NT) sw[w] = es.lvl[w];
         es.ent = sw + (es.ent - es.lvl);
-        es.prod = sw + (es.prod - es.lvl);
+        if (es.smem_sched != 2) es.prod = sw + (es.prod - es.lvl);
         es.lvl = sw;
     }
     __syncthreads();
