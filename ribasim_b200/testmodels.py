@@ -12,6 +12,13 @@ the core reads; geometry, subgrid and concentration tables are not needed on the
     outlet_continuous_control  continuous_control.py:18-86
     user_demand                allocation.py:30-95
     pump_discrete_control      discrete_control.py:23-126
+    flow_condition, level_boundary_condition, tabulated_rating_curve_control,
+    compound_variable_condition, storage_condition, connector_node_flow_condition,
+    transient_condition        discrete_control.py:128-798
+    discrete_control_of_pid_control  pid_control.py:66-152
+    outlet, flow_boundary_interpolation  basic.py:364-407, 590-627
+    flow_boundary_time, transient_pump_outlet  time.py:12-96
+    two_basin                  two_basin.py:10-79
 
 The synthetic generators implement the configurations fixed in SURVEY.md §8(d).
 """
@@ -534,6 +541,22 @@ def flow_boundary_interpolation_model() -> ModelTables:
     return m
 
 
+def transient_pump_outlet_model() -> ModelTables:
+    """Pump and Outlet with time-dependent flow rates
+    (python/ribasim_testmodels/ribasim_testmodels/time.py:59-96)."""
+    m = _model()
+    time = ["2020-01-01 00:00:00", "2020-07-01 00:00:00", "2021-01-01 00:00:00"]
+    flow_rate = [0.0, 1e-5, 1e-5]
+    m.add_node("LevelBoundary", 1, static=dict(level=1.1))
+    m.add_node("Outlet", 2, time=dict(time=time, flow_rate=flow_rate))
+    m.add_node("Basin", 3, state=dict(level=1.0), profile=dict(level=[0.0, 2.0], area=[100.0, 100.0]))
+    m.add_node("Pump", 4, time=dict(time=time, flow_rate=flow_rate))
+    m.add_node("Terminal", 5)
+    for a, b in [(1, 2), (2, 3), (1, 4), (4, 5)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -846,4 +869,5 @@ MODELS = dict(
     transient_condition=transient_condition_model,
     outlet=outlet_model,
     flow_boundary_interpolation=flow_boundary_interpolation_model,
+    transient_pump_outlet=transient_pump_outlet_model,
 )

@@ -228,3 +228,59 @@ def test_outlet_continuous_control_flow_split():
             assert np.linalg.norm(diff) <= 1e-3 * np.linalg.norm(np.maximum(frac * inflow, 0.0)) + 1e-12 * scale
     finally:
         model.finalize()
+
+
+def test_time_dependent_flow_boundary():
+    """core/test/time_test.jl:1-23: the daily mean flows out of the time-varying FlowBoundary
+    follow 1 + sin^2 between March and October (rtol 0.005 on the vector)."""
+    from datetime import timedelta
+
+    model = _model("flow_boundary_time", dt=24 * 24 * 60.0, n_members=1)
+    try:
+        res = model.run(saveat=86400.0)
+        fd = res.flow_data()
+        start = model.tables.starttime
+        summer = np.array([3 <= (start + timedelta(seconds=float(t))).month < 10 for t in fd["time"]])
+        q = fd["flow_rate"][:, (fd["from_node_id"] == 1) & (fd["to_node_id"] == 2), 0].ravel()[summer]
+        t = fd["time"][summer]
+        expected = 1 + np.sin(0.5 * np.pi * (t - t[0]) / (t[-1] - t[0])) ** 2
+        assert np.linalg.norm(q - expected) <= 0.005 * np.linalg.norm(expected)
+    finally:
+        model.finalize()
+
+
+def test_vertical_flux_means():
+    """core/test/time_test.jl:25-48 (basic_transient): mean evaporation ~ area(level) x potential
+    evaporation (atol 1e-5: the area is that of the period's start), mean precipitation = fixed
+    area x precipitation."""
+    model = _model("basic_transient", n_members=1)
+    try:
+        res = model.run(saveat=86400.0)
+        bd = res.basin_data()
+        basin = model.p.basin
+        om_area = None
+        for i in range(len(basin.node_id)):
+            level = bd["level"][:, i, 0]
+            area = np.interp(level, basin.levels[i], basin.areas[i])
+            pot_evap = np.array([basin.forcing["potential_evaporation"][i](float(t)) for t in bd["time"]])
+            assert np.allclose(bd["evaporation"][:, i, 0], area * pot_evap, rtol=0, atol=1e-5)
+            prec = np.array([basin.forcing["precipitation"][i](float(t)) for t in bd["time"]])
+            assert np.allclose(bd["precipitation"][:, i, 0], basin.areas[i][-1] * prec, rtol=1e-8, atol=1e-18)
+    finally:
+        model.finalize()
+
+
+def test_transient_pump_outlet():
+    """core/test/time_test.jl:125-143: the Outlet fills the Basin up to the boundary level; the
+    Pump's time-dependent flow rate is what flows over its inflow link in the second half year."""
+    model = _model("transient_pump_outlet", n_members=1)
+    try:
+        S0 = model.storage()[0, 0]
+        res = model.run(saveat=86400.0)
+        assert S0 == pytest.approx(100.0, rel=1e-6)
+        assert model.storage()[0, 0] == pytest.approx(110.0, rel=3.4e-4)  # `≈ 110.0f0`
+        fd = res.flow_data()
+        flow_4 = fd["flow_rate"][:, fd["link_id"] == 4, 0].ravel()
+        assert np.allclose(flow_4[229:], 1e-5, rtol=1e-6, atol=0)
+    finally:
+        model.finalize()
