@@ -557,6 +557,26 @@ def transient_pump_outlet_model() -> ModelTables:
     return m
 
 
+def cyclic_time_model() -> ModelTables:
+    """Cyclic forcing, LevelBoundary and FlowBoundary series over a century
+    (python/ribasim_testmodels/ribasim_testmodels/basic.py:410-470)."""
+    m = _model(end=datetime(2121, 1, 1), solver=dict(saveat=7 * 24 * 60 * 60.0),
+               interpolation=dict(flow_boundary="linear"))
+    m.add_node("Basin", 1, cyclic_time=True, profile=dict(level=[0.0, 1.0], area=[100.0, 100.0]),
+               time=dict(time=["2020-01-01 00:00:00", "2020-04-01 00:00:00", "2020-07-01 00:00:00",
+                               "2020-10-01 00:00:00", "2021-01-01 00:00:00"],
+                         precipitation=[10.0, 20.0, 10.0, 20.0, 10.0]),
+               state=dict(level=5.0))
+    m.add_node("LinearResistance", 2, static=dict(resistance=1.0))
+    m.add_node("LevelBoundary", 3, cyclic_time=True, time=dict(
+        time=["2020-01-01 00:00:00", "2020-05-01 00:00:00", "2020-10-01 00:00:00"], level=[2.0, 3.0, 2.0]))
+    m.add_node("FlowBoundary", 4, cyclic_time=True, time=dict(
+        time=["2020-01-01 00:00:00", "2020-07-01 00:00:00", "2020-08-01 00:00:00"], flow_rate=[10.0, 20.0, 10.0]))
+    for a, b in [(1, 2), (2, 3), (4, 1)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""

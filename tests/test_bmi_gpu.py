@@ -127,3 +127,4 @@ def test_stroboscopic_forcing(tmp_path):
         assert np.all(d_inf[1::2] == 0.0)
     finally:
         b.finalize()
+

@@ -312,3 +312,25 @@ def test_junction_elimination_link_counts():
     lr = p.nodes["linear_resistance"]
     assert [l.link[0].value for l in lr["inflow_link"]] == [1, 1]
     assert [l.link[1].value for l in lr["outflow_link"]] == [6, 7]
+
+
+def test_cyclic_tstops_goldens():
+    # core/test/time_test.jl:75-88 (`get_timeseries_tstops`)
+    from ribasim_b200.interp import TimeSeries
+    assert TimeSeries([0, 0, 0], [0.5, 1.0, 1.5], kind="linear").tstops(5.0) == [0.5, 1.0, 1.5]
+    assert np.array_equal(TimeSeries([0, 0, 0], [0.5, 1.0, 1.5], kind="linear", periodic=True).tstops(5.0),
+                          np.arange(0, 5.01, 0.5))
+    assert np.allclose(TimeSeries([0, 0], [0.3, 0.5], kind="constant", periodic=True).tstops(1.0),
+                       np.arange(0.1, 0.91, 0.2), rtol=1e-12)
+
+
+def test_cyclic_time_model():
+    # core/test/time_test.jl:90-112: periodic extrapolation of the cyclic series; the precipitation
+    # series contributes 404 tstops over the 101 years of the run
+    from ribasim_b200.testmodels import cyclic_time_model
+    p = build_params(cyclic_time_model())
+    precip = p.basin.forcing["precipitation"][0]
+    assert precip.periodic and p.nodes["level_boundary"]["level"][0].periodic
+    assert p.nodes["flow_boundary"]["flow_rate"][0].periodic
+    assert p.nodes["flow_boundary"]["flow_rate"][0].kind == "linear"
+    assert len(precip.tstops(p.tables.t_end)) == 404
