@@ -200,6 +200,16 @@ class Params:
         return len(self.state_node_id)
 
 
+def _jl(x: float) -> str:
+    """A float as the reference prints it in its messages (shortest digits, exponent form from
+    1e6 and below 1e-4)."""
+    x = float(x)
+    if x != 0.0 and math.isfinite(x) and (abs(x) >= 1e6 or abs(x) < 1e-4):
+        mant, exp = np.format_float_scientific(x, trim="0").split("e")
+        return f"{mant}e{int(exp)}"
+    return repr(x)
+
+
 def _endpoint(nid: NodeID | None) -> tuple[int, int]:
     if nid is None:
         return KIND_NONE, 0
@@ -411,7 +421,10 @@ def build_params(m: ModelTables) -> Params:
             dS = finite_difference(st, lv, float(ar[0]))
         for j in range(len(dS) - 1):
             if dS[j + 1] < 0:
-                raise ValueError(f"Invalid profile for {nid}: decreasing area")
+                raise ValueError(
+                    f"Invalid profile for {nid}. The step from (h={_jl(lv[j])}, S={_jl(st[j])}) to "
+                    f"(h={_jl(lv[j + 1])}, S={_jl(st[j + 1])}) implies a decreasing area compared to "
+                    "lower points in the profile, which is not allowed.")
         # storage_to_level = invert_integral(LinearInterpolation(dS_dh, level))
         inv = LinearTable(dS, lv, left="extension", right="constant")
         if not all(a is None for a in ar):

@@ -101,6 +101,46 @@ def test_profile_roundtrip():
         assert S_back == pytest.approx(S, rel=1e-10, abs=1e-10)
 
 
+def _profiled(profiles: dict[int, dict]) -> ModelTables:
+    """Unconnected Basins with the given profile columns (area and / or storage per level)."""
+    m = ModelTables(starttime=MODELS["bucket"]().starttime, endtime=MODELS["bucket"]().endtime)
+    for node_id, cols in profiles.items():
+        m.add_node("Basin", node_id, profile=cols, state=dict(level=cols["level"][0] + 1e-3))
+    return m
+
+
+def test_basin_profile_initialisation_goldens():
+    # core/test/read_test.jl:93-206 (`interpolate_basin_profile!` with area, storage or both)
+    levels = [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    areas = [(h + 1) * math.pi for h in levels]
+    storages = [math.pi / 2 * ((h + 1) ** 2 - 1) for h in levels]
+    p = build_params(_profiled({1: dict(level=levels, area=areas),
+                                2: dict(level=levels, storage=storages),
+                                3: dict(level=levels, area=areas, storage=storages)}))
+    om = OracleModel(p)
+    s2l = lambda i, S: om.L.orc_storage_to_level(om.h, i, S)  # noqa: E731
+    assert s2l(0, storages[1]) == pytest.approx(s2l(2, storages[1]), rel=1e-8)
+    assert s2l(0, storages[1]) == pytest.approx(s2l(1, storages[1]), rel=1e-8)
+    assert om.L.orc_level_to_area(om.h, 0, levels[0]) == pytest.approx(om.L.orc_level_to_area(om.h, 2, levels[0]))
+    # cylinder: S = 2000 above a 1000 m2 profile given up to 1 m -> level 2 (linear extrapolation)
+    p = build_params(_profiled({1: dict(level=[0.0, 1.0], area=[1000.0, 1000.0])}))
+    om = OracleModel(p)
+    assert om.L.orc_storage_to_level(om.h, 0, 2000.0) == pytest.approx(2.0, rel=1e-8)
+    # linear area
+    p = build_params(_profiled({1: dict(level=[0.0, 1.0], area=[0.001, 1000.0])}))
+    om = OracleModel(p)
+    assert om.L.orc_storage_to_level(om.h, 0, 500.0005 + 1000.0) == pytest.approx(2.0, rel=1e-8)
+
+
+def test_decreasing_area_profile_is_rejected():
+    # core/test/read_test.jl:208-229
+    cols = dict(level=[265.0, 270.0, 275.0, 280.0, 285.0, 287.0],
+                storage=[0.0, 3.551e6, 1.6238e7, 4.5444e7, 1.06217e8, 1.08e8])
+    with pytest.raises(ValueError, match=r"Invalid profile for Basin #1. The step from \(h=285.0, S=1.06217e8\) "
+                                         r"to \(h=287.0, S=1.08e8\) implies a decreasing area"):
+        build_params(_profiled({1: cols}))
+
+
 def test_initial_level_golden():
     # python/ribasim_api/tests/test_bmi.py:102-110 and basic.py:45:
     # storage 1.0 on A=[0.01,1000], h=[0,1] <-> level 0.04471158417652035
