@@ -12,9 +12,11 @@
 //
 // Pinning: reduction_factor, relaxed_root, the profile inverse, the state layout, the
 // incidence matrix A, the Jacobian sparsity pattern and end-of-run storages are checked
-// against the reference's golden values (tests/test_oracle_golden.py).  Per-entry RHS /
-// Jacobian values and PCHIP slopes are NOT pinned by any reference test ("parity unpinned"
-// for those).
+// against the reference's golden values (tests/test_oracle_golden.py), as are the reference's
+// own model tests (equations, control records, run_models, time) and the five PCHIP values it
+// pins (validation_test.jl:7-15).  Per-entry RHS / Jacobian values and the interior PCHIP slopes
+// of longer tables are NOT pinned by any reference test ("parity unpinned" for those; see
+// DESIGN.md).
 //
 // Build: oracle/Makefile -> oracle/librbs_oracle.so   (compiled with -ffp-contract=off so
 // that no FMA contraction changes the reference's operation order).

@@ -141,6 +141,31 @@ def test_decreasing_area_profile_is_rejected():
         build_params(_profiled({1: cols}))
 
 
+def test_qh_interpolation_goldens():
+    # core/test/validation_test.jl:1-44: the only values of the reference's PCHIP rating curve that
+    # its tests pin (constant below the first level, cubic in between, linear above the last)
+    from ribasim_b200.network import NodeID, qh_interpolation
+    itp = qh_interpolation(NodeID("TabulatedRatingCurve", 1, 1), [1.0, 2.0], [0.0, 0.1])
+    expect = {0.0: 0.0, 1.0: 0.0, 1.5: 0.03125, 2.0: 0.1, 3.0: 0.25}
+    for x, q in expect.items():
+        assert itp(x) == pytest.approx(q, rel=1e-12, abs=1e-300)
+    # the same table through the oracle's evaluator (what the device is compared with)
+    m = MODELS["rating_curve"]()
+    for r, (h, q) in zip(m.tables["TabulatedRatingCurve / static"][:2], ((1.0, 0.0), (2.0, 0.1))):
+        r["level"], r["flow_rate"] = h, q
+    m.tables["TabulatedRatingCurve / static"] = m.tables["TabulatedRatingCurve / static"][:2]
+    om = OracleModel(build_params(m))
+    for x, q in expect.items():
+        assert om.L.orc_pchip_eval(om.h, 0, x) == pytest.approx(q, rel=1e-12, abs=1e-300)
+    # validation.jl (`valid_tabulated_curve_level` and friends): the reference's messages
+    for lv, fl, msg in (([1.0, 2.0], [0.1, 0.2], "The `flow_rate` must start at 0."),
+                        ([1.0, 1.0], [0.0, 0.1], "The `level` cannot be repeated."),
+                        ([1.0, 2.0, 3.0], [0.0, 0.2, 0.1],
+                         "The `flow_rate` cannot decrease with increasing `level`.")):
+        with pytest.raises(ValueError, match=msg.replace("`", ".")):
+            qh_interpolation(NodeID("TabulatedRatingCurve", 2, 1), lv, fl)
+
+
 def test_initial_level_golden():
     # python/ribasim_api/tests/test_bmi.py:102-110 and basic.py:45:
     # storage 1.0 on A=[0.01,1000], h=[0,1] <-> level 0.04471158417652035
