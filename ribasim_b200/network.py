@@ -250,7 +250,8 @@ def create_graph(m: ModelTables) -> tuple[Graph, list[NodeID], list[LinkMeta], l
     for r in m.link:
         lt = r["link_type"]
         if lt not in ("flow", "control", "listen", "observation", "none"):
-            raise ValueError(f"Invalid link type {lt}.")
+            raise ValueError(f"Invalid link type '{lt}' for link #{r['link_id']} from node "
+                             f"#{r['from_node_id']} to node #{r['to_node_id']}.")
         if r["from_node_id"] not in by_value or r["to_node_id"] not in by_value:
             raise ValueError(f"Link {r['link_id']} refers to a node that is not in the Node table")
         src, dst = by_value[r["from_node_id"]], by_value[r["to_node_id"]]
@@ -371,8 +372,53 @@ def _control_states(m: ModelTables, node_type: str, node_ids: list[NodeID],
     return out
 
 
+_M = 1 << 62
+# (in_min, in_max, out_min, out_max) per node type: validation.jl:76-116
+N_NEIGHBOR_BOUNDS_FLOW = {
+    "Basin": (0, _M, 0, _M), "LinearResistance": (1, 1, 1, 1), "ManningResistance": (1, 1, 1, 1),
+    "TabulatedRatingCurve": (1, 1, 1, 1), "LevelBoundary": (0, _M, 0, _M), "FlowBoundary": (0, 0, 1, 1),
+    "Pump": (1, 1, 1, 1), "Outlet": (1, 1, 1, 1), "Terminal": (1, _M, 0, 0), "Junction": (1, _M, 1, _M),
+    "PidControl": (0, 0, 0, 0), "ContinuousControl": (0, 0, 0, 0), "DiscreteControl": (0, 0, 0, 0),
+    "UserDemand": (1, _M, 1, 1), "LevelDemand": (0, 0, 0, 0), "FlowDemand": (0, 0, 0, 0),
+    "Observation": (0, 0, 0, 0),
+}
+N_NEIGHBOR_BOUNDS_CONTROL = {
+    "Basin": (0, 1, 0, 0), "LinearResistance": (0, 1, 0, 0), "ManningResistance": (0, 1, 0, 0),
+    "TabulatedRatingCurve": (0, 1, 0, 0), "LevelBoundary": (0, 0, 0, 0), "FlowBoundary": (0, 0, 0, 0),
+    "Pump": (0, 2, 0, 0), "Outlet": (0, 2, 0, 0), "Terminal": (0, 0, 0, 0), "Junction": (0, 0, 0, 0),
+    "PidControl": (0, 1, 1, 1), "ContinuousControl": (0, 0, 1, _M), "DiscreteControl": (0, 0, 1, _M),
+    "UserDemand": (0, 0, 0, 0), "LevelDemand": (0, 0, 1, _M), "FlowDemand": (0, 0, 1, 1),
+    "Observation": (0, 0, 0, 0),
+}
+
+
+def n_neighbor_errors(g: Graph) -> list[str]:
+    """`valid_n_neighbors` (core/src/validation.jl:544-591): the messages of every violated bound,
+    node by node in vertex order, flow links before control links."""
+    out = []
+    for code in sorted(g.label_of):
+        nid = g.label_of[code]
+        for link_type, bounds in (("flow", N_NEIGHBOR_BOUNDS_FLOW), ("control", N_NEIGHBOR_BOUNDS_CONTROL)):
+            if nid.type not in bounds:
+                raise ValueError(f"'n_neighbor_bounds_{link_type}' not defined for {nid.type}.")
+            in_min, in_max, out_min, out_max = bounds[nid.type]
+            n_in, n_out = len(g.inneighbors(nid, link_type)), len(g.outneighbors(nid, link_type))
+            if n_in < in_min:
+                out.append(f"{nid} must have at least {in_min} {link_type} inneighbor(s) (got {n_in}).")
+            if n_in > in_max:
+                out.append(f"{nid} can have at most {in_max} {link_type} inneighbor(s) (got {n_in}).")
+            if n_out < out_min:
+                out.append(f"{nid} must have at least {out_min} {link_type} outneighbor(s) (got {n_out}).")
+            if n_out > out_max:
+                out.append(f"{nid} can have at most {out_max} {link_type} outneighbor(s) (got {n_out}).")
+    return out
+
+
 def build_params(m: ModelTables) -> Params:
     g, node_ids_all, internal, external = create_graph(m)
+    errs = n_neighbor_errors(g)
+    if errs:
+        raise ValueError("Invalid number of connections for certain node types. " + " ".join(errs))
     by_type: dict[str, list[NodeID]] = {}
     for nid in node_ids_all:
         by_type.setdefault(nid.type, []).append(nid)
@@ -573,6 +619,16 @@ def build_params(m: ModelTables) -> Params:
             if len(lookup_t) == 1:
                 lookup_t, lookup_i = [lookup_t[0], lookup_t[0] + 1.0], [lookup_i[0]] * 2
             current_index.append(IndexLookup(lookup_i, lookup_t, periodic=per))
+    # valid_tabulated_curve_level (validation.jl:474-499): over the whole time series the lowest
+    # level of a curve may not lie below the bottom of the upstream Basin
+    for nid, lookup in zip(trc_ids, current_index):
+        src = g.inflow_ids(nid)[0]
+        if src.type != "Basin":
+            continue
+        for k in lookup.u:
+            h_min = interpolations[int(k) - 1].t[1]
+            if h_min < basin_bottom(src):
+                raise ValueError(f"Lowest level of {nid} is lower than bottom of upstream {src}")
     nodes["tabulated_rating_curve"] = dict(
         node_id=trc_ids,
         inflow_link=[inflow_link(n) for n in trc_ids],
@@ -648,6 +704,18 @@ def build_params(m: ModelTables) -> Params:
                 ["flow_rate", "min_flow_rate", "max_flow_rate", "min_upstream_level",
                  "max_downstream_level"]),
         )
+        # valid_flow_rates (validation.jl:321-372): no negative flow rates, in the control states
+        # or — for nodes without control states — in the static / time values
+        controlled = {k[0] for k in d["control_mapping"]}
+        for (nv, cs), upd in d["control_mapping"].items():
+            if upd.get("flow_rate", 0.0) < 0.0:
+                raise ValueError(f"Negative flow rate(s) found. node_id = {node_type} #{nv} control_state = {cs}")
+        for i, nid in enumerate(p_ids):
+            if nid.value in controlled:
+                continue
+            ts = td_flow_rate[i]
+            if (ts is not None and min(ts.u) < 0.0) or (ts is None and flow_rate[i] < 0.0):
+                raise ValueError(f"Negative flow rate(s) for {nid} found.")
         # valid_min_upstream_level! (validation.jl:453-472): default -Inf -> basin bottom
         for i, nid in enumerate(p_ids):
             src = d["inflow_link"][i].link[0]

@@ -334,3 +334,67 @@ def test_cyclic_time_model():
     assert p.nodes["flow_boundary"]["flow_rate"][0].periodic
     assert p.nodes["flow_boundary"]["flow_rate"][0].kind == "linear"
     assert len(precip.tstops(p.tables.t_end)) == 404
+
+
+def test_validation_messages_of_the_reference():
+    """core/test/validation_test.jl: neighbour counts (:46-99), Pump / Outlet flow rate sign
+    (:196-236), link types (:238-262), TabulatedRatingCurve and Outlet upstream levels (:343-399),
+    subgrid tables (:264-299) — same conditions, same messages."""
+    from ribasim_b200.network import Graph, LinkMeta, NodeID, n_neighbor_errors
+    from ribasim_b200.subgrid import Subgrid
+    from ribasim_b200.tables import ModelTables
+
+    # neighbour counts on the reference's hand-made graph
+    g = Graph()
+    ids = {k: NodeID(t, k, 1) for k, t in ((1, "Pump"), (2, "Basin"), (3, "Basin"), (4, "Basin"), (6, "Pump"))}
+    for nid in ids.values():
+        g.add_vertex(nid)
+    for a, b in ((2, 1), (3, 1), (6, 2)):
+        g.add_edge(ids[a], ids[b], LinkMeta(0, "flow", (ids[a], ids[b])))
+    errs = [e for e in n_neighbor_errors(g) if e.startswith("Pump")]
+    assert errs == ["Pump #1 can have at most 1 flow inneighbor(s) (got 2).",
+                    "Pump #1 must have at least 1 flow outneighbor(s) (got 0).",
+                    "Pump #6 must have at least 1 flow inneighbor(s) (got 0)."]
+
+    def outlet_model(**static):
+        m = MODELS["outlet"]()
+        m.tables["Outlet / static"] = [dict(node_id=2, **static)]
+        return m
+
+    with pytest.raises(ValueError, match=r"Negative flow rate\(s\) for Outlet #2 found\."):
+        build_params(outlet_model(flow_rate=-1.0))
+    m = MODELS["flow_condition"]()
+    m.tables["Pump / static"][1]["flow_rate"] = -1.0
+    with pytest.raises(ValueError, match=r"Negative flow rate\(s\) found\."):
+        build_params(m)
+
+    m = MODELS["basic"]()
+    m.link[0]["link_type"] = "foo"
+    with pytest.raises(ValueError, match=r"Invalid link type 'foo' for link #1 from node #1 to node #2\."):
+        build_params(m)
+
+    m = MODELS["tabulated_rating_curve_control"]()
+    for r in m.tables["TabulatedRatingCurve / static"]:
+        if r["level"] == 0.0:
+            r["level"] = -2.0
+    with pytest.raises(ValueError, match="Lowest level of TabulatedRatingCurve #2 is lower than bottom of upstream Basin #1"):
+        build_params(m)
+
+    m = MODELS["level_boundary_condition"]()
+    for r in m.tables["Outlet / static"]:
+        r["min_upstream_level"] = -2.0
+    with pytest.raises(ValueError, match="Minimum upstream level of Outlet #4 is lower than bottom of upstream Basin #3"):
+        build_params(m)
+
+    def subgrid_model(node_id, basin_level, subgrid_level):
+        t = ModelTables(starttime=m.starttime, endtime=m.endtime)
+        t.tables["Basin / subgrid"] = [dict(subgrid_id=1, node_id=node_id, basin_level=b, subgrid_level=s_)
+                                       for b, s_ in zip(basin_level, subgrid_level)]
+        return t
+
+    with pytest.raises(ValueError, match="The node_id of the Basin / subgrid does not exist"):
+        Subgrid(subgrid_model(10, [-1.0, 0.0], [-1.0, 0.0]), [9])
+    with pytest.raises(ValueError, match="Basin / subgrid subgrid_id 1 has repeated basin levels, this cannot be interpolated."):
+        Subgrid(subgrid_model(9, [-1.0, 0.0, 0.0], [-1.0, 0.0, 1.0]), [9])
+    with pytest.raises(ValueError, match="Basin / subgrid subgrid_id 1 has repeated element levels, this cannot be interpolated."):
+        Subgrid(subgrid_model(9, [-1.0, 0.0, 1.0], [-1.0, 0.0, 0.0]), [9])
