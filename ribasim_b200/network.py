@@ -866,13 +866,17 @@ def build_params(m: ModelTables) -> Params:
             raise ValueError(f"Data for {nid} found in neither Static nor Time table.")
         ln = by_value[int(rows[-1]["listen_node_id"])]
         if ln.type != "Basin":
-            raise ValueError(f"Listen node {ln} of {nid} is not a Basin.")
+            raise ValueError(f"Listen node {ln} of {nid} is not a Basin")
         listen.append(ln)
     pid_target_nodes = []
     for nid in pid_ids:
         tgt = g.outneighbors(nid, "control")
         if len(tgt) != 1 or tgt[0].type not in ("Pump", "Outlet"):
             raise ValueError(f"{nid} must control exactly one Pump or Outlet")
+        # valid_pid_connectivity (validation.jl:373-400)
+        ln = listen[len(pid_target_nodes)]
+        if ln not in (g.inflow_ids(tgt[0])[0], g.outflow_ids(tgt[0])[0]):
+            raise ValueError(f"PID listened {ln} is not on either side of controlled {tgt[0]}.")
         pid_target_nodes.append(tgt[0])
     nodes["pid_control"] = dict(
         node_id=pid_ids,
@@ -992,6 +996,9 @@ def build_params(m: ModelTables) -> Params:
         controlled_nodes=[g.outneighbors(n, "control") for n in dc_ids],
     )
     nodes["terminal"] = dict(node_id=ids("Terminal"))
+    errs = discrete_control_errors(nodes, g, m.t_end)
+    if errs:
+        raise ValueError("Invalid discrete control state definition(s). " + " ".join(errs))
 
     p = Params(
         tables=m, graph=g, node_ids_all=node_ids_all, basin=basin, nodes=nodes,
@@ -1026,6 +1033,52 @@ def qh_interpolation(nid: NodeID, level, flow_rate) -> PchipTable:
     level = [level[0] - 1.0] + level
     flow_rate = [0.0] + flow_rate
     return PchipTable(flow_rate, level, left="constant", right="linear")
+
+
+_NODE_KEY = {"Pump": "pump", "Outlet": "outlet", "LinearResistance": "linear_resistance",
+             "ManningResistance": "manning_resistance", "TabulatedRatingCurve": "tabulated_rating_curve",
+             "PidControl": "pid_control"}
+
+
+def discrete_control_errors(nodes: dict[str, dict[str, Any]], g: Graph, t_end: float) -> list[str]:
+    """`valid_discrete_control` (core/src/validation.jl:617-718), the messages in its order."""
+    out = []
+    dc = nodes["discrete_control"]
+    for nid, cvars, lm, targets in zip(dc["node_id"], dc["compound_variables"], dc["logic_mapping"],
+                                       dc["controlled_nodes"]):
+        n_cond = sum(len(cv["threshold_high"]) for cv in cvars)
+        states = list(dict.fromkeys(lm.values()))
+        wrong = ["".join("T" if b else "F" for b in ts) for ts in lm if len(ts) != n_cond]
+        if wrong:
+            lst = ", ".join(f'"{w}"' for w in wrong)
+            out.append(f"{nid} has {n_cond} condition(s), which is inconsistent with these truth state(s): [{lst}].")
+        for tgt in targets:
+            cm = nodes[_NODE_KEY[tgt.type]].get("control_mapping", {}) if tgt.type in _NODE_KEY else {}
+            defined = {cs for (nv, cs) in cm if nv == tgt.value}
+            undefined = [s for s in states if s not in defined]
+            if undefined:
+                lst = ", ".join(f'"{s}"' for s in undefined)
+                out.append(f"These control states from {nid} are not defined for controlled {tgt}: [{lst}].")
+        for cv in cvars:
+            for hi, lo in zip(cv["threshold_high"], cv["threshold_low"]):
+                if any(a > b for a, b in zip(lo.u, hi.u)):
+                    out.append("threshold_low is not less than or equal to threshold_high for "
+                               f"'{nid}'")
+        for cv in cvars:
+            for sv in cv["subvariables"]:
+                la, ln, var = sv["look_ahead"], sv["listen_node_id"], sv["variable"]
+                if la == 0:
+                    continue
+                if ln.type not in ("FlowBoundary", "LevelBoundary"):
+                    out.append(f"Look ahead supplied for non-timeseries listen variable '{var}' "
+                               f"from listen node {ln}.")
+                elif la < 0:
+                    out.append(f"Negative look ahead supplied for listen variable '{var}' "
+                               f"from listen node {ln}.")
+                elif t_end + la > sv["series"].t[-1]:
+                    out.append(f"Look ahead for listen variable '{var}' from listen node {ln} "
+                               "goes past timeseries end during simulation.")
+    return out
 
 
 def expand_logic_mapping(logic: dict[str, str], nid: NodeID) -> dict[tuple[bool, ...], str]:

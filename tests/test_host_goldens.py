@@ -398,3 +398,51 @@ def test_validation_messages_of_the_reference():
         Subgrid(subgrid_model(9, [-1.0, 0.0, 0.0], [-1.0, 0.0, 1.0]), [9])
     with pytest.raises(ValueError, match="Basin / subgrid subgrid_id 1 has repeated element levels, this cannot be interpolated."):
         Subgrid(subgrid_model(9, [-1.0, 0.0, 1.0], [-1.0, 0.0, 0.0]), [9])
+
+
+def test_invalid_discrete_control_messages():
+    """core/test/validation_test.jl:157-194 on the reference's `invalid_discrete_control` model
+    (python/ribasim_testmodels/ribasim_testmodels/invalid.py:56-126): the five messages, in order."""
+    from datetime import datetime
+
+    from ribasim_b200.tables import ModelTables
+    m = ModelTables(starttime=datetime(2020, 1, 1), endtime=datetime(2020, 12, 1))
+    shared = dict(profile=dict(area=[0.01, 1.0], level=[0.0, 1.0]), state=dict(level=1.4112729908597084))
+    m.add_node("Basin", 1, **shared)
+    m.add_node("Pump", 2, static=dict(control_state="bar", flow_rate=0.5 / 3600))
+    m.add_node("Basin", 3, **shared)
+    m.add_node("FlowBoundary", 4, time=dict(time=["2020-01-01 00:00:00", "2020-11-01 00:00:00"],
+                                            flow_rate=[1.0, 2.0]))
+    m.add_node("DiscreteControl", 5,
+               variable=dict(listen_node_id=[1, 4, 4], variable=["level", "flow_rate", "flow_rate"],
+                             look_ahead=[100.0, 40 * 24 * 60 * 60.0, -10.0], compound_variable_id=[1, 2, 3]),
+               condition=dict(threshold_high=[0.5, 1.5, 1.5], compound_variable_id=[1, 2, 3], condition_id=1),
+               logic=dict(truth_state=["FFFF"], control_state=["foo"]))
+    for a, b in [(1, 2), (2, 3), (4, 3), (5, 2)]:
+        m.add_link(a, b)
+    with pytest.raises(ValueError) as err:
+        build_params(m)
+    msg = str(err.value)
+    expected = [
+        'DiscreteControl #5 has 3 condition(s), which is inconsistent with these truth state(s): ["FFFF"].',
+        'These control states from DiscreteControl #5 are not defined for controlled Pump #2: ["foo"].',
+        "Look ahead supplied for non-timeseries listen variable 'level' from listen node Basin #1.",
+        "Look ahead for listen variable 'flow_rate' from listen node FlowBoundary #4 goes past timeseries end during simulation.",
+        "Negative look ahead supplied for listen variable 'flow_rate' from listen node FlowBoundary #4.",
+    ]
+    pos = [msg.find(e) for e in expected]
+    assert all(p >= 0 for p in pos), (msg, pos)
+    assert pos == sorted(pos)
+
+
+def test_pid_connectivity_messages():
+    # core/test/validation_test.jl:101-155
+    m = MODELS["pid_control"]()
+    m.tables["PidControl / time"] = [dict(r, listen_node_id=4) for r in m.tables["PidControl / time"]]
+    with pytest.raises(ValueError, match="Listen node LevelBoundary #4 of PidControl #5 is not a Basin"):
+        build_params(m)
+    m = MODELS["pid_control"]()
+    m.add_node("Basin", 9, profile=dict(area=[1000.0, 1000.0], level=[0.0, 1.0]), state=dict(level=1.0))
+    m.tables["PidControl / time"] = [dict(r, listen_node_id=9) for r in m.tables["PidControl / time"]]
+    with pytest.raises(ValueError, match=r"PID listened Basin #9 is not on either side of controlled Pump #3\."):
+        build_params(m)
