@@ -18,7 +18,7 @@ import math
 import sqlite3
 import tomllib
 from dataclasses import dataclass, field
-from datetime import datetime
+from datetime import datetime, timedelta
 from pathlib import Path
 from typing import Any
 
@@ -202,11 +202,24 @@ def parse_time(x: Any) -> datetime:
     if isinstance(x, datetime):
         return x
     s = str(x).replace("T", " ")
+    ms = 0
     if "." in s:
-        s = s.split(".")[0]
+        s, frac = s.split(".", 1)
+        # extra fractional digits are truncated to milliseconds (parse_time_strings!, read.jl)
+        ms = int((frac + "000")[:3])
     if len(s) == 10:
         s += " 00:00:00"
-    return datetime.strptime(s, TIME_FMT)
+    return datetime.strptime(s, TIME_FMT) + timedelta(milliseconds=ms)
+
+
+def datetime_since(t: float, t0: datetime) -> datetime:
+    """`datetime_since` (core/src/util.jl): seconds since t0 -> datetime, rounded to milliseconds."""
+    return t0 + timedelta(milliseconds=round(1000.0 * t))
+
+
+def seconds_since(t: datetime, t0: datetime) -> float:
+    """`seconds_since` (core/src/util.jl): milliseconds resolution."""
+    return 0.001 * round((t - t0) / timedelta(milliseconds=1))
 
 
 def snake_case(name: str) -> str:

@@ -446,3 +446,20 @@ def test_pid_connectivity_messages():
     m.tables["PidControl / time"] = [dict(r, listen_node_id=9) for r in m.tables["PidControl / time"]]
     with pytest.raises(ValueError, match=r"PID listened Basin #9 is not on either side of controlled Pump #3\."):
         build_params(m)
+
+
+def test_time_helpers_goldens():
+    # core/test/io_test.jl:41-51 (`datetime_since`, `seconds_since`) and :436-468 (`parse_time_strings!`)
+    from datetime import datetime, timedelta
+
+    from ribasim_b200.tables import datetime_since, parse_time, seconds_since
+    t0 = datetime(2020, 1, 1)
+    assert datetime_since(0.0, t0) == t0
+    assert datetime_since(1.0, t0) == t0 + timedelta(seconds=1)
+    assert datetime_since(np.pi, t0) == datetime(2020, 1, 1, 0, 0, 3, 142000)
+    assert seconds_since(t0, t0) == 0.0
+    assert seconds_since(t0 + timedelta(seconds=1), t0) == 1.0
+    assert seconds_since(datetime(2020, 1, 1, 0, 0, 3, 142000), t0) == pytest.approx(3.142)
+    assert parse_time("2020-06-01 12:00:00.000") == datetime(2020, 6, 1, 12)
+    assert parse_time("2020-06-01 12:00:00.123456789") == datetime(2020, 6, 1, 12, 0, 0, 123000)
+    assert parse_time("2020-06-01T12:00:00") == datetime(2020, 6, 1, 12)
