@@ -577,6 +577,34 @@ def cyclic_time_model() -> ModelTables:
     return m
 
 
+def drought_model() -> ModelTables:
+    """A subsection of the LHM Vechtstromen model with a Basin that runs dry (#2189)
+    (python/ribasim_testmodels/ribasim_testmodels/basic.py:472-586)."""
+    m = _model()
+    t0 = "2020-01-01 00:00:00"
+    hi = dict(level=[22.4, 22.41, 25.4])
+    lo = dict(level=[17.25, 17.26, 20.25])
+    m.add_node("Basin", 1558, profile=dict(hi, area=[0.1, 435363.1, 435363.1]), state=dict(level=25.4),
+               time=dict(time=[t0], infiltration=[0.0379294629649877049]))
+    m.add_node("Basin", 1737, profile=dict(hi, area=[0.1, 422367.9, 422367.9]), state=dict(level=25.4),
+               time=dict(time=[t0], infiltration=[0.001642597244767027157]))
+    m.add_node("Basin", 2117, profile=dict(level=[17.24, 17.25, 20.24], area=[0.1, 960850.7, 960850.7]),
+               state=dict(level=20.24))
+    m.add_node("Basin", 2188, profile=dict(lo, area=[0.1, 424545.6, 424545.6]), state=dict(level=20.25))
+    m.add_node("Basin", 2189, profile=dict(hi, area=[0.1, 66326.8, 66326.8]), state=dict(level=25.4),
+               time=dict(time=[t0], infiltration=[0.0165766882781172575]))
+    m.add_node("Basin", 2305, profile=dict(lo, area=[0.1, 9944437.9, 9944437.9]), state=dict(level=20.25))
+    for nid, length in ((1236, 3390.0), (1237, 1430.0), (1238, 2710.0)):
+        m.add_node("ManningResistance", nid, static=dict(length=length, profile_width=25.0,
+                                                         profile_slope=1.0, manning_n=0.04))
+    m.add_node("Outlet", 229, static=dict(flow_rate=2.44, min_upstream_level=25.4))
+    m.add_node("Outlet", 285, static=dict(flow_rate=5.62, min_upstream_level=20.25))
+    for a, b in [(229, 2189), (285, 2117), (1236, 2117), (1237, 2188), (1238, 2188), (1737, 229),
+                 (2188, 285), (2305, 1236), (2189, 1237), (1558, 1238)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -890,4 +918,5 @@ MODELS = dict(
     outlet=outlet_model,
     flow_boundary_interpolation=flow_boundary_interpolation_model,
     transient_pump_outlet=transient_pump_outlet_model,
+    drought=drought_model,
 )

@@ -284,3 +284,20 @@ def test_transient_pump_outlet():
         assert np.allclose(flow_4[229:], 1e-5, rtol=1e-6, atol=0)
     finally:
         model.finalize()
+
+
+def test_drought():
+    """core/test/run_models_test.jl:706-727: Basin #2189 runs dry; after 100 days its storage,
+    storage rate and infiltration are close to zero (the low-storage factor closes the sink)."""
+    model = _model("drought", n_members=2)
+    try:
+        res = model.run(saveat=86400.0)
+        bd = res.basin_data()
+        b = list(bd["node_id"]).index(2189)
+        late = bd["time"] > 100 * 86400.0
+        assert np.all(np.abs(bd["storage"][late, b]) < 0.03)
+        assert np.all(np.abs(bd["storage_rate"][late, b]) < 1e-8)
+        assert np.all(np.abs(bd["infiltration"][late, b]) < 1e-8)
+        assert model.status_counts["newton_failed"] == 0 and model.status_counts["negative_storage"] == 0
+    finally:
+        model.finalize()
