@@ -14,9 +14,9 @@ the core reads; geometry, subgrid and concentration tables are not needed on the
     pump_discrete_control      discrete_control.py:23-126
     flow_condition, level_boundary_condition, tabulated_rating_curve_control,
     compound_variable_condition, storage_condition, connector_node_flow_condition,
-    transient_condition        discrete_control.py:128-798
+    transient_condition, circular_flow  discrete_control.py:128-938
     discrete_control_of_pid_control  pid_control.py:66-152
-    outlet, flow_boundary_interpolation  basic.py:364-407, 590-627
+    outlet, cyclic_time, drought, flow_boundary_interpolation  basic.py:364-627
     flow_boundary_time, transient_pump_outlet  time.py:12-96
     two_basin                  two_basin.py:10-79
 
@@ -605,6 +605,42 @@ def drought_model() -> ModelTables:
     return m
 
 
+def circular_flow_model() -> ModelTables:
+    """Boezem / polder loop with inlets, a Manning reach and a Pump under hysteresis control
+    (python/ribasim_testmodels/ribasim_testmodels/discrete_control.py:801-938)."""
+    m = _model(solver=dict(saveat=3600.0))
+    days = [m.starttime + timedelta(days=k) for k in range(367)]
+    precipitation = np.zeros(367)
+    precipitation[0:90] = 1e-6
+    precipitation[180:270] = 1e-6
+    evaporation = np.zeros(367)
+    evaporation[90:180] = 1e-6
+    evaporation[270:366] = 1e-6
+    for node_id in (3, 4, 6, 9):
+        m.add_node("Basin", node_id, profile=dict(area=[10.0, 10_000.0], level=[-10.0, 1.0]),
+                   time=dict(time=[d.strftime(TIME_FMT) for d in days], drainage=0.0,
+                             potential_evaporation=[float(x) for x in evaporation], infiltration=0.0,
+                             precipitation=[float(x) for x in precipitation]),
+                   state=dict(level=0.9))
+    m.add_node("Outlet", 10, static=dict(flow_rate=10.0, min_upstream_level=1.1))
+    m.add_node("Outlet", 12, static=dict(flow_rate=10.0))
+    m.add_node("Outlet", 5, static=dict(flow_rate=2.0, min_upstream_level=1.0, max_downstream_level=1.0))
+    m.add_node("Outlet", 13, static=dict(flow_rate=2.0, min_upstream_level=1.0, max_downstream_level=0.9))
+    m.add_node("ManningResistance", 2, static=dict(length=900.0, manning_n=0.04, profile_width=6.0,
+                                                   profile_slope=3.0))
+    m.add_node("DiscreteControl", 1,
+               variable=dict(listen_node_id=6, variable="level", compound_variable_id=1),
+               condition=dict(threshold_high=0.95, threshold_low=0.9, compound_variable_id=1, condition_id=1),
+               logic=dict(truth_state=["T", "F"], control_state=["on", "off"]))
+    m.add_node("Pump", 7, static=dict(control_state=["on", "off"], flow_rate=[0.1, 0.0]))
+    m.add_node("LevelBoundary", 11, static=dict(level=1.1))
+    m.add_node("LevelBoundary", 17, static=dict(level=0.9))
+    for a, b in [(2, 9), (3, 5), (3, 2), (5, 4), (4, 13), (13, 6), (6, 7), (7, 9), (9, 10), (11, 12),
+                 (12, 3), (10, 17), (1, 7)]:
+        m.add_link(a, b)
+    return m
+
+
 def tabulated_rating_curve_model() -> ModelTables:
     """One static and one time-varying (cyclic) rating curve between two basins
     (basic.py:276-361)."""
@@ -919,4 +955,5 @@ MODELS = dict(
     flow_boundary_interpolation=flow_boundary_interpolation_model,
     transient_pump_outlet=transient_pump_outlet_model,
     drought=drought_model,
+    circular_flow=circular_flow_model,
 )

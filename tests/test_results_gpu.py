@@ -301,3 +301,36 @@ def test_drought():
         assert model.status_counts["newton_failed"] == 0 and model.status_counts["negative_storage"] == 0
     finally:
         model.finalize()
+
+
+def test_circular_flow_with_hysteresis_control(tmp_path):
+    """core/test/control_test.jl:334-372, from the written control.nc and basin.nc (hourly saveat):
+    the Pump is off initially (level <= 0.9), switches on only above 0.95 and off again only
+    below 0.9.  The first days of the run hold the first three control records."""
+    from scipy.io import netcdf_file
+
+    model = _model("circular_flow", n_members=1)
+    try:
+        from ribasim_b200.results import Results
+        res = Results(model)
+        for k in range(1, 3 * 24 + 1):
+            model.update_until(k * 3600.0)
+            res.save()
+        res.write(tmp_path)
+    finally:
+        model.finalize()
+    with netcdf_file(str(tmp_path / "control.nc"), "r", mmap=False) as ds:
+        control_times = ds.variables["time"][:].copy()
+        truth = [b"".join(row).rstrip(b"\0").decode() for row in ds.variables["truth_state"][:]]
+    with netcdf_file(str(tmp_path / "basin.nc"), "r", mmap=False) as ds:
+        basin_times = ds.variables["time"][:].copy()
+        node_ids = list(ds.variables["node_id"][:])
+        level6 = ds.variables["level"][:][:, node_ids.index(6)].copy()
+    assert len(truth) >= 3 and truth[:3] == ["F", "T", "F"]
+
+    def level_at(t):
+        return level6[np.argmax(basin_times >= t)]
+
+    assert level_at(control_times[0]) <= 0.9 + 1e-10
+    assert level_at(control_times[1]) > 0.95
+    assert level_at(control_times[2]) <= 0.9 + 1e-2
