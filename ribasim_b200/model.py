@@ -70,6 +70,7 @@ class Model:
         alloc_total = np.minimum(ud["demand"], ud["allocated"]).sum(axis=1) \
             if len(ud["node_id"]) else np.zeros(0)
         self.h.set_param("ud_alloc_total", alloc_total)
+        self._ud_demand_uploaded = np.array(ud["demand"], dtype=float, copy=True)
         # forcing at t0 is the same for all members until the caller perturbs it
         self._uploaded = {}
         for name in FORCING_NAMES:
@@ -152,6 +153,12 @@ class Model:
         """Upload the BMI-writable host arrays the caller changed since the last step
         (`basin.infiltration` etc. are written through `get_value_ptr` in the reference,
         core/src/bmi.jl:64-88; here the host arrays are mirrors synced at update boundaries)."""
+        # `user_demand.demand` (static demands; core/src/bmi.jl:82-83): the flow a UserDemand asks
+        # for is min(allocated, demand) summed over the priorities (solve.jl:348-404)
+        ud = self.p.nodes["user_demand"]
+        if len(ud["node_id"]) and not np.array_equal(ud["demand"], self._ud_demand_uploaded):
+            self.h.set_param("ud_alloc_total", np.minimum(ud["demand"], ud["allocated"]).sum(axis=1))
+            self._ud_demand_uploaded = np.array(ud["demand"], dtype=float, copy=True)
         if getattr(self, "_member_forcing", False):
             return
         for name in FORCING_NAMES:

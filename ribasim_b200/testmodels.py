@@ -319,6 +319,24 @@ def user_demand_model() -> ModelTables:
     return m
 
 
+def minimal_subnetwork_model() -> ModelTables:
+    """FlowBoundary -> Basin -> Pump -> Basin with two UserDemand nodes, run without allocation
+    (python/ribasim_testmodels/ribasim_testmodels/allocation.py:187-241)."""
+    m = _model()
+    shared = dict(profile=dict(area=[1000.0, 1000.0], level=[0.0, 1000.0]), state=dict(level=1.0))
+    m.add_node("FlowBoundary", 1, static=dict(flow_rate=2.0e-3))
+    m.add_node("Basin", 2, **shared)
+    m.add_node("Pump", 3, static=dict(flow_rate=4e-3, max_flow_rate=4e-3))
+    m.add_node("Basin", 4, **shared)
+    m.add_node("UserDemand", 5, static=dict(demand=1e-3, return_factor=0.9, min_level=0.9, demand_priority=1))
+    m.add_node("UserDemand", 6, time=dict(time=["2020-01-01 00:00:00", "2020-01-02 00:00:00"],
+                                          demand=[1e-3, 2e-3], return_factor=0.9, min_level=0.9,
+                                          demand_priority=1))
+    for a, b in [(1, 2), (2, 3), (3, 4), (4, 5), (4, 6), (5, 4), (6, 4)]:
+        m.add_link(a, b)
+    return m
+
+
 def pump_discrete_control_model() -> ModelTables:
     m = _model()
     m.add_node("Basin", 1, state=dict(level=1.0),
@@ -956,4 +974,5 @@ MODELS = dict(
     transient_pump_outlet=transient_pump_outlet_model,
     drought=drought_model,
     circular_flow=circular_flow_model,
+    minimal_subnetwork=minimal_subnetwork_model,
 )

@@ -128,3 +128,28 @@ def test_stroboscopic_forcing(tmp_path):
     finally:
         b.finalize()
 
+
+
+def test_user_demand_inflow(tmp_path):
+    """core/test/bmi_test.jl:92-108 (minimal_subnetwork without allocation): the cumulative
+    UserDemand inflows follow the demands, also after a demand is changed through the pointer."""
+    m = MODELS["minimal_subnetwork"]()
+    m.solver.update(algorithm="ImplicitEuler", dt=3600.0)
+    b = _bmi(m.write(tmp_path))
+    try:
+        demand = b.get_value_ptr("user_demand.demand")
+        inflow = b.get_value_ptr("user_demand.cumulative_inflow")
+        day = 86400.0
+        b.update_until(2 * day)
+        assert inflow[0] == pytest.approx(2.0e-3 * day, abs=1e-2)
+        # the block-interpolated demand of #6 doubles at day 1; implicit Euler evaluates the RHS at
+        # the end of a step, so the fixed 1 h step that ends on the knot already sees the new
+        # value (as the reference's ImplicitEuler would): one step of the demand difference on top
+        # of the reference's adaptive-step tolerance
+        assert inflow[1] == pytest.approx(3.0e-3 * day, abs=1e-3 * 3600.0 + 1e-2)
+        assert inflow[1] >= 3.0e-3 * day - 1e-2
+        demand[0] = 3.0e-3
+        b.update_until(3 * day)
+        assert inflow[0] == pytest.approx(5.0e-3 * day, abs=2e-3)
+    finally:
+        b.finalize()
