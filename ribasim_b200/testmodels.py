@@ -337,6 +337,30 @@ def minimal_subnetwork_model() -> ModelTables:
     return m
 
 
+def basic_basin_model(profile: str = "storage") -> ModelTables:
+    """Two monthly FlowBoundary series into a small parabolic Basin that drains over a weir; the
+    profile is given by area, by storage or by both (basic.py:630-760:
+    basic_basin_only_area / basic_basin_only_storage / basic_basin_both_area_and_storage)."""
+    m = ModelTables(starttime=datetime(2022, 1, 1), endtime=datetime(2023, 1, 1))
+    months = [datetime(2022 + (k // 12), k % 12 + 1, 1).strftime(TIME_FMT) for k in range(13)]
+    main = [74.7, 57.9, 63.2, 183.9, 91.8, 47.5, 32.6, 27.6, 26.5, 25.1, 39.3, 37.8, 57.9]
+    minor = [16.3, 3.8, 3.0, 37.6, 18.2, 11.1, 12.9, 12.2, 11.2, 10.8, 15.1, 14.3, 11.8]
+    m.add_node("FlowBoundary", 1, time=dict(time=months, flow_rate=main))
+    m.add_node("FlowBoundary", 2, time=dict(time=months, flow_rate=minor))
+    levels = [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    cols: dict = dict(level=levels)
+    if profile in ("area", "both"):
+        cols["area"] = [(h + 1) * np.pi for h in levels]
+    if profile in ("storage", "both"):
+        cols["storage"] = [np.pi / 2 * ((h + 1) ** 2 - 1) for h in levels]
+    m.add_node("Basin", 3, profile=cols, state=dict(level=4.0))
+    m.add_node("TabulatedRatingCurve", 4, static=dict(level=[0.0, 2.0, 5.0], flow_rate=[0.0, 50.0, 200.0]))
+    m.add_node("Terminal", 5)
+    for a, b in [(1, 3), (2, 3), (3, 4), (4, 5)]:
+        m.add_link(a, b)
+    return m
+
+
 def pump_discrete_control_model() -> ModelTables:
     m = _model()
     m.add_node("Basin", 1, state=dict(level=1.0),

@@ -282,3 +282,29 @@ def test_reference_control_tests_on_gpu():
         assert model.status_counts["newton_failed"] == 0
     finally:
         model.finalize()
+
+
+def test_basin_profile_given_by_area_storage_or_both():
+    """core/test/run_models_test.jl:763-772 (`init_basin_only_storage`) and its sibling models
+    basic_basin_only_area / basic_basin_both_area_and_storage: a small parabolic Basin under river
+    inflows runs to the end whichever way its profile is given, and the three agree on the level
+    (the weir sets it); the oracle gives the same end state."""
+    from oracle.oracle import run_oracle
+    from ribasim_b200.model import Model
+    from ribasim_b200.network import build_params
+    from ribasim_b200.testmodels import basic_basin_model
+
+    levels = {}
+    for profile in ("area", "storage", "both"):
+        p = build_params(basic_basin_model(profile))
+        model = Model(p, n_members=1, dt=3600.0)
+        try:
+            model.run()
+            assert model.status_counts["newton_failed"] == 0 and model.status_counts["negative_storage"] == 0
+            levels[profile] = model.level()[0, 0]
+            u, S, lv, st = run_oracle(p, 3600.0, full_newton=1, max_halvings=20, predictor=1)
+            assert model.storage()[0, 0] == pytest.approx(S[0], rel=1e-6)
+        finally:
+            model.finalize()
+    assert levels["area"] == pytest.approx(levels["both"], rel=1e-12)
+    assert levels["storage"] == pytest.approx(levels["area"], rel=1e-6)
