@@ -35,6 +35,11 @@ class RibasimBmi:
         m = self.model
         f = m.flat.ints
         nb, nu = f["n_basin"], f["n_ud_link"]
+        # `user_demand.demand` is `vec(user_demand.demand)` of a column-major [node, priority]
+        # Matrix (core/src/bmi.jl:82-83, docs/dev/bmi.qmd): node index fastest.  The host mirror is
+        # kept in Fortran order so that the flat array handed out is a view with that layout.
+        ud = m.p.nodes["user_demand"]
+        ud["demand"] = np.asfortranarray(ud["demand"], dtype=np.float64)
         self._values = {
             "basin.storage": np.zeros(nb), "basin.level": np.zeros(nb),
             "basin.cumulative_infiltration": np.zeros(nb),
@@ -42,7 +47,7 @@ class RibasimBmi:
             "basin.cumulative_surface_runoff": np.zeros(nb),
             "basin.subgrid_level": np.full(len(m.subgrid), np.nan),
             "user_demand.cumulative_inflow": np.zeros(nu),
-            "user_demand.demand": m.p.nodes["user_demand"]["demand"].reshape(-1),
+            "user_demand.demand": ud["demand"].reshape(-1, order="F"),
         }
         for name, key in _WRITABLE.items():
             self._values[name] = m.p.basin.vertical_flux[key]

@@ -16,6 +16,7 @@
 #include "../../include/ribasim_b200.h"
 #include "rbs_kernels.cuh"
 #include "rbs_tile.cuh"
+#include "rbs_fused.cuh"
 
 #define RBS_DC_REC_CAP 64  // DiscreteControl changes recorded per member
 
@@ -133,6 +134,14 @@ struct rbs_handle {
     void* d_entc_blob = nullptr;
     size_t entc_smem_bytes = 0;
     bool lin_entc = false;
+    // M members per thread on the compact entry schedule (rbs_fused.cuh); 0 = off
+    int lin_m = 0;
+    int lin_m_sched = 0;         // schedule words in shared memory behind the slots
+    size_t lin_m_smem = 0;
+    // round-2 pass: convergence test + finalize half as one cluster kernel at the END of the pass
+    // in which a member's iteration ended (rbs_fused.cuh); 0 = the round-1 launch sequence
+    int r2_pass = 1;
+    int fin_cluster = 4;
     void* d_ent_blob = nullptr;
     bool lin_ent = false;
     int ent_tile = 2;
@@ -938,6 +947,25 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             }
         }
         if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; h->lin_ent = false; h->lin_entc = false; }
+        // ---- M members per thread (full-Newton path, compact slots): the widest tile that fits
+        if (h->lin_entc) {
+            int want_m = getenv("RBS_LIN_M") ? atoi(getenv("RBS_LIN_M")) : geti(b, "lin_m", -1);
+            int want_sched = getenv("RBS_LIN_M_SCHED") ? atoi(getenv("RBS_LIN_M_SCHED")) : 1;
+            for (int cand : {8, 4}) {
+                if (want_m == 0 || (want_m > 0 && want_m != cand)) continue;
+                size_t slots = (size_t)h->esched_c.n_slots * cand * sizeof(double);
+                size_t sched = (size_t)h->esched_c.n_words * 8;
+                int use_sched = want_sched && slots + sched + 256 <= (size_t)dev_smem;
+                size_t sb = slots + (use_sched ? sched : 0);
+                if (sb + 256 > (size_t)dev_smem) continue;
+                cudaError_t e6 = cand == 8
+                    ? cudaFuncSetAttribute(k_newton_linear_m<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
+                    : cudaFuncSetAttribute(k_newton_linear_m<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+                if (e6 != cudaSuccess) { cudaGetLastError(); continue; }
+                h->lin_m = cand; h->lin_m_sched = use_sched; h->lin_m_smem = sb;
+                break;
+            }
+        }
         apply_carveout(h);
         // ---- cooperative window kernel: needs the entry schedule with 2-member tiles in shared
         // memory and a grid that is co-resident
@@ -974,6 +1002,8 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             }
         }
     }
+    h->r2_pass = getenv("RBS_R2_PASS") ? atoi(getenv("RBS_R2_PASS")) : geti(b, "r2_pass", 1);
+    h->fin_cluster = getenv("RBS_FIN_CLUSTER") ? atoi(getenv("RBS_FIN_CLUSTER")) : geti(b, "fin_cluster", 4);
     bind_net(h);
     n.cc_tab_offset = geti(b, "cc_tab_offset");
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -1024,7 +1054,7 @@ int rbs_set_param_f64(rbs_handle* h, const char* key, const double* host, int64_
     cudaSetDevice(h->device);
     auto it = h->shared.find(key);
     if (it == h->shared.end() || it->second.is_int) return fail(std::string("unknown f64 parameter ") + key);
-    if ((size_t)n * sizeof(double) > it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
+    if ((size_t)std::max<int64_t>(n, 1) * sizeof(double) != it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
     if (n > 0) CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));  // host buffer is borrowed only for the call
     return 0;
@@ -1034,7 +1064,7 @@ int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64
     cudaSetDevice(h->device);
     auto it = h->shared.find(key);
     if (it == h->shared.end() || !it->second.is_int) return fail(std::string("unknown i32 parameter ") + key);
-    if ((size_t)n * sizeof(int32_t) > it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
+    if ((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t) != it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
     if (n > 0) CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1374,7 +1404,20 @@ int rbs_refresh(rbs_handle* h, double t) {
 // level-per-launch kernels when the schedule does not fit in shared memory.
 static void launch_linear(rbs_handle* h, double* c, Pred nw) {
     Net& n = h->net;
-    if (h->lin_ent) {
+    if (h->lin_m > 0 && h->full_newton) {
+        if (!getenv("RBS_TIME_SOLVE_ONLY"))
+        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
+               sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
+        EntSched es = h->esched_c;
+        es.smem_sched = h->lin_m_sched;
+        const int M = h->lin_m, blocks = (n.NA + M - 1) / M;
+        prof_begin(h, "k_newton_linear_m");
+        if (M == 8) k_newton_linear_m<8><<<blocks, RBS_ENT_LANES, h->lin_m_smem, h->cur>>>(n, es, c);
+        else k_newton_linear_m<4><<<blocks, RBS_ENT_LANES, h->lin_m_smem, h->cur>>>(n, es, c);
+        prof_end(h);
+        h->launches++;
+    } else if (h->lin_ent) {
+        if (!getenv("RBS_TIME_SOLVE_ONLY"))
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
                sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
         int et = h->ent_tile, blocks = (n.NA + et - 1) / et, nt = RBS_ENT_LANES * et / 2;
@@ -1458,6 +1501,70 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
                h->max_iter, 0.01, h->full_newton, h->early_exit);
     h->cur = h->stream;
     h->n_passes++;
+}
+
+}  // extern "C"
+template <int CL>
+static cudaError_t launch_finalize_cl(cudaStream_t st, int tiles, const Net& n, const FinArgs& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * CL));
+    cfg.blockDim = dim3(RBS_FIN_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_finalize<CL>, n, a);
+}
+extern "C" {
+
+// Round-2 pass of a member group: one Newton iteration of every member that is not done, then the
+// convergence test and — for the members whose iteration ended — the whole finalize half in one
+// cluster kernel, then the work list of the next pass.
+static int launch_pass_r2(rbs_handle* h, rbs_handle::Group& G, double dt, double h_min, int n_steps) {
+    Net& n = h->net;
+    h->cur = G.stream;
+    n.NA = G.n_active;
+    n.alist = G.d_alist;
+    Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
+    launch_rhs<true, 1>(h, nullptr, nw);
+    if (!h->full_newton) launch_rhs<false, 1>(h, nullptr, nw);
+    double* c = mp(h, "cvec");
+    launch_linear(h, c, nw);
+    {
+        dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 63) / 64, h->n_part);
+        LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
+    }
+    n.NA = n.B;
+    n.alist = nullptr;
+    FinArgs a{};
+    a.from_ts = sp<int>(h, "ud_demand_from_timeseries");
+    a.alloc_total = sp<double>(h, "ud_alloc_total");
+    a.dt = dt; a.h_min = h_min; a.kappa = 0.01;
+    a.max_halvings = h->max_halvings; a.grow_iters = h->grow_iters; a.n_steps = n_steps;
+    a.shrink_log2 = h->shrink_log2; a.predictor = h->predictor;
+    a.n_part = h->n_part; a.max_iter = h->max_iter; a.full_newton = h->full_newton; a.early_exit = h->early_exit;
+    a.m_lo = G.lo; a.m_hi = G.hi;
+    const int tiles = (G.hi - G.lo + 31) / 32;
+    prof_begin(h, "k_finalize");
+    cudaError_t e;
+    switch (h->fin_cluster) {
+        case 8: e = launch_finalize_cl<8>(G.stream, tiles, n, a); break;
+        case 4: e = launch_finalize_cl<4>(G.stream, tiles, n, a); break;
+        case 2: e = launch_finalize_cl<2>(G.stream, tiles, n, a); break;
+        default: e = launch_finalize_cl<1>(G.stream, tiles, n, a); break;
+    }
+    prof_end(h);
+    h->launches++;
+    if (e != cudaSuccess) { h->cur = h->stream; return fail(std::string("k_finalize launch: ") + cudaGetErrorString(e)); }
+    LAUNCH_CFG(h, k_compact_tiles, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_counts);
+    h->cur = h->stream;
+    h->n_passes++;
+    return 0;
 }
 
 int rbs_time_linear(rbs_handle* h, int32_t n_active, int32_t reps, double* ms_per_launch) {
@@ -1615,7 +1722,8 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
     for (auto& G : h->groups) {
         if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, ev_begin, 0));
         h->cur = G.stream;
-        LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts, 0, 0, 0, 0.0, 0, 0);
+        if (h->r2_pass) LAUNCH_CFG(h, k_compact_tiles, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_counts);
+        else LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts, 0, 0, 0, 0.0, 0, 0);
         G.n_active = G.hi - G.lo;
         G.n_limit = 0;
         G.pending = false;
@@ -1659,7 +1767,8 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
                 if (G.n_active == 0) { G.done = true; n_done++; progressed = true; continue; }
             }
             if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
-            launch_pass(h, G, dt, h_min, n_steps);
+            if (h->r2_pass) { if (launch_pass_r2(h, G, dt, h_min, n_steps)) return 1; }
+            else launch_pass(h, G, dt, h_min, n_steps);
             CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
             CUDA_TRY(cudaEventRecord(G.ev, G.stream));
             G.pending = true;

@@ -33,12 +33,34 @@ class RbsError(RuntimeError):
     pass
 
 
+def _sources() -> list[Path]:
+    return [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_coop.cuh", CSRC / "rbs_tile.cuh",
+            CSRC / "rbs_fused.cuh", CSRC / "rbs_math.cuh", PKG_DIR.parent / "include" / "ribasim_b200.h"]
+
+
+def _source_hash() -> str:
+    import hashlib
+
+    hsh = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for s in _sources():
+        hsh.update(s.read_bytes())
+    return hsh.hexdigest()
+
+
+def _hash_file() -> Path:
+    return LIB_PATH.with_name(LIB_PATH.name + ".srchash")
+
+
+def is_stale() -> bool:
+    """True when librbs.so was not built from the sources in the tree (content hash of the sources
+    and flags stored next to the library; robust against copies that do not keep mtimes)."""
+    hf = _hash_file()
+    return not LIB_PATH.exists() or not hf.exists() or hf.read_text().strip() != _source_hash()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile librbs.so for sm_100a in-tree (so that it travels with the repo snapshot)."""
-    srcs = [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_coop.cuh", CSRC / "rbs_tile.cuh", CSRC / "rbs_math.cuh",
-            PKG_DIR.parent / "include" / "ribasim_b200.h"]
-    if not force and LIB_PATH.exists() and all(
-            LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+    if not force and not is_stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(CSRC / "rbs.cu")]
@@ -47,6 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RbsError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    _hash_file().write_text(_source_hash() + "\n")
     if verbose:
         print(res.stderr)
     return LIB_PATH
@@ -59,10 +82,11 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        if os.environ.get("RBS_NO_BUILD"):
+    if os.environ.get("RBS_LIB") or os.environ.get("RBS_NO_BUILD"):
+        if not LIB_PATH.exists():
             raise RbsError(f"{LIB_PATH} is missing (run __graft_entry__.build())")
-        build()
+    else:
+        build()  # no-op unless the sources changed since the library was built
     L = ctypes.CDLL(str(LIB_PATH))
     vp, cp = ctypes.c_void_p, ctypes.c_char_p
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
@@ -202,7 +226,8 @@ class Handle:
     def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
                  device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
                  smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0,
-                 coop_members: int = -1, tile_window: int = -1):
+                 coop_members: int = -1, tile_window: int = -1, lin_m: int = -1,
+                 r2_pass: int = 1, fin_cluster: int = 4):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -281,6 +306,13 @@ class Handle:
             set_i("smem_threads", [smem_threads])
             set_i("lin_mode", [lin_mode])
             set_i("n_groups", [n_groups])
+            # members per thread of the full-Newton solve (rbs_fused.cuh): 8 / 4, 0 = the 2-member
+            # tiles of rbs_kernels.cuh, -1 = the widest that fits
+            set_i("lin_m", [lin_m])
+            # 1: convergence test + finalize half as one cluster kernel per pass (rbs_fused.cuh,
+            # `fin_cluster` blocks per 32-member tile); 0: the round-1 launch sequence
+            set_i("r2_pass", [r2_pass])
+            set_i("fin_cluster", [fin_cluster])
             # ensembles of at most this many members run a window as one cooperative kernel
             # (-1 = the library's default)
             set_i("coop_members", [int(os.environ.get("RBS_COOP_MEMBERS", str(coop_members)))])

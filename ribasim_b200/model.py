@@ -51,6 +51,15 @@ class Model:
         self.sym = sym if sym is not None else analyse(
             self.flat.ints["n_reduced"], self.flat.arrays["wrow_ptr"], self.flat.arrays["wcol"])
         self.B = int(n_members)
+        # The device path is fixed-step implicit Euler with Newton sub-stepping; any
+        # other `solver.algorithm` (core/src/config.jl:368-380; default QNDF) must be asked for
+        # explicitly as ImplicitEuler — nothing is substituted silently.  `dt=` given by the caller
+        # is that explicit request.
+        alg = self.tables.solver_option("algorithm")
+        if dt is None and alg not in (None, "ImplicitEuler"):
+            raise ValueError(
+                f"solver.algorithm = {alg!r} is not available on the device path: only fixed-step "
+                "ImplicitEuler is (set `algorithm = \"ImplicitEuler\"` and `dt` in [solver], or pass dt=)")
         cfg_dt = self.tables.solver_option("dt")
         self.dt = float(dt if dt is not None else (cfg_dt if cfg_dt else 3600.0))
         self.t = 0.0
@@ -73,6 +82,7 @@ class Model:
         self._ud_demand_uploaded = np.array(ud["demand"], dtype=float, copy=True)
         # forcing at t0 is the same for all members until the caller perturbs it
         self._uploaded = {}
+        self._overridden: set[str] = set()  # forcing arrays set per member with set_forcing
         for name in FORCING_NAMES:
             self.h.set_member(name, self.p.basin.vertical_flux[name], broadcast=True)
             self._uploaded[name] = self.p.basin.vertical_flux[name].copy()
@@ -114,13 +124,18 @@ class Model:
             rate = incr / (t1 - t0) if t1 > t0 else incr * 0.0
         self.h.set_member("fb_rate", rate, broadcast=True)
 
-    def set_forcing(self, name: str, values: np.ndarray) -> None:
+    def set_forcing(self, name: str, values: np.ndarray | None) -> None:
         """Overwrite a Basin vertical flux for all members: values `[n_basin][n_members]`
-        (the BMI-writable arrays `basin.infiltration` etc., core/src/bmi.jl:64-88)."""
+        (the BMI-writable arrays `basin.infiltration` etc., core/src/bmi.jl:64-88).  Only the named
+        array stops following its Basin / time table and the BMI host array; `None` hands it back."""
         if name not in FORCING_NAMES:
             raise KeyError(name)
+        if values is None:  # hand the array back to the Basin tables / BMI host arrays
+            self._overridden.discard(name)
+            self._uploaded[name] = None
+            return
         self.h.set_member(name, values)
-        self._member_forcing = True
+        self._overridden.add(name)
 
     def set_member_param(self, name: str, values: np.ndarray | None) -> None:
         """Parameter ensemble: per-member values `[n_nodes][n_members]` of a shared link parameter
@@ -159,11 +174,11 @@ class Model:
         if len(ud["node_id"]) and not np.array_equal(ud["demand"], self._ud_demand_uploaded):
             self.h.set_param("ud_alloc_total", np.minimum(ud["demand"], ud["allocated"]).sum(axis=1))
             self._ud_demand_uploaded = np.array(ud["demand"], dtype=float, copy=True)
-        if getattr(self, "_member_forcing", False):
-            return
         for name in FORCING_NAMES:
+            if name in self._overridden:
+                continue
             arr = self.p.basin.vertical_flux[name]
-            if not np.array_equal(arr, self._uploaded[name], equal_nan=True):
+            if self._uploaded[name] is None or not np.array_equal(arr, self._uploaded[name], equal_nan=True):
                 self.h.set_member(name, arr, broadcast=True)
                 self._uploaded[name] = arr.copy()
 
@@ -171,10 +186,15 @@ class Model:
         if st is not None:
             self.status_counts["newton_failed"] += int(np.count_nonzero(st & 1))
             self.status_counts["negative_storage"] += int(np.count_nonzero(st & 2))
+            if np.any(st & 4):
+                # core/src/callback.jl:671-675
+                m = int(np.flatnonzero(st & 4)[0])
+                raise RuntimeError(
+                    f"No control state specified for a DiscreteControl truth state (member {m}, t = {self.t})")
 
     def _after_step(self) -> None:
         """`update_basin!` at forcing tstops (core/src/callback.jl:846-866)."""
-        if self.t in self._ftstops and not getattr(self, "_member_forcing", False):
+        if self.t in self._ftstops:
             update_vertical_flux(self.p, self.t)
             self._sync_inputs()
 

@@ -153,3 +153,32 @@ def test_user_demand_inflow(tmp_path):
         assert inflow[0] == pytest.approx(5.0e-3 * day, abs=2e-3)
     finally:
         b.finalize()
+
+
+def test_user_demand_demand_layout_is_node_fastest(tmp_path):
+    """`user_demand.demand` is `vec()` of the reference's column-major [node, priority] matrix
+    (core/src/bmi.jl:82-83; docs/dev/bmi.qmd): flat index = node + n_nodes * priority, and the array
+    handed out aliases the model's demand matrix (a coupler writes through it)."""
+    m = MODELS["minimal_subnetwork"]()
+    m.solver.update(algorithm="ImplicitEuler", dt=3600.0)
+    # second demand priority on node 5 only: the matrix becomes 2 nodes x 2 priorities
+    m.tables["UserDemand / static"].append(
+        dict(node_id=5, demand=4e-3, return_factor=0.9, min_level=0.9, demand_priority=2))
+    b = _bmi(m.write(tmp_path))
+    try:
+        flat = b.get_value_ptr("user_demand.demand")
+        mat = b.model.p.nodes["user_demand"]["demand"]
+        assert mat.shape == (2, 2) and flat.shape == (4,)
+        assert np.shares_memory(flat, mat)
+        n_nodes = 2
+        assert flat[0 + n_nodes * 0] == 1e-3 and flat[0 + n_nodes * 1] == 4e-3   # node 5
+        assert flat[1 + n_nodes * 1] == 0.0                                      # node 6 has no priority 2
+        flat[0 + n_nodes * 1] = 7e-3
+        assert mat[0, 1] == 7e-3
+        inflow = b.get_value_ptr("user_demand.cumulative_inflow")
+        b.update_until(86400.0)
+        # node 5 now asks for 1e-3 + 7e-3 (the sum over its priorities, solve.jl:348-404), limited by
+        # what the pump delivers into its basin (4e-3) minus what node 6 takes
+        assert inflow[0] > 1.5e-3 * 86400.0
+    finally:
+        b.finalize()

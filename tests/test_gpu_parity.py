@@ -765,6 +765,77 @@ def test_compact_solve_slots_equal_plain(name, monkeypatch):
         assert s0[k] == s1[k], k
 
 
+@pytest.mark.parametrize("cluster", [1, 4, 8])
+@pytest.mark.parametrize("name", ["basic", "backwater", "user_demand", "pid_control",
+                                  "outlet_continuous_control", "pump_discrete_control", "hws_like"])
+def test_cluster_finalize_pass_equals_round1_launch_sequence(name, cluster):
+    """Round-2 pass: the convergence test and the whole finalize half run as ONE thread-block-cluster
+    kernel at the end of the pass (rbs_fused.cuh k_finalize, cluster barriers between the phases)
+    instead of six launches on a compacted list at the start of the next pass.  Same device
+    functions in the same per-member order: states, storages, status flags, control states and the
+    iteration / sub-step / reject counters are bitwise those of the round-1 sequence; 70 members =
+    two full 32-member tiles and a ragged one."""
+    from ribasim_b200.testmodels import hws_like_model
+    B = 70
+    case = make_case(hws_like_model(n_basins=60, n_days=2) if name == "hws_like" else name, B, seed=43, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    for r2 in (0, 1):
+        h = gpu_handle_for(case, coop_members=0, lin_m=0, r2_pass=r2, fin_cluster=cluster)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if flat["n_dc"] > 0:
+                h.apply_discrete_control()
+                h.refresh(0.0)
+            l0 = h.kernel_launches()
+            st = h.advance(0.0, 3600.0, 5)
+            st |= h.step(5 * 3600.0, 1800.0)
+            launches = h.kernel_launches() - l0
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats(), launches,
+                        h.get_member_i32("dc_state", flat["n_dc"]) if flat["n_dc"] else None))
+        finally:
+            h.close()
+    (u0, S0, st0, stats0, l_r1, dc0), (u1, S1, st1, stats1, l_r2, dc1) = out
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert stats0[k] == stats1[k], k
+    if dc0 is not None:
+        assert np.array_equal(dc0, dc1)
+    assert l_r2 < l_r1
+
+
+@pytest.mark.parametrize("B", [37, 40])
+@pytest.mark.parametrize("lin_m", [4, 8])
+@pytest.mark.parametrize("name", ["basic", "backwater", "pid_control", "pump_discrete_control", "hws_like"])
+def test_m_member_solve_equals_two_member_tiles(name, lin_m, B):
+    """The full-Newton solve with M = 4 / 8 members per thread (rbs_fused.cuh) runs the schedule of
+    the 2-member tiles with the same products, summation order and team butterflies: trajectories
+    are bitwise equal, with aligned member pairs (B = 40: 16-byte copies) and without (B = 37)."""
+    from ribasim_b200.testmodels import hws_like_model
+    case = make_case(hws_like_model(n_basins=120, n_days=2) if name == "hws_like" else name, B, seed=41, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    for m in (0, lin_m):
+        h = gpu_handle_for(case, coop_members=0, lin_m=m)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if flat["n_dc"] > 0:
+                h.apply_discrete_control()
+                h.refresh(0.0)
+            st = h.advance(0.0, 3600.0, 6)
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats()))
+        finally:
+            h.close()
+    (u0, S0, st0, s0), (u1, S1, st1, s1) = out
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert s0[k] == s1[k], k
+
+
 def test_forced_window_argument_errors():
     """The forced-window entry points fail loudly: unknown forcing array, size mismatch, fewer
     slices staged than steps advanced; a window without staged slices is a plain rbs_advance."""
