@@ -100,6 +100,7 @@ struct rbs_handle {
         int* h_counts = nullptr;  // pinned {n_active, n_limit, outer steps completed by all members}
         int n_active = 0, n_limit = 0, min_step = 0;
         bool pending = false, done = false;
+        int* d_tilecnt = nullptr;  // per 64-member tile: row blocks of k_newton_update done
     };
     std::vector<Group> groups;
     double tprev = 0.0;
@@ -140,7 +141,7 @@ struct rbs_handle {
     size_t lin_m_smem = 0;
     // round-2 pass: convergence test + finalize half as one cluster kernel at the END of the pass
     // in which a member's iteration ended (rbs_fused.cuh); 0 = the round-1 launch sequence
-    int r2_pass = 1;
+    int r2_pass = 0;
     int fin_cluster = 4;
     void* d_ent_blob = nullptr;
     bool lin_ent = false;
@@ -385,6 +386,7 @@ void free_groups(rbs_handle* h) {
         if (G.d_llist) cudaFree(G.d_llist);
         if (G.d_counts) cudaFree(G.d_counts);
         if (G.h_counts) cudaFreeHost(G.h_counts);
+        if (G.d_tilecnt) cudaFree(G.d_tilecnt);
         if (G.ev) cudaEventDestroy(G.ev);
         if (G.stream && G.stream != h->stream) cudaStreamDestroy(G.stream);
     }
@@ -412,6 +414,9 @@ int make_groups(rbs_handle* h, int ng) {
         CUDA_TRY(cudaMalloc(&G.d_llist, nb_));
         CUDA_TRY(cudaMalloc(&G.d_counts, 4 * sizeof(int)));
         CUDA_TRY(cudaMallocHost(&G.h_counts, 4 * sizeof(int)));
+        const size_t nt = (size_t)(std::max(G.hi - G.lo, 1) + 63) / 64;
+        CUDA_TRY(cudaMalloc(&G.d_tilecnt, nt * sizeof(int)));
+        CUDA_TRY(cudaMemset(G.d_tilecnt, 0, nt * sizeof(int)));
     }
     return 0;
 }
@@ -949,7 +954,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         if (lin_mode == 0) { h->smem_tile = 0; h->lin_smem = false; h->lin_ent = false; h->lin_entc = false; }
         // ---- M members per thread (full-Newton path, compact slots): the widest tile that fits
         if (h->lin_entc) {
-            int want_m = getenv("RBS_LIN_M") ? atoi(getenv("RBS_LIN_M")) : geti(b, "lin_m", -1);
+            int want_m = getenv("RBS_LIN_M") ? atoi(getenv("RBS_LIN_M")) : geti(b, "lin_m", 0);
             int want_sched = getenv("RBS_LIN_M_SCHED") ? atoi(getenv("RBS_LIN_M_SCHED")) : 1;
             for (int cand : {8, 4}) {
                 if (want_m == 0 || (want_m > 0 && want_m != cand)) continue;
@@ -1002,7 +1007,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             }
         }
     }
-    h->r2_pass = getenv("RBS_R2_PASS") ? atoi(getenv("RBS_R2_PASS")) : geti(b, "r2_pass", 1);
+    h->r2_pass = getenv("RBS_R2_PASS") ? atoi(getenv("RBS_R2_PASS")) : geti(b, "r2_pass", 0);
     h->fin_cluster = getenv("RBS_FIN_CLUSTER") ? atoi(getenv("RBS_FIN_CLUSTER")) : geti(b, "fin_cluster", 4);
     bind_net(h);
     n.cc_tab_offset = geti(b, "cc_tab_offset");
@@ -1483,7 +1488,7 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
         if (n.n_dc > 0) LAUNCH(h, k_discrete_control, (long long)n.n_dc * B, n, 0);
     }
-    // Newton half
+    // Newton half; the last row block of a member tile in k_newton_update runs the convergence test
     n.NA = G.n_active;
     n.alist = G.d_alist;
     Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
@@ -1493,12 +1498,12 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
     launch_linear(h, c, nw);
     {
         dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 63) / 64, h->n_part);
-        LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
+        ConvArgs cv{G.d_tilecnt, h->n_part, h->max_iter, h->full_newton, h->early_exit, 0.01};
+        LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block, cv);
     }
     n.NA = n.B;
     n.alist = nullptr;
-    LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts, 1, h->n_part,
-               h->max_iter, 0.01, h->full_newton, h->early_exit);
+    LAUNCH_CFG(h, k_compact2, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
     h->cur = h->stream;
     h->n_passes++;
 }
@@ -1537,7 +1542,7 @@ static int launch_pass_r2(rbs_handle* h, rbs_handle::Group& G, double dt, double
     launch_linear(h, c, nw);
     {
         dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 63) / 64, h->n_part);
-        LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block);
+        LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block, ConvArgs{});
     }
     n.NA = n.B;
     n.alist = nullptr;
@@ -1695,6 +1700,125 @@ static int advance_tile(rbs_handle* h, double dt, double h_min, int32_t n_steps)
     return 0;
 }
 
+// result slices of the outer steps that every member of every group has completed go out while
+// the stragglers are still computing (every kernel that wrote them has been observed complete)
+static int stream_finished_slices(rbs_handle* h, int n_steps) {
+    if (!h->wout.on) return 0;
+    int ready = n_steps;
+    for (auto& G2 : h->groups) ready = std::min(ready, G2.min_step);
+    if (ready > h->wout.streamed) {
+        auto& w = h->wout;
+        int k0 = w.streamed, cnt = ready - k0;
+        if (w.dev_s)
+            CUDA_TRY(cudaMemcpyAsync((char*)w.host_s + w.slice_s * k0, (char*)w.dev_s + w.slice_s * k0,
+                                     w.slice_s * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (w.dev_f)
+            CUDA_TRY(cudaMemcpyAsync((char*)w.host_f + w.slice_f * k0, (char*)w.dev_f + w.slice_f * k0,
+                                     w.slice_f * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+        w.streamed = ready;
+    }
+    return 0;
+}
+
+// Pass loop of the stream path: a pass per member group and round, the groups on their own streams;
+// the host reads a group's list lengths (12 bytes) after each of its passes to size the next one.
+// (Measured in round 2, profiles/summary_r2.md: list lengths read by the kernels from device
+// memory, so that passes are launched without waiting, cost the latency-bound kernels 5-15 %
+// each — one more dependent load at the head of every thread's chain, or surplus blocks — and win
+// nothing, because the host round trip of one group hides behind the kernels of the others.)
+static int advance_passes(rbs_handle* h, double dt, double h_min, int32_t n_steps) {
+    Net& n = h->net;
+    // safety net only: every attempt either advances the member or halves its sub-step
+    const int64_t max_passes = h->max_passes * n_steps * (int64_t)h->groups.size();
+    int64_t passes = 0;
+    size_t n_done = 0;
+    for (auto& G : h->groups) {
+        if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, h->groups[0].ev, 0));
+        G.n_active = G.hi - G.lo;
+        G.n_limit = 0;
+        G.pending = false;
+        G.done = G.n_active == 0;
+        G.min_step = G.done ? n_steps : 0;
+        n_done += G.done;
+        if (G.done) continue;
+        h->cur = G.stream;
+        CUDA_TRY(cudaMemsetAsync(G.d_counts, 0, 4 * sizeof(int), G.stream));
+        LAUNCH_CFG(h, k_compact2, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
+    }
+    h->cur = h->stream;
+    while (n_done < h->groups.size()) {
+        bool progressed = false;
+        for (auto& G : h->groups) {
+            if (G.done) continue;
+            if (G.pending) {
+                cudaError_t q = cudaEventQuery(G.ev);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) return fail(std::string("rbs_advance: ") + cudaGetErrorString(q));
+                G.pending = false;
+                G.n_active = G.h_counts[0];
+                G.n_limit = G.h_counts[1];
+                G.min_step = G.h_counts[2];
+                if (stream_finished_slices(h, n_steps)) return 1;
+                if (G.n_active == 0) { G.done = true; n_done++; progressed = true; continue; }
+            }
+            if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
+            launch_pass(h, G, dt, h_min, n_steps);
+            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+            CUDA_TRY(cudaEventRecord(G.ev, G.stream));
+            G.pending = true;
+            progressed = true;
+        }
+        if (!progressed && h->groups.size() == 1) cudaEventSynchronize(h->groups[0].ev);
+    }
+    return 0;
+}
+
+// round-2 experiment kept for comparison (RBS_R2_PASS=1): cluster finalize kernel, one host
+// round trip per pass
+static int advance_sync_r2(rbs_handle* h, double dt, double h_min, int32_t n_steps) {
+    Net& n = h->net;
+    for (auto& G : h->groups) {
+        if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, h->groups[0].ev, 0));
+        h->cur = G.stream;
+        LAUNCH_CFG(h, k_compact_tiles, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_counts);
+        G.n_active = G.hi - G.lo;
+        G.n_limit = 0;
+        G.pending = false;
+        G.done = G.n_active == 0;
+        G.min_step = G.done ? n_steps : 0;
+    }
+    h->cur = h->stream;
+    const int64_t max_passes = h->max_passes * n_steps * (int64_t)h->groups.size();
+    int64_t passes = 0;
+    size_t n_done = 0;
+    for (auto& G : h->groups) n_done += G.done;
+    while (n_done < h->groups.size()) {
+        bool progressed = false;
+        for (auto& G : h->groups) {
+            if (G.done) continue;
+            if (G.pending) {
+                cudaError_t q = cudaEventQuery(G.ev);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) return fail(std::string("rbs_advance: ") + cudaGetErrorString(q));
+                G.pending = false;
+                G.n_active = G.h_counts[0];
+                G.n_limit = G.h_counts[1];
+                G.min_step = G.h_counts[2];
+                if (stream_finished_slices(h, n_steps)) return 1;
+                if (G.n_active == 0) { G.done = true; n_done++; progressed = true; continue; }
+            }
+            if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
+            if (launch_pass_r2(h, G, dt, h_min, n_steps)) return 1;
+            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+            CUDA_TRY(cudaEventRecord(G.ev, G.stream));
+            G.pending = true;
+            progressed = true;
+        }
+        if (!progressed && h->groups.size() == 1) cudaEventSynchronize(h->groups[0].ev);
+    }
+    return 0;
+}
+
 static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* status_per_member) {
     cudaSetDevice(h->device);
     Net& n = h->net;
@@ -1719,63 +1843,8 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
     // fork: every group starts from the common begin on its own stream
     cudaEvent_t ev_begin = h->groups[0].ev;
     CUDA_TRY(cudaEventRecord(ev_begin, h->stream));
-    for (auto& G : h->groups) {
-        if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, ev_begin, 0));
-        h->cur = G.stream;
-        if (h->r2_pass) LAUNCH_CFG(h, k_compact_tiles, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_counts);
-        else LAUNCH_CFG(h, k_compact, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts, 0, 0, 0, 0.0, 0, 0);
-        G.n_active = G.hi - G.lo;
-        G.n_limit = 0;
-        G.pending = false;
-        G.done = G.n_active == 0;
-        G.min_step = G.done ? n_steps : 0;
-    }
-    h->cur = h->stream;
-    // safety net only: every attempt either advances the member or halves its sub-step
-    const int64_t max_passes = h->max_passes * n_steps * (int64_t)h->groups.size();
-    int64_t passes = 0;
-    size_t n_done = 0;
-    for (auto& G : h->groups) n_done += G.done;
-    while (n_done < h->groups.size()) {
-        bool progressed = false;
-        for (auto& G : h->groups) {
-            if (G.done) continue;
-            if (G.pending) {
-                cudaError_t q = cudaEventQuery(G.ev);
-                if (q == cudaErrorNotReady) continue;
-                if (q != cudaSuccess) return fail(std::string("rbs_advance: ") + cudaGetErrorString(q));
-                G.pending = false;
-                G.n_active = G.h_counts[0];
-                G.n_limit = G.h_counts[1];
-                G.min_step = G.h_counts[2];
-                if (h->wout.on) {
-                    // every kernel that wrote the slices of steps < ready has been observed complete
-                    int ready = n_steps;
-                    for (auto& G2 : h->groups) ready = std::min(ready, G2.min_step);
-                    if (ready > h->wout.streamed) {
-                        auto& w = h->wout;
-                        int k0 = w.streamed, cnt = ready - k0;
-                        if (w.dev_s)
-                            CUDA_TRY(cudaMemcpyAsync((char*)w.host_s + w.slice_s * k0, (char*)w.dev_s + w.slice_s * k0,
-                                                     w.slice_s * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-                        if (w.dev_f)
-                            CUDA_TRY(cudaMemcpyAsync((char*)w.host_f + w.slice_f * k0, (char*)w.dev_f + w.slice_f * k0,
-                                                     w.slice_f * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-                        w.streamed = ready;
-                    }
-                }
-                if (G.n_active == 0) { G.done = true; n_done++; progressed = true; continue; }
-            }
-            if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
-            if (h->r2_pass) { if (launch_pass_r2(h, G, dt, h_min, n_steps)) return 1; }
-            else launch_pass(h, G, dt, h_min, n_steps);
-            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
-            CUDA_TRY(cudaEventRecord(G.ev, G.stream));
-            G.pending = true;
-            progressed = true;
-        }
-        if (!progressed && h->groups.size() == 1) cudaEventSynchronize(h->groups[0].ev);
-    }
+    if (h->r2_pass) { if (advance_sync_r2(h, dt, h_min, n_steps)) return 1; }
+    else if (advance_passes(h, dt, h_min, n_steps)) return 1;
     // join: every group's last event has been observed complete by the host, so all group
     // streams are idle and later work enqueued on the handle's stream is ordered after them
     h->tprev = t + dt * n_steps;

@@ -1492,10 +1492,37 @@ __device__ __forceinline__ void rbs_update_unit(const Net& n, const double* c, d
         }
     }
 }
+// nlsolve!'s convergence test fused into the update: the last row-block of a 64-member tile to
+// finish (a counter per tile) sums the partial norms in their fixed order and tests its members
+struct ConvArgs {
+    int* tile_counter;  // nullptr = no test here (the caller runs rbs_newton_converge itself)
+    int n_part, max_iter, full_newton, early_exit;
+    double kappa;
+};
+__device__ __forceinline__ void rbs_newton_converge(const Net& n, int m, int n_part, int max_iter,
+                                                    double kappa, int full_newton, int early_exit);
 __global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
-                                int rows_per_block) {
+                                int rows_per_block, ConvArgs cv) {
     __shared__ double sh[2][RBS_DZ_ROWS][33];
+    __shared__ int last;
     rbs_update_unit(n, c, abstol, reltol, rows_per_block, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, sh);
+    if (!cv.tile_counter) return;
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) last = atomicAdd(&cv.tile_counter[blockIdx.x], 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!last) return;
+    if (t == 0) cv.tile_counter[blockIdx.x] = 0;
+    __threadfence();
+    if (t < 64) {
+        const int j = blockIdx.x * 64 + t;
+        if (j < n.NA) {
+            const int m = RBS_MEMBER(n, j);
+            if (n.mphase[m] == PHASE_NEWTON)
+                rbs_newton_converge(n, m, cv.n_part, cv.max_iter, cv.kappa, cv.full_newton, cv.early_exit);
+        }
+    }
 }
 
 // per-member convergence bookkeeping of nlsolve! (OrdinaryDiffEqNonlinearSolve);
@@ -1504,7 +1531,8 @@ __device__ __forceinline__ void rbs_newton_converge(const Net& n, int m, int n_p
                                                     double kappa, int full_newton, int early_exit) {
     int iter = n.miter[m];
     double s = 0.0;
-    for (int p = 0; p < n_part; p++) s += n.norm_part[(long long)p * n.B + m];
+#pragma unroll 8
+    for (int p = 0; p < n_part; p++) s += __ldcg(&n.norm_part[(long long)p * n.B + m]);  // written by other blocks
     double ndz = sqrt(s / n.n_state);
     double eta = n.eta[m];
     int st = 0;  // 0 continue, 1 converged, 2 failed

@@ -75,6 +75,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+SHIM_PATH = PKG_DIR / "libribasim.so"
+
+
+def build_shim(force: bool = False) -> Path:
+    """Compile the `libribasim` stand-in (csrc/libribasim_shim.c, include/libribasim.h): the C ABI
+    of /root/reference/build/libribasim.jl:74-212 over the embedded-Python BMI of this package."""
+    import sysconfig
+
+    src = CSRC / "libribasim_shim.c"
+    if not force and SHIM_PATH.exists() and SHIM_PATH.stat().st_mtime >= src.stat().st_mtime:
+        return SHIM_PATH
+    inc = sysconfig.get_config_var("INCLUDEPY")
+    libdir = sysconfig.get_config_var("LIBDIR")
+    ver = sysconfig.get_config_var("LDVERSION")
+    site = sysconfig.get_paths()["purelib"]
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-fvisibility=hidden", f"-I{inc}",
+           f'-DRBS_REPO_ROOT="{PKG_DIR.parent}"', f'-DRBS_SITE_PACKAGES="{site}"',
+           "-o", str(SHIM_PATH), str(src), f"-L{libdir}", f"-lpython{ver}", "-ldl",
+           f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RbsError(f"gcc failed:\n{res.stdout}\n{res.stderr}")
+    return SHIM_PATH
+
+
 _lib = None
 
 
@@ -226,8 +251,8 @@ class Handle:
     def __init__(self, flat: Flat, sym: Symbolic | None = None, n_members: int = 1,
                  device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
                  smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0,
-                 coop_members: int = -1, tile_window: int = -1, lin_m: int = -1,
-                 r2_pass: int = 1, fin_cluster: int = 4):
+                 coop_members: int = -1, tile_window: int = -1, lin_m: int = 0,
+                 r2_pass: int = 0, fin_cluster: int = 4):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -307,7 +332,7 @@ class Handle:
             set_i("lin_mode", [lin_mode])
             set_i("n_groups", [n_groups])
             # members per thread of the full-Newton solve (rbs_fused.cuh): 8 / 4, 0 = the 2-member
-            # tiles of rbs_kernels.cuh, -1 = the widest that fits
+            # tiles of rbs_kernels.cuh (faster on B200, measured), -1 = the widest that fits
             set_i("lin_m", [lin_m])
             # 1: convergence test + finalize half as one cluster kernel per pass (rbs_fused.cuh,
             # `fin_cluster` blocks per 32-member tile); 0: the round-1 launch sequence

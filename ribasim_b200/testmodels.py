@@ -170,6 +170,21 @@ def bucket_model() -> ModelTables:
     return m
 
 
+def leaky_bucket_model() -> ModelTables:
+    """One Basin with daily forcing that has missing values: a missing value keeps the previous one
+    (python/ribasim_testmodels/ribasim_testmodels/bucket.py:42-70, core/src/callback.jl:826-838)."""
+    m = _model(end=datetime(2020, 1, 5))
+    nan = float("nan")
+    m.add_node("Basin", 1, profile=dict(area=[1000.0, 1000.0], level=[0.0, 1.0]), state=dict(level=1.0))
+    drainage = [0.003, nan, 0.001, 0.002, 0.0]
+    infiltration = [nan, 0.001, 0.002, 0.0, 0.0]
+    m.tables["Basin / time"] = [
+        dict(node_id=1, time=(m.starttime + timedelta(days=k)).strftime(TIME_FMT), drainage=drainage[k],
+             potential_evaporation=nan, infiltration=infiltration[k], precipitation=nan)
+        for k in range(5)]
+    return m
+
+
 def linear_resistance_model() -> ModelTables:
     m = _model()
     m.add_node("Basin", 1, profile=dict(area=[100.0, 100.0], level=[0.0, 10.0]),
@@ -972,6 +987,7 @@ MODELS = dict(
     backwater=backwater_model,
     trivial=trivial_model,
     bucket=bucket_model,
+    leaky_bucket=leaky_bucket_model,
     linear_resistance=linear_resistance_model,
     rating_curve=rating_curve_model,
     rating_curve_between_basins=rating_curve_between_basins_model,

@@ -104,7 +104,9 @@ def test_windowed_update_matches_stepwise(basic_toml):
 def test_stroboscopic_forcing(tmp_path):
     """core/test/run_models_test.jl:593-636: drainage and infiltration written through the BMI
     pointers on alternating days are integrated exactly into the cumulative arrays."""
-    b = _bmi(MODELS["bucket"]().write(tmp_path))
+    m = MODELS["bucket"]()
+    m.solver.update(algorithm="ImplicitEuler", dt=3600.0)
+    b = _bmi(m.write(tmp_path))
     try:
         drn, drn_sum = b.get_value_ptr("basin.drainage"), b.get_value_ptr("basin.cumulative_drainage")
         inf, inf_sum = b.get_value_ptr("basin.infiltration"), b.get_value_ptr("basin.cumulative_infiltration")

@@ -162,7 +162,9 @@ def test_two_basin_subgrid_levels(tmp_path):
     finally:
         model.finalize()
     # BMI: update_subgrid_level fills basin.subgrid_level (core/test/bmi_test.jl:52-90, build/libribasim.jl:98-101)
-    toml = MODELS["two_basin"]().write(tmp_path / "model")
+    m2 = MODELS["two_basin"]()
+    m2.solver.update(algorithm="ImplicitEuler", dt=3600.0)
+    toml = m2.write(tmp_path / "model")
     b = RibasimBmi()
     b.initialize(toml)
     try:
