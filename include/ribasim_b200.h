@@ -175,6 +175,12 @@ int rbs_advance(rbs_handle* h, double t, double dt, int32_t n_steps, int32_t* st
 int rbs_stage_forcing_window(rbs_handle* h, const char* key, const double* pinned_host,
                              int64_t n_entity, int32_t first_step, int32_t n_steps);
 int rbs_commit_forcing_window(rbs_handle* h);
+/* Forcing that changes less often than the outer step (the reference's forcing tstops are the
+ * times of the Basin / time table, core/src/callback.jl:846-866 — daily rows under an hourly
+ * dt): outer step k of a window reads slice (k + phase) / steps_per_slice, so the `first_step` /
+ * `n_steps` of rbs_stage_forcing_window count slices and a day is uploaded once, not 24 times.
+ * Default 1, 0: one slice per outer step.  Applies to the windows advanced after the call. */
+int rbs_set_forcing_slicing(rbs_handle* h, int32_t steps_per_slice, int32_t phase);
 int rbs_advance_window(rbs_handle* h, double t, double dt, int32_t n_steps,
                        double* storage_out_pinned, double* flow_out_pinned,
                        int32_t* status_per_member);

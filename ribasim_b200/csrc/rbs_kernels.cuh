@@ -118,6 +118,9 @@ struct Net {
     // forced window (rbs_advance_window): forcing slices [step][entity][member] per outer step of
     // the window (nullptr = the current array applies to every step) and per-step storage snapshots
     int fw_on;
+    // outer step k of the window reads forcing slice (k + fw_phase) / fw_every (rbs_set_forcing_slicing:
+    // e.g. daily forcing under hourly steps = one slice per 24 steps instead of 24 copies)
+    int fw_every, fw_phase;
     long long fw_sb, fw_sf;  // elements per step: n_basin*B, n_fb*B
     const double *w_precipitation, *w_surface_runoff, *w_potential_evaporation, *w_drainage,
         *w_infiltration, *w_fb_rate;
@@ -136,7 +139,8 @@ struct Net {
 // Forcing array that applies to outer step `idx` of the window.
 __device__ __forceinline__ const double* rbs_fw(const Net& n, const double* cur, const double* win,
                                                 long long stride, int idx) {
-    return (n.fw_on && win) ? win + stride * idx : cur;
+    if (!(n.fw_on && win)) return cur;
+    return win + stride * (n.fw_every > 1 ? (idx + n.fw_phase) / n.fw_every : idx);
 }
 
 // Member predicate of the step path: a kernel launched with `mphase != nullptr` only works on

@@ -136,6 +136,7 @@ def load() -> ctypes.CDLL:
         "rbs_stage_forcing_window": (ctypes.c_int, [vp, cp, dp, i64, i32, i32]),
         "rbs_advance_window": (ctypes.c_int, [vp, f64, f64, i32, dp, dp, ip]),
         "rbs_commit_forcing_window": (ctypes.c_int, [vp]),
+        "rbs_set_forcing_slicing": (ctypes.c_int, [vp, i32, i32]),
         "rbs_host_alloc": (vp, [i64]),
         "rbs_host_free": (None, [vp]),
         "rbs_copy_member_to_device": (ctypes.c_int, [vp, cp, vp, i64]),
@@ -173,7 +174,7 @@ EXPORTED_SYMBOLS = [
     "rbs_builder_create", "rbs_builder_set_i32", "rbs_builder_set_f64", "rbs_builder_destroy",
     "rbs_create", "rbs_destroy", "rbs_last_error", "rbs_version", "rbs_kernel_launches",
     "rbs_set_param_f64", "rbs_set_param_i32", "rbs_set_member_param_f64", "rbs_set_member_f64", "rbs_get_member_f64", "rbs_set_member_f64_async",
-    "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window", "rbs_host_alloc", "rbs_host_free",
+    "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window", "rbs_set_forcing_slicing", "rbs_host_alloc", "rbs_host_free",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
     "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
@@ -427,6 +428,11 @@ class Handle:
         _check(self.L.rbs_stage_forcing_window(
             self.h, key.encode(), ctypes.cast(pinned_ptr, ctypes.POINTER(ctypes.c_double)), n_entity,
             int(first_step), int(n_steps)))
+
+    def set_forcing_slicing(self, steps_per_slice: int = 1, phase: int = 0) -> None:
+        """Outer step k of a forced window reads slice (k + phase) // steps_per_slice (daily forcing
+        under hourly steps: 24, step-of-day of the window's first step)."""
+        _check(self.L.rbs_set_forcing_slicing(self.h, int(steps_per_slice), int(phase)))
 
     def commit_forcing_window(self) -> None:
         """Make the staged slices live now (before the first window)."""

@@ -886,7 +886,12 @@ def hws_like_model(n_basins: int = 500, seed: int = 20260119, n_days: int = 30,
 def random_tree_model(n_basins: int = 100_000, seed: int = 20261019, n_hours: int = 24) -> ModelTables:
     """Random-tree network: `parent[i] = rng.integers(max(0,i-50), i)`,
     connector mix 40 % Manning / 20 % TRC / 20 % Outlet / 10 % Pump / 10 % LR, root drains to a
-    LevelBoundary through a TabulatedRatingCurve, 1 % of the leaves get FlowBoundaries."""
+    LevelBoundary through a TabulatedRatingCurve, 1 % of the leaves get FlowBoundaries.
+
+    The rule makes a tree some thousands of basins deep, so the parameters are those of a drainage
+    network that has a flow regime: bed levels rise away from the root, every connector is sized
+    for the mean inflow that accumulates above it (pump / outlet capacity, resistance, channel
+    width, rating curve), initial levels are a metre above the bed."""
     rng = np.random.default_rng(seed)
     m = ModelTables(starttime=datetime(2023, 1, 1),
                     endtime=datetime(2023, 1, 1) + timedelta(hours=n_hours),
@@ -898,23 +903,36 @@ def random_tree_model(n_basins: int = 100_000, seed: int = 20261019, n_hours: in
     is_leaf[parent[1:]] = False
     kinds = ["ManningResistance", "TabulatedRatingCurve", "Outlet", "Pump", "LinearResistance"]
     probs = np.array([0.4, 0.2, 0.2, 0.1, 0.1])
+    rise = rng.uniform(0.0005, 0.004, size=n_basins)
     bottoms = np.zeros(n_basins)
+    for i in range(1, n_basins):
+        bottoms[i] = bottoms[parent[i]] + rise[i]
+    drainage = rng.uniform(0.0, 2e-4, size=n_basins)
+    leaves = np.flatnonzero(is_leaf)
+    n_fb = max(1, len(leaves) // 100)
+    fb_basin = rng.choice(leaves, size=n_fb, replace=False)
+    fb_rate = rng.lognormal(-3.0, 1.0, size=n_fb)
+    # mean inflow that accumulates above every basin's downstream connector (children have
+    # larger indices than their parents)
+    acc = drainage.copy()
+    np.add.at(acc, fb_basin, fb_rate)
+    for i in range(n_basins - 1, 0, -1):
+        acc[parent[i]] += acc[i]
     node = m.node
     tabs = m.tables
     prof_rows, state_rows, static_rows = [], [], []
     for b in range(n_basins):
         k = int(rng.integers(2, 5))
-        level, area = _random_profile(rng, k, 11.0, 1.0)
-        bottoms[b] = level[0]
+        level, area = _random_profile(rng, k, 11.0, 1.0, bottom=float(bottoms[b]))
         bid = b + 1
         node.append(dict(node_id=bid, node_type="Basin", subnetwork_id=None, route_priority=None,
                          cyclic_time=False))
         for lv, ar in zip(level, area):
             prof_rows.append(dict(node_id=bid, level=float(lv), area=float(ar), storage=None))
-        state_rows.append(dict(node_id=bid, level=float(level[0] + rng.uniform(0.5, 1.5))))
+        state_rows.append(dict(node_id=bid, level=float(level[0] + rng.uniform(0.8, 1.2))))
         static_rows.append(dict(node_id=bid, precipitation=float(rng.uniform(0, 3e-8)),
                                 potential_evaporation=float(rng.uniform(0, 1e-8)),
-                                drainage=float(rng.uniform(0, 1e-2)), infiltration=0.0,
+                                drainage=float(drainage[b]), infiltration=0.0,
                                 surface_runoff=0.0))
     tabs["Basin / profile"] = prof_rows
     tabs["Basin / state"] = state_rows
@@ -924,14 +942,14 @@ def random_tree_model(n_basins: int = 100_000, seed: int = 20261019, n_hours: in
     choice = rng.choice(len(kinds), size=n_basins, p=probs)
     for i in range(1, n_basins):
         kind = kinds[int(choice[i])]
-        _add_connector_fast(m, rng, kind, nid, float(bottoms[i]))
+        _add_connector_fast(m, rng, kind, nid, float(bottoms[i]), float(acc[i]))
         m.link.append(dict(link_id=link_id, from_node_id=i + 1, to_node_id=nid, link_type="flow"))
         m.link.append(dict(link_id=link_id + 1, from_node_id=nid, to_node_id=int(parent[i]) + 1,
                            link_type="flow"))
         link_id += 2
         nid += 1
     # root -> TRC -> LevelBoundary
-    _add_connector_fast(m, rng, "TabulatedRatingCurve", nid, float(bottoms[0]))
+    _add_connector_fast(m, rng, "TabulatedRatingCurve", nid, float(bottoms[0]), float(acc[0]))
     node.append(dict(node_id=nid + 1, node_type="LevelBoundary", subnetwork_id=None,
                      route_priority=None, cyclic_time=False))
     tabs.setdefault("LevelBoundary / static", []).append(
@@ -941,13 +959,10 @@ def random_tree_model(n_basins: int = 100_000, seed: int = 20261019, n_hours: in
                        link_type="flow"))
     link_id += 2
     nid += 2
-    leaves = np.flatnonzero(is_leaf)
-    n_fb = max(1, len(leaves) // 100)
-    for b in rng.choice(leaves, size=n_fb, replace=False):
+    for b, q in zip(fb_basin, fb_rate):
         node.append(dict(node_id=nid, node_type="FlowBoundary", subnetwork_id=None,
                          route_priority=None, cyclic_time=False))
-        tabs.setdefault("FlowBoundary / static", []).append(
-            dict(node_id=nid, flow_rate=float(rng.lognormal(0.0, 1.0))))
+        tabs.setdefault("FlowBoundary / static", []).append(dict(node_id=nid, flow_rate=float(q)))
         m.link.append(dict(link_id=link_id, from_node_id=nid, to_node_id=int(b) + 1,
                            link_type="flow"))
         link_id += 1
@@ -955,27 +970,33 @@ def random_tree_model(n_basins: int = 100_000, seed: int = 20261019, n_hours: in
     return m
 
 
-def _add_connector_fast(m: ModelTables, rng, kind: str, node_id: int, bottom_src: float) -> None:
-    """Like `_add_connector` but appends rows directly (the 100k generator is loop-heavy)."""
+def _add_connector_fast(m: ModelTables, rng, kind: str, node_id: int, bottom_src: float,
+                        q_mean: float) -> None:
+    """Connector sized for the mean flow `q_mean` that arrives at it; appends rows directly (the
+    100k generator is loop-heavy)."""
     m.node.append(dict(node_id=node_id, node_type=kind, subnetwork_id=None, route_priority=None,
                        cyclic_time=False))
     rows = m.tables.setdefault(f"{kind} / static", [])
+    q = max(q_mean, 1e-4)
     if kind == "ManningResistance":
+        # ~0.3 m3/s per metre of width at 1 m depth and a 0.2 m head over 1 km (n = 0.04)
         rows.append(dict(node_id=node_id, length=float(rng.uniform(200.0, 2000.0)),
                          manning_n=float(rng.uniform(0.02, 0.06)),
-                         profile_width=float(rng.uniform(2.0, 30.0)), profile_slope=0.0))
+                         profile_width=float(min(max(q / 0.3 * rng.uniform(0.7, 1.5), 1.0), 2000.0)),
+                         profile_slope=0.0))
     elif kind == "LinearResistance":
-        rows.append(dict(node_id=node_id, resistance=float(rng.uniform(50.0, 5000.0)),
-                         max_flow_rate=float(rng.uniform(5.0, 50.0))))
+        rows.append(dict(node_id=node_id, resistance=float(rng.uniform(0.1, 0.5) / q),
+                         max_flow_rate=float(5.0 * q)))
     elif kind == "TabulatedRatingCurve":
         level, flow = _rating_curve(rng, bottom_src)
-        for lv, q in zip(level, flow):
-            rows.append(dict(node_id=node_id, level=float(lv), flow_rate=float(q)))
+        flow = flow / flow[2] * q * rng.uniform(0.8, 1.6)  # carries the mean flow at ~1 m depth
+        for lv, qq in zip(level, flow):
+            rows.append(dict(node_id=node_id, level=float(lv), flow_rate=float(qq)))
     elif kind == "Outlet":
-        rows.append(dict(node_id=node_id, flow_rate=float(rng.uniform(0.5, 10.0)),
+        rows.append(dict(node_id=node_id, flow_rate=float(q * rng.uniform(1.2, 2.5)),
                          min_upstream_level=bottom_src + 0.2))
     elif kind == "Pump":
-        rows.append(dict(node_id=node_id, flow_rate=float(rng.uniform(0.1, 5.0))))
+        rows.append(dict(node_id=node_id, flow_rate=float(q * rng.uniform(1.2, 2.5))))
 
 
 MODELS = dict(

@@ -524,6 +524,50 @@ def test_forced_window_equals_per_step_forcing():
         assert np.array_equal(last[k], series[k][2 * W - 1])
 
 
+def test_forcing_slicing_equals_repeated_slices():
+    """rbs_set_forcing_slicing: forcing that changes every 3 outer steps, uploaded once per change,
+    = the same forcing uploaded as one slice per outer step, bitwise (a window of 7 steps that
+    starts at step 2 of a slice, so that the phase and a partial last slice are exercised)."""
+    import torch
+    from ribasim_b200.testmodels import hws_like_model
+    B, W, every, phase, dt = 36, 7, 3, 2, 1800.0
+    case = make_case(hws_like_model(n_basins=40, n_days=2), B, seed=29, t=0.0)
+    flat = case["flat"]
+    n, nb, nfb = flat["n_state"], flat["n_basin"], flat["n_fb"]
+    rng = np.random.default_rng(7)
+    keys = {"precipitation": nb, "potential_evaporation": nb, "drainage": nb, "fb_rate": nfb}
+    base = {k: (case["fb_rate"] if k == "fb_rate" else case["forcing"][k]) for k in keys}
+    n_slices = (phase + W - 1) // every + 1
+    slices = {k: np.stack([base[k] * rng.lognormal(0.0, 0.4, size=base[k].shape) for _ in range(n_slices)])
+              for k in keys}
+    per_step = {k: np.stack([slices[k][(s + phase) // every] for s in range(W)]) for k in keys}
+
+    def run(series, slicing):
+        h = gpu_handle_for(case)
+        try:
+            h.set_stepper(full_newton=True)
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if slicing:
+                h.set_forcing_slicing(every, phase)
+            pinned = {k: torch.from_numpy(np.ascontiguousarray(series[k])).pin_memory() for k in keys}
+            out = torch.zeros((W, nb, B), dtype=torch.float64).pin_memory()
+            for k in keys:
+                h.stage_forcing_window(k, pinned[k].data_ptr(), keys[k], series[k].shape[0])
+            h.commit_forcing_window()
+            st = h.advance_window(0.0, dt, W, out.data_ptr())
+            h.synchronize()
+            return h.get_member("u", n), st, out.numpy().copy(), {k: h.get_member(k, keys[k]) for k in keys}
+        finally:
+            h.close()
+
+    u_ref, st_ref, S_ref, _ = run(per_step, False)
+    u, st, S, last = run(slices, True)
+    assert np.array_equal(u, u_ref) and np.array_equal(st, st_ref) and np.array_equal(S, S_ref)
+    for k in keys:
+        assert np.array_equal(last[k], slices[k][n_slices - 1])
+
+
 def test_parameter_ensemble_per_member_overrides():
     """Parameter ensembles (north star (4)): per-member Manning n, LinearResistance resistance and
     Pump / Outlet flow rates, LevelBoundary levels.  RHS and Jacobian of every member match an oracle instance built with
