@@ -115,6 +115,7 @@ __device__ __forceinline__ void rbs_tile_members(const Net& n, int m0, int* mem_
 // `lu` and the reduced right-hand side in `br` (k_assemble_linear); output: x = W^-1 b_r.
 template <int M>
 __global__ void __launch_bounds__(RBS_ENT_LANES) k_newton_linear_m(Net n, EntSched es, double* __restrict__ x) {
+    RBS_PDL();
     constexpr int C = M / 2, NT = RBS_ENT_LANES;
     extern __shared__ double smem[];
     double2* S2 = (double2*)smem;
@@ -209,6 +210,7 @@ __device__ __forceinline__ void rbs_fin_sync() {
 
 template <int CL>
 __global__ void __launch_bounds__(RBS_FIN_THREADS) k_finalize(Net n, FinArgs a) {
+    RBS_PDL();
     const unsigned FULL = 0xffffffffu;
     const int rank = CL > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
     const int tile = blockIdx.x / CL;
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(RBS_FIN_THREADS) k_finalize(Net n, FinArgs a) 
 // counts[0] = list length, counts[2] = outer steps completed by every member of the group.
 __global__ void k_compact_tiles(Net n, int m_lo, int m_hi, int* __restrict__ alist_out,
                                 int* __restrict__ counts) {
+    RBS_PDL();
     __shared__ int sa[1024];
     const int t = threadIdx.x, T = blockDim.x;
     const int nm = m_hi - m_lo;
@@ -329,6 +332,7 @@ __device__ __forceinline__ int rbs_block_exscan(int v, int* warp_tot, int& total
 
 __global__ void __launch_bounds__(1024) k_compact2(Net n, int m_lo, int m_hi, int* __restrict__ alist_out,
                                                    int* __restrict__ llist_out, int* __restrict__ counts) {
+    RBS_PDL();
     __shared__ int wt[32];
     const int t = threadIdx.x, T = blockDim.x;
     const int nm = m_hi - m_lo;

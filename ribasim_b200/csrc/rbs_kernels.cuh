@@ -158,6 +158,13 @@ template <bool JAC> __device__ __forceinline__ bool rbs_skip(const Pred& p, int 
 }
 
 #define RBS_TID (blockIdx.x * (long long)blockDim.x + threadIdx.x)
+// Programmatic dependent launch (step-path kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): let the next kernel's blocks be scheduled
+// as soon as every block of this one has started, and wait here until the previous kernel has
+// completed and its writes are visible.  Takes the launch latency between the dozen short dependent
+// kernels of a pass off the critical path; a no-op for kernels launched the ordinary way.
+#define RBS_PDL() do { asm volatile("griddepcontrol.launch_dependents;"); \
+                       asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
 // member index of position j in the launch domain (compacted list of active members)
 #define RBS_MEMBER(n, j) ((n).alist ? (n).alist[(j)] : (j))
 
@@ -200,6 +207,7 @@ __device__ __forceinline__ RbsEnd rbs_fetch_end(const Net& n, int kind, int idx,
 
 // ---- exact cumulative forcing up to the RHS time (solve.jl:137-150, 86-99) -------------------
 __global__ void k_exact(Net n, double t, double tprev) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int b = (int)(tid / n.NA);
     if (b >= n.n_basin) return;
@@ -230,6 +238,7 @@ __device__ __forceinline__ double rbs_red_in(const double* a, const double* b, l
 template <int MODE>
 __global__ void k_reduce(Net n, const double* __restrict__ a, const double* __restrict__ b,
                          double* __restrict__ out, double dt, double inv_dt) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int r = (int)(tid / n.NA);
     if (r >= n.n_reduced) return;
@@ -320,6 +329,7 @@ __device__ __forceinline__ void rbs_basin_item(const Net& n, const double* ur, b
 template <bool JAC, int SRC>
 __global__ void __launch_bounds__(256, 6) k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
                         int flag_negative) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int b = (int)(tid / n.NA);
     if (b >= n.n_reduced) return;
@@ -447,6 +457,7 @@ __device__ __forceinline__ void rbs_link_item(const Net& n, int s, int m, int ph
 
 template <bool JAC>
 __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int li = (int)(tid / n.NA);
     int count = phase == 0 ? n.n_conn : n_list;
@@ -490,6 +501,7 @@ __device__ __forceinline__ void rbs_cc_item(const Net& n, int i, int m) {
 
 template <bool JAC>
 __global__ void k_continuous_control(Net n, Pred pred) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int i = (int)(tid / n.NA);
     if (i >= n.n_cc) return;
@@ -579,6 +591,7 @@ __device__ __forceinline__ void rbs_pid_item(const Net& n, const double* ur, int
 }
 template <bool JAC>
 __global__ void k_pid(Net n, const double* __restrict__ ur, Pred pred, int fuse_link) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int i = (int)(tid / n.NA);
     if (i >= n.n_pid) return;
@@ -600,6 +613,7 @@ __device__ __forceinline__ double rbs_w_entry(const Net& n, int e, int m, double
     return acc;
 }
 __global__ void k_assemble_w(Net n, double inv_gamma) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int e = (int)(tid / n.NA);
     if (e >= n.nnz_w) return;
@@ -629,6 +643,7 @@ __device__ __forceinline__ void rbs_lu_entry(const Net& n, int e, int m, double 
 // wide mode: one launch per dependency level, grid over (entries of the level) x members
 template <bool FROM_J>
 __global__ void k_lu_level(Net n, int e0, int e1, double inv_gamma, Pred pred) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int e = e0 + (int)(tid / n.NA);
     if (e >= e1) return;
@@ -642,6 +657,7 @@ __global__ void k_lu_level(Net n, int e0, int e1, double inv_gamma, Pred pred) {
 template <bool FROM_J>
 __global__ void k_lu_tile(Net n, const int* __restrict__ level_ptr, int n_levels, int tile,
                           double inv_gamma, Pred pred) {
+    RBS_PDL();
     int m0 = blockIdx.x * tile;
     int tm = min(tile, n.NA - m0);
     if (tm <= 0) return;
@@ -679,6 +695,7 @@ __device__ __forceinline__ double rbs_solve_rhs(const Net& n, const double* __re
 }
 template <bool FROM_DU>
 __global__ void k_solve_load(Net n, const double* __restrict__ b, Pred pred) {  // xs = P b
+    RBS_PDL();
     long long tid = RBS_TID;
     int i = (int)(tid / n.NA);
     if (i >= n.n_reduced) return;
@@ -701,6 +718,7 @@ __device__ __forceinline__ void rbs_bwd_row(const Net& n, int pos, int m) {
     n.xs[(long long)i * n.B + m] = v / n.lu[(long long)n.lu_diag[i] * n.B + m];
 }
 __global__ void k_solve_level(Net n, int p0, int p1, int backward, Pred pred) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int pos = p0 + (int)(tid / n.NA);
     if (pos >= p1) return;
@@ -712,6 +730,7 @@ template <bool FROM_DU>
 __global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __restrict__ x,
                              const int* __restrict__ fwd_level_ptr, int n_fwd,
                              const int* __restrict__ bwd_level_ptr, int n_bwd, int tile, Pred pred) {
+    RBS_PDL();
     int m0 = blockIdx.x * tile;
     int tm = min(tile, n.NA - m0);
     if (tm <= 0) return;
@@ -744,6 +763,7 @@ __global__ void k_solve_tile(Net n, const double* __restrict__ b, double* __rest
     }
 }
 __global__ void k_solve_store(Net n, double* __restrict__ x, Pred pred) {  // x = P^T xs
+    RBS_PDL();
     long long tid = RBS_TID;
     int i = (int)(tid / n.NA);
     if (i >= n.n_reduced) return;
@@ -777,6 +797,7 @@ template <int TILE, class IT>
 __global__ void __launch_bounds__(1024)
 k_newton_linear(Net n, LinSched sc, const IT* __restrict__ blob, const int* __restrict__ lsrc_ptr,
                 const int* __restrict__ lsrc_code, double* __restrict__ x) {
+    RBS_PDL();
     extern __shared__ double smem[];
     double* xs_s = smem;                               // [n_reduced][TILE]
     IT* ix = (IT*)(xs_s + (size_t)n.n_reduced * TILE);
@@ -959,6 +980,7 @@ __device__ __forceinline__ void rbs_assemble_item(const Net& n, const int* __res
 #define RBS_MPT 2
 __global__ void k_assemble_linear(Net n, const int* __restrict__ dsrc_ptr,
                                   const int* __restrict__ dsrc_code) {
+    RBS_PDL();
     const int n_tiles = (n.NA + 63) >> 6;
     long long tid = RBS_TID;
     const int lane = (int)(tid & 31);
@@ -1006,6 +1028,7 @@ template <class IT>
 __global__ void __launch_bounds__(1024)
 k_newton_linear_smem(Net n, LduSched sc, const IT* __restrict__ blob, int write_lu,
                      double* __restrict__ x) {
+    RBS_PDL();
     constexpr int TILE = 8;
     extern __shared__ double smem[];
     double* lu_s = smem;                               // [n_lu][TILE]
@@ -1306,7 +1329,14 @@ __device__ __forceinline__ void rbs_lin_tile(const Net& n, EntSched es, double* 
         mem_s[jj] = mm;
         fac_s[jj] = mm >= 0 && n.mjac[mm] != 0;
     }
-    if (es.smem_sched) {
+    if (es.smem_sched == 3) {
+        // 3: the product words only — they are the gathered loads of the level loop (a lane's
+        // products lie anywhere in the list); level and entry words are coalesced and stay behind L1
+        unsigned long long* sw = (unsigned long long*)(S + (size_t)es.n_slots * TILE);
+        const int n_prod = es.n_words - (int)(es.prod - es.lvl);
+        for (int w = threadIdx.x; w < n_prod; w += NT) sw[w] = es.prod[w];
+        es.prod = sw;
+    } else if (es.smem_sched) {
         // 1: the whole schedule behind the slots; 2: level and entry words only (a lane's entry
         // word heads its dependent chain in every level; the product words stay behind L1)
         unsigned long long* sw = (unsigned long long*)(S + (size_t)es.n_slots * TILE);
@@ -1358,6 +1388,7 @@ __device__ __forceinline__ void rbs_lin_tile(const Net& n, EntSched es, double* 
 template <int TILE>
 __global__ void __launch_bounds__(RBS_ENT_LANES * TILE / 2)
 k_newton_linear_ent(Net n, EntSched es, int write_lu, double* __restrict__ x) {
+    RBS_PDL();
     extern __shared__ double smem[];
     rbs_lin_tile<TILE>(n, es, smem, blockIdx.x * TILE, write_lu, x);
 }
@@ -1433,6 +1464,7 @@ __device__ __forceinline__ double rbs_clamp_state(double v, double up, double lo
 __global__ void k_limit_flow(Net n, double* __restrict__ u, const double* __restrict__ uprev,
                              double dt, const int* __restrict__ from_ts,
                              const double* __restrict__ alloc_total) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int s = (int)(tid / n.NA);
     if (s >= n.off_integral) return;
@@ -1507,6 +1539,7 @@ __device__ __forceinline__ void rbs_newton_converge(const Net& n, int m, int n_p
                                                     double kappa, int full_newton, int early_exit);
 __global__ void k_newton_update(Net n, const double* __restrict__ c, double abstol, double reltol,
                                 int rows_per_block, ConvArgs cv) {
+    RBS_PDL();
     __shared__ double sh[2][RBS_DZ_ROWS][33];
     __shared__ int last;
     rbs_update_unit(n, c, abstol, reltol, rows_per_block, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, sh);
@@ -1576,6 +1609,7 @@ __device__ __forceinline__ void rbs_newton_converge(const Net& n, int m, int n_p
 __global__ void k_compact(Net n, int m_lo, int m_hi, int* __restrict__ alist_out,
                           int* __restrict__ llist_out, int* __restrict__ counts, int converge,
                           int n_part, int max_iter, double kappa, int full_newton, int early_exit) {
+    RBS_PDL();
     __shared__ int sa[1024], sl[1024];
     int t = threadIdx.x, T = blockDim.x;
     int nm = m_hi - m_lo;
@@ -1651,6 +1685,7 @@ __device__ __forceinline__ void rbs_exact_update(const Net& n, int b, int m, boo
 
 // start of an outer step [t0, t0 + dt]: uprev <- u, first attempt length, predictor, exact
 __global__ void k_step_begin(Net n, double dt, int predictor) {
+    RBS_PDL();
     long long tid = RBS_TID;
     long long total = (long long)n.n_state * n.B;
     int m = (int)(tid % n.B);
@@ -1704,6 +1739,7 @@ __device__ __forceinline__ void rbs_step_limit_item(const Net& n, const int* __r
 
 __global__ void k_step_limit(Net n, const int* __restrict__ from_ts,
                              const double* __restrict__ alloc_total) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int s = (int)(tid / n.NA);
     if (s >= n.n_state) return;
@@ -1765,6 +1801,7 @@ __device__ __forceinline__ void rbs_step_decide_item(const Net& n, double dt, do
 
 __global__ void k_step_decide(Net n, double dt, double h_min, int max_halvings, int grow_iters,
                               int n_steps, int shrink_log2) {
+    RBS_PDL();
     int j = (int)RBS_TID;
     if (j >= n.NA) return;
     rbs_step_decide_item(n, dt, h_min, max_halvings, grow_iters, n_steps, shrink_log2, RBS_MEMBER(n, j));
@@ -1806,6 +1843,7 @@ __device__ __forceinline__ void rbs_step_apply_item(const Net& n, int predictor,
 }
 
 __global__ void k_step_apply(Net n, int predictor) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int ent = (int)(tid / n.NA);
     if (ent >= n.n_state + n.n_basin) return;
@@ -1862,6 +1900,7 @@ __device__ __forceinline__ void rbs_discrete_control_item(const Net& n, int init
 }
 
 __global__ void k_discrete_control(Net n, int initial) {
+    RBS_PDL();
     long long tid = RBS_TID;
     int i = (int)(tid / n.NA);
     if (i >= n.n_dc) return;
@@ -1869,10 +1908,12 @@ __global__ void k_discrete_control(Net n, int initial) {
 }
 
 __global__ void k_fill(double* p, long long nelem, double v) {
+    RBS_PDL();
     long long tid = RBS_TID;
     if (tid < nelem) p[tid] = v;
 }
 __global__ void k_broadcast(double* __restrict__ dst, const double* __restrict__ src, int n_entity, int B) {
+    RBS_PDL();
     long long tid = RBS_TID;
     if (tid < (long long)n_entity * B) dst[tid] = src[tid / B];
 }
