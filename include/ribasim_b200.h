@@ -232,6 +232,14 @@ void rbs_host_free(void* p);
 void* rbs_device_ptr(rbs_handle* h, const char* key);
 /* The CUDA stream all work of this handle is ordered on (cudaStream_t as void*). */
 void* rbs_stream(rbs_handle* h);
+/* Final result gather, the only collective of the design (members are sharded over
+ * the GPUs of a box and never exchange anything inside the time loop; the reference has no
+ * analogue, one `Ribasim.Model` is one process): ncclAllGather of the member array `key`
+ * ("storage", "u", ...) over the ranks of the caller's communicator (`ncclComm_t`, created by the
+ * host with NCCL.jl / ncclCommInitRank) on the handle's stream.  Every rank must hold the same
+ * number of members; recv_device receives [n_ranks][n_entity][n_members_local] doubles (rank
+ * blocks in rank order, each in the library's member-fastest layout).  NCCL is bound at call time. */
+int rbs_gather(rbs_handle* h, void* nccl_comm, const char* key, int64_t n_entity, void* recv_device);
 int rbs_synchronize(rbs_handle* h);
 
 #ifdef __cplusplus

@@ -4,6 +4,8 @@
 // the `Net` kernel argument, launch sequencing of one RHS / Jacobian / linear solve / Newton
 // step.  There is no CPU compute path: without a usable CUDA device rbs_create fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdio>
@@ -1333,6 +1335,37 @@ void* rbs_host_alloc(int64_t bytes) {
     return p;
 }
 void rbs_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// The one collective of the design: all-gather of a per-member array over the
+// ranks of the caller's NCCL communicator.  NCCL is bound at call time (the library the host
+// process already uses, else libnccl.so.2), so that librbs.so itself loads without it.
+int rbs_gather(rbs_handle* h, void* nccl_comm, const char* key, int64_t n_entity, void* recv_device) {
+    if (!h || !nccl_comm || !key || !recv_device) return fail("rbs_gather: null argument");
+    cudaSetDevice(h->device);
+    auto it = h->member.find(key);
+    if (it == h->member.end() || it->second.is_int) return fail(std::string("unknown member array ") + key);
+    if (h->member_entities[key] != n_entity) return fail(std::string("member array size mismatch: ") + key);
+    typedef ncclResult_t (*all_gather_fn)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    typedef const char* (*err_fn)(ncclResult_t);
+    static all_gather_fn all_gather = nullptr;
+    static err_fn err_string = nullptr;
+    if (!all_gather) {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return fail(std::string("rbs_gather: NCCL not found: ") + dlerror());
+        all_gather = (all_gather_fn)dlsym(lib, "ncclAllGather");
+        err_string = (err_fn)dlsym(lib, "ncclGetErrorString");
+        if (!all_gather) return fail("rbs_gather: ncclAllGather not found in the NCCL library");
+    }
+    const size_t count = (size_t)n_entity * h->B;
+    if (count == 0) return 0;
+    ncclResult_t r = all_gather(it->second.p, recv_device, count, ncclFloat64, (ncclComm_t)nccl_comm, h->stream);
+    if (r != ncclSuccess)
+        return fail(std::string("rbs_gather: ncclAllGather: ") + (err_string ? err_string(r) : "error"));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_gather");
+}
 
 int rbs_synchronize(rbs_handle* h) {
     if (!h) return fail("rbs_synchronize: null handle");

@@ -276,7 +276,7 @@ def storage_to_level(S: float, level, dSdh, slope, cumS) -> float:
 def _pchip_end(h1, h2, del1, del2):
     """Three-point end slope with the shape-preserving caps of Moler's `pchipend`."""
     d = ((2 * h1 + h2) * del1 - h1 * del2) / (h1 + h2)
-    sgn = lambda x: (x > 0) - (x < 0)  # noqa: E731
+    sgn = lambda x: int(x > 0) - int(x < 0)  # noqa: E731
     if sgn(d) != sgn(del1):
         return 0.0
     if sgn(del1) != sgn(del2) and abs(d) > abs(3 * del1):

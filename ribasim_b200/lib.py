@@ -161,6 +161,7 @@ def load() -> ctypes.CDLL:
         "rbs_device_ptr": (vp, [vp, cp]),
         "rbs_stream": (vp, [vp]),
         "rbs_synchronize": (ctypes.c_int, [vp]),
+        "rbs_gather": (ctypes.c_int, [vp, vp, cp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # raises AttributeError if the symbol is missing
@@ -177,7 +178,7 @@ EXPORTED_SYMBOLS = [
     "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window", "rbs_set_forcing_slicing", "rbs_host_alloc", "rbs_host_free",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
-    "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize",
+    "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize", "rbs_gather",
 ]
 
 
@@ -565,6 +566,11 @@ class Handle:
 
     def device_ptr(self, key: str) -> int:
         return int(self.L.rbs_device_ptr(self.h, key.encode()) or 0)
+
+    def gather(self, nccl_comm: int, key: str, n_entity: int, recv_device_ptr: int) -> None:
+        """ncclAllGather of a member array over the caller's communicator (rbs_gather)."""
+        _check(self.L.rbs_gather(self.h, ctypes.c_void_p(nccl_comm), key.encode(), int(n_entity),
+                                 ctypes.c_void_p(recv_device_ptr)))
 
     def synchronize(self) -> None:
         _check(self.L.rbs_synchronize(self.h))

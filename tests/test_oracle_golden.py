@@ -166,6 +166,58 @@ def test_qh_interpolation_goldens():
             qh_interpolation(NodeID("TabulatedRatingCurve", 2, 1), lv, fl)
 
 
+def test_pchip_pinned_against_scipy():
+    """Interior slopes and values of the PCHIP tables, pinned against an independent implementation
+    of the same published algorithm (Fritsch-Butland harmonic-mean interior slopes, three-point
+    shape-preserving end slopes = DataInterpolations' `PCHIPInterpolation`,
+    scipy.interpolate.PchipInterpolator): the host's `interp.py`, and the oracle's evaluator on a
+    rating curve (with the prepended point (h0 - 1, 0), constant extrapolation below and linear
+    above, core/src/util.jl:101-141).  Non-uniform tables of 2..11 points: monotone, with flat
+    pieces, and arbitrary."""
+    from scipy.interpolate import PchipInterpolator
+    from ribasim_b200.interp import PchipTable, du_pchip
+
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n = int(rng.integers(2, 12))
+        t = np.cumsum(rng.uniform(0.05, 3.0, size=n))
+        kind = trial % 3
+        if kind == 0:
+            u = np.cumsum(rng.uniform(0, 2, size=n))
+        elif kind == 1:
+            u = rng.normal(size=n)
+        else:
+            u = np.concatenate([[0.0], np.cumsum(rng.choice([0.0, 1.0, 0.3], size=n - 1))])
+        sp = PchipInterpolator(t, u)
+        ds = sp.derivative()(t)
+        d = np.array(du_pchip(list(u), list(t)))
+        assert np.max(np.abs(d - ds) / np.maximum(1.0, np.abs(ds))) <= 1e-13, (trial, d, ds)
+        tab = PchipTable(u, t, "constant", "linear")
+        for x in rng.uniform(t[0], t[-1], size=40):
+            assert tab(float(x)) == pytest.approx(float(sp(x)), rel=1e-13, abs=1e-13)
+        # extrapolation: constant below, linear with the end-knot derivative above
+        assert tab(t[0] - 1.7) == u[0]
+        assert tab(t[-1] + 2.5) == pytest.approx(u[-1] + 2.5 * ds[-1], rel=1e-13, abs=1e-13)
+    # the oracle's evaluator (what the device is compared with to 1e-12) on rating curves
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        k = int(rng.integers(5, 9))
+        level = 1.0 + np.concatenate([[0.0], np.cumsum(rng.uniform(0.1, 2.0, size=k - 1))])
+        flow = np.concatenate([[0.0], np.cumsum(rng.uniform(0.0, 3.0, size=k - 1) * rng.choice([0.0, 1.0, 1.0], size=k - 1))])
+        m = MODELS["rating_curve"]()
+        proto = m.tables["TabulatedRatingCurve / static"][0]
+        m.tables["TabulatedRatingCurve / static"] = [dict(proto, level=float(h), flow_rate=float(q))
+                                                     for h, q in zip(level, flow)]
+        om = OracleModel(build_params(m))
+        ta, ua = np.concatenate([[level[0] - 1.0], level]), np.concatenate([[0.0], flow])
+        sp = PchipInterpolator(ta, ua)
+        for x in np.concatenate([rng.uniform(ta[0], ta[-1], size=60), level]):
+            assert om.L.orc_pchip_eval(om.h, 0, float(x)) == pytest.approx(float(sp(x)), rel=1e-13, abs=1e-14)
+        assert om.L.orc_pchip_eval(om.h, 0, float(ta[0] - 3.0)) == 0.0
+        slope = float(sp.derivative()(ta[-1]))
+        assert om.L.orc_pchip_eval(om.h, 0, float(ta[-1] + 1.5)) == pytest.approx(ua[-1] + 1.5 * slope, rel=1e-13, abs=1e-14)
+
+
 def test_initial_level_golden():
     # python/ribasim_api/tests/test_bmi.py:102-110 and basic.py:45:
     # storage 1.0 on A=[0.01,1000], h=[0,1] <-> level 0.04471158417652035
