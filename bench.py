@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline workload only")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel timing pass")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="bracket the device-resident timed leg with cudaProfilerStart/Stop (for "
+                         "`ncu --profile-from-start off`) and stop after it")
     return ap.parse_args()
 
 
@@ -448,9 +451,19 @@ class Run:
         sampler = ClockSampler(local_rank)
         sampler.start()
         s0, l0 = h.stats(), h.kernel_launches()
+        if args.ncu_range:
+            self.torch.cuda.profiler.start()
         ms = self.timed(run)
+        if args.ncu_range:
+            self.torch.cuda.profiler.stop()
         s1, l1 = h.stats(), h.kernel_launches()
         value = self.total * steps / (ms * 1e-3)
+        if args.ncu_range:
+            sampler.stop()
+            print(f"profiled leg: {steps} steps, {ms / steps:.4f} ms/step, {l1 - l0} launches, "
+                  f"{(s1['newton_iters'] - s0['newton_iters']) / (self.nm * steps):.3f} Newton iterations per "
+                  f"member-step", file=sys.stderr)
+            raise SystemExit(0)
         # -- end to end through the C ABI with HOST buffers: every window uploads its daily forcing
         # slices from pinned memory and downloads the storages of every outer step; the upload of
         # window k+1 and the download of window k-1 overlap with window k

@@ -232,6 +232,12 @@ void rbs_host_free(void* p);
 void* rbs_device_ptr(rbs_handle* h, const char* key);
 /* The CUDA stream all work of this handle is ordered on (cudaStream_t as void*). */
 void* rbs_stream(rbs_handle* h);
+/* For an integrator that lives above the seams (adaptive QNDF, core/src/config.jl:368-380): an
+ * accepted step of length dt advances the exactly integrated forcing — cumulative precipitation,
+ * surface runoff, drainage and boundary inflow (`update_cumulative_flows!`, core/src/callback.jl:
+ * 131-170) — with the rates in force, and tprev by dt; rbs_rhs / rbs_jac at a later time then see
+ * S = S0 + A u + the exact inflows up to that time (core/src/solve.jl:137-150). */
+int rbs_accept_step(rbs_handle* h, double dt);
 /* Final result gather, the only collective of the design (members are sharded over
  * the GPUs of a box and never exchange anything inside the time loop; the reference has no
  * analogue, one `Ribasim.Model` is one process): ncclAllGather of the member array `key`

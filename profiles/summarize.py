@@ -28,26 +28,27 @@ KEYS = [
 ]
 
 
-def launch_list():
-    src = OUT / f"launches_{tag}.csv"
+def launch_list(name=None, what=None):
+    name = name or tag
+    src = OUT / f"launches_{name}.csv"
     if not src.exists():
         return
     lines = [l for l in src.read_text().splitlines(True) if not l.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
-        name = row["Kernel Name"].split("(")[0].replace("void ", "")
+        kname = row["Kernel Name"].split("(")[0].replace("void ", "")
         v = float(row["Metric Value"].replace(",", ""))
         unit = row["Metric Unit"]
         us = v / 1e3 if unit == "ns" else (v * 1e3 if unit == "ms" else v)
-        a = agg.setdefault(name, [0, 0.0, 0.0])
+        a = agg.setdefault(kname, [0, 0.0, 0.0])
         a[0] += 1
         a[1] += us
         a[2] = max(a[2], us)
     tot = sum(a[1] for a in agg.values())
-    with open(ROOT / "profiles" / f"launches_{tag}.txt", "w") as f:
+    with open(ROOT / "profiles" / f"launches_{name}.txt", "w") as f:
         f.write("# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none\n"
-                "# python profiles/run_profile.py --steps 4   (window of 4 steady-state steps, 4096 members,\n"
-                "# 500 basins, one member group; per-launch times are cold-cache and serialised)\n")
+                f"# {what or 'python profiles/run_profile.py --steps 4   (window of 4 steady-state steps, 4096 members, 500 basins, one member group)'}\n"
+                "# per-launch times are cold-cache and serialised: compare the SHARES with roofline.kernels_ms\n")
         f.write(f"{'kernel':34s} {'launches':>8s} {'total_us':>10s} {'mean_us':>9s} {'max_us':>9s} {'share':>6s}\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k:34s} {a[0]:8d} {a[1]:10.1f} {a[1] / a[0]:9.1f} {a[2]:9.1f} {a[1] / tot:6.3f}\n")
@@ -55,15 +56,20 @@ def launch_list():
 
 
 def full_reports():
-    for rep in sorted(OUT.glob(f"{tag}_k_*.ncu-rep")):
-        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True,
-                             text=True).stdout
-        rows = list(csv.reader(raw.splitlines()))
+    reps = sorted(OUT.glob(f"{tag}_k_*.ncu-rep")) + sorted(OUT.glob(f"{tag}_k_*.raw.csv"))
+    for rep in reps:
+        if rep.suffix == ".csv":  # converted on the GPU box (`ncu -i REP --page raw --csv`)
+            raw = rep.read_text()
+            rep = rep.with_name(rep.name.replace(".raw.csv", ""))
+        else:
+            raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True,
+                                 text=True).stdout
+        rows = list(csv.reader([ln for ln in raw.splitlines() if not ln.startswith("==")]))
         if len(rows) < 3:
             continue
         hdr, units, vals = rows[0], rows[1], rows[2]
         d = dict(zip(hdr, zip(units, vals)))
-        with open(ROOT / "profiles" / f"{rep.stem}.txt", "w") as f:
+        with open(ROOT / "profiles" / f"{rep.stem if rep.suffix == '.ncu-rep' else rep.name}.txt", "w") as f:
             f.write(f"# ncu --set full --clock-control none --import-source on, one launch of {d.get('Kernel Name', ('', '?'))[1]}\n")
             for k in KEYS:
                 if k in d:
@@ -98,7 +104,14 @@ def summary_table():
             out.write(f"| `{name}` | {us:.1f} | {mb:.1f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {100 * gbs / 8000:.0f} |\n")
 
 
-launch_list()
+if tag == "r1":
+    launch_list()
+else:
+    launch_list(tag, "python bench.py --ncu-range --steps 4 --spinup 48 --no-extra --no-cpu-baseline --no-profile --groups 1"
+                     "   (the device-resident timed leg: one window of 4 steps, 4096 members, 500 basins)")
+    launch_list(tag + "tree", "python bench.py --ncu-range --workload tree --steps 1 --spinup 3 --warmup 1 --no-extra "
+                              "--no-cpu-baseline --no-profile --groups 1   (one step of the 100k-basin tree, 256 members, "
+                              "still in its start-up transient)")
 full_reports()
 summary_table()
 print("written:", sorted(p.name for p in (ROOT / "profiles").glob(f"*{tag}*")))

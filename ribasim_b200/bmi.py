@@ -74,7 +74,8 @@ class RibasimBmi:
         return self._require().t_end
 
     def get_time_step(self) -> float:
-        return self._require().dt
+        m = self._require()
+        return m.qndf.h if m.adaptive and m.qndf.h > 0 else m.dt
 
     def get_time_units(self) -> str:
         return "s"

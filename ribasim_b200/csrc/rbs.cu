@@ -103,7 +103,8 @@ struct rbs_handle {
         int* h_counts = nullptr;  // pinned {n_active, n_limit, outer steps completed by all members}
         int n_active = 0, n_limit = 0, min_step = 0;
         bool pending = false, done = false;
-        int* d_tilecnt = nullptr;  // per 64-member tile: row blocks of k_newton_update done
+        int* d_tilecnt = nullptr;  // per 64-member tile: row blocks of k_newton_update done; [n_tiles]: k_limit_post_decide
+        int n_tiles = 0;
     };
     std::vector<Group> groups;
     double tprev = 0.0;
@@ -156,6 +157,9 @@ struct rbs_handle {
     int *d_lsrc_ptr = nullptr, *d_lsrc_code = nullptr;
     std::vector<int> list_phase[3];
     bool pid_fused = false;  // k_pid also formulates its controlled pump / outlet
+    bool pid_kd_nonzero = false;  // a PidControl derivative gain is in force (its D-term reads flows)
+    bool pid_cs_kd_nonzero = false;  // ... in a control-state parameter row
+    bool fuse_small = true;       // fewer, fused launches per pass (RBS_FUSE=0: the plain sequence)
     // cooperative window kernel (rbs_coop.cuh): used when the ensemble is small
     int coop_members = 0;    // use it for ensembles of at most this many members (0 = never)
     int coop_blocks = 0;     // co-resident grid size (0 = unavailable)
@@ -338,13 +342,16 @@ template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pr
     Net& n = h->net;
     long long B = n.NA;
     LAUNCH_AS(h, JAC ? "k_basin<jac>" : "k_basin<rhs>", (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, 0);
-    LAUNCH_AS(h, JAC ? "k_links<jac>" : "k_links<rhs>", k_links<JAC>, (long long)n.n_conn * B, n, 0, nullptr, 0, pred);
+    // the PidControl items ride in the links launch when nothing reads a flow in between
+    n.pid_in_links = (SRC == 1 && h->pid_fused && !h->pid_kd_nonzero && n.n_cc == 0 && h->fuse_small) ? 1 : 0;
+    LAUNCH_AS(h, JAC ? "k_links<jac>" : "k_links<rhs>", k_links<JAC>, (long long)(n.n_conn + (n.pid_in_links ? n.n_pid : 0)) * B, n, 0,
+              nullptr, 0, pred);
     if (n.n_cc > 0) {
         LAUNCH_AS(h, JAC ? "k_continuous_control<jac>" : "k_continuous_control<rhs>", k_continuous_control<JAC>, (long long)n.n_cc * B, n, pred);
         LAUNCH_AS(h, JAC ? "k_links_cc<jac>" : "k_links_cc<rhs>", k_links<JAC>, (long long)h->list_phase[1].size() * B, n, 1, h->d_list_phase[1],
                   (int)h->list_phase[1].size(), pred);
     }
-    if (n.n_pid > 0) {
+    if (n.n_pid > 0 && !n.pid_in_links) {
         LAUNCH_AS(h, JAC ? "k_pid<jac>" : "k_pid<rhs>", k_pid<JAC>, (long long)n.n_pid * B, n, n.ur, pred, h->pid_fused ? 1 : 0);
         if (!h->pid_fused)
             LAUNCH_AS(h, JAC ? "k_links_pid<jac>" : "k_links_pid<rhs>", k_links<JAC>, (long long)h->list_phase[2].size() * B, n, 2, h->d_list_phase[2],
@@ -436,8 +443,9 @@ int make_groups(rbs_handle* h, int ng) {
         CUDA_TRY(cudaMalloc(&G.d_counts, 4 * sizeof(int)));
         CUDA_TRY(cudaMallocHost(&G.h_counts, 4 * sizeof(int)));
         const size_t nt = (size_t)(std::max(G.hi - G.lo, 1) + 63) / 64;
-        CUDA_TRY(cudaMalloc(&G.d_tilecnt, nt * sizeof(int)));
-        CUDA_TRY(cudaMemset(G.d_tilecnt, 0, nt * sizeof(int)));
+        G.n_tiles = (int)nt;
+        CUDA_TRY(cudaMalloc(&G.d_tilecnt, (nt + 1) * sizeof(int)));
+        CUDA_TRY(cudaMemset(G.d_tilecnt, 0, (nt + 1) * sizeof(int)));
     }
     return 0;
 }
@@ -676,6 +684,12 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             }
         }
         h->pid_fused = ok && n.n_pid > 0;
+        auto itk = b->d.find("pid_cs_derivative");
+        if (itk != b->d.end()) for (double v : itk->second) h->pid_cs_kd_nonzero |= v != 0.0;
+        auto itd = b->d.find("pid_derivative");
+        h->pid_kd_nonzero = h->pid_cs_kd_nonzero;
+        if (itd != b->d.end()) for (double v : itd->second) h->pid_kd_nonzero |= v != 0.0;
+        h->fuse_small = getenv("RBS_FUSE") ? atoi(getenv("RBS_FUSE")) != 0 : geti(b, "fuse_small", 1) != 0;
     }
     for (int ph = 1; ph <= 2; ph++) {
         std::string key = std::string("list_phase") + char('0' + ph);
@@ -1097,6 +1111,11 @@ int rbs_set_param_f64(rbs_handle* h, const char* key, const double* host, int64_
     if ((size_t)std::max<int64_t>(n, 1) * sizeof(double) != it->second.bytes) return fail(std::string("parameter size mismatch: ") + key);
     if (n > 0) CUDA_TRY(cudaMemcpyAsync(it->second.p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));  // host buffer is borrowed only for the call
+    if (!strcmp(key, "pid_derivative")) {
+        bool nz = h->pid_cs_kd_nonzero;
+        for (int64_t k = 0; k < n; k++) nz |= host[k] != 0.0;
+        h->pid_kd_nonzero = nz;
+    }
     return 0;
 }
 int rbs_set_param_i32(rbs_handle* h, const char* key, const int32_t* host, int64_t n) {
@@ -1459,6 +1478,17 @@ int rbs_limit_flow(rbs_handle* h, double* u, const double* uprev, double dt, dou
     return check_async(h, "rbs_limit_flow");
 }
 
+int rbs_accept_step(rbs_handle* h, double dt) {
+    if (!h) return fail("rbs_accept_step: null handle");
+    if (!(dt >= 0)) return fail("rbs_accept_step: dt must not be negative");
+    cudaSetDevice(h->device);
+    Net& n = h->net;
+    LAUNCH(h, k_accumulate_forcing, (long long)(n.n_basin + n.n_fb) * n.B, n, dt);
+    h->tprev += dt;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_async(h, "rbs_accept_step");
+}
+
 int rbs_refresh(rbs_handle* h, double t) {
     if (!h) return fail("rbs_refresh: null handle");
     cudaSetDevice(h->device);
@@ -1550,8 +1580,13 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
         Pred lim{n.mphase, PHASE_LIMIT, nullptr};
         LAUNCH_AS(h, "k_basin_limit_pre", (k_basin<false, 1>), (long long)n.n_reduced * B, n, nullptr, false, lim, 1);
         LAUNCH(h, k_step_limit, (long long)n.n_state * B, n, from_ts, alloc_total);
-        LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, 2);
-        LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps, h->shrink_log2);
+        if (h->fuse_small && G.n_limit <= 512) {  // the last block decides: two rounds of its 256 threads at most
+            LAUNCH(h, k_limit_post_decide, (long long)n.n_reduced * B, n, lim, G.d_tilecnt + G.n_tiles, dt, h_min,
+                   h->max_halvings, h->grow_iters, n_steps, h->shrink_log2);
+        } else {
+            LAUNCH_AS(h, "k_basin_limit_post", (k_basin<false, 2>), (long long)n.n_reduced * B, n, nullptr, false, lim, 2);
+            LAUNCH(h, k_step_decide, B, n, dt, h_min, h->max_halvings, h->grow_iters, n_steps, h->shrink_log2);
+        }
         LAUNCH(h, k_step_apply, (long long)(n.n_state + n.n_basin) * B, n, h->predictor);
         if (n.n_dc > 0) LAUNCH(h, k_discrete_control, (long long)n.n_dc * B, n, 0);
     }

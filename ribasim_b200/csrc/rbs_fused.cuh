@@ -363,3 +363,30 @@ __global__ void __launch_bounds__(1024) k_compact2(Net n, int m_lo, int m_hi, in
         counts[0] = ta; counts[1] = tl; counts[2] = mn; counts[3] = passes;
     }
 }
+
+
+// ---- finalize half: storage of the clamped state + accept / reject in one launch -----------------
+// k_basin<false, 2> (members the limiter changed) followed by k_step_decide: the decision needs the
+// negative-storage flags of all basins, so the last block to finish (a counter) takes it for the
+// members of the list.  Same device functions, same results; one launch less per pass.
+__global__ void __launch_bounds__(256) k_limit_post_decide(Net n, Pred pred, int* __restrict__ counter, double dt,
+                                                           double h_min, int max_halvings, int grow_iters,
+                                                           int n_steps, int shrink_log2) {
+    RBS_PDL();
+    __shared__ int last;
+    const long long tid = RBS_TID;
+    const int b = (int)(tid / n.NA);
+    if (b < n.n_reduced) {
+        const int m = RBS_MEMBER(n, (int)(tid - (long long)b * n.NA));
+        if (!rbs_skip<false>(pred, m)) rbs_basin_item<false, 2>(n, nullptr, false, 2, b, m);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *counter = 0;
+    __threadfence();
+    for (int j = threadIdx.x; j < n.NA; j += blockDim.x)
+        rbs_step_decide_item(n, dt, h_min, max_halvings, grow_iters, n_steps, shrink_log2, RBS_MEMBER(n, j));
+}

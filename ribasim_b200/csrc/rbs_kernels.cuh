@@ -134,6 +134,9 @@ struct Net {
     double* dc_rec_t;
     int *dc_rec_ns, *dc_rec_bits;
     int* mroll;  // set by k_step_decide: the decision completed an outer step
+    // 1 = the PidControl items run inside the phase-0 launch of k_links (allowed when no controller
+    // reads a flow: all derivative gains zero, no ContinuousControl; decided on the host)
+    int pid_in_links;
 };
 
 // Forcing array that applies to outer step `idx` of the window.
@@ -389,8 +392,9 @@ __device__ __forceinline__ void rbs_link_item(const Net& n, int s, int m, int ph
         int control = outlet ? n.outlet_control_type[k] : n.pump_control_type[k];
         if (control != phase) {
             // controllers read du of flows that are not formulated yet: those must read 0
-            // (water_balance! zeroes du first, core/src/solve.jl:54)
-            if (phase == 0) n.du[so] = 0.0;
+            // (water_balance! zeroes du first, core/src/solve.jl:54); not when the PID item of the
+            // same launch writes the flow and nobody reads it in between
+            if (phase == 0 && !(control == CONTROL_PID && n.pid_in_links)) n.du[so] = 0.0;
             return;
         }
         controlled = control != CONTROL_NONE;
@@ -456,14 +460,22 @@ __device__ __forceinline__ void rbs_link_item(const Net& n, int s, int m, int ph
 }
 
 template <bool JAC>
+__device__ __forceinline__ void rbs_pid_item(const Net& n, const double* ur, int fuse_link, int i, int m);
+
+template <bool JAC>
 __global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
     RBS_PDL();
     long long tid = RBS_TID;
     int li = (int)(tid / n.NA);
-    int count = phase == 0 ? n.n_conn : n_list;
+    int count = phase == 0 ? n.n_conn + (n.pid_in_links ? n.n_pid : 0) : n_list;
     if (li >= count) return;
     int m = RBS_MEMBER(n, (int)(tid - (long long)li * n.NA));
     if (rbs_skip<JAC>(pred, m)) return;
+    if (phase == 0 && li >= n.n_conn) {
+        // PidControl item with its controlled pump / outlet (what k_pid does, one launch less)
+        rbs_pid_item<JAC>(n, n.ur, 1, li - n.n_conn, m);
+        return;
+    }
     rbs_link_item<JAC>(n, phase == 0 ? li : list[li], m, phase);
 }
 
@@ -1905,6 +1917,25 @@ __global__ void k_discrete_control(Net n, int initial) {
     int i = (int)(tid / n.NA);
     if (i >= n.n_dc) return;
     rbs_discrete_control_item(n, initial, i, RBS_MEMBER(n, (int)(tid - (long long)i * n.NA)));
+}
+
+// Host-driven steppers (the seam path: an integrator above the C ABI owns the step control): an
+// accepted step of length dt moves the exactly integrated forcing forward
+// (update_cumulative_flows!, core/src/callback.jl:131-170); same arithmetic as rbs_exact_update.
+__global__ void k_accumulate_forcing(Net n, double dt) {
+    RBS_PDL();
+    long long tid = RBS_TID;
+    const long long nb = (long long)n.n_basin * n.B;
+    if (tid < nb) {
+        const int b = (int)(tid / n.B);
+        const double P = n.fixed_area[b] * n.precipitation[tid];
+        n.cum_precipitation[tid] += P * dt;
+        n.cum_surface_runoff[tid] += dt * n.surface_runoff[tid];
+        n.cum_drainage[tid] += dt * n.drainage[tid];
+        return;
+    }
+    tid -= nb;
+    if (tid < (long long)n.n_fb * n.B) n.fb_cum[tid] += n.fb_rate[tid] * dt;
 }
 
 __global__ void k_fill(double* p, long long nelem, double v) {

@@ -162,6 +162,7 @@ def load() -> ctypes.CDLL:
         "rbs_stream": (vp, [vp]),
         "rbs_synchronize": (ctypes.c_int, [vp]),
         "rbs_gather": (ctypes.c_int, [vp, vp, cp, i64, vp]),
+        "rbs_accept_step": (ctypes.c_int, [vp, f64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # raises AttributeError if the symbol is missing
@@ -178,7 +179,7 @@ EXPORTED_SYMBOLS = [
     "rbs_get_member_f64_async", "rbs_stage_forcing_window", "rbs_advance_window", "rbs_commit_forcing_window", "rbs_set_forcing_slicing", "rbs_host_alloc", "rbs_host_free",
     "rbs_copy_member_to_device", "rbs_get_member_i32", "rbs_apply_discrete_control", "rbs_set_tprev", "rbs_reduce", "rbs_rhs", "rbs_jac", "rbs_solve", "rbs_limit_flow",
     "rbs_step_implicit_euler", "rbs_advance", "rbs_set_solver", "rbs_set_stepper", "rbs_set_groups", "rbs_get_stats", "rbs_refresh",
-    "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize", "rbs_gather",
+    "rbs_time_linear", "rbs_profile", "rbs_profile_report", "rbs_device_ptr", "rbs_stream", "rbs_synchronize", "rbs_gather", "rbs_accept_step",
 ]
 
 
@@ -525,6 +526,10 @@ class Handle:
         st = np.zeros(self.B, dtype=np.int32) if want_status else None
         _check(self.L.rbs_advance(self.h, t, dt, int(n_steps), _ip(st)))
         return st
+
+    def accept_step(self, dt: float) -> None:
+        """Advance the exactly integrated forcing and tprev by an accepted step (rbs_accept_step)."""
+        _check(self.L.rbs_accept_step(self.h, float(dt)))
 
     def refresh(self, t: float) -> None:
         _check(self.L.rbs_refresh(self.h, t))

@@ -56,10 +56,12 @@ class Model:
         # explicitly as ImplicitEuler — nothing is substituted silently.  `dt=` given by the caller
         # is that explicit request.
         alg = self.tables.solver_option("algorithm")
-        if dt is None and alg not in (None, "ImplicitEuler"):
+        self.adaptive = dt is None and alg == "QNDF"
+        if dt is None and alg not in (None, "ImplicitEuler", "QNDF"):
             raise ValueError(
-                f"solver.algorithm = {alg!r} is not available on the device path: only fixed-step "
-                "ImplicitEuler is (set `algorithm = \"ImplicitEuler\"` and `dt` in [solver], or pass dt=)")
+                f"solver.algorithm = {alg!r} is not available on the device path: QNDF (adaptive, the "
+                "reference's default) and fixed-step ImplicitEuler are (set `algorithm` and `dt` in "
+                "[solver], or pass dt=)")
         cfg_dt = self.tables.solver_option("dt")
         self.dt = float(dt if dt is not None else (cfg_dt if cfg_dt else 3600.0))
         self.t = 0.0
@@ -98,11 +100,33 @@ class Model:
         # (core/src/callback.jl:631-634), then the caches are refreshed with them
         if self.flat.ints["n_dc"] > 0:
             self.h.apply_discrete_control()
+            # a truth state without a control state is an error at t = 0 already
+            # (core/src/callback.jl:671-675); the step path zeroes the status word at every step
+            st0 = self.h.get_member_i32("status", 1)[0]
+            if np.any(st0 & 4):
+                raise RuntimeError("No control state specified for a DiscreteControl truth state at t = 0 "
+                                   f"(member {int(np.flatnonzero(st0 & 4)[0])})")
             self.h.refresh(0.0)
         self.status_counts = dict(newton_failed=0, negative_storage=0)
         from .subgrid import Subgrid
 
         self.subgrid = Subgrid(self.tables, [n.value for n in self.p.basin.node_id])
+        self.qndf = None
+        if self.adaptive:
+            # adaptive QNDF above the seams (qndf.py): per-state reltol vector with the PID
+            # integral states unmasked (core/src/util.jl:733-743)
+            from .qndf import Qndf
+
+            nst = self.flat.ints["n_state"]
+            relmask = np.ones(nst, dtype=bool)
+            relmask[self.flat.ints["off_integral"]:] = False
+            dtmax = self.tables.solver_option("dtmax")
+            self.qndf = Qndf(_SeamBackend(self), np.zeros((nst, self.B)), 0.0,
+                             self.tables.solver_option("abstol"), self.tables.solver_option("reltol"),
+                             relmask, dtmin=self.tables.solver_option("dtmin") or 0.0,
+                             dtmax=dtmax if dtmax else None,
+                             maxiters=int(self.tables.solver_option("maxiters")),
+                             dt0=cfg_dt if cfg_dt else None)
 
     # ------------------------------------------------------------------ forcing / parameters
     def _push_time_params(self, t: float) -> None:
@@ -162,7 +186,25 @@ class Model:
     def update(self, want_status: bool = True):
         """One solver step (BMI.update, core/src/bmi.jl:36-39)."""
         self._sync_inputs()
+        if self.adaptive:
+            return self._qndf_step(self._next_stop(self.t_end))
         return self._step_to(self._next_time(self.t_end), want_status)
+
+    def _qndf_step(self, t_limit: float):
+        """One accepted adaptive step that does not pass `t_limit`, then the reference's
+        step-boundary callbacks: exact forcing bookkeeping, DiscreteControl, tolerance decrease,
+        forcing update at tstops (core/src/callback.jl:7-83)."""
+        q = self.qndf
+        h_done = q.step(t_limit)
+        self.t = q.t
+        self.h.accept_step(h_done)
+        self.h.set_member("u", q.u)
+        self.h.refresh(self.t)  # caches and flows at the new state (results, BMI, DiscreteControl)
+        if self.flat.ints["n_dc"] > 0:
+            self.h.apply_discrete_control()
+        q.decrease_tolerance()
+        self._after_step()
+        return None
 
     def _sync_inputs(self) -> None:
         """Upload the BMI-writable host arrays the caller changed since the last step
@@ -228,6 +270,9 @@ class Model:
         is taken on its own with the parameters of that instant, like the reference's RHS."""
         if time < self.t:
             raise ValueError("The model has already passed the given timestamp.")
+        while self.adaptive and self.t < time:
+            self._sync_inputs()
+            self._qndf_step(self._next_stop(time))
         while self.t < time:
             self._sync_inputs()
             t_stop = self._next_stop(time)
@@ -324,3 +369,42 @@ class Model:
 
     def finalize(self) -> None:
         self.h.close()
+
+
+class _SeamBackend:
+    """The device behind the SciML plug-in seams of the C ABI, as `qndf.Qndf` uses it."""
+
+    def __init__(self, model: "Model"):
+        self.m = model
+        self.h = model.h
+        f = model.flat
+        self.jcol = np.asarray(f.arrays["jcol"], dtype=np.int64)
+        rp = np.asarray(f.arrays["jrow_ptr"], dtype=np.int64)
+        self.jrow = np.repeat(np.arange(f.ints["n_state"]), np.diff(rp))
+        self.n = f.ints["n_state"]
+        self.jv = None
+
+    def prepare(self, t0: float, t1: float) -> None:
+        self.m._push_time_params(t1)
+        self.m._push_fb_rate(t0, t1)
+
+    def reduce(self, u):
+        return self.h.reduce(u)
+
+    def rhs(self, ur, t):
+        du, c = self.h.rhs(ur, t, with_cache=True)
+        return du, c["storage"]
+
+    def factor(self, ur, t, gamma):
+        self.jv, _ = self.h.jac(ur, t, gamma)
+
+    def solve(self, b):
+        return self.h.solve(b)
+
+    def jmul(self, c):
+        out = np.zeros((self.n, c.shape[1]))
+        np.add.at(out, self.jrow, self.jv * c[self.jcol])
+        return out
+
+    def limit(self, u, uprev, dt, t):
+        return self.h.limit_flow(u, uprev, dt, t)

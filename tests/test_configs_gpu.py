@@ -308,3 +308,72 @@ def test_basin_profile_given_by_area_storage_or_both():
             model.finalize()
     assert levels["area"] == pytest.approx(levels["both"], rel=1e-12)
     assert levels["storage"] == pytest.approx(levels["area"], rel=1e-6)
+
+
+# ----------------------------------------------------------------------------- adaptive QNDF
+from ribasim_b200.model import Model  # noqa: E402
+from ribasim_b200.network import build_params  # noqa: E402
+from ribasim_b200.testmodels import MODELS  # noqa: E402
+
+
+def test_qndf_trivial_regression_on_gpu():
+    """core/regression_test/regression_test.jl:15-41: the trivial model with the reference's
+    default algorithm (QNDF, here above the device seams) at abstol = reltol = 1e-7."""
+    m = MODELS["trivial"]()
+    m.solver.update(algorithm="QNDF", abstol=1e-7, reltol=1e-7)
+    model = Model(build_params(m))
+    try:
+        assert model.adaptive
+        model.update_until(model.t_end)
+        S, lv = model.storage()[:, 0], model.level()[:, 0]
+        g = golden("trivial_regression")
+        assert S[0] == pytest.approx(g["storage"], abs=g["storage_atol"])
+        assert lv[0] == pytest.approx(g["level"], abs=g["level_atol"])
+        assert model.qndf.n_steps < 2000  # adaptive: the fixed-step path would take 8784 hourly steps
+    finally:
+        model.finalize()
+
+
+def test_qndf_basic_end_state_on_gpu_and_matches_oracle_backend():
+    """core/test/run_models_test.jl:221-222 with the default solver settings (QNDF, 1e-5), and the
+    same integrator on the CPU oracle: both backends take the same accepted steps."""
+    from tests.test_qndf import run_qndf
+    model = Model(build_params(MODELS["basic"]()))
+    try:
+        assert model.adaptive
+        model.update_until(model.t_end)
+        S = model.storage()[:, 0]
+        steps = model.qndf.n_steps
+    finally:
+        model.finalize()
+    g = golden("basic_end_storage")
+    assert np.allclose(S, g["storage"], atol=g["atol"], rtol=0)
+    q, S_o, _ = run_qndf("basic")
+    assert np.allclose(S, S_o, rtol=1e-6, atol=1e-6)
+    assert abs(steps - q.n_steps) <= max(3, q.n_steps // 100)
+
+
+def test_qndf_ensemble_in_lockstep_meets_tolerance_per_member():
+    """Members with different forcing under one step size / order: every member agrees with its own
+    single-instance QNDF run within the solver tolerance."""
+    p = build_params(MODELS["basic"]())
+    t_end = 20 * 86400.0
+    ens = Model(p, n_members=3)
+    nb = ens.flat.ints["n_basin"]
+    scale = np.array([1.0, 3.0, 0.2])
+    try:
+        ens.set_forcing("precipitation", p.basin.vertical_flux["precipitation"][:, None] * scale[None, :])
+        ens.update_until(t_end)
+        S_ens = ens.storage()
+    finally:
+        ens.finalize()
+    for j, f in enumerate(scale):
+        one = Model(build_params(MODELS["basic"]()), n_members=1)
+        try:
+            one.set_forcing("precipitation", one.p.basin.vertical_flux["precipitation"][:, None] * f)
+            one.update_until(t_end)
+            S1 = one.storage()[:, 0]
+        finally:
+            one.finalize()
+        assert S_ens.shape == (nb, 3)
+        assert np.allclose(S_ens[:, j], S1, rtol=1e-3, atol=1e-3), j

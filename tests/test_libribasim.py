@@ -279,3 +279,24 @@ def test_plain_c_host_runs_a_model(shim_path, tmp_path):
     assert lines["unknown_var"] == "1 Unknown variable unknown_node.unknown_variable"
     assert lines["backwards"].startswith("1 ") and "already passed" in lines["backwards"]
     assert lines["update_finalized"] == "1 Model not initialized"
+
+
+@pytest.mark.gpu
+def test_default_toml_runs_adaptive_qndf(api, tmp_path):
+    """The reference's test models ask for its default algorithm, QNDF (python/ribasim_api/tests/
+    test_bmi.py writes them unchanged): `update` takes one adaptive step, `update_until` lands
+    exactly on the requested time (test_bmi.py:41-57)."""
+    from ribasim_b200.testmodels import MODELS
+
+    toml = MODELS["basic"]().write(tmp_path / "basic_default")
+    api.initialize(toml)
+    api.update()
+    t1 = api.get_current_time()
+    assert 0.0 < t1 < 3600.0           # the first adaptive step is short
+    assert api.get_time_step() > 0.0
+    api.update_until(60.0)
+    assert api.get_current_time() == pytest.approx(60.0)
+    api.update_until(86400.0)
+    assert api.get_current_time() == pytest.approx(86400.0)
+    s = api.get_value_ptr("basin.storage")
+    assert np.all(np.isfinite(s)) and np.all(s > 0)
