@@ -27,7 +27,7 @@ import bench  # noqa: E402
 from ribasim_b200.ensemble import perturbed_forcing  # noqa: E402
 from ribasim_b200.model import Model  # noqa: E402
 
-p, flat, sym = bench.build_workload(args.basins)
+p, flat, sym, _ = bench.build_workload(args.basins)
 model = Model(p, n_members=args.members, dt=bench.DT, flat=flat, sym=sym,
               full_newton=bool(args.full_newton), smem_tile=args.smem_tile,
               n_groups=args.groups)
