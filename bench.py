@@ -277,7 +277,8 @@ def cpu_sample(workload: str, cores: int, requested: int, members_local: int) ->
         return requested or min(cores, 16), 2
     if workload == "backwater":
         return 1, 240
-    return requested or min(members_local, 32 * cores), 24
+    # ~10-30 s of host work at ~1.7 k member-steps/s per core, spin-up included
+    return requested or min(members_local, 64 * cores), 96
 
 
 def reference_arm(args):

@@ -605,7 +605,10 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         if (upload(h, "basin_obs", obs, true)) return bail("param alloc");
     }
     // per-member arrays
-    h->rows_per_block = 64;
+    // rows of the state vector per block of k_newton_update (a thread walks rows_per_block / 8 rows one
+    // after the other): fixed for every ensemble size, because the partition fixes the summation order
+    // of the convergence norm and member results must not depend on the batch
+    h->rows_per_block = getenv("RBS_ROWS_PER_BLOCK") ? std::max(8, atoi(getenv("RBS_ROWS_PER_BLOCK"))) : geti(b, "rows_per_block", 64);
     h->n_part = (n.n_state + h->rows_per_block - 1) / h->rows_per_block;
     struct MD { const char* key; int64_t n; };
     MD mds[] = {
@@ -632,11 +635,12 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                        alloc_member(h, "dc_rec_bits", RBS_DC_REC_CAP, true)))
         return bail("member alloc");
     // no control state set yet
-    cudaMemsetAsync(h->member["dc_state"].p, 0xFF, h->member["dc_state"].bytes, h->stream);
+    if (cudaMemsetAsync(h->member["dc_state"].p, 0xFF, h->member["dc_state"].bytes, h->stream) != cudaSuccess)
+        return bail("dc_state init");
     {
         DevArr a; a.bytes = sizeof(int); a.is_int = true;
         if (cudaMalloc(&a.p, a.bytes) != cudaSuccess) return bail("active_count alloc");
-        cudaMemsetAsync(a.p, 0, a.bytes, h->stream);
+        if (cudaMemsetAsync(a.p, 0, a.bytes, h->stream) != cudaSuccess) return bail("active_count init");
         h->member["active_count"] = a; h->member_entities["active_count"] = 0;
     }
     // eta_old starts at 1 (nlsolver.ηold)
@@ -754,13 +758,13 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             for (size_t k = 0; k < blob.size(); k++) b16[k] = blob[k] < 0 ? (uint16_t)0xFFFF : (uint16_t)blob[k];
             idx_bytes = b16.size() * sizeof(uint16_t);
             if (cudaMalloc(&h->d_blob, std::max<size_t>(idx_bytes, 2)) != cudaSuccess) return bail("schedule alloc");
-            cudaMemcpyAsync(h->d_blob, b16.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream);
-            cudaStreamSynchronize(h->stream);
+            if (cudaMemcpyAsync(h->d_blob, b16.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("schedule upload");
         } else {
             idx_bytes = blob.size() * sizeof(int32_t);
             if (cudaMalloc(&h->d_blob, std::max<size_t>(idx_bytes, 4)) != cudaSuccess) return bail("schedule alloc");
-            cudaMemcpyAsync(h->d_blob, blob.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream);
-            cudaStreamSynchronize(h->stream);
+            if (cudaMemcpyAsync(h->d_blob, blob.data(), idx_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("schedule upload");
         }
         int want = geti(b, "smem_tile", -1);  // -1 auto (32), 0 off, else 8 / 16 / 32
         int dev_smem = 0;
@@ -845,11 +849,11 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 if (s16) {
                     std::vector<uint16_t> b16(blob2.size());
                     for (size_t k = 0; k < blob2.size(); k++) b16[k] = blob2[k] < 0 ? (uint16_t)0xFFFF : (uint16_t)blob2[k];
-                    cudaMemcpyAsync(h->d_blob2, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice, h->stream);
-                    cudaStreamSynchronize(h->stream);
+                    if (cudaMemcpyAsync(h->d_blob2, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("schedule upload");
                 } else {
-                    cudaMemcpyAsync(h->d_blob2, blob2.data(), blob2.size() * 4, cudaMemcpyHostToDevice, h->stream);
-                    cudaStreamSynchronize(h->stream);
+                    if (cudaMemcpyAsync(h->d_blob2, blob2.data(), blob2.size() * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("schedule upload");
                 }
                 cudaError_t e2 = s16
                     ? cudaFuncSetAttribute(k_newton_linear_smem<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
@@ -916,8 +920,8 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                         (es.smem_sched == 3 ? (o_perm - o_prod) * 8 : es.smem_sched == 2 ? o_prod * 8 : es.smem_sched ? (size_t)es.n_words * 8 : 0);
             if (ok && sb + 256 <= (size_t)dev_smem) {
                 if (cudaMalloc(&h->d_ent_blob, hb.size() * 8) != cudaSuccess) return bail("schedule alloc");
-                cudaMemcpyAsync(h->d_ent_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream);
-                cudaStreamSynchronize(h->stream);
+                if (cudaMemcpyAsync(h->d_ent_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("schedule upload");
                 const unsigned long long* d = (const unsigned long long*)h->d_ent_blob;
                 es.lvl = d + o_lvl; es.ent = d + o_ent; es.prod = d + o_prod;
                 es.perm = (const uint16_t*)(d + o_perm);
@@ -974,8 +978,8 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                     : (n_members <= 1024 && ((size_t)es.n_slots * h->ent_tile * sizeof(double) + o_perm * 8 + 1024) * 2 <= (size_t)227 * 1024 ? 1 : 0);
                 es.n_load = (int)le.size();
                 if (cudaMalloc(&h->d_entc_blob, hb.size() * 8) != cudaSuccess) return bail("schedule alloc");
-                cudaMemcpyAsync(h->d_entc_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream);
-                cudaStreamSynchronize(h->stream);
+                if (cudaMemcpyAsync(h->d_entc_blob, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("schedule upload");
                 const unsigned long long* d = (const unsigned long long*)h->d_entc_blob;
                 es.lvl = d; es.ent = d + o_ent; es.prod = d + o_prod;
                 es.perm = (const uint16_t*)(d + o_perm);
