@@ -377,3 +377,29 @@ def test_qndf_ensemble_in_lockstep_meets_tolerance_per_member():
             one.finalize()
         assert S_ens.shape == (nb, 3)
         assert np.allclose(S_ens[:, j], S1, rtol=1e-3, atol=1e-3), j
+
+
+def test_qndf_discrete_control_record_on_gpu():
+    """core/test/control_test.jl:33-44 with the default solver: the adaptive run walks through the
+    same control states with the same truth states (the record times are step ends, so they follow
+    the integrator's own step sequence); :374-383: the storage condition switches below 7506 m3."""
+    m = Model(build_params(MODELS["pump_discrete_control"]()))
+    try:
+        assert m.adaptive
+        m.update_until(m.t_end)
+        rec = m.control_record()
+    finally:
+        m.finalize()
+    g = golden("pump_discrete_control_record")
+    assert [r[1] for r in rec] == g["control_node_id"]
+    assert [r[3] for r in rec] == g["control_state"]
+    assert [r[2] for r in rec] == g["truth_state"]
+    m = Model(build_params(MODELS["storage_condition"]()))
+    try:
+        m.update_until(m.t_end)
+        rec, S = m.control_record(), m.storage()[:, 0]
+    finally:
+        m.finalize()
+    gs = golden("control_records")["storage_condition"]
+    assert [r[3] for r in rec] == gs["control_state"] and [r[2] for r in rec] == gs["truth_state"]
+    assert S[0] < gs["storage_below"]
