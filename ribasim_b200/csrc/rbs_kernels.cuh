@@ -161,6 +161,13 @@ template <bool JAC> __device__ __forceinline__ bool rbs_skip(const Pred& p, int 
 }
 
 #define RBS_TID (blockIdx.x * (long long)blockDim.x + threadIdx.x)
+// resident blocks per SM the register allocation of the two big RHS kernels is bounded for
+#ifndef RBS_BASIN_BLOCKS
+#define RBS_BASIN_BLOCKS 6
+#endif
+#ifndef RBS_LINKS_BLOCKS
+#define RBS_LINKS_BLOCKS 4
+#endif
 // Programmatic dependent launch (step-path kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization): let the next kernel's blocks be scheduled
 // as soon as every block of this one has started, and wait here until the previous kernel has
@@ -330,7 +337,7 @@ __device__ __forceinline__ void rbs_basin_item(const Net& n, const double* ur, b
 }
 
 template <bool JAC, int SRC>
-__global__ void __launch_bounds__(256, 6) k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
+__global__ void __launch_bounds__(256, RBS_BASIN_BLOCKS) k_basin(Net n, const double* __restrict__ ur, bool write_du, Pred pred,
                         int flag_negative) {
     RBS_PDL();
     long long tid = RBS_TID;
@@ -463,7 +470,7 @@ template <bool JAC>
 __device__ __forceinline__ void rbs_pid_item(const Net& n, const double* ur, int fuse_link, int i, int m);
 
 template <bool JAC>
-__global__ void __launch_bounds__(256, 4) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
+__global__ void __launch_bounds__(256, RBS_LINKS_BLOCKS) k_links(Net n, int phase, const int* __restrict__ list, int n_list, Pred pred) {
     RBS_PDL();
     long long tid = RBS_TID;
     int li = (int)(tid / n.NA);
