@@ -160,6 +160,7 @@ struct rbs_handle {
     bool pid_kd_nonzero = false;  // a PidControl derivative gain is in force (its D-term reads flows)
     bool pid_cs_kd_nonzero = false;  // ... in a control-state parameter row
     bool fuse_small = true;       // fewer, fused launches per pass (RBS_FUSE=0: the plain sequence)
+    int iters_per_pass = 1;       // Newton iterations launched per pass (small ensembles: 3)
     // cooperative window kernel (rbs_coop.cuh): used when the ensemble is small
     int coop_members = 0;    // use it for ensembles of at most this many members (0 = never)
     int coop_blocks = 0;     // co-resident grid size (0 = unavailable)
@@ -693,6 +694,10 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         auto itd = b->d.find("pid_derivative");
         h->pid_kd_nonzero = h->pid_cs_kd_nonzero;
         if (itd != b->d.end()) for (double v : itd->second) h->pid_kd_nonzero |= v != 0.0;
+        {
+            const int want = getenv("RBS_ITERS_PER_PASS") ? atoi(getenv("RBS_ITERS_PER_PASS")) : geti(b, "iters_per_pass", -1);
+            h->iters_per_pass = want > 0 ? std::min(want, 10) : 1;
+        }
         h->fuse_small = getenv("RBS_FUSE") ? atoi(getenv("RBS_FUSE")) != 0 : geti(b, "fuse_small", 1) != 0;
     }
     for (int ph = 1; ph <= 2; ph++) {
@@ -1598,11 +1603,16 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
     n.NA = G.n_active;
     n.alist = G.d_alist;
     Pred nw{n.mphase, PHASE_NEWTON, n.mjac};
-    launch_rhs<true, 1>(h, nullptr, nw);
-    if (!h->full_newton) launch_rhs<false, 1>(h, nullptr, nw);
     double* c = mp(h, "cvec");
-    launch_linear(h, c, nw);
-    {
+    // Small ensembles: several Newton iterations per pass.  Every kernel of the Newton half is
+    // predicated on the member's phase and the convergence test runs inside k_newton_update, so
+    // members whose iteration ended simply sit out the rest of the pass; the finalize half, the
+    // compaction and the host round trip are then paid once per `iters_per_pass` iterations (most
+    // members need three).  Same per-member arithmetic, bitwise the same results.
+    for (int rep = 0; rep < h->iters_per_pass; rep++) {
+        launch_rhs<true, 1>(h, nullptr, nw);
+        if (!h->full_newton) launch_rhs<false, 1>(h, nullptr, nw);
+        launch_linear(h, c, nw);
         dim3 block(32, RBS_DZ_ROWS), grid((n.NA + 63) / 64, h->n_part);
         ConvArgs cv{G.d_tilecnt, h->n_part, h->max_iter, h->full_newton, h->early_exit, 0.01};
         LAUNCH_CFG(h, k_newton_update, grid, block, n, c, h->abstol, h->reltol, h->rows_per_block, cv);
