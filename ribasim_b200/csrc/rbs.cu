@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -160,7 +162,8 @@ struct rbs_handle {
     bool pid_kd_nonzero = false;  // a PidControl derivative gain is in force (its D-term reads flows)
     bool pid_cs_kd_nonzero = false;  // ... in a control-state parameter row
     bool fuse_small = true;       // fewer, fused launches per pass (RBS_FUSE=0: the plain sequence)
-    int iters_per_pass = 1;       // Newton iterations launched per pass (small ensembles: 3)
+    int iters_per_pass = 1;       // Newton iterations launched per pass (measured: 1 is best)
+    bool host_threads = false;    // one host thread per member group in the pass loop (measured: no gain)
     // cooperative window kernel (rbs_coop.cuh): used when the ensemble is small
     int coop_members = 0;    // use it for ensembles of at most this many members (0 = never)
     int coop_blocks = 0;     // co-resident grid size (0 = unavailable)
@@ -174,6 +177,20 @@ struct rbs_handle {
 };
 
 namespace {
+
+// Launch state of the calling thread.  The pass loop of a window runs one host thread per member
+// group; each has its own copy of the kernel argument `Net` (launch domain, work list) and its own
+// stream, so that the helpers below can be shared.  Without a context the handle's own apply.
+struct LaunchCtx {
+    Net net;
+    cudaStream_t cur = nullptr;
+    int64_t launches = 0, n_passes = 0;
+};
+thread_local LaunchCtx* tl_ctx = nullptr;
+inline Net& net_of(rbs_handle* h) { return tl_ctx ? tl_ctx->net : h->net; }
+inline cudaStream_t& cur_of(rbs_handle* h) { return tl_ctx ? tl_ctx->cur : h->cur; }
+inline int64_t& launches_of(rbs_handle* h) { return tl_ctx ? tl_ctx->launches : h->launches; }
+inline int64_t& passes_of(rbs_handle* h) { return tl_ctx ? tl_ctx->n_passes : h->n_passes; }
 
 inline int grid_for(long long total, int block = 256) { return (int)((total + block - 1) / block); }
 
@@ -323,9 +340,9 @@ inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
 #define LAUNCH_CFG_AS(h, label, kernel, grid, block, ...)                                      \
     do {                                                                                       \
         prof_begin((h), label);                                                                \
-        launch_k((h)->pdl && !(h)->profiling, kernel, dim3(grid), dim3(block), 0, (h)->cur, __VA_ARGS__); \
+        launch_k((h)->pdl && !(h)->profiling, kernel, dim3(grid), dim3(block), 0, cur_of(h), __VA_ARGS__); \
         prof_end(h);                                                                           \
-        (h)->launches++;                                                                       \
+        launches_of(h)++;                                                                      \
     } while (0)
 #define LAUNCH_CFG(h, kernel, grid, block, ...) LAUNCH_CFG_AS(h, #kernel, kernel, grid, block, __VA_ARGS__)
 
@@ -340,7 +357,7 @@ inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
 // RHS phases on the caches prepared by k_exact / k_step_apply: ur -> du (and J values when JAC).
 // SRC 0 reads u_reduced from `ur`; SRC 1 fuses reduce_state!(uprev + z) into the basin kernel.
 template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pred pred = Pred{nullptr, 0, nullptr}) {
-    Net& n = h->net;
+    Net& n = net_of(h);
     long long B = n.NA;
     LAUNCH_AS(h, JAC ? "k_basin<jac>" : "k_basin<rhs>", (k_basin<JAC, SRC>), (long long)n.n_reduced * B, n, ur, true, pred, 0);
     // the PidControl items ride in the links launch when nothing reads a flow in between
@@ -361,7 +378,7 @@ template <bool JAC, int SRC> void launch_rhs(rbs_handle* h, const double* ur, Pr
 }
 // W = A J - I/gamma and its LU.  FROM_J: assembled on the fly (step path, per-member gamma = h).
 template <bool FROM_J> void launch_factor(rbs_handle* h, double inv_gamma, Pred pred = Pred{nullptr, 0, nullptr}) {
-    Net& n = h->net;
+    Net& n = net_of(h);
     long long B = n.NA;
     if (!FROM_J) LAUNCH(h, k_assemble_w, (long long)n.nnz_w * B, n, inv_gamma);
     int n_levels = (int)h->lu_level_ptr.size() - 1;
@@ -378,7 +395,7 @@ template <bool FROM_J> void launch_factor(rbs_handle* h, double inv_gamma, Pred 
 }
 
 template <bool FROM_DU> void launch_solve(rbs_handle* h, const double* b, double* x, Pred pred = Pred{nullptr, 0, nullptr}) {
-    Net& n = h->net;
+    Net& n = net_of(h);
     long long B = n.NA;
     int n_fwd = (int)h->fwd_level_ptr.size() - 1, n_bwd = (int)h->bwd_level_ptr.size() - 1;
     if (h->tile_mode) {
@@ -698,6 +715,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
             const int want = getenv("RBS_ITERS_PER_PASS") ? atoi(getenv("RBS_ITERS_PER_PASS")) : geti(b, "iters_per_pass", -1);
             h->iters_per_pass = want > 0 ? std::min(want, 10) : 1;
         }
+        h->host_threads = getenv("RBS_HOST_THREADS") ? atoi(getenv("RBS_HOST_THREADS")) != 0 : geti(b, "host_threads", 0) != 0;
         h->fuse_small = getenv("RBS_FUSE") ? atoi(getenv("RBS_FUSE")) != 0 : geti(b, "fuse_small", 1) != 0;
     }
     for (int ph = 1; ph <= 2; ph++) {
@@ -1513,7 +1531,7 @@ int rbs_refresh(rbs_handle* h, double t) {
 // Newton linear solve of the members in the launch domain: fused factor+solve kernel, or the
 // level-per-launch kernels when the schedule does not fit in shared memory.
 static void launch_linear(rbs_handle* h, double* c, Pred nw) {
-    Net& n = h->net;
+    Net& n = net_of(h);
     if (h->lin_m > 0 && h->full_newton) {
         if (!getenv("RBS_TIME_SOLVE_ONLY"))
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
@@ -1522,10 +1540,10 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
         es.smem_sched = h->lin_m_sched;
         const int M = h->lin_m, blocks = (n.NA + M - 1) / M;
         prof_begin(h, "k_newton_linear_m");
-        if (M == 8) k_newton_linear_m<8><<<blocks, RBS_ENT_LANES, h->lin_m_smem, h->cur>>>(n, es, c);
-        else k_newton_linear_m<4><<<blocks, RBS_ENT_LANES, h->lin_m_smem, h->cur>>>(n, es, c);
+        if (M == 8) k_newton_linear_m<8><<<blocks, RBS_ENT_LANES, h->lin_m_smem, cur_of(h)>>>(n, es, c);
+        else k_newton_linear_m<4><<<blocks, RBS_ENT_LANES, h->lin_m_smem, cur_of(h)>>>(n, es, c);
         prof_end(h);
-        h->launches++;
+        launches_of(h)++;
     } else if (h->lin_ent) {
         if (!getenv("RBS_TIME_SOLVE_ONLY"))
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
@@ -1539,34 +1557,34 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
         const size_t sb = cmp ? h->entc_smem_bytes : h->ent_smem_bytes;
         prof_begin(h, "k_newton_linear_ent");
         const bool pdl = h->pdl && !h->profiling;
-        if (et == 2) launch_k(pdl, k_newton_linear_ent<2>, dim3(blocks), dim3(nt), sb, h->cur, n, es, wl, c);
-        else if (et == 4) launch_k(pdl, k_newton_linear_ent<4>, dim3(blocks), dim3(nt), sb, h->cur, n, es, wl, c);
-        else launch_k(pdl, k_newton_linear_ent<8>, dim3(blocks), dim3(nt), sb, h->cur, n, es, wl, c);
+        if (et == 2) launch_k(pdl, k_newton_linear_ent<2>, dim3(blocks), dim3(nt), sb, cur_of(h), n, es, wl, c);
+        else if (et == 4) launch_k(pdl, k_newton_linear_ent<4>, dim3(blocks), dim3(nt), sb, cur_of(h), n, es, wl, c);
+        else launch_k(pdl, k_newton_linear_ent<8>, dim3(blocks), dim3(nt), sb, cur_of(h), n, es, wl, c);
         prof_end(h);
-        h->launches++;
+        launches_of(h)++;
     } else if (h->lin_smem) {
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
                sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
         int blocks = (n.NA + 7) / 8;
         prof_begin(h, "k_newton_linear_smem");
         if (h->lin_smem16)
-            k_newton_linear_smem<uint16_t><<<blocks, h->smem_threads, h->lin_smem_bytes, h->cur>>>(
+            k_newton_linear_smem<uint16_t><<<blocks, h->smem_threads, h->lin_smem_bytes, cur_of(h)>>>(
                 n, h->dsched, (const uint16_t*)h->d_blob2, h->full_newton ? 0 : 1, c);
         else
-            k_newton_linear_smem<int32_t><<<blocks, h->smem_threads, h->lin_smem_bytes, h->cur>>>(
+            k_newton_linear_smem<int32_t><<<blocks, h->smem_threads, h->lin_smem_bytes, cur_of(h)>>>(
                 n, h->dsched, (const int32_t*)h->d_blob2, h->full_newton ? 0 : 1, c);
         prof_end(h);
-        h->launches++;
+        launches_of(h)++;
     } else if (h->smem_tile > 0) {
         int blocks = (n.NA + h->smem_tile - 1) / h->smem_tile;
         prof_begin(h, "k_newton_linear");
-#define RUN_LIN(T, IT) k_newton_linear<T, IT><<<blocks, h->smem_threads, h->smem_bytes, h->cur>>>( \
+#define RUN_LIN(T, IT) k_newton_linear<T, IT><<<blocks, h->smem_threads, h->smem_bytes, cur_of(h)>>>( \
             n, h->sched, (const IT*)h->d_blob, h->d_lsrc_ptr, h->d_lsrc_code, c)
         if (h->sched16) { if (h->smem_tile == 32) RUN_LIN(32, uint16_t); else if (h->smem_tile == 16) RUN_LIN(16, uint16_t); else RUN_LIN(8, uint16_t); }
         else { if (h->smem_tile == 32) RUN_LIN(32, int32_t); else if (h->smem_tile == 16) RUN_LIN(16, int32_t); else RUN_LIN(8, int32_t); }
 #undef RUN_LIN
         prof_end(h);
-        h->launches++;
+        launches_of(h)++;
     } else {
         launch_factor<true>(h, -1.0, nw);
         launch_solve<true>(h, nullptr, c, Pred{n.mphase, PHASE_NEWTON, nullptr});
@@ -1577,8 +1595,8 @@ static void launch_linear(rbs_handle* h, double* c, Pred nw) {
 // The finalize half runs on the compacted list of members in PHASE_LIMIT, the Newton half on
 // the compacted list of members that are not DONE, so a pass costs what its active members cost.
 static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h_min, int n_steps) {
-    Net& n = h->net;
-    h->cur = G.stream;
+    Net& n = net_of(h);
+    cur_of(h) = G.stream;
     const int* from_ts = sp<int>(h, "ud_demand_from_timeseries");
     const double* alloc_total = sp<double>(h, "ud_alloc_total");
     if (G.n_limit > 0) {
@@ -1620,8 +1638,8 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
     n.NA = n.B;
     n.alist = nullptr;
     LAUNCH_CFG(h, k_compact2, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
-    h->cur = h->stream;
-    h->n_passes++;
+    if (!tl_ctx) h->cur = h->stream;
+    passes_of(h)++;
 }
 
 }  // extern "C"
@@ -1892,6 +1910,81 @@ static int advance_passes(rbs_handle* h, double dt, double h_min, int32_t n_step
     return 0;
 }
 
+// The same pass loop with one host thread per member group: a group's next pass is launched the
+// moment its counts arrive, instead of when the single host thread gets back to it after launching
+// the other groups' passes (a dozen launches each).  Every thread launches through its own
+// LaunchCtx (kernel argument copy + stream); shared bookkeeping is under a mutex.
+static int group_worker(rbs_handle* h, int gi, double dt, double h_min, int32_t n_steps, int64_t max_passes,
+                        std::mutex& mu, int& rc, std::string& err) {
+    cudaSetDevice(h->device);
+    rbs_handle::Group& G = h->groups[gi];
+    LaunchCtx ctx;
+    ctx.net = h->net;
+    ctx.cur = G.stream;
+    tl_ctx = &ctx;
+    static const bool trace = getenv("RBS_TRACE_PASSES") != nullptr;
+    int my_rc = 0;
+    auto body = [&]() -> int {
+        int64_t passes = 0;
+        while (!G.done) {
+            { std::lock_guard<std::mutex> lk(mu); if (rc) return 0; }
+            if (++passes > max_passes) return fail("rbs_advance: pass limit exceeded");
+            launch_pass(h, G, dt, h_min, n_steps);
+            CUDA_TRY(cudaMemcpyAsync(G.h_counts, G.d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+            CUDA_TRY(cudaEventRecord(G.ev, G.stream));
+            CUDA_TRY(cudaEventSynchronize(G.ev));
+            G.n_active = G.h_counts[0];
+            G.n_limit = G.h_counts[1];
+            if (trace) fprintf(stderr, "pass g%d %lld active %d limit %d min_step %d\n", gi, (long long)passes,
+                               G.n_active, G.n_limit, G.h_counts[2]);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                G.min_step = G.h_counts[2];
+                if (stream_finished_slices(h, n_steps)) return 1;
+            }
+            if (G.n_active == 0) G.done = true;
+        }
+        return 0;
+    };
+    my_rc = body();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        h->launches += ctx.launches;
+        h->n_passes += ctx.n_passes;
+        if (my_rc && !rc) { rc = my_rc; err = g_err; }
+    }
+    tl_ctx = nullptr;
+    return my_rc;
+}
+
+static int advance_passes_mt(rbs_handle* h, double dt, double h_min, int32_t n_steps) {
+    Net& n = h->net;
+    const int64_t max_passes = h->max_passes * n_steps;
+    for (auto& G : h->groups) {
+        if (G.stream != h->stream) CUDA_TRY(cudaStreamWaitEvent(G.stream, h->groups[0].ev, 0));
+        G.n_active = G.hi - G.lo;
+        G.n_limit = 0;
+        G.pending = false;
+        G.done = G.n_active == 0;
+        G.min_step = G.done ? n_steps : 0;
+        if (G.done) continue;
+        h->cur = G.stream;
+        CUDA_TRY(cudaMemsetAsync(G.d_counts, 0, 4 * sizeof(int), G.stream));
+        LAUNCH_CFG(h, k_compact2, 1, 1024, n, G.lo, G.hi, G.d_alist, G.d_llist, G.d_counts);
+    }
+    h->cur = h->stream;
+    std::mutex mu;
+    int rc = 0;
+    std::string err;
+    std::vector<std::thread> workers;
+    for (int gi = 1; gi < (int)h->groups.size(); gi++)
+        workers.emplace_back(group_worker, h, gi, dt, h_min, n_steps, max_passes, std::ref(mu), std::ref(rc), std::ref(err));
+    group_worker(h, 0, dt, h_min, n_steps, max_passes, mu, rc, err);
+    for (auto& w : workers) w.join();
+    if (rc) return fail(err);
+    return 0;
+}
+
 // round-2 experiment kept for comparison (RBS_R2_PASS=1): cluster finalize kernel, one host
 // round trip per pass
 static int advance_sync_r2(rbs_handle* h, double dt, double h_min, int32_t n_steps) {
@@ -1963,6 +2056,7 @@ static int advance_impl(rbs_handle* h, double t, double dt, int32_t n_steps, int
     cudaEvent_t ev_begin = h->groups[0].ev;
     CUDA_TRY(cudaEventRecord(ev_begin, h->stream));
     if (h->r2_pass) { if (advance_sync_r2(h, dt, h_min, n_steps)) return 1; }
+    else if (h->host_threads && h->groups.size() > 1 && !h->profiling) { if (advance_passes_mt(h, dt, h_min, n_steps)) return 1; }
     else if (advance_passes(h, dt, h_min, n_steps)) return 1;
     // join: every group's last event has been observed complete by the host, so all group
     // streams are idle and later work enqueued on the handle's stream is ordered after them
