@@ -78,7 +78,7 @@ def parse_args():
 WORKLOAD_DEFAULTS = {
     # workload: (basins, members in total, spin-up steps)
     "hws": (500, 4096, 240),
-    "tree": (100_000, 256, 72),
+    "tree": (100_000, 256, 120),
     "backwater": (51, 1, 240),
 }
 
