@@ -1251,9 +1251,14 @@ __device__ __forceinline__ void rbs_cp_async_wait_all() {
 }
 
 // facmask: bit 0 / 1 set = first / second member of this thread's pair refreshes its factors
-template <int TILE>
-__device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, int lv0, int lv1,
-                                               unsigned facmask) {
+// schedule word: through the read-only global path when the schedule lives in global memory (a
+// generic load would decide the address space per access), a plain load when it is in shared memory
+template <bool GL> __device__ __forceinline__ unsigned long long rbs_ldw(const unsigned long long* p) {
+    return GL ? __ldg(p) : *p;
+}
+template <int TILE, bool GL>
+__device__ __forceinline__ void rbs_ent_levels_impl(double* S, const EntSched& es, int lv0, int lv1,
+                                                    unsigned facmask) {
     constexpr int TPL = TILE / 2;            // threads per entry lane
     constexpr int EL = RBS_ENT_LANES;
     const int lane_e = threadIdx.x / TPL;
@@ -1262,7 +1267,7 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, in
     const unsigned long long* ent = es.ent;
     const unsigned long long* prod = es.prod;
     for (int lv = lv0; lv < lv1; lv++) {
-        const unsigned long long lw = es.lvl[lv];
+        const unsigned long long lw = rbs_ldw<GL>(es.lvl + lv);
         const int e0 = (int)(lw & 0xFFFFu), e1 = (int)((lw >> 16) & 0xFFFFu), tl = (int)(lw >> 32);
         // warps whose lanes get no entry in the first pass have none in the later ones either:
         // they go straight to the barrier
@@ -1274,12 +1279,12 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, in
                 double a0 = 0.0, a1 = 0.0;
                 unsigned e = 0, q0 = 0, cf = 0;
                 if (valid) {
-                    const unsigned long long ew = ent[k];
+                    const unsigned long long ew = rbs_ldw<GL>(ent + k);
                     e = (unsigned)ew & 0xFFFFu; q0 = ((unsigned)ew) >> 16; cf = (unsigned)(ew >> 32);
                     const unsigned q1 = q0 + (cf & 0xFFu);
 #pragma unroll 2
                     for (unsigned q = q0 + t; q < q1; q += ts) {
-                        const unsigned long long pw = prod[q];
+                        const unsigned long long pw = rbs_ldw<GL>(prod + q);
                         const double2 l = *(const double2*)(Sc + ((unsigned)pw & 0xFFFFu) * TILE);
                         const double2 p = *(const double2*)(Sc + (((unsigned)pw) >> 16) * TILE);
                         const double2 u = *(const double2*)(Sc + ((unsigned)(pw >> 32) & 0xFFFFu) * TILE);
@@ -1306,7 +1311,7 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, in
                     double2 v = o;
                     if (cf & RBS_ENT_SCALE) {
                         // the reciprocal pivot: p of the first product, or q0 itself without products
-                        const unsigned r = (cf & 0xFFu) ? (((unsigned)prod[q0]) >> 16) : q0;
+                        const unsigned r = (cf & 0xFFu) ? (((unsigned)rbs_ldw<GL>(prod + q0)) >> 16) : q0;
                         const double2 rv = *(const double2*)(Sc + r * TILE);
                         v.x *= rv.x; v.y *= rv.y;
                     }
@@ -1325,6 +1330,13 @@ __device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, in
         if (blockIdx.x == 0 && threadIdx.x == 0 && lv < 64) g_lin_lvl[lv] = clock64();
 #endif
     }
+}
+
+template <int TILE>
+__device__ __forceinline__ void rbs_ent_levels(double* S, const EntSched& es, int lv0, int lv1,
+                                               unsigned facmask) {
+    if (es.smem_sched == 0) rbs_ent_levels_impl<TILE, true>(S, es, lv0, lv1, facmask);
+    else rbs_ent_levels_impl<TILE, false>(S, es, lv0, lv1, facmask);
 }
 
 // Newton linear solve of one member tile per block on the entry schedule; input as for
