@@ -22,7 +22,7 @@
 #include "rbs_tile.cuh"
 #include "rbs_fused.cuh"
 
-#define RBS_DC_REC_CAP 64  // DiscreteControl changes recorded per member
+#define RBS_DC_REC_CAP 64  // DiscreteControl changes recorded per member (default; builder key dc_rec_cap)
 
 namespace {
 
@@ -158,6 +158,7 @@ struct rbs_handle {
     size_t smem_bytes = 0;
     int *d_lsrc_ptr = nullptr, *d_lsrc_code = nullptr;
     std::vector<int> list_phase[3];
+    int dc_rec_cap = RBS_DC_REC_CAP;  // DiscreteControl changes recorded per member
     bool pid_fused = false;  // k_pid also formulates its controlled pump / outlet
     bool pid_kd_nonzero = false;  // a PidControl derivative gain is in force (its D-term reads flows)
     bool pid_cs_kd_nonzero = false;  // ... in a control-state parameter row
@@ -298,7 +299,7 @@ void bind_net(rbs_handle* h) {
     M_I(mphase); M_I(mjac); M_I(miter); M_I(mconv); M_I(mneg); M_I(mneg2); M_I(mclamp); M_I(mlast); M_I(maction);
     M_I(cnt_iters); M_I(cnt_sub); M_I(cnt_rej); M_I(mstep); M_I(mroll);
     M_I(dc_truth); M_I(dc_state); M_I(cnt_dc);
-    n.dc_rec_cap = n.n_dc > 0 ? RBS_DC_REC_CAP : 0;
+    n.dc_rec_cap = n.n_dc > 0 ? h->dc_rec_cap : 0;
     n.dc_rec_t = n.n_dc > 0 ? mp(h, "dc_rec_t") : nullptr;
     n.dc_rec_ns = n.n_dc > 0 ? (int*)h->member["dc_rec_ns"].p : nullptr;
     n.dc_rec_bits = n.n_dc > 0 ? (int*)h->member["dc_rec_bits"].p : nullptr;
@@ -649,8 +650,9 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
     if (alloc_member(h, "dc_truth", n.n_dc_cond, true) || alloc_member(h, "dc_state", n.n_dc, true))
         return bail("member alloc");
-    if (n.n_dc > 0 && (alloc_member(h, "dc_rec_t", RBS_DC_REC_CAP) || alloc_member(h, "dc_rec_ns", RBS_DC_REC_CAP, true) ||
-                       alloc_member(h, "dc_rec_bits", RBS_DC_REC_CAP, true)))
+    h->dc_rec_cap = std::max(1, geti(b, "dc_rec_cap", RBS_DC_REC_CAP));
+    if (n.n_dc > 0 && (alloc_member(h, "dc_rec_t", h->dc_rec_cap) || alloc_member(h, "dc_rec_ns", h->dc_rec_cap, true) ||
+                       alloc_member(h, "dc_rec_bits", h->dc_rec_cap, true)))
         return bail("member alloc");
     // no control state set yet
     if (cudaMemsetAsync(h->member["dc_state"].p, 0xFF, h->member["dc_state"].bytes, h->stream) != cudaSuccess)

@@ -255,7 +255,7 @@ class Handle:
                  device: int = 0, lu_mode: int = -1, lu_tile: int = 0, smem_tile: int = -1,
                  smem_threads: int = 1024, lin_mode: int = -1, n_groups: int = 0,
                  coop_members: int = -1, tile_window: int = -1, lin_m: int = 0,
-                 r2_pass: int = 0, fin_cluster: int = 4):
+                 r2_pass: int = 0, fin_cluster: int = 4, dc_rec_cap: int = 64):
         self.L = load()
         self.flat = flat
         if sym is None:
@@ -341,6 +341,8 @@ class Handle:
             # `fin_cluster` blocks per 32-member tile); 0: the round-1 launch sequence
             set_i("r2_pass", [r2_pass])
             set_i("fin_cluster", [fin_cluster])
+            # DiscreteControl state changes recorded per member (`discrete_control.record`)
+            set_i("dc_rec_cap", [dc_rec_cap])
             # ensembles of at most this many members run a window as one cooperative kernel
             # (-1 = the library's default)
             set_i("coop_members", [int(os.environ.get("RBS_COOP_MEMBERS", str(coop_members)))])

@@ -40,7 +40,7 @@ class Model:
                  full_newton: bool = True, predictor: bool = True, max_halvings: int = 20,
                  grow_iters: int = 4, early_exit: bool = True, shrink_log2: int = 2,
                  smem_tile: int = -1, smem_threads: int = 1024,
-                 lin_mode: int = -1, n_groups: int = 0):
+                 lin_mode: int = -1, n_groups: int = 0, dc_record_cap: int = 64):
         if isinstance(model, Params):
             self.p = model
         else:
@@ -71,7 +71,8 @@ class Model:
         self._k_stop = 0
         self.h = lib.Handle(self.flat, self.sym, n_members=self.B, device=device, lu_mode=lu_mode,
                             lu_tile=lu_tile, smem_tile=smem_tile, smem_threads=smem_threads,
-                            lin_mode=lin_mode, n_groups=n_groups)
+                            lin_mode=lin_mode, n_groups=n_groups, dc_rec_cap=dc_record_cap)
+        self.DC_RECORD_CAP = int(dc_record_cap)
         self.h.set_solver(self.tables.solver_option("abstol"), self.tables.solver_option("reltol"))
         self.h.set_stepper(full_newton, predictor, max_halvings, grow_iters, early_exit, shrink_log2)
         n = self.p.nodes
@@ -336,7 +337,7 @@ class Model:
         `flat.dc_state_names[i]`."""
         return self.h.get_member_i32("dc_state", self.flat.ints["n_dc"])
 
-    DC_RECORD_CAP = 64  # RBS_DC_REC_CAP of the library
+    DC_RECORD_CAP = 64  # control state changes recorded per member (constructor: dc_record_cap)
 
     def control_record(self, member: int = 0) -> list[tuple[float, int, str, str]]:
         """`discrete_control.record` of one member (core/src/callback.jl:698-716):
@@ -350,7 +351,8 @@ class Model:
         if cnt > cap:
             import warnings
 
-            warnings.warn(f"member {member} changed control state {cnt} times; only the first {cap} are recorded")
+            warnings.warn(f"member {member} changed control state {cnt} times; only the first {cap} are recorded "
+                          "(Model(..., dc_record_cap=N) keeps more)")
             cnt = cap
         t = self.h.get_member("dc_rec_t", cap)[:cnt, member]
         ns = self.h.get_member_i32("dc_rec_ns", cap)[:cnt, member]

@@ -403,3 +403,21 @@ def test_qndf_discrete_control_record_on_gpu():
     gs = golden("control_records")["storage_condition"]
     assert [r[3] for r in rec] == gs["control_state"] and [r[2] for r in rec] == gs["truth_state"]
     assert S[0] < gs["storage_below"]
+
+
+def test_discrete_control_record_capacity_is_configurable():
+    """`discrete_control.record` grows without bound in the reference (core/src/callback.jl:698-716);
+    here the per-member capacity is a constructor argument: the hysteresis model changes state
+    hundreds of times in a year and every change is kept."""
+    import warnings
+    m = Model(build_params(MODELS["circular_flow"]()), dt=3600.0, dc_record_cap=1024)
+    try:
+        m.update_until(120 * 86400.0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            rec = m.control_record()
+    finally:
+        m.finalize()
+    assert len(rec) > 64
+    assert all(a[0] <= b[0] for a, b in zip(rec, rec[1:]))
+    assert {r[3] for r in rec} == {"on", "off"}
