@@ -701,7 +701,8 @@ def main():
 def ncu_traffic(group: str):
     """Summed dram read+write bytes per launch of the kernels of the group from the committed
     `ncu --set full` captures of full 4096-member launches (profiles/r2_*.txt, else r1_*), or None."""
-    kernels = {"linear_solve": ["k_newton_linear_ent", "k_assemble_linear"],
+    lane = (ROOT / "profiles" / "r2_k_newton_linear_lane.txt").exists()  # full launches take the lane kernel
+    kernels = {"linear_solve": ["k_newton_linear_lane" if lane else "k_newton_linear_ent", "k_assemble_linear"],
                "rhs_jacobian": ["k_basin", "k_links"],
                "newton_update": ["k_newton_update"], "limiter_accept": ["k_step_apply"]}.get(group)
     if not kernels:

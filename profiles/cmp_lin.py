@@ -11,7 +11,7 @@ from ribasim_b200.ensemble import perturbed_forcing  # noqa: E402
 from ribasim_b200.model import Model  # noqa: E402
 
 B = 72
-p, flat, sym = bench.build_workload(500)
+p, flat, sym, _ = bench.build_workload(500)
 base, fb = bench.base_forcing(p, 0)
 forcing = perturbed_forcing(base, fb, range(B), 0)
 res = {}

@@ -9,7 +9,7 @@ from ribasim_b200.ensemble import perturbed_forcing  # noqa: E402
 from ribasim_b200.model import Model  # noqa: E402
 
 B = 4096
-p, flat, sym = bench.build_workload(500)
+p, flat, sym, _ = bench.build_workload(500)
 model = Model(p, n_members=B, dt=bench.DT, flat=flat, sym=sym, full_newton=True)
 h = model.h
 t = 0.0

@@ -11,7 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import bench
     from ribasim_b200.model import Model
 
-    p, flat, sym = bench.build_workload(500)
+    p, flat, sym, _ = bench.build_workload(500)
     model = Model(p, n_members=4096, dt=bench.DT, flat=flat, sym=sym, full_newton=True)
     h = model.h
     t = 0.0

@@ -21,6 +21,7 @@
 #include "rbs_kernels.cuh"
 #include "rbs_tile.cuh"
 #include "rbs_fused.cuh"
+#include "rbs_lane.cuh"
 
 #define RBS_DC_REC_CAP 64  // DiscreteControl changes recorded per member (default; builder key dc_rec_cap)
 
@@ -141,6 +142,11 @@ struct rbs_handle {
     void* d_entc_blob = nullptr;
     size_t entc_smem_bytes = 0;
     bool lin_entc = false;
+    int lin_lane = 0;            // member-per-lane solve on global slots (rbs_lane.cuh): warps per block, 0 = off
+    int lane_min = 2048;         // launches of at least this many members take it (measured crossover with the shared-memory kernel)
+    LaneTape lane_tape{};
+    void* d_lane_blob = nullptr;
+    size_t lane_smem = 0;
     // M members per thread on the compact entry schedule (rbs_fused.cuh); 0 = off
     int lin_m = 0;
     int lin_m_sched = 0;         // schedule words in shared memory behind the slots
@@ -640,11 +646,14 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
         {"cum_precipitation", n.n_basin}, {"cum_surface_runoff", n.n_basin},
         {"cum_drainage", n.n_basin}, {"exact", n.n_basin}, {"storage_prev", n.n_basin},
         {"level_prev", n.n_basin}, {"fb_rate", n.n_fb}, {"fb_cum", n.n_fb}, {"frp", n.n_pump},
-        {"fro", n.n_outlet}, {"jv", n.nnz_j}, {"wv", n.nnz_w}, {"lu", n.n_lu},
+        {"fro", n.n_outlet}, {"jv", n.nnz_j}, {"wv", n.nnz_w},
+        // factor slots; the rows behind n_lu hold the right-hand-side column of the member-per-lane solve
+        {"lu", n.n_lu + n.n_reduced},
         {"norm_part", h->n_part}, {"ndz", 1}, {"ndz_prev", 1}, {"eta", 1},
         {"zlast", n.n_state}, {"ustep", n.n_state}, {"mh", 1}, {"mhnom", 1}, {"melapsed", 1}, {"mhlast", 1},
     };
     for (auto& md : mds) if (alloc_member(h, md.key, md.n)) return bail("member alloc");
+    h->member_entities["lu"] = n.n_lu;
     for (const char* k : {"nstat", "status", "mphase", "mjac", "miter", "mconv", "mneg", "mneg2", "mclamp", "mlast",
                           "maction", "cnt_iters", "cnt_sub", "cnt_rej", "mstep", "mroll", "cnt_dc"})
         if (alloc_member(h, k, 1, true)) return bail("member alloc");
@@ -1043,6 +1052,97 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 break;
             }
         }
+        // ---- member per lane on global slots (rbs_lane.cuh): the plain entry schedule unrolled into
+        // one linear tape of 16-byte records per warp, offsets ready-made for this ensemble size
+        if (h->lin_ent) {
+            int wl = getenv("RBS_LIN_LANE") ? atoi(getenv("RBS_LIN_LANE")) : geti(b, "lin_lane", 32);
+            h->lane_min = getenv("RBS_LIN_LANE_MIN") ? atoi(getenv("RBS_LIN_LANE_MIN")) : geti(b, "lin_lane_min", 2048);
+            const int NW = wl <= 0 ? 0 : wl >= 32 ? 32 : wl >= 16 ? 16 : 8;
+            auto &ee = geta("ent_e"), &eq = geta("ent_q0"), &ec = geta("ent_cf");
+            auto &pl = geta("ent_prod_l"), &pp = geta("ent_prod_p"), &pu = geta("ent_prod_u");
+            auto &lp = geta("ent_lvl_ptr"), &tm_ = geta("ent_team_log"), &pm = geta("perm");
+            const int y0 = n.n_lu, n_lv = h->esched.n_elim + h->esched.n_bwd;
+            const unsigned long long Bq = (unsigned long long)n.B;
+            bool ok = NW > 0 && (unsigned long long)(n.n_lu + n.n_reduced) * Bq < (1ull << 32);
+            std::map<int, int> piv_of;
+            std::vector<unsigned> piv_off;
+            if (ok)
+                for (size_t k = 0; k < ee.size(); k++) {
+                    if (ec[k] & 0x400) ok = false;  // FRESH belongs to the compact layout
+                    if (ec[k] & 0x100) { piv_of[ee[k]] = (int)piv_off.size(); piv_off.push_back((unsigned)(ee[k] * Bq)); }
+                }
+            auto pidx = [&](int slot) -> unsigned {
+                auto it = piv_of.find(slot);
+                if (it == piv_of.end()) { ok = false; return 0u; }
+                return (unsigned)it->second * 256u;
+            };
+            std::vector<std::vector<uint4>> tp(std::max(NW, 1));
+            auto entry_hdr = [&](int k, int cnt, bool bwd) {
+                const int e = ee[k];
+                unsigned flags = (unsigned)ec[k] & 0x300u, py = 0, xo = 0;
+                if (e >= y0) flags |= RBS_LANE_Y;
+                if (bwd) flags |= RBS_LANE_BWD;
+                if (flags & RBS_LANE_RCP) py = pidx(e);
+                if (flags & RBS_LANE_SCALE) py = pidx((ec[k] & 0xFF) ? pp[eq[k]] : eq[k]);
+                if (bwd && e >= y0) xo = (unsigned)(pm[e - y0] * Bq);
+                if (bwd && e < y0) ok = false;
+                return make_uint4((unsigned)(e * Bq), py, (unsigned)cnt | flags, xo);
+            };
+            auto product = [&](int q) { return make_uint4((unsigned)(pl[q] * Bq), pidx(pp[q]), (unsigned)(pu[q] * Bq), 0u); };
+            for (int lv = 0; ok && lv < n_lv; lv++) {
+                const int e0 = lp[lv], e1 = lp[lv + 1], tl = tm_[lv], ts = 1 << tl;
+                const bool bwd = lv >= h->esched.n_elim;
+                if (tl > 0 && ((e1 - e0) << tl) <= NW) {
+                    for (int w = 0; w < NW; w++) {
+                        const bool has = w < ((e1 - e0) << tl);
+                        const int t = w & (ts - 1);
+                        tp[w].push_back(make_uint4(has ? 1u : 0u, 1u, (unsigned)tl, (unsigned)t));
+                        if (!has) continue;
+                        const int k = e0 + (w >> tl), q0 = eq[k], cnt = ec[k] & 0xFF;
+                        std::vector<int> qs;
+                        for (int q = q0 + t; q < q0 + cnt; q += ts) qs.push_back(q);
+                        tp[w].push_back(entry_hdr(k, (int)qs.size(), bwd));
+                        for (int q : qs) tp[w].push_back(product(q));
+                    }
+                } else {
+                    for (int w = 0; w < NW; w++) {
+                        const int cnt_w = e0 + w < e1 ? (e1 - e0 - w + NW - 1) / NW : 0;
+                        tp[w].push_back(make_uint4((unsigned)cnt_w, 0u, (unsigned)tl, 0u));
+                        for (int k = e0 + w; k < e1; k += NW) {
+                            const int q0 = eq[k], cnt = ec[k] & 0xFF;
+                            tp[w].push_back(entry_hdr(k, cnt, bwd));
+                            for (int q = q0; q < q0 + cnt; q++) tp[w].push_back(product(q));
+                        }
+                    }
+                }
+            }
+            const size_t sb = ((size_t)NW * 32 + piv_off.size() * 32) * sizeof(double);
+            if (ok && sb + 1024 <= (size_t)dev_smem) {
+                std::vector<uint4> recs;
+                std::vector<int> start(NW);
+                for (int w = 0; w < NW; w++) { start[w] = (int)recs.size(); recs.insert(recs.end(), tp[w].begin(), tp[w].end()); }
+                recs.resize(recs.size() + 32, make_uint4(0, 0, 0, 0));  // the reader is one record and two lines ahead
+                std::vector<int> iperm(n.n_reduced, 0);
+                for (int i = 0; i < n.n_reduced && i < (int)pm.size(); i++) iperm[pm[i]] = i;
+                const size_t b_rec = recs.size() * sizeof(uint4), b_start = (size_t)NW * sizeof(int), b_piv = (piv_off.size() + 3) / 4 * 4 * sizeof(unsigned);
+                const size_t b_ip = iperm.size() * sizeof(int);
+                if (cudaMalloc(&h->d_lane_blob, b_rec + b_start + b_piv + b_ip + 16) != cudaSuccess) return bail("lane tape alloc");
+                char* d = (char*)h->d_lane_blob;
+                if (cudaMemcpyAsync(d, recs.data(), b_rec, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaMemcpyAsync(d + b_rec, start.data(), b_start, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaMemcpyAsync(d + b_rec + b_start, piv_off.data(), piv_off.size() * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaMemcpyAsync(d + b_rec + b_start + b_piv, iperm.data(), b_ip, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(h->stream) != cudaSuccess) return bail("lane tape upload");
+                LaneTape& lt = h->lane_tape;
+                lt.rec = (const uint4*)d; lt.start = (const int*)(d + b_rec); lt.piv_off = (const unsigned*)(d + b_rec + b_start);
+                lt.n_lv = n_lv; lt.n_piv = (int)piv_off.size(); lt.iperm = (const int*)(d + b_rec + b_start + b_piv);
+                cudaError_t e7 = NW == 32 ? cudaFuncSetAttribute(k_newton_linear_lane<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
+                               : NW == 16 ? cudaFuncSetAttribute(k_newton_linear_lane<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)
+                                          : cudaFuncSetAttribute(k_newton_linear_lane<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+                if (e7 == cudaSuccess) { h->lin_lane = NW; h->lane_smem = sb; }
+                else cudaGetLastError();
+            }
+        }
         apply_carveout(h);
         // ---- cooperative window kernel: needs the entry schedule with 2-member tiles in shared
         // memory and a grid that is co-resident
@@ -1121,6 +1221,7 @@ void rbs_destroy(rbs_handle* h) {
     if (h->d_blob2) cudaFree(h->d_blob2);
     if (h->d_ent_blob) cudaFree(h->d_ent_blob);
     if (h->d_entc_blob) cudaFree(h->d_entc_blob);
+    if (h->d_lane_blob) cudaFree(h->d_lane_blob);
     if (h->d_coop_counters) cudaFree(h->d_coop_counters);
     if (h->h_coop_counters) cudaFreeHost(h->h_coop_counters);
     if (h->d_alist) cudaFree(h->d_alist);
@@ -1534,7 +1635,21 @@ int rbs_refresh(rbs_handle* h, double t) {
 // level-per-launch kernels when the schedule does not fit in shared memory.
 static void launch_linear(rbs_handle* h, double* c, Pred nw) {
     Net& n = net_of(h);
-    if (h->lin_m > 0 && h->full_newton) {
+    if (h->lin_lane > 0 && h->lin_ent && n.NA >= h->lane_min) {
+        n.lane_iperm = h->lane_tape.iperm;
+        if (!getenv("RBS_TIME_SOLVE_ONLY"))
+        LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
+               sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));
+        n.lane_iperm = nullptr;
+        const int blocks = (n.NA + 31) / 32;
+        const bool pdl = h->pdl && !h->profiling;
+        prof_begin(h, "k_newton_linear_lane");
+        if (h->lin_lane == 32) launch_k(pdl, k_newton_linear_lane<32>, dim3(blocks), dim3(1024), h->lane_smem, cur_of(h), n, h->lane_tape, c);
+        else if (h->lin_lane == 16) launch_k(pdl, k_newton_linear_lane<16>, dim3(blocks), dim3(512), h->lane_smem, cur_of(h), n, h->lane_tape, c);
+        else launch_k(pdl, k_newton_linear_lane<8>, dim3(blocks), dim3(256), h->lane_smem, cur_of(h), n, h->lane_tape, c);
+        prof_end(h);
+        launches_of(h)++;
+    } else if (h->lin_m > 0 && h->full_newton) {
         if (!getenv("RBS_TIME_SOLVE_ONLY"))
         LAUNCH(h, k_assemble_linear, (long long)(n.n_lu + n.n_reduced) * ((n.NA + 32 * RBS_MPT - 1) / (32 * RBS_MPT)) * 32, n,
                sp<int>(h, "dsrc_ptr"), sp<int>(h, "dsrc_code"));

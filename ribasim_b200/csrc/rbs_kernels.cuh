@@ -137,6 +137,9 @@ struct Net {
     // 1 = the PidControl items run inside the phase-0 launch of k_links (allowed when no controller
     // reads a flow: all derivative gains zero, no ContinuousControl; decided on the host)
     int pid_in_links;
+    // member-per-lane solve (rbs_lane.cuh): k_assemble_linear writes reduced right-hand-side row r
+    // straight into row n_lu + lane_iperm[r] of `lu` (the solve's y column) instead of `br`
+    const int* lane_iperm;
 };
 
 // Forcing array that applies to outer step `idx` of the window.
@@ -1029,8 +1032,9 @@ __global__ void k_assemble_linear(Net n, const int* __restrict__ dsrc_ptr,
         if (m1 >= 0) n.lu[(long long)e * n.B + m1] = v1;
     } else {
         int r = e - n.n_lu;
-        if (m0 >= 0) n.br[(long long)r * n.B + m0] = rbs_solve_rhs<true>(n, nullptr, r, m0);
-        if (m1 >= 0) n.br[(long long)r * n.B + m1] = rbs_solve_rhs<true>(n, nullptr, r, m1);
+        double* dst = n.lane_iperm ? n.lu + (long long)(n.n_lu + n.lane_iperm[r]) * n.B : n.br + (long long)r * n.B;
+        if (m0 >= 0) dst[m0] = rbs_solve_rhs<true>(n, nullptr, r, m0);
+        if (m1 >= 0) dst[m1] = rbs_solve_rhs<true>(n, nullptr, r, m1);
     }
 }
 

@@ -35,7 +35,7 @@ class RbsError(RuntimeError):
 
 def _sources() -> list[Path]:
     return [CSRC / "rbs.cu", CSRC / "rbs_kernels.cuh", CSRC / "rbs_coop.cuh", CSRC / "rbs_tile.cuh",
-            CSRC / "rbs_fused.cuh", CSRC / "rbs_math.cuh", PKG_DIR.parent / "include" / "ribasim_b200.h"]
+            CSRC / "rbs_fused.cuh", CSRC / "rbs_lane.cuh", CSRC / "rbs_math.cuh", PKG_DIR.parent / "include" / "ribasim_b200.h"]
 
 
 def _source_hash() -> str:

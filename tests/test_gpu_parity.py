@@ -877,6 +877,43 @@ def test_compact_solve_slots_equal_plain(name, monkeypatch):
         assert s0[k] == s1[k], k
 
 
+@pytest.mark.parametrize("full_newton", [1, 0])
+@pytest.mark.parametrize("warps", [32, 16, 8])
+@pytest.mark.parametrize("name", ["basic", "backwater", "pid_control", "pump_discrete_control", "hws_like"])
+def test_lane_solve_equals_shared_memory_solve(name, warps, full_newton, monkeypatch):
+    """Member-per-lane solve on global slots (rbs_lane.cuh, `RBS_LIN_LANE` = warps per block): the
+    entry schedule of the shared-memory kernel with the mapping turned around (lane = member, warp =
+    entry, team partial sums as per-lane accumulators combined in the butterfly's order), so the
+    trajectories are bitwise those of k_newton_linear_ent — with full Newton and with frozen factors
+    (members that keep their factors only update the right-hand-side column); 70 members = two
+    full blocks of 32 and a ragged one."""
+    from ribasim_b200.testmodels import hws_like_model
+    B = 70
+    case = make_case(hws_like_model(n_basins=120, n_days=2) if name == "hws_like" else name, B, seed=41, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    monkeypatch.setenv("RBS_LIN_LANE_MIN", "0")  # by default only launches of >= 2048 members take it
+    for lane in ("0", str(warps)):
+        monkeypatch.setenv("RBS_LIN_LANE", lane)
+        h = gpu_handle_for(case, coop_members=0)
+        try:
+            h.set_stepper(full_newton=bool(full_newton))
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            if flat["n_dc"] > 0:
+                h.apply_discrete_control()
+                h.refresh(0.0)
+            st = h.advance(0.0, 3600.0, 6)
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats()))
+        finally:
+            h.close()
+    (u0, S0, st0, s0), (u1, S1, st1, s1) = out
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert s0[k] == s1[k], k
+
+
 @pytest.mark.parametrize("cluster", [1, 4, 8])
 @pytest.mark.parametrize("name", ["basic", "backwater", "user_demand", "pid_control",
                                   "outlet_continuous_control", "pump_discrete_control", "hws_like"])
