@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1077,16 +1078,23 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                 return (unsigned)it->second * 256u;
             };
             std::vector<std::vector<uint4>> tp(std::max(NW, 1));
+            auto kind_of = [&](int k, bool bwd) -> unsigned {
+                const int e = ee[k];
+                const bool rcp = (ec[k] & 0x100) != 0, scale = (ec[k] & 0x200) != 0;
+                if (bwd) { if (e < y0 || !scale || rcp) ok = false; return RBS_LANE_K_YB; }
+                if (scale || (rcp && e >= y0)) ok = false;
+                return rcp ? RBS_LANE_K_RCP : e >= y0 ? RBS_LANE_K_YF : RBS_LANE_K_FAC;
+            };
             auto entry_hdr = [&](int k, int cnt, bool bwd) {
                 const int e = ee[k];
-                unsigned flags = (unsigned)ec[k] & 0x300u, py = 0, xo = 0;
-                if (e >= y0) flags |= RBS_LANE_Y;
-                if (bwd) flags |= RBS_LANE_BWD;
-                if (flags & RBS_LANE_RCP) py = pidx(e);
-                if (flags & RBS_LANE_SCALE) py = pidx((ec[k] & 0xFF) ? pp[eq[k]] : eq[k]);
-                if (bwd && e >= y0) xo = (unsigned)(pm[e - y0] * Bq);
-                if (bwd && e < y0) ok = false;
-                return make_uint4((unsigned)(e * Bq), py, (unsigned)cnt | flags, xo);
+                const unsigned kind = kind_of(k, bwd);
+                unsigned py = 0, xo = 0;
+                if (kind == RBS_LANE_K_RCP) py = pidx(e);
+                if (kind == RBS_LANE_K_YB) {
+                    py = pidx((ec[k] & 0xFF) ? pp[eq[k]] : eq[k]);
+                    xo = (unsigned)(pm[e - y0] * Bq);
+                }
+                return make_uint4((unsigned)(e * Bq), py, (unsigned)cnt | (kind << 16), xo);
             };
             auto product = [&](int q) { return make_uint4((unsigned)(pl[q] * Bq), pidx(pp[q]), (unsigned)(pu[q] * Bq), 0u); };
             for (int lv = 0; ok && lv < n_lv; lv++) {
@@ -1105,14 +1113,40 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
                         for (int q : qs) tp[w].push_back(product(q));
                     }
                 } else {
+                    // entries to warps: longest first to the least loaded warp (instruction estimate);
+                    // a warp's entries then go into runs of one kind and, without teams, one count
+                    std::vector<int> ks;
+                    for (int k = e0; k < e1; k++) ks.push_back(k);
+                    auto cost = [&](int k) { return 30 + 11 * (ec[k] & 0xFF) + ((ec[k] & 0x100) ? 25 : 0); };
+                    std::stable_sort(ks.begin(), ks.end(), [&](int a, int b2) { return cost(a) > cost(b2); });
+                    std::vector<std::vector<int>> mine(NW);
+                    std::vector<long long> load(NW, 0);
+                    for (int k : ks) {
+                        int best = 0;
+                        for (int w = 1; w < NW; w++) if (load[w] < load[best]) best = w;
+                        mine[best].push_back(k);
+                        load[best] += cost(k);
+                    }
                     for (int w = 0; w < NW; w++) {
-                        const int cnt_w = e0 + w < e1 ? (e1 - e0 - w + NW - 1) / NW : 0;
-                        tp[w].push_back(make_uint4((unsigned)cnt_w, 0u, (unsigned)tl, 0u));
-                        for (int k = e0 + w; k < e1; k += NW) {
-                            const int q0 = eq[k], cnt = ec[k] & 0xFF;
-                            tp[w].push_back(entry_hdr(k, cnt, bwd));
-                            for (int q = q0; q < q0 + cnt; q++) tp[w].push_back(product(q));
+                        auto code = [&](int k) -> unsigned { const unsigned cnt = ec[k] & 0xFF; return tl == 0 && cnt <= 4 ? cnt : RBS_LANE_DYN; };
+                        auto key = [&](int k) { return (kind_of(k, bwd) << 8) | code(k); };
+                        std::stable_sort(mine[w].begin(), mine[w].end(), [&](int a, int b2) { return key(a) < key(b2); });
+                        std::vector<uint4> body;
+                        unsigned n_runs = 0;
+                        for (size_t a = 0; a < mine[w].size();) {
+                            size_t z = a;
+                            while (z < mine[w].size() && key(mine[w][z]) == key(mine[w][a])) z++;
+                            body.push_back(make_uint4(kind_of(mine[w][a], bwd), code(mine[w][a]), (unsigned)(z - a), 0u));
+                            for (size_t y = a; y < z; y++) {
+                                const int k = mine[w][y], q0 = eq[k], cnt = ec[k] & 0xFF;
+                                body.push_back(entry_hdr(k, cnt, bwd));
+                                for (int q = q0; q < q0 + cnt; q++) body.push_back(product(q));
+                            }
+                            n_runs++;
+                            a = z;
                         }
+                        tp[w].push_back(make_uint4(n_runs, 0u, (unsigned)tl, 0u));
+                        tp[w].insert(tp[w].end(), body.begin(), body.end());
                     }
                 }
             }

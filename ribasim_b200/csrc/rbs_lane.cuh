@@ -31,10 +31,6 @@
 // k_newton_linear_ent).
 #pragma once
 
-#define RBS_LANE_RCP 0x100u     // as RBS_ENT_RCP / RBS_ENT_SCALE
-#define RBS_LANE_SCALE 0x200u
-#define RBS_LANE_Y 0x800u       // target is a right-hand-side slot (every member updates it)
-#define RBS_LANE_BWD 0x1000u    // backward-substitution entry: the value is final, also stored to x
 
 struct LaneTape {
     const uint4* rec;        // records of all warps
@@ -44,12 +40,22 @@ struct LaneTape {
     const int* iperm;        // reduced row -> position in the elimination order
 };
 // record layouts
-//   level header : x = entries of this warp (team level: 1 if the warp has a unit), y = 1 for a team
+//   level header : x = runs of this warp (team level: 1 if the warp has a unit), y = 1 for a team
 //                  level, z = tl, w = team member t of this warp's unit
+//   run header   : x = kind (RBS_LANE_K_*), y = products per entry (0..4) or RBS_LANE_DYN (every
+//                  entry header carries its own count), z = entries
 //   entry header : x = element offset of the target slot, y = byte offset of its pivot row in shared
 //                  memory (RCP: the pivot this entry produces, SCALE: the pivot it is scaled by),
-//                  z = product count of this record run | flags, w = element offset in x (BWD)
+//                  z = product count | flags, w = element offset in x (BWD)
 //   product      : x = element offset of l, y = byte offset of the pivot row, z = element offset of u
+// A warp's entries of a level are independent, so the host sorts them into runs of one kind and —
+// in levels without teams — one product count: the loop body of a run is straight-line code (no
+// flag tests, no count dispatch, constant tape stride).
+#define RBS_LANE_K_RCP 0u   // pivot: v = 1 / (old - acc) -> shared memory (+ `lu` for members that refactor)
+#define RBS_LANE_K_FAC 1u   // factor slot: v = old - acc, members that refactor
+#define RBS_LANE_K_YF 2u    // right-hand-side slot in the elimination (fused forward substitution)
+#define RBS_LANE_K_YB 3u    // backward substitution: v = old * pivot - acc, final: also stored to x
+#define RBS_LANE_DYN 0xFFu
 
 // address of element `off` of a member column: one IMAD.WIDE (written as PTX so that the compiler
 // does not re-derive the column base from its parts for every operand)
@@ -115,69 +121,161 @@ __device__ __forceinline__ double rbs_lane_products(const uint4* __restrict__ tp
 
 template <int V> struct RbsInt { static constexpr int value = V; };
 
+// per-thread context of the lane kernel
+struct LaneCtx {
+    double* Lm;        // this lane's member column of `lu`
+    double* xm;        // ... of the solution vector
+    char* piv;         // ... of the pivots in shared memory
+    bool live, fac;    // lane has a member in the Newton phase / that member refactors
+};
+
+template <int KIND>
+__device__ __forceinline__ void rbs_lane_finish(const LaneCtx& c, const uint4 eh, double o, double acc) {
+    if (KIND == (int)RBS_LANE_K_RCP) {
+        const double v = 1.0 / (o - acc);
+        if (c.fac || !c.live) *(double*)(c.piv + eh.y) = v;
+        if (c.fac) *rbs_lane_at(c.Lm, eh.x) = v;
+    } else if (KIND == (int)RBS_LANE_K_FAC) {
+        if (c.fac) *rbs_lane_at(c.Lm, eh.x) = o - acc;
+    } else if (KIND == (int)RBS_LANE_K_YF) {
+        if (c.live) *rbs_lane_at(c.Lm, eh.x) = o - acc;
+    } else {
+        const double v = o * *(const double*)(c.piv + eh.y) - acc;
+        if (c.live) {
+            *rbs_lane_at(c.Lm, eh.x) = v;
+            *rbs_lane_at(c.xm, eh.w) = v;
+        }
+    }
+}
+
+// two entries of CNT products each at once: the loads of both are in flight together (an entry is a
+// chain of dependent round trips — header, operands, reciprocal — and a warp has nothing else to
+// issue meanwhile)
+template <int KIND, int CNT>
+__device__ __forceinline__ void rbs_lane_pair(const LaneCtx& c, const uint4* __restrict__ tp) {
+    constexpr int NP = CNT > 0 ? CNT : 1;
+    const uint4 e0 = __ldg(tp), e1 = __ldg(tp + 1 + CNT);
+    uint4 r0[NP], r1[NP];
+#pragma unroll
+    for (int j = 0; j < CNT; j++) { r0[j] = __ldg(tp + 1 + j); r1[j] = __ldg(tp + 2 + CNT + j); }
+    rbs_lane_prefetch(tp + 16);
+    const double o0 = *rbs_lane_at(c.Lm, e0.x), o1 = *rbs_lane_at(c.Lm, e1.x);
+    double l0[NP], u0[NP], p0[NP], l1[NP], u1[NP], p1[NP];
+#pragma unroll
+    for (int j = 0; j < CNT; j++) {
+        l0[j] = *rbs_lane_at(c.Lm, r0[j].x); u0[j] = *rbs_lane_at(c.Lm, r0[j].z);
+        l1[j] = *rbs_lane_at(c.Lm, r1[j].x); u1[j] = *rbs_lane_at(c.Lm, r1[j].z);
+        p0[j] = *(const double*)(c.piv + r0[j].y); p1[j] = *(const double*)(c.piv + r1[j].y);
+    }
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < CNT; j++) { a0 = a0 + (l0[j] * p0[j]) * u0[j]; a1 = a1 + (l1[j] * p1[j]) * u1[j]; }
+    rbs_lane_finish<KIND>(c, e0, o0, a0);
+    rbs_lane_finish<KIND>(c, e1, o1, a1);
+}
+
+// one run of n entries of one kind; CNT >= 0: every entry has CNT products (levels without teams)
+template <int KIND, int CNT, int TS>
+__device__ __forceinline__ const uint4* rbs_lane_run(const LaneCtx& c, const uint4* __restrict__ tp, int n) {
+    if (CNT >= 0 && CNT <= 2) {
+#pragma unroll 1
+        for (; n >= 2; n -= 2) {
+            rbs_lane_pair<KIND, (CNT >= 0 && CNT <= 2 ? CNT : 0)>(c, tp);
+            tp += 2 * (1 + CNT);
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const uint4 eh = __ldg(tp);
+        rbs_lane_prefetch(tp + 16);
+        const double o = *rbs_lane_at(c.Lm, eh.x);
+        double acc = 0.0;
+        if (CNT >= 0) {
+            if (CNT > 0) {
+                double a[1] = {0.0};
+                rbs_lane_chunk<(CNT > 0 ? CNT : 1), 0, 1>(tp + 1, a, c.Lm, c.piv);
+                acc = a[0];
+            }
+            tp += 1 + CNT;
+        } else {
+            const int cnt = (int)(eh.z & 0xFFu);
+            acc = rbs_lane_products<TS>(tp + 1, cnt, c.Lm, c.piv);
+            tp += 1 + cnt;
+        }
+        rbs_lane_finish<KIND>(c, eh, o, acc);
+    }
+    return tp;
+}
+template <int KIND, int TS>
+__device__ __forceinline__ const uint4* rbs_lane_run_kind(const LaneCtx& c, const uint4* __restrict__ tp,
+                                                          unsigned cnt_code, int n) {
+    if (TS == 1) {
+        switch (cnt_code) {
+        case 0: return rbs_lane_run<KIND, 0, 1>(c, tp, n);
+        case 1: return rbs_lane_run<KIND, 1, 1>(c, tp, n);
+        case 2: return rbs_lane_run<KIND, 2, 1>(c, tp, n);
+        case 3: return rbs_lane_run<KIND, 3, 1>(c, tp, n);
+        case 4: return rbs_lane_run<KIND, 4, 1>(c, tp, n);
+        default: break;
+        }
+    }
+    return rbs_lane_run<KIND, -1, TS>(c, tp, n);
+}
+// the runs of this warp in a level without warp teams
+template <int TS>
+__device__ __forceinline__ const uint4* rbs_lane_level(const LaneCtx& c, const uint4* __restrict__ tp, int n_runs) {
+    for (int r = 0; r < n_runs; r++) {
+        const uint4 rh = __ldg(tp);
+        tp++;
+        if (rh.x == RBS_LANE_K_RCP) tp = rbs_lane_run_kind<(int)RBS_LANE_K_RCP, TS>(c, tp, rh.y, (int)rh.z);
+        else if (rh.x == RBS_LANE_K_FAC) tp = rbs_lane_run_kind<(int)RBS_LANE_K_FAC, TS>(c, tp, rh.y, (int)rh.z);
+        else if (rh.x == RBS_LANE_K_YF) tp = rbs_lane_run_kind<(int)RBS_LANE_K_YF, TS>(c, tp, rh.y, (int)rh.z);
+        else tp = rbs_lane_run_kind<(int)RBS_LANE_K_YB, TS>(c, tp, rh.y, (int)rh.z);
+    }
+    return tp;
+}
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32)
 k_newton_linear_lane(Net n, LaneTape tape, double* __restrict__ x) {
     RBS_PDL();
     extern __shared__ double lane_smem[];
     double* part_s = lane_smem;                            // [NW][32] team partial sums
-    char* piv = (char*)(lane_smem + NW * 32);              // [n_piv][32] reciprocal pivots
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
     int m = j < n.NA ? RBS_MEMBER(n, j) : -1;
     if (m >= 0 && n.mphase[m] != PHASE_NEWTON) m = -1;
-    const bool live = m >= 0;
-    const bool fac = live && n.mjac[m] != 0;
+    LaneCtx c;
+    c.live = m >= 0;
+    c.fac = c.live && n.mjac[m] != 0;
     // lanes without a member compute on the columns of the block's first member and store nothing
-    const int ma = live ? m : RBS_MEMBER(n, blockIdx.x * 32);
-    double* Lm = n.lu + ma;
-    double* xm = x + ma;
-    piv += lane * 8;
+    const int ma = c.live ? m : RBS_MEMBER(n, blockIdx.x * 32);
+    c.Lm = n.lu + ma;
+    c.xm = x + ma;
+    c.piv = (char*)(lane_smem + NW * 32) + lane * 8;       // [n_piv][32] reciprocal pivots
     LIN_CLK(0);
     // the right-hand-side column is already behind the factor slots (k_assemble_linear, Net::lane_iperm);
     // members that keep their factors need their stored pivots
-    if (__syncthreads_or(live && !fac))
-        for (int i = w; i < tape.n_piv; i += NW) *(double*)(piv + i * 256) = *rbs_lane_at(Lm, tape.piv_off[i]);
+    if (__syncthreads_or(c.live && !c.fac))
+        for (int i = w; i < tape.n_piv; i += NW) *(double*)(c.piv + i * 256) = *rbs_lane_at(c.Lm, tape.piv_off[i]);
     __syncthreads();
     LIN_CLK(2);
     const uint4* __restrict__ tp = tape.rec + tape.start[w];
-    uint4 cur = __ldg(tp);
     rbs_lane_prefetch(tp + 8);
-    rbs_lane_prefetch(tp + 16);
-    auto finish = [&](const uint4 eh, double o, double acc) {
-        double v = o;
-        if (eh.z & RBS_LANE_SCALE) v *= *(const double*)(piv + eh.y);
-        v -= acc;
-        if (eh.z & RBS_LANE_Y) {
-            if (live) {
-                *rbs_lane_at(Lm, eh.x) = v;
-                if (eh.z & RBS_LANE_BWD) *rbs_lane_at(xm, eh.w) = v;
-            }
-        } else {
-            if (eh.z & RBS_LANE_RCP) {
-                v = 1.0 / v;
-                if (fac || !live) *(double*)(piv + eh.y) = v;
-            }
-            if (fac) *rbs_lane_at(Lm, eh.x) = v;
-        }
-    };
     for (int lv = 0; lv < tape.n_lv; lv++) {
-        const uint4 lh = cur;   // level header; `cur` is always the record at tp, loaded one step ahead
+        const uint4 lh = __ldg(tp);
         tp++;
-        cur = __ldg(tp);
         if (lh.y) {
             // narrow level: one unit (entry, team member) per warp, partial sums through shared memory
             uint4 eh = make_uint4(0, 0, 0, 0);
             double o = 0.0;
             if (lh.x) {
-                eh = cur;
+                eh = __ldg(tp);
+                rbs_lane_prefetch(tp + 16);
                 const int cnt = (int)(eh.z & 0xFFu);
-                const uint4* tn = tp + 1 + cnt;
-                cur = __ldg(tn);
-                rbs_lane_prefetch(tn + 16);
-                if (lh.w == 0) o = *rbs_lane_at(Lm, eh.x);
-                part_s[w * 32 + lane] = rbs_lane_products<1>(tp + 1, cnt, Lm, piv);
-                tp = tn;
+                if (lh.w == 0) o = *rbs_lane_at(c.Lm, eh.x);
+                part_s[w * 32 + lane] = rbs_lane_products<1>(tp + 1, cnt, c.Lm, c.piv);
+                tp += 1 + cnt;
             }
             __syncthreads();
             if (lh.x && lh.w == 0) {
@@ -189,30 +287,18 @@ k_newton_linear_lane(Net n, LaneTape tape, double* __restrict__ x) {
                 a[0] += a[1]; a[2] += a[3]; a[4] += a[5]; a[6] += a[7];
                 if (tl >= 2) { a[0] += a[2]; a[4] += a[6]; }
                 if (tl >= 3) { a[0] += a[4]; }
-                finish(eh, o, a[0]);
+                const unsigned kind = eh.z >> 16;
+                if (kind == RBS_LANE_K_RCP) rbs_lane_finish<(int)RBS_LANE_K_RCP>(c, eh, o, a[0]);
+                else if (kind == RBS_LANE_K_FAC) rbs_lane_finish<(int)RBS_LANE_K_FAC>(c, eh, o, a[0]);
+                else if (kind == RBS_LANE_K_YF) rbs_lane_finish<(int)RBS_LANE_K_YF>(c, eh, o, a[0]);
+                else rbs_lane_finish<(int)RBS_LANE_K_YB>(c, eh, o, a[0]);
             }
         } else {
-            // the entries of this warp, their whole product lists inside the warp (the switch on the
-            // level's team size stays outside the entry loop)
-            auto entries = [&](auto ts_tag) {
-                constexpr int TS = decltype(ts_tag)::value;
-                for (int i = 0; i < (int)lh.x; i++) {
-                    const uint4 eh = cur;
-                    const int cnt = (int)(eh.z & 0xFFu);
-                    const uint4* tn = tp + 1 + cnt;
-                    cur = __ldg(tn);   // next header: its round trip overlaps this entry's operands
-                    rbs_lane_prefetch(tn + 16);
-                    const double o = *rbs_lane_at(Lm, eh.x);
-                    const double acc = rbs_lane_products<TS>(tp + 1, cnt, Lm, piv);
-                    tp = tn;
-                    finish(eh, o, acc);
-                }
-            };
             const int tl = (int)lh.z;
-            if (tl == 0) entries(RbsInt<1>{});
-            else if (tl == 1) entries(RbsInt<2>{});
-            else if (tl == 2) entries(RbsInt<4>{});
-            else entries(RbsInt<8>{});
+            if (tl == 0) tp = rbs_lane_level<1>(c, tp, (int)lh.x);
+            else if (tl == 1) tp = rbs_lane_level<2>(c, tp, (int)lh.x);
+            else if (tl == 2) tp = rbs_lane_level<4>(c, tp, (int)lh.x);
+            else tp = rbs_lane_level<8>(c, tp, (int)lh.x);
         }
         __syncthreads();
 #ifdef RBS_LIN_PROFILE
