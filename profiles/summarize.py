@@ -102,20 +102,21 @@ def summary_table():
                   "|---|---|---|---|---|---|\n")
         for name, us, mb, gbs in rows:
             out.write(f"| `{name}` | {us:.1f} | {mb:.1f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {100 * gbs / 8000:.0f} |\n")
-        newton = [r for r in rows if any(k in r[0] for k in ("k_basin<1", "k_links<1", "k_assemble_linear",
-                                                               "k_newton_linear_ent", "k_newton_update"))]
-        if len(newton) == 5:
-            mb = sum(r[2] for r in newton)
-            us = sum(r[1] for r in newton)
-            # SURVEY 8(d) for the 500-basin network: B_rhs + B_jac + B_solve per member and iteration
-            alg_kb = (48 * 500 + 8 * 1086 + 16 * 10 + 32 * 500 + 8 * 10 + 8 * 2138 + 8 * 1621 + 16 * 510) / 1e3
-            out.write(f"\nOne Newton iteration of 4096 members (the five kernels above it consists of): {mb:.0f} MB of DRAM "
-                      f"traffic in {us:.0f} us = {mb * 1e3 / 4096:.0f} KB per member against {alg_kb:.0f} KB of algorithmic "
-                      f"bytes (SURVEY 8(d): B_rhs + B_jac + B_solve): {mb * 1e3 / 4096 / alg_kb:.1f}x.  Every phase boundary is "
-                      "a kernel boundary in the member-fastest layout: level / factor and their partials, the J values "
-                      "(written by k_links, read by k_assemble_linear and by k_newton_update), the factor slots and the "
-                      "reduced right-hand side round-trip through HBM, and the full-state vectors z and du are read by "
-                      "three kernels.\n")
+        for solve in ("k_newton_linear_ent", "k_newton_linear_lane"):
+          newton = [r for r in rows if any(k in r[0] for k in ("k_basin<1", "k_links<1", "k_assemble_linear",
+                                                                 solve, "k_newton_update"))]
+          if len(newton) == 5:
+              mb = sum(r[2] for r in newton)
+              us = sum(r[1] for r in newton)
+              # SURVEY 8(d) for the 500-basin network: B_rhs + B_jac + B_solve per member and iteration
+              alg_kb = (48 * 500 + 8 * 1086 + 16 * 10 + 32 * 500 + 8 * 10 + 8 * 2138 + 8 * 1621 + 16 * 510) / 1e3
+              out.write(f"\nOne Newton iteration of 4096 members (basin, links, assembly, `{solve}`, update): {mb:.0f} MB of DRAM "
+                        f"traffic in {us:.0f} us = {mb * 1e3 / 4096:.0f} KB per member against {alg_kb:.0f} KB of algorithmic "
+                        f"bytes (SURVEY 8(d): B_rhs + B_jac + B_solve): {mb * 1e3 / 4096 / alg_kb:.1f}x.  Every phase boundary is "
+                        "a kernel boundary in the member-fastest layout: level / factor and their partials, the J values "
+                        "(written by k_links, read by k_assemble_linear and by k_newton_update), the factor slots and the "
+                        "reduced right-hand side round-trip through HBM, and the full-state vectors z and du are read by "
+                        "three kernels.\n")
 
 
 if tag == "r1":

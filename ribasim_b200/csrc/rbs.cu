@@ -143,6 +143,7 @@ struct rbs_handle {
     void* d_entc_blob = nullptr;
     size_t entc_smem_bytes = 0;
     bool lin_entc = false;
+    double limit_frac = 0.0;     // see launch_pass
     int lin_lane = 0;            // member-per-lane solve on global slots (rbs_lane.cuh): warps per block, 0 = off
     int lane_min = 2048;         // launches of at least this many members take it (measured crossover with the shared-memory kernel)
     LaneTape lane_tape{};
@@ -634,6 +635,7 @@ rbs_handle* rbs_create(const rbs_builder* b, int32_t n_members, int32_t device) 
     // rows of the state vector per block of k_newton_update (a thread walks rows_per_block / 8 rows one
     // after the other): fixed for every ensemble size, because the partition fixes the summation order
     // of the convergence norm and member results must not depend on the batch
+    h->limit_frac = getenv("RBS_LIMIT_FRAC") ? std::min(1.0, std::max(0.0, atof(getenv("RBS_LIMIT_FRAC")))) : 0.0;
     h->rows_per_block = getenv("RBS_ROWS_PER_BLOCK") ? std::max(8, atoi(getenv("RBS_ROWS_PER_BLOCK"))) : geti(b, "rows_per_block", 64);
     h->n_part = (n.n_state + h->rows_per_block - 1) / h->rows_per_block;
     struct MD { const char* key; int64_t n; };
@@ -1750,7 +1752,11 @@ static void launch_pass(rbs_handle* h, rbs_handle::Group& G, double dt, double h
     cur_of(h) = G.stream;
     const int* from_ts = sp<int>(h, "ud_demand_from_timeseries");
     const double* alloc_total = sp<double>(h, "ud_alloc_total");
-    if (G.n_limit > 0) {
+    // The finalize half may wait until the members whose iteration ended are at least
+    // `limit_frac` of the group's unfinished members (RBS_LIMIT_FRAC, default 0 = every pass): its
+    // kernels then walk a denser list (fewer launches, less sector over-fetch) at the price of idle
+    // passes for the members that wait.  Same per-member arithmetic whatever the pass it runs in.
+    if (G.n_limit > 0 && (double)G.n_limit >= h->limit_frac * (double)G.n_active) {
         // finalize half: members whose Newton iteration ended in the previous pass
         n.NA = G.n_limit;
         n.alist = G.d_llist;
