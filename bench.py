@@ -704,7 +704,9 @@ def ncu_traffic(group: str):
     lane = (ROOT / "profiles" / "r2_k_newton_linear_lane.txt").exists()  # full launches take the lane kernel
     kernels = {"linear_solve": ["k_newton_linear_lane" if lane else "k_newton_linear_ent", "k_assemble_linear"],
                "rhs_jacobian": ["k_basin", "k_links"],
-               "newton_update": ["k_newton_update"], "limiter_accept": ["k_step_apply"]}.get(group)
+               "newton_update": ["k_newton_update"],
+               # first finalize half of the profiled window: 2001 of the 4096 members (decide / compaction: negligible)
+               "limiter_accept": ["k_basin_limit_pre", "k_step_limit", "k_basin_limit_post", "k_step_apply"]}.get(group)
     if not kernels:
         return None
     total = 0.0
@@ -767,7 +769,8 @@ def roofline(flat, sym, report, s0, s1, args):
         "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(report.items())},
         "how": "one simulated day repeated on a single stream with one CUDA-event pair per launch; "
                "bytes = per-member algorithmic bytes x member-launches executed; traffic = summed ncu "
-               "DRAM bytes of the group's kernels for one full 4096-member launch each",
+               "DRAM bytes of the group's kernels for one launch each out of profiles/r2_k_*.txt (Newton half: full "
+               "4096-member launches; limiter / accept: the first finalize half of the profiled window, 2001 members)",
     }
 
 

@@ -914,6 +914,38 @@ def test_lane_solve_equals_shared_memory_solve(name, warps, full_newton, monkeyp
         assert s0[k] == s1[k], k
 
 
+def test_lane_solve_taken_by_large_launches(monkeypatch):
+    """Default selection: a launch of at least 2048 members (one member group of 2100 here) takes the
+    member-per-lane solve, smaller ones the shared-memory kernel; members finish at different passes,
+    so both kernels serve the same window — and the trajectories are bitwise those of a run with
+    the lane kernel switched off."""
+    B = 2100
+    case = make_case("basic", B, seed=43, t=0.0)
+    flat = case["flat"]
+    n, nb = flat["n_state"], flat["n_basin"]
+    out = []
+    for lane in ("0", None):
+        if lane is None:
+            monkeypatch.delenv("RBS_LIN_LANE", raising=False)
+        else:
+            monkeypatch.setenv("RBS_LIN_LANE", lane)
+        h = gpu_handle_for(case, coop_members=0, n_groups=1)
+        try:
+            h.refresh(0.0)
+            h.set_member("level_prev", h.get_member("level", nb))
+            h.profile(True)
+            st = h.advance(0.0, 3600.0, 4)
+            rep = h.profile_report()
+            out.append((h.get_member("u", n), h.get_member("storage", nb), st, h.stats(), rep))
+        finally:
+            h.close()
+    (u0, S0, st0, s0, r0), (u1, S1, st1, s1, r1) = out
+    assert "k_newton_linear_lane" not in r0 and r1.get("k_newton_linear_lane", (0, 0.0))[0] > 0
+    assert np.array_equal(u0, u1) and np.array_equal(S0, S1) and np.array_equal(st0, st1)
+    for k in ("substeps", "newton_iters", "rejects", "failed"):
+        assert s0[k] == s1[k], k
+
+
 @pytest.mark.parametrize("cluster", [1, 4, 8])
 @pytest.mark.parametrize("name", ["basic", "backwater", "user_demand", "pid_control",
                                   "outlet_continuous_control", "pump_discrete_control", "hws_like"])
