@@ -38,7 +38,10 @@ typedef struct rbs_handle rbs_handle;   /* one ensemble shard resident on one de
  * Replaces the in-memory `ParametersIndependent` the Julia core builds in
  * `Parameters(db, config)` (core/src/read.jl:1692-1802).  The host fills named Int32 /
  * Float64 arrays (names listed in DESIGN.md §"descriptor keys"; produced by
- * ribasim_b200/flatten.py and ribasim_b200/symbolic.py) and hands the builder to rbs_create. */
+ * ribasim_b200/flatten.py and ribasim_b200/symbolic.py) and hands the builder to rbs_create.
+ * Optional tuning keys (one int32 each): "n_groups", "coop_members", "ent_tile", "lin_m",
+ * "lin_lane" (warps per block of the member-per-lane solve, 0 = off, default 32) and
+ * "lin_lane_min" (launches of at least this many members take it, default 2048), "dc_rec_cap". */
 rbs_builder* rbs_builder_create(void);
 int rbs_builder_set_i32(rbs_builder* b, const char* key, const int32_t* data, int64_t n);
 int rbs_builder_set_f64(rbs_builder* b, const char* key, const double* data, int64_t n);
