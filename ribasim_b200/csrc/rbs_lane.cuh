@@ -15,9 +15,11 @@
 //
 // Schedule.  `rbs_create` unrolls the entry schedule into one linear tape of 16-byte records per
 // warp (level header, entry header, products with ready-made element offsets `slot * B`): a warp
-// streams through its tape with 128-bit loads, nothing is searched or decoded at run time.  The
-// kernel is bound by instruction issue (one block per SM, 32 members), so the tape exists to keep
-// the instruction count per product at ~11.
+// streams through its tape with 128-bit loads (lines prefetched into L1 ahead of the reader),
+// nothing is searched or decoded at run time.  A warp's entries of a level are sorted into runs of
+// one kind and product count, so a run's loop body is straight-line code (~11 instructions per
+// product, ~35 per two-product entry).  Measured: a block is bound by the operand
+// round trips to L2 and the level barrier, not by instruction issue.
 //
 // Teams.  A team level of the entry schedule (2^tl lanes share an entry's product list: lane t
 // sums the products q0 + t, q0 + t + 2^tl, ...; the partial sums are combined by a shuffle
@@ -30,7 +32,6 @@
 // Replaces: the KLU refactor + solve of core/src/differentiation.jl:321-345 (same role as
 // k_newton_linear_ent).
 #pragma once
-
 
 struct LaneTape {
     const uint4* rec;        // records of all warps
